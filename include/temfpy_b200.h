@@ -1,0 +1,238 @@
+/*
+ * temfpy_b200 -- C ABI of the B200-native mean-field -> MPS hot path.
+ *
+ * The reference (temfpy/temfpy, pure Python) has no FFI boundary of its own: its boundary for this
+ * path is the public Python API (slater.py / schmidt_utils.py / ...).  Every entry point below
+ * replaces the arithmetic behind one reference function; the citation after "replaces:" is the
+ * reference file:line (relative to /root/reference/src/temfpy/).  The Python shim in
+ * temfpy_b200/ binds these symbols with ctypes (see INTEGRATION.md for the stub a reference
+ * maintainer would add).
+ *
+ * Conventions
+ *  - every matrix is column-major with an explicit leading dimension; the correlation matrix is
+ *    Hermitian so its NumPy (row-major) buffer can be passed unchanged (real symmetric case);
+ *  - "dev" pointers are device pointers into caller-owned buffers (PyTorch allocations), "host"
+ *    pointers are plain host memory; nothing here allocates device memory;
+ *  - `stream` is a cudaStream_t passed as void*; all device work is enqueued on it and the call
+ *    returns without synchronising unless stated;
+ *  - return value: 0 = ok, <0 = error class (TMF_ERR_*), message via tmf_last_error().
+ */
+#ifndef TEMFPY_B200_H
+#define TEMFPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMF_OK 0
+#define TMF_ERR_VALUE (-1)     /* -> ValueError   (bad argument, capacity exceeded)          */
+#define TMF_ERR_ASSERT (-2)    /* -> AssertionError (reference asserts, e.g. slater.py:394)  */
+#define TMF_ERR_RUNTIME (-3)   /* -> RuntimeError (CUDA failure, no device)                  */
+
+#define TMF_SIDE_L 0
+#define TMF_SIDE_R 1
+#define TMF_MAX_MODES 64       /* entangled modes per bond handled by the 64-bit occupation masks */
+
+/* library --------------------------------------------------------------------------------- */
+int tmf_version(void);
+const char *tmf_last_error(void);
+/* 1 if this build runs kernels on a CUDA device, 0 for the host simulator used by CPU tests. */
+int tmf_is_cuda(void);
+int tmf_device_count(void);
+
+/* K2 -- correlation matrix build.  replaces: slater.py:1177 (C = v @ HT(v)).
+ * C (L x L, ldc) = Phi * Phi^T with Phi row-major L x N (row stride ldphi, NumPy layout); real
+ * symmetric, FP64 DMMA tiles. */
+int tmf_corr_build(const double *phi_dev, int L, int N, int ldphi, double *C_dev, int ldc,
+                   void *stream);
+
+/* General grouped FP64 GEMM used by the mode extraction (exposed for tests / profiling).
+ * Jobs are described on the host; descriptors are copied into `desc_dev` (njobs * 128 bytes). */
+typedef struct tmf_gemm_job {
+  const double *A, *B;
+  double *C;
+  const int *a_idx, *b_idx;            /* optional column gathers for op(A) rows / op(B) cols   */
+  const double *row_scale, *col_scale; /* optional epilogue scalings                            */
+  int M, N, K;
+  int lda, ldb, ldc;
+  int transA, transB;                  /* op(A) is M x K, op(B) is K x N                        */
+  int a_row_off, b_row_off;            /* row offset applied along K inside A / B               */
+  double alpha, beta;
+  int pad_[4];
+} tmf_gemm_job;
+int64_t tmf_gemm_desc_bytes(int njobs);    /* size of desc_dev for the call below */
+int tmf_gemm_grouped(const tmf_gemm_job *jobs_host, int njobs, void *desc_dev, void *stream);
+
+/* K3/K4 -- per-bond Schmidt-mode extraction.  replaces: slater.py:324-375 (diag_and_separate:
+ * eigh :347, split :350, reorder :353-370) for every (bond, side) job of a chain at once.
+ *
+ * For job j the diagonal block A = C[:x,:x] (side L) or C[x:,x:] (side R) of the projector C is
+ * decomposed into k_j entangled eigenpairs (cutoff < e < 1-cutoff) and an orthonormal basis of
+ * the "filled" eigenspace (e >= 1-cutoff).  Output per job, column-major with ld = n_j at
+ * V_dev + v_off[j]:  columns [0,k) entangled modes ordered by decreasing *left* eigenvalue
+ * (the order of the reference's `e` array), columns [k, k+f) filled basis.
+ *   e_dev[j*TMF_MAX_MODES + i]  left-eigenvalue of entangled mode i
+ *   info_dev[4*j + {0,1,2,3}] = k, f, status (0 ok, 1 sketch rank exhausted -> rerun wider), n
+ * `work_dev` must hold tmf_slater_modes_workspace() bytes.  r_sketch in {64,128}. */
+int64_t tmf_slater_modes_workspace(int L, int njobs, const int *job_x, const int *job_side,
+                                   int r_sketch);
+int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int njobs, const int *job_x,
+                             const int *job_side, double cutoff, int r_sketch,
+                             const int64_t *v_off, double *V_dev, double *e_dev, int *info_dev,
+                             void *work_dev, int64_t work_bytes, void *stream);
+
+/* centre bond: pair left and right entangled modes.  replaces: utils.py:19-96 (block_svd) as
+ * called from slater.py:407, and the odd-index sign flips of slater.py:410.
+ * VL (nL x k), VR (nR x k) are the entangled columns of the two jobs of the centre bond in the
+ * common "mode i" order; they are rotated in place so that C_LR = VL diag(sv) VR^T, sv > 0. */
+int tmf_block_svd_pair(const double *C_dev, int L, int ldc, int x, int k, const double *e_host,
+                       double degeneracy_tol, double *VL_dev, int ldl, double *VR_dev, int ldr,
+                       void *work_dev, int64_t work_bytes, void *stream);
+
+/* K6/K7 -- best-first enumeration of the most probable occupation subsets (HOST, multi-threaded
+ * over bonds).  replaces: schmidt_utils.py:211-324 (lowest_sums), :99-185 (StoppingCondition
+ * __call__/truncate), slater.py:673-689 (sort by charge, sector table, Schmidt values).
+ *
+ * Single-problem form (mirrors lowest_sums): a[k] and base = sum(a[a<0]) are supplied by the
+ * caller (NumPy computes them in the reference).  sectors: list of allowed charges or NULL.
+ * Outputs in heap order: sums_out[n], sets_out[n] (bit i = entry i of `a` selected). */
+int tmf_lowest_sums(const double *a, int k, double base, int chi_max, double svd_min,
+                    double degeneracy_tol, const int *sectors, int n_sectors, int filled_left,
+                    int filled_right, int cap, double *sums_out, uint64_t *sets_out, int *n_out,
+                    int *n_checked);
+
+/* Batched bond form: for bond b, e[b*TMF_MAX_MODES + i], k[b], filled_left[b].
+ * Outputs per bond (capacity `cap` rows each): masks sorted stably by left charge, un-normalised
+ * Schmidt values, left charges, chi[b], and the sector table (sec_q, sec_start; sec_n[b] sectors,
+ * capacity TMF_MAX_MODES+1 per bond). */
+int tmf_bond_vectors_batched(int nbonds, const double *e, const int *k, const int *filled_left,
+                             int chi_max, double svd_min, double degeneracy_tol,
+                             const int *sectors, int n_sectors, int cap, uint64_t *masks,
+                             double *lam, int *charge, int *chi, int *sec_q, int *sec_start,
+                             int *sec_n, int n_threads);
+
+/* a7/a8 planning (HOST).  replaces the integer bookkeeping of slater.py:760-825
+ * (_select_orbitals), :1027-1058 (physical orbital, stable row sort) and :1106-1141 (charge
+ * blocks) for one site.  See temfpy_b200/csrc/plan.cpp for the exact field semantics. */
+typedef struct tmf_site_plan {
+  int mode;          /* 0 = left, 1 = right                                              */
+  int physical;      /* 1: bra carries the site's orbital                                */
+  int n_bra, n_ket;  /* number of sites the bra / ket orbitals live on                   */
+  int k_bra, k_ket;  /* entangled modes of the two bonds                                 */
+  int f_bra, f_ket;  /* filled orbitals of the two bonds                                 */
+  int k_always;      /* size of the square "always" block (min of the two sides)         */
+  int s_bra, s_ket;  /* rows / cols of the sometimes matrix                              */
+  int n_rows;        /* bra rows (2*chi_bra with physical leg)                           */
+  int chi_bra, chi_ket;
+  int n_blocks;
+  int qtotal;
+} tmf_site_plan;
+
+/* Plans one site.  Inputs: the two bonds' masks (sorted, from tmf_bond_vectors_batched), charges.
+ * Outputs (caller-allocated, capacities in brackets):
+ *   bra_cols[k_bra+f_bra+1], ket_cols[k_ket+f_ket]: stored-V column index of every O row / col
+ *       in the order [always block (k_always) | sometimes part], -1 = physical orbital;
+ *   bra_sign / ket_sign: the reordering signs;
+ *   bra_masks[n_rows], ket_masks[chi_ket]: occupation of the sometimes rows / cols (bit t = row t);
+ *   row_p[n_rows], row_alpha[n_rows]: physical index and bond index of every bra row;
+ *   blocks[n_blocks*6]: bra_row_start, n_bra_rows, ket_start, n_ket, minor size, charge q_ket. */
+int tmf_slater_site_plan(int mode, int n_bra, int n_ket, int k_bra, int f_bra, int nferm_bra,
+                         int chi_bra, const uint64_t *masks_bra, const int *charge_bra, int k_ket,
+                         int f_ket, int nferm_ket, int chi_ket, const uint64_t *masks_ket,
+                         const int *charge_ket, tmf_site_plan *plan, int *bra_cols,
+                         double *bra_sign, int *ket_cols, double *ket_sign, uint64_t *bra_masks,
+                         uint64_t *ket_masks, int *row_p, int *row_alpha, int *blocks);
+
+/* K8+K9 -- overlap of the two mode bases and Schur complement, batched over sites.
+ * replaces: slater.py:1071 (O = HT(v_bra) @ v_ket) and :1073-1090 (det_always, sometimes
+ * matrix).  Site descriptors (host) are copied to desc_dev.  For site s:
+ *   O (rows = bra_cols order, cols = ket_cols order) is formed in work, the leading k_always
+ *   block is LU-factored with partial pivoting restricted to its rows, S_dev + s_off[s] receives
+ *   the (s_bra x s_ket) Schur complement (column-major, ld = s_bra), det_dev[s] = det(always). */
+typedef struct tmf_site_job {
+  const double *Vb, *Vk;       /* stored mode matrices of the bra / ket bond-side             */
+  const int *bra_cols, *ket_cols;       /* device arrays (rows / cols of O), -1 = physical     */
+  const double *bra_sign, *ket_sign;    /* device arrays                                      */
+  double *O;                   /* rows x cols workspace, ld = rows                            */
+  double *S;                   /* output (rows-k) x (cols-k), ld = rows-k                     */
+  double *det;                 /* output scalar                                               */
+  int ldb, ldk;
+  int n_bra, n_ket;            /* sites                                                       */
+  int mode, physical;
+  int rows, cols, k_always;    /* O is rows x cols                                            */
+  int phys_row;                /* row of O holding the physical orbital (-1: none)            */
+  int pad_[4];
+} tmf_site_job;
+int64_t tmf_site_desc_bytes(int nsites);   /* size of desc_dev for the call below */
+int tmf_site_overlap_schur_batched(const tmf_site_job *jobs_host, int nsites, void *desc_dev,
+                                   void *stream);
+
+/* K10 -- all minors of all charge blocks of all sites.  replaces: slater.py:828-869
+ * (_tensor_block: gather + batched det) and the det_always scaling of :1137.
+ * Block descriptors (host) are copied to desc_dev.  For block b:
+ *   out[a * n_ket + c] = det_always * det(S[rows(bra_masks[a])][:, cols(ket_masks[c])])
+ * with S (s_bra x s_ket, column-major ld = s_bra).  Rows/cols of a minor are the set bits in
+ * ascending order (slater.py:857-867). */
+typedef struct tmf_minor_block {
+  const double *S;
+  const double *det;           /* device scalar (det_always) or NULL for 1.0                  */
+  const uint64_t *bra_masks;   /* n_bra masks                                                 */
+  const uint64_t *ket_masks;   /* n_ket masks                                                 */
+  double *out;                 /* n_bra x n_ket row-major                                     */
+  int s_bra, s_ket, n_bra, n_ket, minor, pad_;
+} tmf_minor_block;
+int64_t tmf_minor_desc_bytes(int nblocks); /* size of desc_dev for the call below */
+int tmf_minors_blocks(const tmf_minor_block *blocks_host, int nblocks, void *desc_dev,
+                      void *stream);
+
+
+/* Chain driver -- replaces the per-site loop of slater.C_to_MPS (slater.py:1216-1353) for the
+ * sites [site_lo, site_hi) of one chain (one call sequence per GPU; shards need no communication).
+ *   create -> modes_sizes -> [caller allocates] -> modes (device + one D2H sync) -> enumerate (host)
+ *   -> tensor_sizes -> [caller allocates] -> tensors (device, asynchronous) -> bond/site accessors.
+ * Result layout: block b of site s is a dense row-major (n_bra_rows x n_ket) matrix at
+ * out_dev + block_off[b]; its rows follow the reference's bra-pipe order (row_p, row_alpha). */
+typedef struct tmf_chain tmf_chain;
+tmf_chain *tmf_chain_create(int L, int ortho_center, int n_fermion, int chi_max, double svd_min,
+                            double degeneracy_tol, const int *sectors, int n_sectors, int r_sketch,
+                            int site_lo, int site_hi, int n_threads);
+void tmf_chain_destroy(tmf_chain *c);
+int tmf_chain_modes_sizes(tmf_chain *c, int64_t *q /* njobs, V doubles, workspace bytes */);
+int tmf_chain_modes(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, double *e_dev,
+                    int *info_dev, void *work_dev, int64_t work_bytes, void *stream);
+int tmf_chain_enumerate(tmf_chain *c);
+int tmf_chain_tensor_sizes(tmf_chain *c, int64_t *q /* plan bytes, O, S doubles, sites, blocks,
+                                                       out doubles, max chi */);
+int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, void *plan_dev,
+                      int64_t plan_bytes, double *O_dev, double *S_dev, double *det_dev,
+                      double *out_dev, void *stream);
+int tmf_chain_bond(tmf_chain *c, int bond, int *q /* chi, k, filled_left, n_sectors, jobL, jobR,
+                   fL, fR */, const double **lam, const int **charge, const uint64_t **masks,
+                   const int **sec_q, const int **sec_start, const double **e);
+int tmf_chain_site(tmf_chain *c, int site, tmf_site_plan *plan, const int **blocks,
+                   const int64_t **block_off, const int **row_p, const int **row_alpha,
+                   int64_t *offs /* O offset, S offset, det index */);
+int64_t tmf_chain_job_voff(tmf_chain *c, int job);
+
+/* K14 -- Gutzwiller projection of one pair of fermion sites onto a spin-1/2 site.
+ * replaces: the TeNPy arithmetic behind gutzwiller.py:227 (group_sites(2)) and :242 (iproject)
+ * (abrikosov) resp. :409, :424 (abrikosov_ph).  Jobs: out (m x n) = A (m x k) * B (k x n), all
+ * row-major dense charge blocks; this is a thin wrapper over the grouped GEMM. */
+typedef struct tmf_gutz_job {
+  const double *A, *B;
+  double *out;
+  int m, k, n, pad_;
+} tmf_gutz_job;
+int tmf_gutzwiller_site(const tmf_gutz_job *jobs_host, int njobs, void *desc_dev, void *stream);
+
+/* FP64 peak probe used by bench.py for the roofline denominator: runs `iters` dependent-free
+ * DFMA chains on every SM and returns the elapsed ms through *ms_out (synchronises). */
+int tmf_fp64_peak_probe(int iters, double *sink_dev, float *ms_out, double *flops_out,
+                        void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

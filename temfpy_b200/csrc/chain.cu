@@ -1,0 +1,473 @@
+// Native driver of the Slater -> MPS chain: replaces the per-site Python loop of
+// slater.C_to_MPS (slater.py:1216-1353) for a contiguous range of sites [site_lo, site_hi).
+//
+//   tmf_chain_modes    K3 for every needed (bond, side), one D2H of the (tiny) spectra, then on the
+//                      host (threads over bonds / sites): best-first enumeration (K6/K7), sector
+//                      tables, per-site planning;
+//   tmf_chain_tensors  centre-bond pairing (K4), one upload of all plans, K8+K9 and K10 launches.
+// Device buffers are owned by the caller (PyTorch); results (Schmidt values, charges, sector and
+// block tables) stay in host vectors owned by the chain object until tmf_chain_destroy.
+#include <algorithm>
+#include <cmath>
+#include <stdexcept>
+#include <thread>
+
+#include "cta.hpp"
+#include "hostlogic.hpp"
+
+namespace tmf {
+int gemm_grouped(const tmf_gemm_job *jobs, int njobs, void *desc_dev, void *stream);
+int64_t gemm_desc_bytes(int njobs);
+}  // namespace tmf
+
+extern "C" int64_t tmf_site_desc_bytes(int nsites);
+extern "C" int64_t tmf_minor_desc_bytes(int nblocks);
+
+struct ChainSide {
+  int job = -1, n = 0, k = 0, f = 0;
+  int64_t v_off = 0;
+};
+struct ChainBond {
+  bool used = false;
+  ChainSide side[2];  // TMF_SIDE_L, TMF_SIDE_R
+  int k = 0, filled_left = 0;
+  tmf::BondVectors bv;
+};
+struct ChainSite {
+  int site = 0, mode = 0, bra_bond = 0, ket_bond = 0;
+  tmf::SitePlan plan;
+  int64_t o_off = 0, s_off = 0;
+  std::vector<int64_t> block_off;
+};
+
+struct tmf_chain {
+  int L = 0, oc = 0, nferm = 0, r_sketch = 64, site_lo = 0, site_hi = 0, n_threads = 0;
+  tmf::TruncPar tp;
+  std::vector<int> job_x, job_side;
+  std::vector<int64_t> v_off;
+  int64_t v_elems = 0;
+  std::vector<ChainBond> bonds;
+  std::vector<ChainSite> sites;
+  std::vector<double> e_host;
+  std::vector<int> info_host;
+  int64_t o_elems = 0, s_elems = 0, out_elems = 0, plan_bytes = 0;
+  int nblocks = 0, max_chi = 0;
+  bool enumerated = false;
+};
+
+namespace {
+
+template <class F>
+void parallel_for(int n, int n_threads, F f) {
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  n_threads = std::max(1, std::min(n_threads, n));
+  std::vector<std::thread> th;
+  std::vector<std::string> err(n_threads);
+  std::vector<int> code(n_threads, 0);
+  auto body = [&](int t) {
+    try {
+      for (int i = t; i < n; i += n_threads) f(i);
+    } catch (const std::invalid_argument &e) {
+      code[t] = TMF_ERR_VALUE;
+      err[t] = e.what();
+    } catch (const std::exception &e) {
+      code[t] = TMF_ERR_ASSERT;
+      err[t] = e.what();
+    }
+  };
+  for (int t = 1; t < n_threads; ++t) th.emplace_back(body, t);
+  body(0);
+  for (auto &x : th) x.join();
+  for (int t = 0; t < n_threads; ++t)
+    if (code[t]) throw std::runtime_error(std::to_string(code[t]) + "|" + err[t]);
+}
+
+// one-sided Jacobi SVD of a small m x m matrix (column-major): M = U diag(s) V^T
+void small_svd(std::vector<double> G, int m, std::vector<double> &U, std::vector<double> &V) {
+  V.assign((size_t)m * m, 0.0);
+  for (int i = 0; i < m; ++i) V[(size_t)i * m + i] = 1.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    bool any = false;
+    for (int p = 0; p < m; ++p)
+      for (int q = p + 1; q < m; ++q) {
+        double a = 0, b = 0, c = 0;
+        for (int r = 0; r < m; ++r) {
+          a += G[p * m + r] * G[p * m + r];
+          b += G[q * m + r] * G[q * m + r];
+          c += G[p * m + r] * G[q * m + r];
+        }
+        if (c == 0.0 || std::fabs(c) <= 1e-15 * std::sqrt(a) * std::sqrt(b)) continue;
+        any = true;
+        double zeta = (b - a) / (2 * c);
+        double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1 + zeta * zeta));
+        double cs = 1 / std::sqrt(1 + t * t), sn = cs * t;
+        for (int r = 0; r < m; ++r) {
+          double x = G[p * m + r], y = G[q * m + r];
+          G[p * m + r] = cs * x - sn * y;
+          G[q * m + r] = sn * x + cs * y;
+          x = V[p * m + r]; y = V[q * m + r];
+          V[p * m + r] = cs * x - sn * y;
+          V[q * m + r] = sn * x + cs * y;
+        }
+      }
+    if (!any) break;
+  }
+  U.assign((size_t)m * m, 0.0);
+  for (int c = 0; c < m; ++c) {
+    double s = 0;
+    for (int r = 0; r < m; ++r) s += G[c * m + r] * G[c * m + r];
+    s = std::sqrt(s);
+    for (int r = 0; r < m; ++r) U[c * m + r] = (s > 0) ? G[c * m + r] / s : (r == c ? 1.0 : 0.0);
+  }
+}
+
+int fail(int code, const std::string &msg) {
+  tmf::set_error(msg);
+  return code;
+}
+int fail_from(const std::exception &e) {
+  std::string w = e.what();
+  auto bar = w.find('|');
+  if (bar != std::string::npos && (w[0] == '-' )) {
+    int code = std::atoi(w.substr(0, bar).c_str());
+    tmf::set_error(w.substr(bar + 1));
+    return code;
+  }
+  tmf::set_error(w);
+  return TMF_ERR_RUNTIME;
+}
+
+}  // namespace
+
+extern "C" {
+
+tmf_chain *tmf_chain_create(int L, int ortho_center, int n_fermion, int chi_max, double svd_min,
+                            double degeneracy_tol, const int *sectors, int n_sectors, int r_sketch,
+                            int site_lo, int site_hi, int n_threads) {
+  if (L <= 0 || ortho_center < 0 || ortho_center > L || site_lo < 0 || site_hi > L || site_lo >= site_hi) {
+    tmf::set_error("tmf_chain_create: bad geometry");
+    return nullptr;
+  }
+  tmf_chain *c = new tmf_chain();
+  c->L = L; c->oc = ortho_center; c->nferm = n_fermion; c->r_sketch = r_sketch;
+  c->site_lo = site_lo; c->site_hi = site_hi; c->n_threads = n_threads;
+  c->tp.chi_max = chi_max; c->tp.svd_min = svd_min; c->tp.degeneracy_tol = degeneracy_tol;
+  if (sectors && n_sectors >= 0) {
+    c->tp.filter = true;
+    c->tp.sectors.assign(sectors, sectors + n_sectors);
+  }
+  c->bonds.resize(L + 1);
+  auto need = [&](int bond, int side) {
+    ChainBond &b = c->bonds[bond];
+    b.used = true;
+    if (b.side[side].job >= 0) return;
+    ChainSide &s = b.side[side];
+    s.job = (int)c->job_x.size();
+    s.n = (side == TMF_SIDE_L) ? bond : L - bond;
+    s.v_off = c->v_elems;
+    c->v_elems += (int64_t)s.n * s.n + 32;  // + slack keeps every matrix 256-byte aligned
+    c->v_elems = (c->v_elems + 31) & ~int64_t(31);
+    c->job_x.push_back(bond);
+    c->job_side.push_back(side);
+    c->v_off.push_back(s.v_off);
+  };
+  for (int i = site_lo; i < site_hi; ++i) {
+    const int side = (i >= ortho_center) ? TMF_SIDE_R : TMF_SIDE_L;
+    need(i, side);
+    need(i + 1, side);
+    if (i == ortho_center || i + 1 == ortho_center) {  // centre bond: both sides + pairing
+      need(ortho_center, TMF_SIDE_L);
+      need(ortho_center, TMF_SIDE_R);
+    }
+  }
+  return c;
+}
+
+void tmf_chain_destroy(tmf_chain *c) { delete c; }
+
+int tmf_chain_modes_sizes(tmf_chain *c, int64_t *q) {
+  q[0] = (int64_t)c->job_x.size();
+  q[1] = c->v_elems;
+  q[2] = tmf_slater_modes_workspace(c->L, (int)c->job_x.size(), c->job_x.data(), c->job_side.data(),
+                                    c->r_sketch);
+  return TMF_OK;
+}
+
+int tmf_chain_modes(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, double *e_dev,
+                    int *info_dev, void *work_dev, int64_t work_bytes, void *stream) {
+  const int nj = (int)c->job_x.size();
+  const double cutoff = c->tp.svd_min * c->tp.svd_min;  // slater.py:318
+  int rc = tmf_slater_modes_batched(C_dev, c->L, ldc, nj, c->job_x.data(), c->job_side.data(), cutoff,
+                                    c->r_sketch, c->v_off.data(), V_dev, e_dev, info_dev, work_dev,
+                                    work_bytes, stream);
+  if (rc) return rc;
+  c->e_host.resize((size_t)nj * TMF_MAX_MODES);
+  c->info_host.resize((size_t)nj * 4);
+  rc = tmf::copy_d2h_sync(c->info_host.data(), info_dev, sizeof(int) * 4 * (size_t)nj, stream);
+  if (rc) return rc;
+  rc = tmf::copy_d2h_sync(c->e_host.data(), e_dev, sizeof(double) * TMF_MAX_MODES * (size_t)nj, stream);
+  if (rc) return rc;
+  for (int j = 0; j < nj; ++j) {
+    const int st = c->info_host[4 * j + 2];
+    if (st & 2) return fail(TMF_ERR_VALUE, "more than 64 entangled modes on one bond");
+    if (st & 1)
+      return fail(TMF_ERR_VALUE,
+                  "range sketch too narrow for this entanglement spectrum: rerun with a larger r_sketch");
+  }
+  return TMF_OK;
+}
+
+// host: enumeration + planning.  Requires tmf_chain_modes to have completed.
+int tmf_chain_enumerate(tmf_chain *c) {
+  try {
+    std::vector<int> used;
+    for (int b = 0; b <= c->L; ++b)
+      if (c->bonds[b].used) used.push_back(b);
+    for (int b : used) {
+      ChainBond &B = c->bonds[b];
+      for (int s = 0; s < 2; ++s)
+        if (B.side[s].job >= 0) {
+          B.side[s].k = c->info_host[4 * B.side[s].job];
+          B.side[s].f = c->info_host[4 * B.side[s].job + 1];
+        }
+      const ChainSide &Ls = B.side[TMF_SIDE_L], &Rs = B.side[TMF_SIDE_R];
+      if (Ls.job >= 0 && Rs.job >= 0 && Ls.k != Rs.k)
+        throw std::runtime_error("-2|number of entangled modes differs between the two sides (slater.py:394)");
+      B.k = (Ls.job >= 0) ? Ls.k : Rs.k;
+      // slater.py:145-174: filled-left count, inferred from n_fermion when only vR is known
+      B.filled_left = (Ls.job >= 0) ? Ls.f : c->nferm - B.k - Rs.f;
+    }
+    parallel_for((int)used.size(), c->n_threads, [&](int u) {
+      ChainBond &B = c->bonds[used[u]];
+      const int job = (B.side[TMF_SIDE_L].job >= 0) ? B.side[TMF_SIDE_L].job : B.side[TMF_SIDE_R].job;
+      tmf::bond_vectors(c->e_host.data() + (size_t)job * TMF_MAX_MODES, B.k, B.filled_left, c->tp, B.bv);
+    });
+    c->sites.clear();
+    for (int i = c->site_lo; i < c->site_hi; ++i) {
+      ChainSite s;
+      s.site = i;
+      if (i >= c->oc) { s.mode = 1; s.bra_bond = i + 1; s.ket_bond = i; }   // slater.py:1301-1310
+      else { s.mode = 0; s.bra_bond = i; s.ket_bond = i + 1; }               // slater.py:1326-1335
+      c->sites.push_back(std::move(s));
+    }
+    parallel_for((int)c->sites.size(), c->n_threads, [&](int u) {
+      ChainSite &s = c->sites[u];
+      const int side = s.mode == 1 ? TMF_SIDE_R : TMF_SIDE_L;
+      const ChainBond &bb = c->bonds[s.bra_bond], &kb = c->bonds[s.ket_bond];
+      const ChainSide &bs = bb.side[side], &ks = kb.side[side];
+      tmf::site_plan(s.mode, bs.n, ks.n, bb.k, bs.f, c->nferm, (int)bb.bv.masks.size(),
+                     bb.bv.masks.data(), bb.bv.charge.data(), kb.k, ks.f, c->nferm,
+                     (int)kb.bv.masks.size(), kb.bv.masks.data(), kb.bv.charge.data(), s.plan);
+    });
+    // offsets
+    c->o_elems = c->s_elems = c->out_elems = 0;
+    c->nblocks = 0;
+    c->max_chi = 0;
+    int64_t plan = 0;
+    for (ChainSite &s : c->sites) {
+      const tmf_site_plan &h = s.plan.h;
+      const int rows = h.k_always + h.s_bra, cols = h.k_always + h.s_ket;
+      s.o_off = c->o_elems;
+      c->o_elems += ((int64_t)rows * cols + 31) & ~int64_t(31);
+      s.s_off = c->s_elems;
+      c->s_elems += ((int64_t)h.s_bra * h.s_ket + 31) & ~int64_t(31);
+      s.block_off.clear();
+      for (int b = 0; b < h.n_blocks; ++b) {
+        s.block_off.push_back(c->out_elems);
+        c->out_elems += (int64_t)s.plan.blocks[6 * b + 1] * s.plan.blocks[6 * b + 3];
+      }
+      c->nblocks += h.n_blocks;
+      c->max_chi = std::max(c->max_chi, std::max(h.chi_bra, h.chi_ket));
+      plan += tmf::align256(4 * (int64_t)rows) + tmf::align256(4 * (int64_t)cols) +
+              tmf::align256(8 * (int64_t)rows) + tmf::align256(8 * (int64_t)cols) +
+              tmf::align256(8 * (int64_t)h.n_rows) + tmf::align256(8 * (int64_t)h.chi_ket);
+    }
+    const int kc = c->bonds[c->oc].used ? c->bonds[c->oc].k : 0;
+    const int64_t pair = tmf::align256(8 * (int64_t)c->L * (kc + 1)) * 3 + tmf::align256(8 * (int64_t)kc * kc) * 3 +
+                         tmf::gemm_desc_bytes(4) + 4096;
+    c->plan_bytes = plan + tmf_site_desc_bytes((int)c->sites.size()) + tmf_minor_desc_bytes(c->nblocks) +
+                    pair + 4096;
+    c->enumerated = true;
+    return TMF_OK;
+  } catch (const std::exception &e) {
+    return fail_from(e);
+  }
+}
+
+// q = {plan_bytes, o_elems, s_elems, n_sites, n_blocks, out_elems, max_chi}
+int tmf_chain_tensor_sizes(tmf_chain *c, int64_t *q) {
+  if (!c->enumerated) return fail(TMF_ERR_VALUE, "tmf_chain_enumerate has not run");
+  q[0] = c->plan_bytes; q[1] = c->o_elems; q[2] = c->s_elems; q[3] = (int64_t)c->sites.size();
+  q[4] = c->nblocks; q[5] = c->out_elems; q[6] = c->max_chi;
+  return TMF_OK;
+}
+
+static int centre_pairing(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, tmf::Arena &ar,
+                          void *stream) {
+  ChainBond &B = c->bonds[c->oc];
+  if (!B.used || B.side[0].job < 0 || B.side[1].job < 0 || B.k == 0) return TMF_OK;
+  const int k = B.k, x = c->oc, nL = x, nR = c->L - x;
+  double *VL = V_dev + B.side[TMF_SIDE_L].v_off, *VR = V_dev + B.side[TMF_SIDE_R].v_off;
+  double *T1 = ar.take<double>((int64_t)nL * k), *tmpL = ar.take<double>((int64_t)nL * k);
+  double *tmpR = ar.take<double>((int64_t)nR * k);
+  double *M = ar.take<double>((int64_t)k * k), *RotL = ar.take<double>((int64_t)k * k);
+  double *RotR = ar.take<double>((int64_t)k * k);
+  void *desc = ar.take<unsigned char>(tmf::gemm_desc_bytes(4));
+  if (!ar.ok()) return fail(TMF_ERR_VALUE, "plan workspace too small (pairing)");
+  auto mk = [](const double *A, int lda, int tA, const double *Bm, int ldb, double *Cm, int ldc_, int Mm,
+               int Nn, int Kk) {
+    tmf_gemm_job j;
+    std::memset(&j, 0, sizeof(j));
+    j.A = A; j.B = Bm; j.C = Cm; j.lda = lda; j.ldb = ldb; j.ldc = ldc_;
+    j.M = Mm; j.N = Nn; j.K = Kk; j.transA = tA; j.transB = 0; j.alpha = 1.0; j.beta = 0.0;
+    return j;
+  };
+  // T1 = C_LR VR ;  M = VL^T T1   (utils.py:87-89)
+  tmf_gemm_job j1 = mk(C_dev + (int64_t)x * ldc, ldc, 0, VR, nR, T1, nL, nL, k, nR);
+  int rc = tmf::gemm_grouped(&j1, 1, desc, stream);
+  if (rc) return rc;
+  tmf_gemm_job j2 = mk(VL, nL, 1, T1, nL, M, k, k, k, nL);
+  rc = tmf::gemm_grouped(&j2, 1, desc, stream);
+  if (rc) return rc;
+  std::vector<double> Mh((size_t)k * k), RL((size_t)k * k, 0.0), RR((size_t)k * k, 0.0);
+  rc = tmf::copy_d2h_sync(Mh.data(), M, sizeof(double) * Mh.size(), stream);
+  if (rc) return rc;
+  const double *e = c->e_host.data() + (size_t)B.side[TMF_SIDE_L].job * TMF_MAX_MODES;
+  int a = 0;
+  while (a < k) {  // groups of (nearly) degenerate eigenvalues (utils.py:71-78)
+    int b = a + 1;
+    while (b < k && !(std::fabs(e[b] - e[b - 1]) > c->tp.degeneracy_tol)) ++b;
+    const int m = b - a;
+    std::vector<double> G((size_t)m * m), U, V;
+    for (int cc = 0; cc < m; ++cc)
+      for (int r = 0; r < m; ++r) G[(size_t)cc * m + r] = Mh[(size_t)(a + cc) * k + a + r];
+    small_svd(G, m, U, V);
+    for (int cc = 0; cc < m; ++cc)
+      for (int r = 0; r < m; ++r) {
+        RL[(size_t)(a + cc) * k + a + r] = U[(size_t)cc * m + r];
+        RR[(size_t)(a + cc) * k + a + r] = V[(size_t)cc * m + r];
+      }
+    a = b;
+  }
+  // anticommutation signs (slater.py:410): reference column j of vRE is mode k-1-j; odd j flips
+  for (int i = 0; i < k; ++i)
+    if ((k - 1 - i) & 1)
+      for (int r = 0; r < k; ++r) RR[(size_t)i * k + r] = -RR[(size_t)i * k + r];
+  rc = tmf::copy_h2d(RotL, RL.data(), sizeof(double) * RL.size(), stream);
+  if (rc) return rc;
+  rc = tmf::copy_h2d(RotR, RR.data(), sizeof(double) * RR.size(), stream);
+  if (rc) return rc;
+  tmf_gemm_job j3[2] = {mk(VL, nL, 0, RotL, k, tmpL, nL, nL, k, k), mk(VR, nR, 0, RotR, k, tmpR, nR, nR, k, k)};
+  rc = tmf::gemm_grouped(j3, 2, desc, stream);
+  if (rc) return rc;
+#if defined(TMF_HOSTSIM)
+  std::memcpy(VL, tmpL, sizeof(double) * (size_t)nL * k);
+  std::memcpy(VR, tmpR, sizeof(double) * (size_t)nR * k);
+#else
+  rc = tmf::check_cuda(cudaMemcpyAsync(VL, tmpL, sizeof(double) * (size_t)nL * k, cudaMemcpyDeviceToDevice,
+                                       (cudaStream_t)stream), "pairing copy");
+  if (rc) return rc;
+  rc = tmf::check_cuda(cudaMemcpyAsync(VR, tmpR, sizeof(double) * (size_t)nR * k, cudaMemcpyDeviceToDevice,
+                                       (cudaStream_t)stream), "pairing copy");
+  if (rc) return rc;
+#endif
+  return TMF_OK;
+}
+
+int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, void *plan_dev,
+                      int64_t plan_bytes, double *O_dev, double *S_dev, double *det_dev, double *out_dev,
+                      void *stream) {
+  if (!c->enumerated) return fail(TMF_ERR_VALUE, "tmf_chain_enumerate has not run");
+  if (plan_bytes < c->plan_bytes) return fail(TMF_ERR_VALUE, "plan workspace too small");
+  tmf::Arena ar(plan_dev, plan_bytes);
+  int rc = centre_pairing(c, C_dev, ldc, V_dev, ar, stream);
+  if (rc) return rc;
+  // ---- one blob with every per-site index / sign / mask array ------------------------------
+  const int ns = (int)c->sites.size();
+  unsigned char *blob_dev = ar.take<unsigned char>(0);
+  std::vector<unsigned char> blob;
+  auto add = [&](const void *p, size_t bytes) {
+    size_t off = (blob.size() + 255) & ~size_t(255);
+    blob.resize(off + bytes);
+    if (bytes) std::memcpy(blob.data() + off, p, bytes);
+    return blob_dev + off;
+  };
+  std::vector<tmf_site_job> sj(ns);
+  std::vector<tmf_minor_block> mb;
+  mb.reserve(c->nblocks);
+  for (int u = 0; u < ns; ++u) {
+    ChainSite &s = c->sites[u];
+    const tmf_site_plan &h = s.plan.h;
+    const int side = s.mode == 1 ? TMF_SIDE_R : TMF_SIDE_L;
+    const ChainSide &bs = c->bonds[s.bra_bond].side[side], &ks = c->bonds[s.ket_bond].side[side];
+    const int rows = h.k_always + h.s_bra, cols = h.k_always + h.s_ket;
+    tmf_site_job &j = sj[u];
+    std::memset(&j, 0, sizeof(j));
+    j.Vb = V_dev + bs.v_off; j.Vk = V_dev + ks.v_off;
+    j.ldb = std::max(bs.n, 1); j.ldk = std::max(ks.n, 1);
+    j.bra_cols = reinterpret_cast<const int *>(add(s.plan.bra_cols.data(), 4 * (size_t)rows));
+    j.ket_cols = reinterpret_cast<const int *>(add(s.plan.ket_cols.data(), 4 * (size_t)cols));
+    j.bra_sign = reinterpret_cast<const double *>(add(s.plan.bra_sign.data(), 8 * (size_t)rows));
+    j.ket_sign = reinterpret_cast<const double *>(add(s.plan.ket_sign.data(), 8 * (size_t)cols));
+    j.O = O_dev + s.o_off; j.S = S_dev + s.s_off; j.det = det_dev + u;
+    j.n_bra = h.n_bra; j.n_ket = h.n_ket; j.mode = h.mode; j.physical = h.physical;
+    j.rows = rows; j.cols = cols; j.k_always = h.k_always;
+    j.phys_row = -1;
+    for (int r = 0; r < rows; ++r)
+      if (s.plan.bra_cols[r] < 0) j.phys_row = r;
+    const uint64_t *bm = reinterpret_cast<const uint64_t *>(add(s.plan.bra_masks.data(), 8 * (size_t)h.n_rows));
+    const uint64_t *km = reinterpret_cast<const uint64_t *>(add(s.plan.ket_masks.data(), 8 * (size_t)h.chi_ket));
+    for (int b = 0; b < h.n_blocks; ++b) {
+      const int *bl = &s.plan.blocks[6 * b];
+      tmf_minor_block k;
+      std::memset(&k, 0, sizeof(k));
+      k.S = j.S; k.det = j.det;
+      k.bra_masks = bm + bl[0]; k.ket_masks = km + bl[2];
+      k.out = out_dev + s.block_off[b];
+      k.s_bra = h.s_bra; k.s_ket = h.s_ket; k.n_bra = bl[1]; k.n_ket = bl[3]; k.minor = bl[4];
+      mb.push_back(k);
+    }
+  }
+  ar.take<unsigned char>((int64_t)blob.size());
+  void *site_desc = ar.take<unsigned char>(tmf_site_desc_bytes(ns));
+  void *minor_desc = ar.take<unsigned char>(tmf_minor_desc_bytes((int)mb.size()));
+  if (!ar.ok()) return fail(TMF_ERR_VALUE, "plan workspace too small");
+  rc = tmf::copy_h2d(blob_dev, blob.data(), blob.size(), stream);
+  if (rc) return rc;
+  rc = tmf_site_overlap_schur_batched(sj.data(), ns, site_desc, stream);
+  if (rc) return rc;
+  return tmf_minors_blocks(mb.data(), (int)mb.size(), minor_desc, stream);
+}
+
+// ---- result accessors (host pointers stay valid until tmf_chain_destroy) ----------------------
+int tmf_chain_bond(tmf_chain *c, int bond, int *q, const double **lam, const int **charge,
+                   const uint64_t **masks, const int **sec_q, const int **sec_start,
+                   const double **e) {
+  if (bond < 0 || bond > c->L || !c->bonds[bond].used || !c->enumerated)
+    return fail(TMF_ERR_VALUE, "bond not available on this shard");
+  const ChainBond &B = c->bonds[bond];
+  q[0] = (int)B.bv.masks.size(); q[1] = B.k; q[2] = B.filled_left; q[3] = (int)B.bv.sec_q.size();
+  q[4] = B.side[0].job; q[5] = B.side[1].job; q[6] = B.side[0].f; q[7] = B.side[1].f;
+  *lam = B.bv.lam.data(); *charge = B.bv.charge.data(); *masks = B.bv.masks.data();
+  *sec_q = B.bv.sec_q.data(); *sec_start = B.bv.sec_start.data();
+  const int job = (B.side[0].job >= 0) ? B.side[0].job : B.side[1].job;
+  *e = c->e_host.data() + (size_t)job * TMF_MAX_MODES;
+  return TMF_OK;
+}
+
+int tmf_chain_site(tmf_chain *c, int site, tmf_site_plan *plan, const int **blocks,
+                   const int64_t **block_off, const int **row_p, const int **row_alpha,
+                   int64_t *offs) {
+  if (site < c->site_lo || site >= c->site_hi || !c->enumerated)
+    return fail(TMF_ERR_VALUE, "site not available on this shard");
+  const ChainSite &s = c->sites[site - c->site_lo];
+  *plan = s.plan.h;
+  *blocks = s.plan.blocks.data(); *block_off = s.block_off.data();
+  *row_p = s.plan.row_p.data(); *row_alpha = s.plan.row_alpha.data();
+  offs[0] = s.o_off; offs[1] = s.s_off; offs[2] = site - c->site_lo;
+  return TMF_OK;
+}
+
+int64_t tmf_chain_job_voff(tmf_chain *c, int job) { return c->v_off[job]; }
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+// CTA-level programming helpers shared by every kernel.
+//
+// Kernels are written as bulk-synchronous CTA programs: phases made of parallel-for loops over
+// work items (PAR_FOR) or threads (THREAD_FOR), separated by CTA_SYNC().  With nvcc this maps to
+// blockDim-strided loops and __syncthreads().  With -DTMF_HOSTSIM the same source is compiled by
+// g++ into a sequential CTA simulator (one "thread" at a time, phases in program order) that the
+// CPU test-suite uses to check kernel *logic* without a GPU (tests/hostsim/; never loaded by the
+// package itself, which requires the CUDA build).
+#pragma once
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/temfpy_b200.h"
+
+namespace tmf {
+void set_error(const std::string &msg);
+}
+
+#if defined(TMF_HOSTSIM)
+// ------------------------------------------------------------------------------------------
+#define TMF_GLOBAL static void
+#define TMF_DEVICE static inline
+#define TMF_HD static inline
+#define TMF_RESTRICT
+namespace tmfsim {
+extern thread_local int block_id;
+extern thread_local int n_threads;
+extern thread_local unsigned char *smem;
+}  // namespace tmfsim
+#define BLOCK_ID (tmfsim::block_id)
+#define NTHREADS (tmfsim::n_threads)
+#define PAR_FOR(i, n) for (int i = 0; i < (int)(n); ++i)
+#define THREAD_FOR(t) for (int t = 0; t < tmfsim::n_threads; ++t)
+#define CTA_SYNC() ((void)0)
+#define DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(tmfsim::smem)
+
+namespace tmf {
+template <class K, class... Args>
+inline int launch(K kernel, int grid, int block, size_t smem_bytes, void * /*stream*/, Args... args) {
+  std::vector<unsigned char> smem(smem_bytes + 64);
+  tmfsim::n_threads = block;
+  tmfsim::smem = smem.data();
+  for (int b = 0; b < grid; ++b) {
+    tmfsim::block_id = b;
+    kernel(args...);
+  }
+  return TMF_OK;
+}
+inline int copy_h2d(void *dst, const void *src, size_t bytes, void *) {
+  std::memcpy(dst, src, bytes);
+  return TMF_OK;
+}
+inline int copy_d2h_sync(void *dst, const void *src, size_t bytes, void *) {
+  std::memcpy(dst, src, bytes);
+  return TMF_OK;
+}
+inline int memset_dev(void *dst, int v, size_t bytes, void *) {
+  std::memset(dst, v, bytes);
+  return TMF_OK;
+}
+inline int stream_sync(void *) { return TMF_OK; }
+}  // namespace tmf
+
+#else
+// ------------------------------------------------------------------------------------------
+#include <cuda_runtime.h>
+#define TMF_GLOBAL __global__ void
+#define TMF_DEVICE __device__ __forceinline__
+#define TMF_HD __host__ __device__ __forceinline__
+#define TMF_RESTRICT __restrict__
+#define BLOCK_ID ((int)blockIdx.x)
+#define NTHREADS ((int)blockDim.x)
+#define PAR_FOR(i, n) for (int i = threadIdx.x; i < (int)(n); i += blockDim.x)
+#define THREAD_FOR(t) for (int t = threadIdx.x, t##_once = 1; t##_once; t##_once = 0)
+#define CTA_SYNC() __syncthreads()
+#define DYN_SMEM(type, name)                                           \
+  extern __shared__ __align__(16) unsigned char tmf_dyn_smem_raw[];    \
+  type *name = reinterpret_cast<type *>(tmf_dyn_smem_raw)
+
+namespace tmf {
+inline int check_cuda(cudaError_t e, const char *what) {
+  if (e == cudaSuccess) return TMF_OK;
+  set_error(std::string(what) + ": " + cudaGetErrorString(e));
+  return TMF_ERR_RUNTIME;
+}
+template <class K, class... Args>
+inline int launch(K kernel, int grid, int block, size_t smem_bytes, void *stream, Args... args) {
+  if (grid <= 0) return TMF_OK;
+  if (smem_bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_bytes);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute");
+  }
+  kernel<<<grid, block, smem_bytes, (cudaStream_t)stream>>>(args...);
+  return check_cuda(cudaGetLastError(), "kernel launch");
+}
+inline int copy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
+  if (bytes == 0) return TMF_OK;
+  return check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream),
+                    "cudaMemcpyAsync H2D");
+}
+inline int copy_d2h_sync(void *dst, const void *src, size_t bytes, void *stream) {
+  if (bytes) {
+    int rc = check_cuda(
+        cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream),
+        "cudaMemcpyAsync D2H");
+    if (rc) return rc;
+  }
+  return check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
+}
+inline int memset_dev(void *dst, int v, size_t bytes, void *stream) {
+  if (bytes == 0) return TMF_OK;
+  return check_cuda(cudaMemsetAsync(dst, v, bytes, (cudaStream_t)stream), "cudaMemsetAsync");
+}
+inline int stream_sync(void *stream) {
+  return check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
+}
+}  // namespace tmf
+#endif
+
+namespace tmf {
+// Aligned bump allocator over a caller-provided workspace.
+struct Arena {
+  unsigned char *base;
+  int64_t size, used = 0;
+  Arena(void *p, int64_t bytes) : base(static_cast<unsigned char *>(p)), size(bytes) {}
+  template <class T>
+  T *take(int64_t count) {
+    int64_t off = (used + 255) & ~int64_t(255);
+    used = off + count * (int64_t)sizeof(T);
+    return reinterpret_cast<T *>(base + off);  // validity is checked by the caller via ok()
+  }
+  bool ok() const { return base == nullptr || used <= size; }
+};
+inline int64_t align256(int64_t b) { return (b + 255) & ~int64_t(255); }
+}  // namespace tmf

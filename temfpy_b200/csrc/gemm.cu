@@ -1,0 +1,238 @@
+// Grouped FP64 GEMM on the sm_100a DMMA pipe (mma.sync.m8n8k4.f64).
+//
+// One launch processes a list of independent, differently sized problems
+//     C_j (M x N) = alpha * diag(row_scale) * op(A_j) * op(B_j) * diag(col_scale) + beta * C_j
+// (all column-major).  It is the workhorse of the mode extraction (range finder B*Omega,
+// projections Q^T B, Rayleigh-Ritz blocks), of the overlap O = V_bra^T V_ket (slater.py:1071),
+// of C = Phi Phi^T (slater.py:1177) and of the Gutzwiller block products.
+//
+// CTA tile 64 x 64 x 16, 256 threads = 8 warps in a 4 x 2 arrangement, each warp owns a 16 x 32
+// accumulator (2 x 4 DMMA tiles).  Operand tiles are staged in shared memory "k-contiguous" with a
+// row stride of 20 doubles, which makes every fragment load (8 rows x 4 k) conflict-free, and are
+// double-buffered with register prefetch of the next k-tile.  Tiles of all jobs are enumerated by
+// a prefix table so that one grid covers the whole group (grid >> 148 for the chain workloads).
+#include "cta.hpp"
+
+namespace tmf {
+
+constexpr int TM = 64, TN = 64, TK = 16, LDS_STRIDE = 20;
+
+struct GemmDesc {
+  tmf_gemm_job job;
+};
+static_assert(sizeof(tmf_gemm_job) == 128, "descriptor must be 128 bytes");
+
+TMF_DEVICE double load_a(const tmf_gemm_job &j, int m, int k) {
+  if (m >= j.M || k >= j.K) return 0.0;
+  if (j.transA) {
+    int col = j.a_idx ? j.a_idx[m] : m;
+    if (col < 0) return 0.0;
+    return j.A[(int64_t)col * j.lda + k + j.a_row_off];
+  }
+  return j.A[(int64_t)k * j.lda + m];
+}
+TMF_DEVICE double load_b(const tmf_gemm_job &j, int k, int n) {
+  if (n >= j.N || k >= j.K) return 0.0;
+  if (j.transB) return j.B[(int64_t)k * j.ldb + n];
+  int col = j.b_idx ? j.b_idx[n] : n;
+  if (col < 0) return 0.0;
+  return j.B[(int64_t)col * j.ldb + k + j.b_row_off];
+}
+TMF_DEVICE void store_c(const tmf_gemm_job &j, int m, int n, double acc) {
+  if (m >= j.M || n >= j.N) return;
+  double v = j.alpha * acc;
+  if (j.row_scale) v *= j.row_scale[m];
+  if (j.col_scale) v *= j.col_scale[n];
+  double *p = j.C + (int64_t)n * j.ldc + m;
+  if (j.beta != 0.0) v += j.beta * (*p);
+  *p = v;
+}
+
+// binary search: largest j with prefix[j] <= tile
+TMF_DEVICE int find_job(const int *prefix, int njobs, int tile) {
+  int lo = 0, hi = njobs;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (prefix[mid] <= tile) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+#if defined(TMF_HOSTSIM)
+TMF_GLOBAL gemm_grouped_kernel(const tmf_gemm_job *jobs, const int *prefix, int njobs) {
+  const int tile = BLOCK_ID;
+  const int jid = find_job(prefix, njobs, tile);
+  const tmf_gemm_job &j = jobs[jid];
+  const int t = tile - prefix[jid];
+  const int tiles_m = (j.M + TM - 1) / TM;
+  const int m0 = (t % tiles_m) * TM, n0 = (t / tiles_m) * TN;
+  for (int n = n0; n < n0 + TN && n < j.N; ++n)
+    for (int m = m0; m < m0 + TM && m < j.M; ++m) {
+      double acc = 0.0;
+      for (int k = 0; k < j.K; ++k) acc += load_a(j, m, k) * load_b(j, k, n);
+      store_c(j, m, n, acc);
+    }
+}
+#else
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256)
+gemm_grouped_kernel(const tmf_gemm_job *__restrict__ jobs, const int *__restrict__ prefix,
+                    int njobs) {
+  __shared__ double As[2][TM * LDS_STRIDE];
+  __shared__ double Bs[2][TN * LDS_STRIDE];
+  __shared__ tmf_gemm_job js;
+  const int tile = blockIdx.x;
+  const int jid = find_job(prefix, njobs, tile);
+  if (threadIdx.x < sizeof(tmf_gemm_job) / 8)
+    reinterpret_cast<uint64_t *>(&js)[threadIdx.x] =
+        reinterpret_cast<const uint64_t *>(&jobs[jid])[threadIdx.x];
+  __syncthreads();
+  const tmf_gemm_job &j = js;
+  const int t = tile - prefix[jid];
+  const int tiles_m = (j.M + TM - 1) / TM;
+  const int m0 = (t % tiles_m) * TM, n0 = (t / tiles_m) * TN;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
+
+  // global -> register staging: 4 elements of each operand per thread and k-tile.
+  // k-contiguous operands: consecutive threads walk k; otherwise they walk the row index.
+  const bool a_kc = j.transA != 0, b_kc = j.transB == 0;
+  double ra[4], rb[4];
+  auto ldg = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = tid + 256 * i;
+      int r = a_kc ? (e >> 4) : (e & 63), kk = a_kc ? (e & 15) : (e >> 6);
+      ra[i] = load_a(j, m0 + r, k0 + kk);
+      r = b_kc ? (e >> 4) : (e & 63);
+      kk = b_kc ? (e & 15) : (e >> 6);
+      rb[i] = load_b(j, k0 + kk, n0 + r);
+    }
+  };
+  auto sts = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = tid + 256 * i;
+      int r = a_kc ? (e >> 4) : (e & 63), kk = a_kc ? (e & 15) : (e >> 6);
+      As[buf][r * LDS_STRIDE + kk] = ra[i];
+      r = b_kc ? (e >> 4) : (e & 63);
+      kk = b_kc ? (e & 15) : (e >> 6);
+      Bs[buf][r * LDS_STRIDE + kk] = rb[i];
+    }
+  };
+
+  double acc[2][4][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+  const int nk = (j.K + TK - 1) / TK;
+  int buf = 0;
+  if (nk > 0) {
+    ldg(0);
+    sts(0);
+  }
+  __syncthreads();
+  const int fr = lane >> 2, fk = lane & 3;
+  for (int kt = 0; kt < nk; ++kt) {
+    if (kt + 1 < nk) ldg((kt + 1) * TK);
+    const double *as = As[buf], *bs = Bs[buf];
+#pragma unroll
+    for (int ks = 0; ks < TK; ks += 4) {
+      double fa[2], fb[4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) fa[a] = as[(wm + a * 8 + fr) * LDS_STRIDE + ks + fk];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) fb[b] = bs[(wn + b * 8 + fr) * LDS_STRIDE + ks + fk];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dmma(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
+    }
+    if (kt + 1 < nk) sts(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  // epilogue: fragment (row = lane/4, cols = 2*(lane%4) + {0,1})
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      int m = m0 + wm + a * 8 + fr, n = n0 + wn + b * 8 + 2 * fk;
+      store_c(j, m, n, acc[a][b][0]);
+      store_c(j, m, n + 1, acc[a][b][1]);
+    }
+}
+#endif
+
+// Host launcher: builds the tile prefix table and uploads descriptors + table into desc_dev.
+int gemm_grouped(const tmf_gemm_job *jobs, int njobs, void *desc_dev, void *stream) {
+  if (njobs <= 0) return TMF_OK;
+  std::vector<int> prefix(njobs + 1, 0);
+  for (int i = 0; i < njobs; ++i) {
+    int tm = (jobs[i].M + TM - 1) / TM, tn = (jobs[i].N + TN - 1) / TN;
+    if (jobs[i].M <= 0 || jobs[i].N <= 0) tm = tn = 0;
+    prefix[i + 1] = prefix[i] + tm * tn;
+  }
+  const int ntiles = prefix[njobs];
+  if (ntiles == 0) return TMF_OK;
+  unsigned char *d = static_cast<unsigned char *>(desc_dev);
+  int rc = copy_h2d(d, jobs, sizeof(tmf_gemm_job) * (size_t)njobs, stream);
+  if (rc) return rc;
+  int *dprefix = reinterpret_cast<int *>(d + sizeof(tmf_gemm_job) * (size_t)njobs);
+  rc = copy_h2d(dprefix, prefix.data(), sizeof(int) * (size_t)(njobs + 1), stream);
+  if (rc) return rc;
+  return launch(gemm_grouped_kernel, ntiles, 256, 0, stream,
+                reinterpret_cast<const tmf_gemm_job *>(d), (const int *)dprefix, njobs);
+}
+
+int gemm_launch_uploaded(const tmf_gemm_job *jobs_dev, const int *prefix_dev, int njobs, int ntiles,
+                         void *stream) {
+  if (ntiles <= 0) return TMF_OK;
+  return launch(gemm_grouped_kernel, ntiles, 256, 0, stream, jobs_dev, prefix_dev, njobs);
+}
+
+int64_t gemm_desc_bytes(int njobs) {
+  return align256((int64_t)sizeof(tmf_gemm_job) * njobs + 4 * (int64_t)(njobs + 1));
+}
+
+}  // namespace tmf
+
+extern "C" int64_t tmf_gemm_desc_bytes(int njobs) { return tmf::gemm_desc_bytes(njobs) + 256; }
+
+extern "C" int tmf_gemm_grouped(const tmf_gemm_job *jobs_host, int njobs, void *desc_dev,
+                                void *stream) {
+  return tmf::gemm_grouped(jobs_host, njobs, desc_dev, stream);
+}
+
+extern "C" int tmf_corr_build(const double *phi_dev, int L, int N, int ldphi, double *C_dev,
+                              int ldc, void *stream) {
+  // slater.py:1177: C = Phi Phi^T with Phi given row-major (L x N, row stride ldphi), i.e. as the
+  // column-major N x L matrix M = Phi^T: C = M^T M, both operands k-contiguous.
+  static void *scratch = nullptr;
+#if !defined(TMF_HOSTSIM)
+  if (!scratch) {
+    if (cudaMalloc(&scratch, 1024) != cudaSuccess) {
+      tmf::set_error("cudaMalloc(descriptor scratch) failed");
+      return TMF_ERR_RUNTIME;
+    }
+  }
+#else
+  static unsigned char host_scratch[1024];
+  scratch = host_scratch;
+#endif
+  tmf_gemm_job j;
+  std::memset(&j, 0, sizeof(j));
+  j.A = phi_dev; j.B = phi_dev; j.C = C_dev;
+  j.M = L; j.N = L; j.K = N;
+  j.lda = ldphi; j.ldb = ldphi; j.ldc = ldc;
+  j.transA = 1; j.transB = 0;
+  j.alpha = 1.0; j.beta = 0.0;
+  return tmf::gemm_grouped(&j, 1, scratch, stream);
+}

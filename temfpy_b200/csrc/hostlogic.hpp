@@ -1,0 +1,57 @@
+// Host-side (CPU) integer/ordering logic of the Slater -> MPS path: best-first subset enumeration,
+// Schmidt-vector tables and per-site planning.  These are the parts of the reference that are
+// inherently sequential integer bookkeeping (schmidt_utils.py:211-324, slater.py:633-700,
+// :760-825, :1027-1058, :1106-1141); everything that is floating-point heavy runs in the CUDA
+// kernels.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/temfpy_b200.h"
+
+namespace tmf {
+
+struct TruncPar {
+  int chi_max = -1;  // <0: unlimited
+  double svd_min = 1e-6;
+  double degeneracy_tol = 1e-12;
+  std::vector<int> sectors;  // empty + !filter -> all sectors
+  bool filter = false;
+  bool is_sector(int q) const;
+};
+
+// schmidt_utils.py:211-324.  Returns sums (heap order, truncated) and masks.
+void lowest_sums(const double *a, int k, double base, const TruncPar &tp, int filled_left,
+                 int filled_right, std::vector<double> &sums, std::vector<uint64_t> &sets,
+                 int *n_checked);
+
+struct BondVectors {
+  int k = 0, filled_left = 0;
+  std::vector<uint64_t> masks;  // sorted stably by left charge
+  std::vector<double> lam;      // un-normalised Schmidt values
+  std::vector<int> charge;      // left charge of every vector
+  std::vector<int> sec_q, sec_start;  // sector table (sec_start has one extra entry)
+};
+
+// slater.py:633-700 on top of lowest_sums; e = left eigenvalues of the entangled modes.
+void bond_vectors(const double *e, int k, int filled_left, const TruncPar &tp, BondVectors &out);
+
+struct SitePlan {
+  tmf_site_plan h{};
+  std::vector<int> bra_cols, ket_cols;
+  std::vector<double> bra_sign, ket_sign;
+  std::vector<uint64_t> bra_masks, ket_masks;
+  std::vector<int> row_p, row_alpha;
+  std::vector<int> blocks;  // 6 ints per block
+};
+
+// Throws std::runtime_error on inconsistent input.
+void site_plan(int mode, int n_bra, int n_ket, int k_bra, int f_bra, int nferm_bra, int chi_bra,
+               const uint64_t *masks_bra, const int *charge_bra, int k_ket, int f_ket,
+               int nferm_ket, int chi_ket, const uint64_t *masks_ket, const int *charge_ket,
+               SitePlan &out);
+
+void set_error(const std::string &msg);
+
+}  // namespace tmf

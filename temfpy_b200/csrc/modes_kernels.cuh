@@ -1,0 +1,508 @@
+// CTA kernels of the Schmidt-mode extraction (K3/K4): panel orthonormalisation, one-sided Jacobi
+// (small SVD / symmetric eigenproblem in shared memory), pivoted Cholesky of the filled-space
+// projector, and the direct small-block eigen-solver.  All written in the PAR_FOR/CTA_SYNC
+// style of cta.hpp so that the CPU simulator executes the very same source.
+#pragma once
+#include "cta.hpp"
+
+namespace tmf {
+
+constexpr int PANEL_W = 16;        // panel width of the block Gram-Schmidt
+constexpr int JAC_MAX_SWEEPS = 40;
+constexpr int SMALL_N = 64;        // blocks up to this size are diagonalised directly
+constexpr int JAC_SMEM_J_MAX = 96; // above this the Jacobi rotation matrix lives in global memory
+constexpr int R_SKETCH_MAX = 160;  // G (r x r) must fit in shared memory
+
+// ---------------------------------------------------------------------------------------------
+// column norms (squared) of a column-major matrix: one CTA per job
+// ---------------------------------------------------------------------------------------------
+struct NormJob {
+  const double *Y;
+  double *out;  // ncols
+  int rows, ld, ncols, pad_;
+};
+TMF_GLOBAL colnorm_kernel(const NormJob *jobs) {
+  const NormJob jb = jobs[BLOCK_ID];
+  DYN_SMEM(double, part);  // ncols * 33
+  PAR_FOR(item, jb.ncols * 32) {
+    int c = item >> 5, lane = item & 31;
+    const double *y = jb.Y + (int64_t)c * jb.ld;
+    double s = 0.0;
+    for (int r = lane; r < jb.rows; r += 32) s += y[r] * y[r];
+    part[c * 33 + lane] = s;
+  }
+  CTA_SYNC();
+  PAR_FOR(c, jb.ncols) {
+    double s = 0.0;
+    for (int l = 0; l < 32; ++l) s += part[c * 33 + l];
+    jb.out[c] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// panel MGS2: orthonormalises ncols (<= PANEL_W) columns in place.  Columns whose norm falls
+// below rel_tol * (norm before any projection) are numerically dependent and are set to zero.
+// ---------------------------------------------------------------------------------------------
+struct PanelJob {
+  double *P;            // rows x ncols, column-major, ld
+  const double *norm0;  // squared norms of the original columns (ncols)
+  int *nzero;           // incremented for every zeroed column (may be null)
+  int rows, ld, ncols, use_smem;
+};
+
+TMF_GLOBAL panel_mgs2_kernel(const PanelJob *jobs, double rel_tol2) {
+  const PanelJob jb = jobs[BLOCK_ID];
+  if (jb.rows <= 0 || jb.ncols <= 0) return;
+  DYN_SMEM(double, sm);
+  double *part = sm;                        // PANEL_W * 33
+  double *coef = part + PANEL_W * 33;       // PANEL_W
+  double *red = coef + PANEL_W;             // 32 + 2
+  double *panel = red + 40;                 // rows * ncols when use_smem
+  double *P = jb.P;
+  int ld = jb.ld;
+  if (jb.use_smem) {
+    PAR_FOR(idx, jb.rows * jb.ncols) {
+      int c = idx / jb.rows, r = idx - c * jb.rows;
+      panel[idx] = jb.P[(int64_t)c * jb.ld + r];
+    }
+    CTA_SYNC();
+    P = panel;
+    ld = jb.rows;
+  }
+  for (int j = 0; j < jb.ncols; ++j) {
+    double *pj = P + (int64_t)j * ld;
+    for (int pass = 0; pass < 2 && j > 0; ++pass) {
+      PAR_FOR(item, j * 32) {
+        int i = item >> 5, lane = item & 31;
+        const double *pi = P + (int64_t)i * ld;
+        double s = 0.0;
+        for (int r = lane; r < jb.rows; r += 32) s += pi[r] * pj[r];
+        part[i * 33 + lane] = s;
+      }
+      CTA_SYNC();
+      PAR_FOR(i, j) {
+        double s = 0.0;
+        for (int l = 0; l < 32; ++l) s += part[i * 33 + l];
+        coef[i] = s;
+      }
+      CTA_SYNC();
+      PAR_FOR(r, jb.rows) {
+        double v = pj[r];
+        for (int i = 0; i < j; ++i) v -= coef[i] * P[(int64_t)i * ld + r];
+        pj[r] = v;
+      }
+      CTA_SYNC();
+    }
+    PAR_FOR(lane, 32) {
+      double s = 0.0;
+      for (int r = lane; r < jb.rows; r += 32) s += pj[r] * pj[r];
+      red[lane] = s;
+    }
+    CTA_SYNC();
+    PAR_FOR(one, 1) {
+      double s = 0.0;
+      for (int l = 0; l < 32; ++l) s += red[l];
+      double scale = 0.0;
+      if (s > rel_tol2 * jb.norm0[j] && s > 0.0) scale = 1.0 / sqrt(s);
+      else if (jb.nzero) *jb.nzero += 1;
+      red[32] = scale;
+    }
+    CTA_SYNC();
+    const double scale = red[32];
+    PAR_FOR(r, jb.rows) pj[r] *= scale;
+    CTA_SYNC();
+  }
+  if (jb.use_smem) {
+    PAR_FOR(idx, jb.rows * jb.ncols) {
+      int c = idx / jb.rows, r = idx - c * jb.rows;
+      jb.P[(int64_t)c * jb.ld + r] = panel[idx];
+    }
+  }
+}
+inline size_t panel_smem_bytes(int rows, int ncols, bool use_smem) {
+  return sizeof(double) * (size_t)(PANEL_W * 33 + PANEL_W + 40 + (use_smem ? (size_t)rows * ncols : 0));
+}
+
+// ---------------------------------------------------------------------------------------------
+// one-sided Jacobi on the columns of G (n x n, ldg) with accumulation in J (n x n, ldj).
+// On exit the columns of G are mutually orthogonal, G_out = G_in * J, J orthogonal.
+//   * SVD use:  G = R  -> singular values = column norms, right singular vectors = J
+//   * eigen use: G = symmetric PSD matrix -> eigenvalues = column norms, eigenvectors = J
+// Parallel round-robin ordering; `rot` (n/2 * 2 doubles), `part` (n/2 * 33 * 3) and `flag` are
+// shared scratch.  n may be odd (a bye is inserted).
+// ---------------------------------------------------------------------------------------------
+TMF_DEVICE void jacobi_onesided(double *G, int ldg, double *J, int ldj, int n, double *rot,
+                                double *part, int *flag) {
+  if (n < 2) return;
+  const int np = (n + 1) & ~1;  // padded to even; index np-1 == n is a bye when n is odd
+  const int half = np / 2;
+  for (int sweep = 0; sweep < JAC_MAX_SWEEPS; ++sweep) {
+    PAR_FOR(one, 1) *flag = 0;
+    CTA_SYNC();
+    for (int round = 0; round < np - 1; ++round) {
+      // circle method: position i of the top row meets position i of the bottom row
+      PAR_FOR(item, half * 32) {
+        int pr = item >> 5, lane = item & 31;
+        int p = (pr == 0) ? np - 1 : (round + pr) % (np - 1);
+        int q = (round + np - 1 - pr) % (np - 1);
+        double a = 0.0, b = 0.0, c = 0.0;
+        if (p < n && q < n) {
+          const double *gp = G + (int64_t)p * ldg, *gq = G + (int64_t)q * ldg;
+          for (int r = lane; r < n; r += 32) {
+            double x = gp[r], y = gq[r];
+            a += x * x;
+            b += y * y;
+            c += x * y;
+          }
+        }
+        double *pp = part + (pr * 33 + lane) * 3;
+        pp[0] = a; pp[1] = b; pp[2] = c;
+      }
+      CTA_SYNC();
+      PAR_FOR(pr, half) {
+        double a = 0.0, b = 0.0, c = 0.0;
+        for (int l = 0; l < 32; ++l) {
+          const double *pp = part + (pr * 33 + l) * 3;
+          a += pp[0]; b += pp[1]; c += pp[2];
+        }
+        double cs = 1.0, sn = 0.0;
+        if (c != 0.0 && fabs(c) > 1e-15 * sqrt(a) * sqrt(b)) {
+          double zeta = (b - a) / (2.0 * c);
+          double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          cs = 1.0 / sqrt(1.0 + t * t);
+          sn = cs * t;
+          *flag = 1;  // benign race: every writer stores 1
+        }
+        rot[2 * pr] = cs;
+        rot[2 * pr + 1] = sn;
+      }
+      CTA_SYNC();
+      PAR_FOR(item, half * n) {
+        int pr = item / n, r = item - pr * n;
+        int p = (pr == 0) ? np - 1 : (round + pr) % (np - 1);
+        int q = (round + np - 1 - pr) % (np - 1);
+        double cs = rot[2 * pr], sn = rot[2 * pr + 1];
+        if (p < n && q < n && sn != 0.0) {
+          double *gp = G + (int64_t)p * ldg + r, *gq = G + (int64_t)q * ldg + r;
+          double x = *gp, y = *gq;
+          *gp = cs * x - sn * y;
+          *gq = sn * x + cs * y;
+          double *jp = J + (int64_t)p * ldj + r, *jq = J + (int64_t)q * ldj + r;
+          x = *jp; y = *jq;
+          *jp = cs * x - sn * y;
+          *jq = sn * x + cs * y;
+        }
+      }
+      CTA_SYNC();
+    }
+    const int any = *flag;
+    CTA_SYNC();
+    if (!any) break;
+  }
+}
+inline size_t jacobi_scratch_doubles(int n) {
+  int half = ((n + 1) & ~1) / 2;
+  return (size_t)half * 2 + (size_t)half * 33 * 3 + 8;
+}
+
+// ranks `key[0..n)` by decreasing value (ties by index); flagged entries only.  rank_out[i] = -1
+// for unflagged entries.  Returns nothing; count of flagged entries in *count.
+TMF_DEVICE void rank_desc(const double *key, const int *flagged, int n, int *rank_out, int *count) {
+  PAR_FOR(i, n) {
+    int r = -1;
+    if (flagged[i]) {
+      r = 0;
+      for (int j = 0; j < n; ++j)
+        if (flagged[j] && (key[j] > key[i] || (key[j] == key[i] && j < i))) ++r;
+    }
+    rank_out[i] = r;
+  }
+  PAR_FOR(one, 1) {
+    int c = 0;
+    for (int j = 0; j < n; ++j) c += flagged[j] ? 1 : 0;
+    *count = c;
+  }
+  CTA_SYNC();
+}
+
+// ---------------------------------------------------------------------------------------------
+// SVD of the small triangular factor: selects the entangled directions.
+//   in : Rw (rr x rr, ld = rr)   out: Jsel (rr x rr): right singular vectors with
+//        s^2 > thr first (k0 of them), remaining columns zero;  k0 -> *k0_out; status flag.
+// ---------------------------------------------------------------------------------------------
+struct SvdSelJob {
+  const double *Rw;
+  double *Jsel;
+  double *Jwork;      // rr x rr global scratch for the rotations when they do not fit in smem
+  int *k0_out;
+  int *info;          // info[2] |= 1 when the sketch did not reach the noise floor
+  const int *nzero;   // number of numerically dependent sketch columns (rank exhausted if > 0)
+  int rr, complete;   // complete: the sketch spans the whole range of B (rr == min(n, m))
+};
+TMF_GLOBAL svd_select_kernel(const SvdSelJob *jobs, double thr, double floor2) {
+  const SvdSelJob jb = jobs[BLOCK_ID];
+  const int n = jb.rr;
+  if (n <= 0) {
+    PAR_FOR(one, 1) *jb.k0_out = 0;
+    return;
+  }
+  DYN_SMEM(double, sm);
+  double *G = sm, *s2 = G + n * n, *rot = s2 + n;
+  double *part = rot + ((n + 1) & ~1);
+  int *iw = reinterpret_cast<int *>(part + (((n + 1) & ~1) / 2) * 33 * 3 + 2);
+  int *flag = iw, *sel = iw + 2, *rank = sel + n, *cnt = rank + n;
+  double *J = (n > JAC_SMEM_J_MAX) ? jb.Jwork : reinterpret_cast<double *>(cnt + 6);
+  PAR_FOR(idx, n * n) {
+    G[idx] = jb.Rw[idx];
+    J[idx] = ((idx / n) == (idx % n)) ? 1.0 : 0.0;
+  }
+  CTA_SYNC();
+  jacobi_onesided(G, n, J, n, n, rot, part, flag);
+  PAR_FOR(c, n) {
+    double s = 0.0;
+    for (int r = 0; r < n; ++r) s += G[c * n + r] * G[c * n + r];
+    s2[c] = s;
+    sel[c] = (s > thr) ? 1 : 0;
+  }
+  CTA_SYNC();
+  rank_desc(s2, sel, n, rank, cnt);
+  PAR_FOR(idx, n * n) jb.Jsel[idx] = 0.0;
+  CTA_SYNC();
+  PAR_FOR(idx, n * n) {
+    int c = idx / n, r = idx - c * n;
+    if (rank[c] >= 0) jb.Jsel[rank[c] * n + r] = J[idx];
+  }
+  PAR_FOR(one, 1) {
+    *jb.k0_out = *cnt;
+    // adequacy of the sketch: either the range of B was exhausted (dependent columns were
+    // dropped) or the smallest captured singular value is far below the entanglement threshold.
+    double smin = s2[0], smax = s2[0];
+    for (int c = 1; c < n; ++c) { smin = fmin(smin, s2[c]); smax = fmax(smax, s2[c]); }
+    bool ok = jb.complete || (jb.nzero && *jb.nzero > 0) || smin <= floor2 * smax || smax == 0.0;
+    if (!ok) jb.info[2] |= 1;
+  }
+}
+inline size_t svdsel_smem_bytes(int n) {
+  int np = (n + 1) & ~1;
+  size_t nj = (n > JAC_SMEM_J_MAX) ? 0 : (size_t)n * n;
+  return sizeof(double) * ((size_t)n * n + nj + n + np + (size_t)(np / 2) * 33 * 3 + 2) +
+         sizeof(int) * ((size_t)2 * n + 12);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rayleigh-Ritz on the selected subspace: eigen-decomposition of TE (leading k0 x k0 block).
+//   out: Zsel (rr x rr): eigenvectors of the entangled eigenvalues (cutoff <= e < 1-cutoff),
+//        ordered by decreasing LEFT eigenvalue, zero-padded;  e_left -> e_out[0..k);
+//        info[0] = k;  eside_out[0..k) = eigenvalue on this side (used by the Cholesky step).
+// ---------------------------------------------------------------------------------------------
+struct RitzJob {
+  const double *TE;   // rr x rr, ld = rr
+  double *Zsel;       // rr x rr
+  double *Jwork;      // rr x rr global scratch (see SvdSelJob)
+  const int *k0;
+  double *e_out;      // TMF_MAX_MODES
+  double *eside_out;  // TMF_MAX_MODES
+  int *info;
+  int rr, side;
+};
+TMF_GLOBAL ritz_kernel(const RitzJob *jobs, double cutoff) {
+  const RitzJob jb = jobs[BLOCK_ID];
+  const int n = jb.rr;
+  const int k0 = (n > 0) ? *jb.k0 : 0;
+  if (n <= 0 || k0 <= 0) {
+    PAR_FOR(one, 1) jb.info[0] = 0;
+    if (n > 0) { PAR_FOR(idx, n * n) jb.Zsel[idx] = 0.0; }
+    return;
+  }
+  DYN_SMEM(double, sm);
+  double *G = sm, *ev = G + n * n, *key = ev + n, *rot = key + n;
+  double *part = rot + ((n + 1) & ~1);
+  int *iw = reinterpret_cast<int *>(part + (((n + 1) & ~1) / 2) * 33 * 3 + 2);
+  int *flag = iw, *sel = iw + 2, *rank = sel + n, *cnt = rank + n;
+  double *J = (n > JAC_SMEM_J_MAX) ? jb.Jwork : reinterpret_cast<double *>(cnt + 6);
+  PAR_FOR(idx, k0 * k0) {
+    int c = idx / k0, r = idx - c * k0;
+    // symmetrise the Rayleigh quotient matrix
+    G[c * n + r] = 0.5 * (jb.TE[c * n + r] + jb.TE[r * n + c]);
+    J[c * n + r] = (c == r) ? 1.0 : 0.0;
+  }
+  CTA_SYNC();
+  jacobi_onesided(G, n, J, n, k0, rot, part, flag);
+  PAR_FOR(c, k0) {
+    double s = 0.0;
+    for (int r = 0; r < k0; ++r) s += G[c * n + r] * G[c * n + r];
+    double e = sqrt(s);
+    ev[c] = e;
+    sel[c] = (e >= cutoff && e < 1.0 - cutoff) ? 1 : 0;
+    key[c] = (jb.side == TMF_SIDE_L) ? e : 1.0 - e;  // left eigenvalue
+  }
+  CTA_SYNC();
+  rank_desc(key, sel, k0, rank, cnt);
+  PAR_FOR(idx, n * n) jb.Zsel[idx] = 0.0;
+  CTA_SYNC();
+  PAR_FOR(idx, k0 * k0) {
+    int c = idx / k0, r = idx - c * k0;
+    if (rank[c] >= 0) jb.Zsel[rank[c] * n + r] = J[c * n + r];
+  }
+  PAR_FOR(c, k0) {
+    if (rank[c] >= 0 && rank[c] < TMF_MAX_MODES) {
+      jb.e_out[rank[c]] = key[c];
+      jb.eside_out[rank[c]] = ev[c];
+    }
+  }
+  PAR_FOR(one, 1) {
+    jb.info[0] = *cnt;
+    if (*cnt > TMF_MAX_MODES) jb.info[2] |= 2;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pivoted Cholesky of the filled-space projector P1 = A - U diag(w) U^T  (never formed).
+// P1 is (numerically) an orthogonal projector, so its Cholesky factor has orthonormal columns:
+// F (n x f) is an orthonormal basis of the eigenvalue-1 space of A.  Diagonal pivoting keeps
+// every pivot >= rank/n.  One CTA per job; F and U stream from L2.
+// ---------------------------------------------------------------------------------------------
+struct CholJob {
+  const double *A;     // n x n block of C, lda
+  double *V;           // output matrix: columns [0,k) = U (input), [k, k+f) = F (output); ld = n
+  const double *w;     // eigenvalues of U's columns on this side (k of them)
+  int *info;           // reads info[0] = k, writes info[1] = f
+  int n, lda, max_cols, pad_;
+};
+TMF_GLOBAL pivchol_kernel(const CholJob *jobs, double tol) {
+  const CholJob jb = jobs[BLOCK_ID];
+  const int n = jb.n;
+  if (n <= 0) return;
+  const int k = jb.info[0];
+  DYN_SMEM(double, sm);
+  double *d = sm, *col = d + n, *lp = col + n, *red = lp + n + TMF_MAX_MODES;  // red: 64 + 64
+  int *ired = reinterpret_cast<int *>(red + 72);
+  const double *U = jb.V;
+  double *F = jb.V + (int64_t)k * n;
+  PAR_FOR(i, n) {
+    double s = jb.A[(int64_t)i * jb.lda + i];
+    for (int m = 0; m < k; ++m) s -= jb.w[m] * U[(int64_t)m * n + i] * U[(int64_t)m * n + i];
+    d[i] = s;
+  }
+  CTA_SYNC();
+  int f = 0;
+  const int fmax = jb.max_cols - k;
+  for (; f < fmax; ++f) {
+    // argmax of d (two-level)
+    PAR_FOR(lane, 32) {
+      double best = -1.0;
+      int bi = 0;
+      for (int i = lane; i < n; i += 32)
+        if (d[i] > best) { best = d[i]; bi = i; }
+      red[lane] = best;
+      ired[lane] = bi;
+    }
+    CTA_SYNC();
+    PAR_FOR(one, 1) {
+      double best = red[0];
+      int bi = ired[0];
+      for (int l = 1; l < 32; ++l)
+        if (red[l] > best || (red[l] == best && ired[l] < bi)) { best = red[l]; bi = ired[l]; }
+      red[40] = best;
+      ired[40] = bi;
+    }
+    CTA_SYNC();
+    const double dmax = red[40];
+    const int p = ired[40];
+    if (!(dmax > tol)) break;
+    PAR_FOR(m, k + f) lp[m] = (m < k) ? jb.w[m] * U[(int64_t)m * n + p] : F[(int64_t)(m - k) * n + p];
+    CTA_SYNC();
+    PAR_FOR(i, n) {
+      double c = jb.A[(int64_t)p * jb.lda + i];
+      for (int m = 0; m < k; ++m) c -= U[(int64_t)m * n + i] * lp[m];
+      for (int m = 0; m < f; ++m) c -= F[(int64_t)m * n + i] * lp[k + m];
+      col[i] = c;
+    }
+    CTA_SYNC();
+    const double piv = col[p];
+    if (!(piv > 0.0)) break;
+    const double inv = 1.0 / sqrt(piv);
+    PAR_FOR(i, n) {
+      double l = col[i] * inv;
+      F[(int64_t)f * n + i] = l;
+      d[i] = (i == p) ? -1.0 : d[i] - l * l;
+    }
+    CTA_SYNC();
+  }
+  PAR_FOR(one, 1) jb.info[1] = f;
+}
+inline size_t pivchol_smem_bytes(int n) {
+  return sizeof(double) * ((size_t)3 * n + TMF_MAX_MODES + 72) + sizeof(int) * 48;
+}
+
+// ---------------------------------------------------------------------------------------------
+// direct path for small blocks (n <= SMALL_N): full Jacobi eigen-decomposition of A in shared
+// memory, then split into entangled / filled exactly like slater.py:350-370.
+// ---------------------------------------------------------------------------------------------
+struct SmallJob {
+  const double *A;
+  double *V;       // n x n output, ld = n: [entangled (k) | filled (f)]
+  double *e_out;   // TMF_MAX_MODES
+  int *info;       // k, f, status, n
+  int n, lda, side, pad_;
+};
+TMF_GLOBAL small_modes_kernel(const SmallJob *jobs, double cutoff) {
+  const SmallJob jb = jobs[BLOCK_ID];
+  const int n = jb.n;
+  if (n <= 0) {
+    PAR_FOR(one, 1) { jb.info[0] = 0; jb.info[1] = 0; }
+    return;
+  }
+  DYN_SMEM(double, sm);
+  double *G = sm, *J = G + n * n, *ev = J + n * n, *key = ev + n, *rot = key + n;
+  double *part = rot + ((n + 1) & ~1);
+  int *iw = reinterpret_cast<int *>(part + (((n + 1) & ~1) / 2) * 33 * 3 + 2);
+  int *flag = iw, *sel = iw + 2, *rank = sel + n, *cnt = rank + n, *fil = cnt + 2, *frank = fil + n;
+  PAR_FOR(idx, n * n) {
+    int c = idx / n, r = idx - c * n;
+    G[idx] = 0.5 * (jb.A[(int64_t)c * jb.lda + r] + jb.A[(int64_t)r * jb.lda + c]);
+    J[idx] = (c == r) ? 1.0 : 0.0;
+  }
+  CTA_SYNC();
+  jacobi_onesided(G, n, J, n, n, rot, part, flag);
+  PAR_FOR(c, n) {
+    double s = 0.0;
+    for (int r = 0; r < n; ++r) s += G[c * n + r] * G[c * n + r];
+    double e = sqrt(s);
+    ev[c] = e;
+    sel[c] = (e >= cutoff && e < 1.0 - cutoff) ? 1 : 0;
+    fil[c] = (e >= 1.0 - cutoff) ? 1 : 0;
+    key[c] = (jb.side == TMF_SIDE_L) ? e : 1.0 - e;
+  }
+  CTA_SYNC();
+  rank_desc(key, sel, n, rank, cnt);
+  const int k = *cnt;
+  CTA_SYNC();
+  rank_desc(ev, fil, n, frank, cnt);
+  const int f = *cnt;
+  PAR_FOR(idx, n * n) {
+    int c = idx / n, r = idx - c * n;
+    int dst = rank[c] >= 0 ? rank[c] : (frank[c] >= 0 ? k + frank[c] : -1);
+    if (dst >= 0) jb.V[(int64_t)dst * n + r] = J[idx];
+  }
+  PAR_FOR(c, n)
+    if (rank[c] >= 0 && rank[c] < TMF_MAX_MODES) jb.e_out[rank[c]] = key[c];
+  PAR_FOR(one, 1) {
+    jb.info[0] = k;
+    jb.info[1] = f;
+    if (k > TMF_MAX_MODES) jb.info[2] |= 2;
+  }
+}
+inline size_t ritz_smem_bytes(int n) {
+  int np = (n + 1) & ~1;
+  size_t nj = (n > JAC_SMEM_J_MAX) ? 0 : (size_t)n * n;
+  return sizeof(double) * ((size_t)n * n + nj + 2 * n + np + (size_t)(np / 2) * 33 * 3 + 2) +
+         sizeof(int) * ((size_t)2 * n + 12);
+}
+inline size_t small_smem_bytes(int n) {
+  int np = (n + 1) & ~1;
+  return sizeof(double) * ((size_t)2 * n * n + 2 * n + np + (size_t)(np / 2) * 33 * 3 + 2) +
+         sizeof(int) * ((size_t)4 * n + 12);
+}
+
+}  // namespace tmf

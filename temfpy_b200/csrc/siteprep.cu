@@ -1,0 +1,207 @@
+// K8 + K9: overlap of the mode bases of two neighbouring bonds and Schur complement.
+//
+// reference: slater.py:1071  O = HT(v_bra) @ v_ket   (after _select_orbitals reordered / signed
+// the columns, :1066-1067) and :1073-1090 (det of the always-always block, sometimes matrix
+// D - C A^-1 B).  The explicit inverse of the reference is replaced by a blocked LU of the
+// k x k always block whose elimination is carried through the remaining rows and columns: after
+// k steps the trailing (rows-k) x (cols-k) block *is* the Schur complement and the product of the
+// pivots is det_always.  Pivoting is restricted to the rows of the always block.
+//
+// O is produced by the grouped DMMA GEMM (column gathers + sign scalings in the epilogue); the LU
+// runs one CTA per site with 16-wide panels staged in shared memory.
+#include "cta.hpp"
+
+namespace tmf {
+
+int gemm_launch_uploaded(const tmf_gemm_job *jobs_dev, const int *prefix_dev, int njobs, int ntiles,
+                         void *stream);
+
+constexpr int NB = 16;
+static_assert(sizeof(tmf_site_job) == 128, "site descriptor must be 128 bytes");
+
+TMF_GLOBAL schur_kernel(const tmf_site_job *jobs) {
+  const tmf_site_job jb = jobs[BLOCK_ID];
+  const int rows = jb.rows, cols = jb.cols, k = jb.k_always, ld = jb.rows;
+  double *O = jb.O;
+  DYN_SMEM(double, sm);
+  double *Lp = sm;                      // rows x NB  (column-major, ld = nr of the current panel)
+  double *Up = Lp + (size_t)rows * NB;  // NB x cols  (row-major, ld = nc)
+  double *red = Up + (size_t)cols * NB; // 40
+  int *ired = reinterpret_cast<int *>(red + 40);  // 40 + NB
+  int *piv = ired + 40;
+  if (rows <= 0 || cols <= 0) {
+    PAR_FOR(one, 1) *jb.det = 1.0;
+    return;
+  }
+  // physical orbital row: <n_i| overlaps = one row of the ket mode matrix (slater.py:1030-1051)
+  if (jb.physical && jb.phys_row >= 0) {
+    const int src = (jb.mode == 1) ? 0 : jb.n_bra;
+    PAR_FOR(n, cols) {
+      int c = jb.ket_cols[n];
+      double v = (c >= 0) ? jb.Vk[(int64_t)c * jb.ldk + src] : 0.0;
+      O[(int64_t)n * ld + jb.phys_row] = v * jb.bra_sign[jb.phys_row] * jb.ket_sign[n];
+    }
+  }
+  PAR_FOR(one, 1) red[36] = 1.0;  // running determinant
+  CTA_SYNC();
+
+  for (int t0 = 0; t0 < k; t0 += NB) {
+    const int w = (k - t0 < NB) ? (k - t0) : NB;
+    const int nr = rows - t0;         // panel rows t0 .. rows-1
+    const int lim = k - t0;           // rows eligible as pivots (always block)
+    PAR_FOR(idx, nr * w) {
+      int c = idx / nr, r = idx - c * nr;
+      Lp[c * nr + r] = O[(int64_t)(t0 + c) * ld + t0 + r];
+    }
+    CTA_SYNC();
+    for (int j = 0; j < w; ++j) {
+      PAR_FOR(lane, 32) {
+        double best = -1.0;
+        int bi = j;
+        for (int r = j + lane; r < lim; r += 32) {
+          double a = fabs(Lp[j * nr + r]);
+          if (a > best) { best = a; bi = r; }
+        }
+        red[lane] = best;
+        ired[lane] = bi;
+      }
+      CTA_SYNC();
+      PAR_FOR(one, 1) {
+        double best = red[0];
+        int bi = ired[0];
+        for (int l = 1; l < 32; ++l)
+          if (red[l] > best || (red[l] == best && ired[l] < bi)) { best = red[l]; bi = ired[l]; }
+        piv[j] = bi;
+        double pv = Lp[j * nr + bi];
+        red[36] *= (bi != j) ? -pv : pv;
+        red[37] = (pv != 0.0) ? 1.0 / pv : 0.0;
+      }
+      CTA_SYNC();
+      const int p = piv[j];
+      if (p != j) {
+        PAR_FOR(c, w) {
+          double a = Lp[c * nr + j];
+          Lp[c * nr + j] = Lp[c * nr + p];
+          Lp[c * nr + p] = a;
+        }
+        CTA_SYNC();
+      }
+      const double inv = red[37];
+      PAR_FOR(r, nr - j - 1) Lp[j * nr + j + 1 + r] *= inv;
+      CTA_SYNC();
+      const int hr = nr - j - 1;
+      PAR_FOR(idx, (w - j - 1) * hr) {
+        int c = j + 1 + idx / hr, r = j + 1 + idx % hr;
+        Lp[c * nr + r] -= Lp[j * nr + r] * Lp[c * nr + j];
+      }
+      CTA_SYNC();
+    }
+    PAR_FOR(idx, nr * w) {
+      int c = idx / nr, r = idx - c * nr;
+      O[(int64_t)(t0 + c) * ld + t0 + r] = Lp[c * nr + r];
+    }
+    const int nc = cols - t0 - w;
+    // row interchanges + forward substitution on the block row, one thread per column
+    PAR_FOR(jc, nc) {
+      double *col = O + (int64_t)(t0 + w + jc) * ld + t0;
+      for (int j = 0; j < w; ++j) {
+        int p = piv[j];
+        if (p != j) { double a = col[j]; col[j] = col[p]; col[p] = a; }
+      }
+      double u[NB];
+      for (int a = 0; a < w; ++a) {
+        double v = col[a];
+        for (int b = 0; b < a; ++b) v -= Lp[b * nr + a] * u[b];
+        u[a] = v;
+      }
+      for (int a = 0; a < w; ++a) {
+        col[a] = u[a];
+        Up[a * nc + jc] = u[a];
+      }
+    }
+    CTA_SYNC();
+    // trailing update with 4 x 4 register tiles
+    const int mr = nr - w;
+    const int ti = (mr + 3) / 4, tj = (nc + 3) / 4;
+    PAR_FOR(tile, ti * tj) {
+      int i0 = (tile % ti) * 4, j0 = (tile / ti) * 4;
+      double acc[4][4];
+      for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+      for (int kk = 0; kk < w; ++kk) {
+        double l[4], u[4];
+        for (int a = 0; a < 4; ++a) l[a] = (i0 + a < mr) ? Lp[kk * nr + w + i0 + a] : 0.0;
+        for (int b = 0; b < 4; ++b) u[b] = (j0 + b < nc) ? Up[kk * nc + j0 + b] : 0.0;
+        for (int a = 0; a < 4; ++a)
+          for (int b = 0; b < 4; ++b) acc[a][b] += l[a] * u[b];
+      }
+      for (int b = 0; b < 4; ++b)
+        for (int a = 0; a < 4; ++a)
+          if (i0 + a < mr && j0 + b < nc)
+            O[(int64_t)(t0 + w + j0 + b) * ld + t0 + w + i0 + a] -= acc[a][b];
+    }
+    CTA_SYNC();
+  }
+  const int sr = rows - k, sc = cols - k;
+  PAR_FOR(idx, sr * sc) {
+    int c = idx / sr, r = idx - c * sr;
+    jb.S[(int64_t)c * sr + r] = O[(int64_t)(k + c) * ld + k + r];
+  }
+  PAR_FOR(one, 1) *jb.det = red[36];
+}
+
+static size_t schur_smem_bytes(int rows, int cols) {
+  return sizeof(double) * ((size_t)(rows + cols) * NB + 40) + sizeof(int) * (40 + NB + 8);
+}
+
+}  // namespace tmf
+
+extern "C" int tmf_site_overlap_schur_batched(const tmf_site_job *jobs_host, int nsites,
+                                              void *desc_dev, void *stream) {
+  using namespace tmf;
+  if (nsites <= 0) return TMF_OK;
+  // descriptor layout in desc_dev: site jobs | gemm jobs | gemm prefix
+  std::vector<tmf_gemm_job> g(nsites);
+  std::vector<int> prefix(nsites + 1, 0);
+  size_t smem = 0;
+  for (int s = 0; s < nsites; ++s) {
+    const tmf_site_job &sj = jobs_host[s];
+    tmf_gemm_job &j = g[s];
+    std::memset(&j, 0, sizeof(j));
+    j.A = sj.Vb; j.B = sj.Vk; j.C = sj.O;
+    j.a_idx = sj.bra_cols; j.b_idx = sj.ket_cols;
+    j.row_scale = sj.bra_sign; j.col_scale = sj.ket_sign;
+    j.M = sj.rows; j.N = sj.cols; j.K = sj.n_bra;
+    j.lda = sj.ldb; j.ldb = sj.ldk; j.ldc = sj.rows;
+    j.transA = 1; j.transB = 0;
+    j.a_row_off = 0;
+    j.b_row_off = (sj.physical && sj.mode == 1) ? 1 : 0;  // right mode: ket site 0 is the new site
+    j.alpha = 1.0; j.beta = 0.0;
+    int tm = (j.M + 63) / 64, tn = (j.N + 63) / 64;
+    if (j.M <= 0 || j.N <= 0) tm = tn = 0;
+    prefix[s + 1] = prefix[s] + tm * tn;
+    smem = std::max(smem, schur_smem_bytes(sj.rows, sj.cols));
+  }
+  if (smem > 220 * 1024) {
+    set_error("site too large for the shared-memory LU panels (rows + cols > ~1700)");
+    return TMF_ERR_VALUE;
+  }
+  unsigned char *d = static_cast<unsigned char *>(desc_dev);
+  const size_t o_site = 0, o_gemm = align256(sizeof(tmf_site_job) * (size_t)nsites);
+  const size_t o_pref = o_gemm + align256(sizeof(tmf_gemm_job) * (size_t)nsites);
+  int rc = copy_h2d(d + o_site, jobs_host, sizeof(tmf_site_job) * (size_t)nsites, stream);
+  if (rc) return rc;
+  rc = copy_h2d(d + o_gemm, g.data(), sizeof(tmf_gemm_job) * (size_t)nsites, stream);
+  if (rc) return rc;
+  rc = copy_h2d(d + o_pref, prefix.data(), sizeof(int) * (size_t)(nsites + 1), stream);
+  if (rc) return rc;
+  rc = gemm_launch_uploaded(reinterpret_cast<const tmf_gemm_job *>(d + o_gemm),
+                            reinterpret_cast<const int *>(d + o_pref), nsites, prefix[nsites], stream);
+  if (rc) return rc;
+  return launch(schur_kernel, nsites, 256, smem, stream,
+                reinterpret_cast<const tmf_site_job *>(d + o_site));
+}
+
+extern "C" int64_t tmf_site_desc_bytes(int nsites) {
+  return tmf::align256(128 * (int64_t)nsites) * 2 + tmf::align256(4 * (int64_t)(nsites + 1)) + 256;
+}
