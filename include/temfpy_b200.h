@@ -83,13 +83,9 @@ int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int njobs, con
                              const int64_t *v_off, double *V_dev, double *e_dev, int *info_dev,
                              void *work_dev, int64_t work_bytes, void *stream);
 
-/* centre bond: pair left and right entangled modes.  replaces: utils.py:19-96 (block_svd) as
- * called from slater.py:407, and the odd-index sign flips of slater.py:410.
- * VL (nL x k), VR (nR x k) are the entangled columns of the two jobs of the centre bond in the
- * common "mode i" order; they are rotated in place so that C_LR = VL diag(sv) VR^T, sv > 0. */
-int tmf_block_svd_pair(const double *C_dev, int L, int ldc, int x, int k, const double *e_host,
-                       double degeneracy_tol, double *VL_dev, int ldl, double *VR_dev, int ldr,
-                       void *work_dev, int64_t work_bytes, void *stream);
+/* centre bond (K4): the pairing of left and right entangled modes -- utils.py:19-96 (block_svd) as
+ * called from slater.py:407, and the odd-index sign flips of slater.py:410 -- is part of
+ * tmf_chain_tensors (GEMMs V_L^T C_LR V_R on the device, SVD of the k x k degenerate groups). */
 
 /* K6/K7 -- best-first enumeration of the most probable occupation subsets (HOST, multi-threaded
  * over bonds).  replaces: schmidt_utils.py:211-324 (lowest_sums), :99-185 (StoppingCondition

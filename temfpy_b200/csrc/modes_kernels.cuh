@@ -199,6 +199,20 @@ TMF_DEVICE void jacobi_onesided(double *G, int ldg, double *J, int ldj, int n, d
     CTA_SYNC();
     if (!any) break;
   }
+  // the product of ~n * sweeps plane rotations drifts from orthonormality by ~1e-14: renormalise the
+  // columns of J (first-order repair; the residual non-orthogonality only enters at second order)
+  PAR_FOR(c, n) {
+    double s = 0.0;
+    for (int r = 0; r < n; ++r) s += J[(int64_t)c * ldj + r] * J[(int64_t)c * ldj + r];
+    rot[c] = (s > 0.0) ? 1.0 / sqrt(s) : 1.0;
+  }
+  CTA_SYNC();
+  PAR_FOR(idx, n * n) {
+    int c = idx / n, r = idx - c * n;
+    J[(int64_t)c * ldj + r] *= rot[c];
+    G[(int64_t)c * ldg + r] *= rot[c];
+  }
+  CTA_SYNC();
 }
 inline size_t jacobi_scratch_doubles(int n) {
   int half = ((n + 1) & ~1) / 2;
@@ -328,10 +342,19 @@ TMF_GLOBAL ritz_kernel(const RitzJob *jobs, double cutoff) {
   }
   CTA_SYNC();
   jacobi_onesided(G, n, J, n, k0, rot, part, flag);
+  // eigenvalues as Rayleigh quotients of the *original* matrix: the rotated columns of G carry the
+  // accumulated rounding of all sweeps (~ sweeps * k * eps), the quotient only k * eps.
+  PAR_FOR(idx, k0 * k0) {
+    int c = idx / k0, r = idx - c * k0;
+    double s = 0.0;
+    for (int q = 0; q < k0; ++q) s += 0.5 * (jb.TE[q * n + r] + jb.TE[r * n + q]) * J[c * n + q];
+    G[c * n + r] = s;
+  }
+  CTA_SYNC();
   PAR_FOR(c, k0) {
     double s = 0.0;
-    for (int r = 0; r < k0; ++r) s += G[c * n + r] * G[c * n + r];
-    double e = sqrt(s);
+    for (int r = 0; r < k0; ++r) s += J[c * n + r] * G[c * n + r];
+    double e = s;
     ev[c] = e;
     sel[c] = (e >= cutoff && e < 1.0 - cutoff) ? 1 : 0;
     key[c] = (jb.side == TMF_SIDE_L) ? e : 1.0 - e;  // left eigenvalue
@@ -465,10 +488,19 @@ TMF_GLOBAL small_modes_kernel(const SmallJob *jobs, double cutoff) {
   }
   CTA_SYNC();
   jacobi_onesided(G, n, J, n, n, rot, part, flag);
+  // eigenvalues as Rayleigh quotients of the original block (see ritz_kernel)
+  PAR_FOR(idx, n * n) {
+    int c = idx / n, r = idx - c * n;
+    double s = 0.0;
+    for (int q = 0; q < n; ++q)
+      s += 0.5 * (jb.A[(int64_t)q * jb.lda + r] + jb.A[(int64_t)r * jb.lda + q]) * J[c * n + q];
+    G[idx] = s;
+  }
+  CTA_SYNC();
   PAR_FOR(c, n) {
     double s = 0.0;
-    for (int r = 0; r < n; ++r) s += G[c * n + r] * G[c * n + r];
-    double e = sqrt(s);
+    for (int r = 0; r < n; ++r) s += J[c * n + r] * G[c * n + r];
+    double e = s;
     ev[c] = e;
     sel[c] = (e >= cutoff && e < 1.0 - cutoff) ? 1 : 0;
     fil[c] = (e >= 1.0 - cutoff) ? 1 : 0;

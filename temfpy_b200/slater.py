@@ -1,0 +1,207 @@
+"""Tools for converting Slater determinants into matrix product states (MPS).
+
+Drop-in for ``temfpy.slater`` (reference slater.py): same entry points and keyword surface
+(``correlation_matrix``, ``spinful_correlation_matrix``, ``C_to_MPS``, ``H_to_MPS``,
+``C_to_iMPS``, ``H_to_iMPS``, ``SchmidtVectors``), with every floating-point stage running in the
+hand-written CUDA kernels of ``csrc/`` behind the C ABI of ``include/temfpy_b200.h``.  There is no
+CPU fallback: without the CUDA library or without a GPU every entry point raises ``RuntimeError``.
+
+Return type: TeNPy is not installed in this image, so the drivers return a
+:class:`temfpy_b200.mps.BlockMPS` (same leg labels, charges, Schmidt values and form) and convert
+it with ``.to_tenpy()`` when ``tenpy`` is importable (``as_tenpy=None`` = automatic).
+"""
+from __future__ import annotations
+
+import importlib.util
+import logging
+from dataclasses import dataclass
+from typing import Literal
+
+import numpy as np
+
+from . import engine, iMPS as _iMPS
+from .mps import BlockMPS
+from .schmidt_utils import StoppingCondition, to_stopping_condition
+from .testing import _DIAG_TOL
+from .utils import HT, normalize_SV
+
+logger = logging.getLogger(__name__)
+
+_backend = None
+
+
+def _be():
+    global _backend
+    if _backend is None:
+        _backend = engine.TorchBackend()
+    return _backend
+
+
+def _want_tenpy(as_tenpy):
+    if as_tenpy is None:
+        return importlib.util.find_spec("tenpy") is not None
+    return bool(as_tenpy)
+
+
+def _real_or_raise(M, what):
+    M = np.asarray(M)
+    if np.iscomplexobj(M):
+        if np.allclose(M.imag, 0.0, rtol=0, atol=1e-14):
+            return np.ascontiguousarray(M.real, dtype=np.float64)
+        raise NotImplementedError(f"complex {what}: the sm_100a kernels of this release are FP64 real "
+                                  "(complex128 variant: see DESIGN.md 'out of scope')")
+    return np.ascontiguousarray(M, dtype=np.float64)
+
+
+#### High-level functions ####
+def correlation_matrix(H: np.ndarray, N: int | None = None) -> tuple[np.ndarray, int]:
+    r"""Ground-state correlation matrix of a mean-field Hamiltonian (slater.py:1150-1180).
+
+    The one-off ``eigh(H)`` (K1) stays on LAPACK like in the reference; the rank-N update
+    ``C = Phi Phi^T`` (K2) runs on the DMMA GEMM (``tmf_corr_build``)."""
+    be = _be()
+    H = _real_or_raise(H, "Hamiltonian")
+    e, v = np.linalg.eigh(H)
+    if N is None:
+        occupied = e < 0
+        v = v[:, occupied]
+        N = int(occupied.sum())
+    else:
+        v = v[:, :N]
+    L = len(H)
+    if N == 0:
+        return np.zeros((L, L)), 0
+    phi = be.from_host(np.ascontiguousarray(v).ravel())
+    Cd = be.empty(L * L, np.float64)
+    engine.check(be.lib, be.lib.tmf_corr_build(be.ptr(phi), L, N, N, be.ptr(Cd), L, be.stream))
+    be.sync()
+    return be.to_host(Cd, L * L).reshape(L, L), N
+
+
+def spinful_correlation_matrix(C: np.ndarray, ph: bool = True):
+    r"""Enlarged correlation matrix for spinful fermions (slater.py:1183-1213)."""
+    n, m = C.shape
+    assert n == m, f"Got non-square {C.shape} correlation matrix"
+    C2 = np.zeros((2 * n, 2 * n), dtype=C.dtype)
+    C2[::2, ::2] = C
+    C2[1::2, 1::2] = (np.eye(n) - C) if ph else C
+    return C2
+
+
+def _prepare_C(C, spinful):
+    if spinful == "simple":
+        C = spinful_correlation_matrix(C, False)
+    elif spinful == "PH":
+        C = spinful_correlation_matrix(C, True)
+    elif spinful is not None:
+        raise ValueError(f"`spinful` must be 'simple', 'PH', or `None`, got {spinful!r}")
+    L = len(C)
+    assert C.shape == (L, L), f"Got non-square {C.shape} correlation matrix"
+    return _real_or_raise(C, "correlation matrix")
+
+
+def _check_projector(C, tol=1e-8):
+    """The mode extraction uses C^2 = C (a Slater determinant); anything else is not an input the
+    reference could convert either (its centre-bond assertion eL + eR = 1, slater.py:404)."""
+    dev = np.abs(C @ C - C).max() if len(C) <= 256 else np.abs(C[:64] @ C - C[:64]).max()
+    if dev > tol:
+        raise ValueError(f"`C` is not the correlation matrix of a Slater determinant (max|C^2 - C| = {dev:.2e})")
+
+
+def _chain_to_mps(res: engine.ChainResult, unit_cell_width) -> BlockMPS:
+    L = res.L
+    lams = [normalize_SV(res.bonds[x].schmidt_values, logger) for x in range(L + 1)]   # slater.py:1296
+    oc = res.ortho_center
+    return BlockMPS(L=L, tensors=[res.sites[i] for i in range(L)], lams=lams,
+                    charges=[res.bonds[x].charge for x in range(L + 1)],
+                    form=["A"] * oc + ["B"] * (L - oc), unit_cell_width=unit_cell_width,     # slater.py:1348
+                    ortho_center=oc, meta=dict(stats=res.stats, bonds=res.bonds))
+
+
+def C_to_MPS(C: np.ndarray, trunc_par: dict | StoppingCondition, *, diag_tol: float = _DIAG_TOL,
+             ortho_center: int = None, spinful: Literal["simple", "PH", None] = None,
+             unit_cell_width: int | None = None, as_tenpy: bool | None = None):
+    r"""MPS representation of a Slater determinant from its correlation matrix
+    (slater.py:1216-1353; same parameters)."""
+    trunc_par = to_stopping_condition(trunc_par)
+    if unit_cell_width is None:
+        unit_cell_width = len(C)
+    elif len(C) % unit_cell_width != 0:
+        raise ValueError(f"{unit_cell_width = } does not divide system size {len(C)}")
+    be = _be()
+    C = _prepare_C(C, spinful)
+    _check_projector(C)
+    L = len(C)
+    n_fermion = int(np.round(np.trace(C)))                                   # slater.py:414
+    logger.info("Central bond %d", ortho_center or L // 2)
+    Cd = be.from_host(C.ravel())
+    res = engine.run_chain(be, Cd, L, L, trunc_par, n_fermion, ortho_center=ortho_center)
+    mps = _chain_to_mps(res, unit_cell_width)
+    return mps.to_tenpy() if _want_tenpy(as_tenpy) else mps
+
+
+def H_to_MPS(H: np.ndarray, trunc_par: dict | StoppingCondition, *, diag_tol: float = _DIAG_TOL,
+             ortho_center: int = None, spinful: Literal["simple", "PH", None] = None,
+             unit_cell_width: int | None = None, as_tenpy: bool | None = None):
+    r"""MPS representation of a Slater determinant from its single body Hamiltonian
+    (slater.py:1568-1627)."""
+    C, _ = correlation_matrix(H)
+    return C_to_MPS(C, trunc_par, diag_tol=diag_tol, ortho_center=ortho_center, spinful=spinful,
+                    unit_cell_width=unit_cell_width, as_tenpy=as_tenpy)
+
+
+#### Schmidt vectors of a single bond ####
+@dataclass(frozen=True)
+class SchmidtVectors:
+    r"""Schmidt vectors of a Slater determinant on one bond (reference slater.py:494-755).
+
+    Holds what the reference's object exposes to users -- occupation ``sets`` of the entangled
+    modes, ``schmidt_values`` and the charge table ``idx_L`` -- computed by the native path."""
+    e: np.ndarray
+    sets: np.ndarray
+    schmidt_values: np.ndarray
+    idx_L: dict
+    n_filled_left: int
+    nL: int
+    nR: int
+    n_fermion: int
+
+    @property
+    def n_schmidt(self) -> int:
+        return len(self.schmidt_values)
+
+    @property
+    def n_entangled(self) -> int:
+        return self.e.size
+
+    @classmethod
+    def from_correlation_matrix(cls, C, x, trunc_par, *, which="LR", diag_tol=_DIAG_TOL):
+        which = which.upper()
+        assert ("L" in which) or ("R" in which), "`which` must specify at least one of (L)eft or (R)ight"
+        trunc_par = to_stopping_condition(trunc_par)
+        be = _be()
+        C = _real_or_raise(C, "correlation matrix")
+        L = len(C)
+        nf = int(np.round(np.trace(C)))
+        oc = x if which == "LR" else (min(x + 1, L) if which == "L" else max(x - 1, 0))
+        lo = min(max(x - 1, 0), L - 1) if which != "R" else min(x, L - 1)
+        if which == "R" and x == L:
+            lo = L - 1
+        Cd = be.from_host(C.ravel())
+        res = engine.run_chain(be, Cd, L, L, trunc_par, nf, ortho_center=oc or None, site_lo=lo, site_hi=lo + 1,
+                               fetch_tensors=False)
+        b = res.bonds[x]
+        return cls(e=b.e, sets=b.sets, schmidt_values=b.schmidt_values, idx_L=b.idx_L,
+                   n_filled_left=b.filled_left, nL=x, nR=L - x, n_fermion=nf)
+
+
+def C_to_iMPS(C_short, C_long, trunc_par, sites_per_cell, cut, **kwargs):
+    r"""iMPS representation of a Slater determinant from correlation matrices (slater.py:1356-1565)."""
+    return _iMPS.slater_C_to_iMPS(C_short, C_long, trunc_par, sites_per_cell, cut, **kwargs)
+
+
+def H_to_iMPS(H_short, H_long, trunc_par, sites_per_cell, cut, **kwargs):
+    r"""iMPS representation of a Slater determinant from Hamiltonians (slater.py:1630-1734)."""
+    C_short, _ = correlation_matrix(H_short)
+    C_long, _ = correlation_matrix(H_long)
+    return C_to_iMPS(C_short, C_long, trunc_par, sites_per_cell, cut, **kwargs)

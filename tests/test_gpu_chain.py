@@ -1,0 +1,150 @@
+"""End-to-end parity of the CUDA path (through the C ABI / public API) against the oracle, the
+reference fixtures and size-independent properties at full size."""
+import numpy as np
+import pytest
+
+import slater_oracle as so
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["slater_random_L12", "slater_random_L20_chi24", "slater_random_L11_N4",
+                                  "slater_random_L40", "slater_chain_L16"])
+def test_reference_fixtures(gpu_backend, name):
+    g = helpers.golden(name)
+    tp = helpers.golden_trunc(g)
+    res = helpers.run_native(gpu_backend, g["C"], tp, int(g["N"]))
+    helpers.compare_mps(helpers.golden_dense_mps(g), helpers.chain_to_dense(res), tp)
+
+
+@pytest.mark.parametrize("L,seed", [(8, 8), (10, 10), (12, 12)])
+def test_exact_slater_amplitudes(gpu_backend, L, seed):
+    H = helpers.random_hamiltonian(L, seed)
+    Cm, n = so.correlation_matrix(H)
+    Phi = np.linalg.eigh(H)[1][:, :n]
+    res = helpers.run_native(gpu_backend, Cm, {"chi_max": 4096, "svd_min": 1e-7}, n)
+    psi = so.mps_to_state(helpers.chain_to_dense(res))
+    assert abs(abs(np.vdot(so.exact_slater_state(Phi), psi)) - 1) < 1e-13
+
+
+@pytest.mark.parametrize("L,chi,seed,decay", [(96, 40, 11, 2.0), (150, 48, 5, 2.0), (260, 64, 3, 2.0),
+                                              (160, 80, 2, 4.0)])
+def test_random_hamiltonians_vs_oracle(gpu_backend, L, chi, seed, decay):
+    """Generic (non-degenerate) inputs: bond dimensions and charge sectors bit-exact, Schmidt values /
+    entropies / overlap within the tolerances of BASELINE.json (see helpers.compare_mps)."""
+    Cm, n = so.correlation_matrix(helpers.random_hamiltonian(L, seed, decay))
+    tp = {"chi_max": chi}
+    res = helpers.run_native(gpu_backend, Cm, tp, n)
+    rep = helpers.compare_mps(so.C_to_MPS(Cm, tp), helpers.chain_to_dense(res), tp)
+    assert rep["ambiguous"] == [] and rep["overlap"] >= 1 - 1e-10
+
+
+def test_cfg1_hopping_chain_L64(gpu_backend):
+    """BASELINE configs[0]: NN tight-binding chain, L=64, half filling, chi_max=64.  The particle-hole
+    symmetric chain has exactly degenerate Schmidt multiplets at the chi_max cut; those bonds are
+    audited (helpers.ambiguous_bonds) and compared by spectrum, all others exactly."""
+    L = 64
+    Cm, n = so.correlation_matrix(so.hopping_chain(L))
+    tp = {"chi_max": 64}
+    res = helpers.run_native(gpu_backend, Cm, tp, n)
+    ref = so.C_to_MPS(Cm, tp)
+    got = helpers.chain_to_dense(res)
+    rep = helpers.compare_mps(ref, got, tp, check_overlap=False)
+    assert len(rep["ambiguous"]) < L // 2
+    o = abs(so.mps_overlap(ref, got)) / np.sqrt(abs(so.mps_overlap(ref, ref) * so.mps_overlap(got, got)))
+    assert o > 1 - 1e-7          # both are chi=64 truncations of the same state (truncation error 3e-8)
+
+
+def test_spinful_ph_chain(gpu_backend):
+    """cfg3 input: spinful 'PH' correlation matrix (doubly degenerate entanglement spectrum)."""
+    L = 40
+    Cm, _ = so.correlation_matrix(helpers.random_hamiltonian(L, 21))
+    C2 = so.spinful_correlation_matrix(Cm, True)
+    tp = {"chi_max": 4000, "svd_min": 1e-5}
+    res = helpers.run_native(gpu_backend, C2, tp)
+    ref = so.C_to_MPS(C2, tp)
+    got = helpers.chain_to_dense(res)
+    assert ref.chi == got.chi
+    assert np.abs(so.entropies(ref.lams) - so.entropies(got.lams)).max() < 1e-10
+    o = abs(so.mps_overlap(ref, got)) / np.sqrt(abs(so.mps_overlap(ref, ref) * so.mps_overlap(got, got)))
+    assert o >= 1 - 1e-9
+
+
+def test_cylinder_width4(gpu_backend):
+    """cfg4 family (smaller): square-lattice Fermi sea on a width-4 cylinder."""
+    H = helpers.cylinder_hamiltonian(16, 4) + 1e-3 * helpers.random_hamiltonian(64, 2)
+    Cm, n = so.correlation_matrix(H)
+    tp = {"chi_max": 128}
+    res = helpers.run_native(gpu_backend, Cm, tp, n)
+    helpers.compare_mps(so.C_to_MPS(Cm, tp), helpers.chain_to_dense(res), tp)
+
+
+def test_public_api_and_errors(gpu_backend):
+    from temfpy_b200 import slater
+    H = helpers.random_hamiltonian(32, 4)
+    C, N = slater.correlation_matrix(H)
+    Co, No = so.correlation_matrix(H)
+    assert N == No and np.abs(C - Co).max() < 1e-14
+    mps = slater.H_to_MPS(H, {"chi_max": 30}, as_tenpy=False)
+    ref = so.C_to_MPS(Co, {"chi_max": 30})
+    assert mps.chi == ref.chi[1:-1] and mps.form == ref.form
+    assert np.abs(mps.entanglement_entropy() - so.entropies(ref.lams)[1:-1]).max() < 1e-10
+    with pytest.raises(ValueError):
+        slater.C_to_MPS(C, {"chi_max": 8}, unit_cell_width=5)
+    with pytest.raises(ValueError):
+        slater.C_to_MPS(C, {"chi_max": 8}, spinful="up")
+    with pytest.raises(ValueError):
+        slater.C_to_MPS(0.5 * np.eye(8), {"chi_max": 8})        # not a Slater determinant
+    with pytest.raises(TypeError):
+        slater.C_to_MPS(C, 8)
+    sv = slater.SchmidtVectors.from_correlation_matrix(C, 16, {"chi_max": 30})
+    ov = so.bond_vectors_from_C(Co, 16, {"chi_max": 30})
+    assert np.array_equal(sv.sets, ov.sets) and {k: (s.start, s.stop) for k, s in sv.idx_L.items()} == ov.idx_L
+
+
+def test_shards_bit_identical(gpu_backend):
+    """Multi-GPU plan on one device: sharded ranges reproduce the unsharded Schmidt data bit for bit."""
+    L = 120
+    Cm, n = so.correlation_matrix(helpers.random_hamiltonian(L, 6))
+    tp = {"chi_max": 64}
+    full = helpers.run_native(gpu_backend, Cm, tp, n)
+    for lo, hi in [(0, 30), (30, 60), (60, 90), (90, 120)]:
+        part = helpers.run_native(gpu_backend, Cm, tp, n, site_lo=lo, site_hi=hi)
+        for x in range(lo, hi + 1):
+            assert np.array_equal(part.bonds[x].schmidt_values, full.bonds[x].schmidt_values)
+            assert np.array_equal(part.bonds[x].masks, full.bonds[x].masks)
+        for i in range(lo, hi):
+            assert np.allclose(np.abs(part.sites[i].dense()), np.abs(full.sites[i].dense()), atol=1e-13)
+
+
+def test_full_size_properties_L1024(gpu_backend):
+    """BASELINE metric configuration (L=1024, chi_max=1024, svd_min=1e-7) through size-independent
+    properties: normalisation of every Schmidt vector, chi <= chi_max, contiguous charge sectors,
+    canonical-form residual of sampled site tensors, particle-number sum rule."""
+    L = 1024
+    Cm, n = so.correlation_matrix(so.hopping_chain(L))
+    tp = {"chi_max": 1024, "svd_min": 1e-7}
+    res = helpers.run_native(gpu_backend, Cm, tp, n)
+    chis = [res.bonds[x].chi for x in range(L + 1)]
+    assert max(chis) <= 1024 and chis[0] == chis[-1] == 1 and max(chis) > 1000
+    for x in range(0, L + 1, 37):
+        b = res.bonds[x]
+        lam = b.schmidt_values / np.linalg.norm(b.schmidt_values)
+        assert np.all(np.diff(b.charge) >= 0)
+        # <N_left> from the Schmidt spectrum == trace of C_LL
+        assert abs((lam ** 2 * b.charge).sum() - np.trace(Cm[:x, :x])) < 1e-6
+        # Schmidt weight kept
+        assert abs(np.linalg.norm(b.schmidt_values) - 1) < 1e-6
+    for i in (0, 5, 300, 511, 512, 700, 1023):
+        T = res.sites[i].dense()
+        E = np.einsum("apb,apc->bc", T, T) if i < 512 else np.einsum("apb,cpb->ac", T, T)
+        # isometry up to the truncation of the neighbouring bond
+        assert np.abs(E - np.eye(len(E))).max() < 1e-5
+    # entropy profile against the oracle on a few bonds (full oracle chain takes ~10 min on CPU)
+    trunc = so.Trunc.make(tp)
+    for x in (3, 512, 900):
+        vo = so.bond_vectors_from_C(Cm, x, trunc, "LR" if x == 512 else ("R" if x > 512 else "L"))
+        a = vo.lam / np.linalg.norm(vo.lam)
+        b = res.bonds[x].schmidt_values / np.linalg.norm(res.bonds[x].schmidt_values)
+        assert abs(so.entropies([a])[0] - so.entropies([b])[0]) < 1e-10

@@ -1,0 +1,104 @@
+"""The CUDA kernel sources executed by the CPU simulator (tests/hostsim) through the same C ABI and
+the same Python driver as on the GPU; compared with the oracle / the reference fixtures.  CPU only.
+These tests check kernel *logic* (indexing, pivoting, signs, planning); the DMMA tile code itself
+is covered by the -m gpu tests."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import slater_oracle as so
+from temfpy_b200 import _lib
+from tests import helpers
+
+
+@pytest.mark.parametrize("name", ["slater_random_L12", "slater_random_L20_chi24", "slater_random_L11_N4",
+                                  "slater_random_L40"])
+def test_chain_vs_reference_fixture(sim_backend, name):
+    g = helpers.golden(name)
+    tp = helpers.golden_trunc(g)
+    res = helpers.run_native(sim_backend, g["C"], tp, int(g["N"]))
+    rep = helpers.compare_mps(helpers.golden_dense_mps(g), helpers.chain_to_dense(res), tp)
+    assert rep["ambiguous"] == []
+
+
+def test_chain_exact_amplitudes(sim_backend):
+    L = 10
+    H = helpers.random_hamiltonian(L, 77)
+    Cm, n = so.correlation_matrix(H)
+    Phi = np.linalg.eigh(H)[1][:, :n]
+    res = helpers.run_native(sim_backend, Cm, {"chi_max": 4096, "svd_min": 1e-7}, n)
+    psi = so.mps_to_state(helpers.chain_to_dense(res))
+    assert abs(abs(np.vdot(so.exact_slater_state(Phi), psi)) - 1) < 1e-13
+
+
+def test_chain_sketch_path_vs_oracle(sim_backend):
+    """Blocks larger than 64 sites go through the range-sketch / Rayleigh-Ritz / Cholesky path."""
+    L = 150
+    Cm, n = so.correlation_matrix(helpers.random_hamiltonian(L, 5))
+    tp = {"chi_max": 48}
+    res = helpers.run_native(sim_backend, Cm, tp, n)
+    rep = helpers.compare_mps(so.C_to_MPS(Cm, tp), helpers.chain_to_dense(res), tp)
+    assert rep["ambiguous"] == []
+
+
+def test_chain_ortho_center_and_shards(sim_backend):
+    """Sharded conversion == unsharded, bit for bit (multi-GPU without a cluster)."""
+    L = 30
+    Cm, n = so.correlation_matrix(helpers.random_hamiltonian(L, 9))
+    tp = {"chi_max": 32}
+    full = helpers.run_native(sim_backend, Cm, tp, n, ortho_center=11)
+    ref = so.C_to_MPS(Cm, tp, ortho_center=11)
+    helpers.compare_mps(ref, helpers.chain_to_dense(full), tp)
+    for lo, hi in [(0, 7), (7, 19), (19, 30)]:
+        part = helpers.run_native(sim_backend, Cm, tp, n, ortho_center=11, site_lo=lo, site_hi=hi)
+        for x in range(lo, hi + 1):
+            assert np.array_equal(part.bonds[x].schmidt_values, full.bonds[x].schmidt_values)
+            assert np.array_equal(part.bonds[x].charge, full.bonds[x].charge)
+        for i in range(lo, hi):
+            # tensors may differ by the sign gauge of a boundary bond that only one shard pairs
+            a, b = part.sites[i].dense(), full.sites[i].dense()
+            assert np.allclose(np.abs(a), np.abs(b), atol=1e-13)
+
+
+def test_minors_kernel_vs_tensor_block(sim_backend):
+    """K10 stage test: same S / masks as the oracle -> every block equal to _tensor_block."""
+    lib = sim_backend.lib
+    Cm, _ = so.correlation_matrix(helpers.random_hamiltonian(48, 4))
+    tp = {"chi_max": 64}
+    ket = so.bond_vectors_from_C(Cm, 24, tp)
+    bra = so.bond_vectors_from_C(Cm, 25, tp, "R")
+    td = so.tensor_data(bra, ket, "right")
+    sb, sk = td.S.shape
+    S = np.asfortranarray(td.S).ravel(order="F").copy()
+    pack = lambda sets: (sets.astype(np.uint64) << np.arange(sets.shape[1], dtype=np.uint64)[None, :]).sum(axis=1).astype(np.uint64)
+    bm, km = pack(td.sets_bra), pack(td.sets_ket)
+    det = np.array([td.det_always])
+    blocks, outs, want = [], [], []
+    for q in np.unique(td.q_ket):
+        kr = np.flatnonzero(td.q_ket == q); br = np.flatnonzero(td.q_bra == q - td.qtotal)
+        if not br.size:
+            continue
+        out = np.zeros(br.size * kr.size)
+        b = _lib.MinorBlock(S=S.ctypes.data, det=det.ctypes.data, bra_masks=bm[br[0]:].ctypes.data,
+                            ket_masks=km[kr[0]:].ctypes.data, out=out.ctypes.data, s_bra=sb, s_ket=sk,
+                            n_bra=br.size, n_ket=kr.size, minor=int(td.sets_ket[kr[0]].sum()))
+        blocks.append(b); outs.append(out)
+        want.append(td.det_always * so.tensor_block(td.S, td.sets_bra[br], td.sets_ket[kr]))
+    arr = (_lib.MinorBlock * len(blocks))(*blocks)
+    desc = np.zeros(lib.tmf_minor_desc_bytes(len(blocks)), np.uint8)
+    _lib.check(lib, lib.tmf_minors_blocks(arr, len(blocks), desc.ctypes.data, None))
+    for o, w in zip(outs, want):
+        assert np.allclose(o.reshape(w.shape), w, rtol=0, atol=1e-14)
+
+
+def test_gemm_grouped_semantics(sim_backend):
+    lib = sim_backend.lib
+    rng = np.random.default_rng(0)
+    A = np.asfortranarray(rng.normal(size=(70, 33))); B = np.asfortranarray(rng.normal(size=(33, 45)))
+    Cc = np.asfortranarray(rng.normal(size=(70, 45))); C0 = Cc.copy()
+    j = _lib.GemmJob(A=A.ctypes.data, B=B.ctypes.data, C=Cc.ctypes.data, M=70, N=45, K=33, lda=70, ldb=33,
+                     ldc=70, transA=0, transB=0, alpha=2.0, beta=-1.0)
+    desc = np.zeros(lib.tmf_gemm_desc_bytes(1), np.uint8)
+    _lib.check(lib, lib.tmf_gemm_grouped((_lib.GemmJob * 1)(j), 1, desc.ctypes.data, None))
+    assert np.allclose(Cc, 2 * A @ B - C0, atol=1e-12)
