@@ -124,12 +124,13 @@ typedef struct tmf_site_plan {
   int chi_bra, chi_ket;
   int n_blocks;
   int qtotal;
+  int ka_bra, ka_ket; /* always-occupied orbitals of the bra / ket side (k_always = min)    */
 } tmf_site_plan;
 
 /* Plans one site.  Inputs: the two bonds' masks (sorted, from tmf_bond_vectors_batched), charges.
  * Outputs (caller-allocated, capacities in brackets):
  *   bra_cols[k_bra+f_bra+1], ket_cols[k_ket+f_ket]: stored-V column index of every O row / col
- *       in the order [always block (k_always) | sometimes part], -1 = physical orbital;
+ *       in the order [all always orbitals (ka_bra / ka_ket) | sometimes orbitals], -1 = physical;
  *   bra_sign / ket_sign: the reordering signs;
  *   bra_masks[n_rows], ket_masks[chi_ket]: occupation of the sometimes rows / cols (bit t = row t);
  *   row_p[n_rows], row_alpha[n_rows]: physical index and bond index of every bra row;
@@ -144,21 +145,23 @@ int tmf_slater_site_plan(int mode, int n_bra, int n_ket, int k_bra, int f_bra, i
 /* K8+K9 -- overlap of the two mode bases and Schur complement, batched over sites.
  * replaces: slater.py:1071 (O = HT(v_bra) @ v_ket) and :1073-1090 (det_always, sometimes
  * matrix).  Site descriptors (host) are copied to desc_dev.  For site s:
- *   O (rows = bra_cols order, cols = ket_cols order) is formed in work, the leading k_always
- *   block is LU-factored with partial pivoting restricted to its rows, S_dev + s_off[s] receives
- *   the (s_bra x s_ket) Schur complement (column-major, ld = s_bra), det_dev[s] = det(always). */
+ *   O (rows = bra_cols order, cols = ket_cols order) is formed in work; k = min(ka_bra, ka_ket)
+ *   elimination steps with pivoting over the always orbitals of the larger side; S receives the
+ *   (s_bra x s_ket) Schur complement in the reference's row / column order (surplus always
+ *   orbitals after the sometimes ones for right tensors, before them for left tensors),
+ *   det = +-det(always block) (the sign is a global phase of the site tensor). */
 typedef struct tmf_site_job {
   const double *Vb, *Vk;       /* stored mode matrices of the bra / ket bond-side             */
   const int *bra_cols, *ket_cols;       /* device arrays (rows / cols of O), -1 = physical     */
   const double *bra_sign, *ket_sign;    /* device arrays                                      */
-  double *O;                   /* rows x cols workspace, ld = rows                            */
-  double *S;                   /* output (rows-k) x (cols-k), ld = rows-k                     */
+  double *O;                   /* (ka_bra + sb) x (ka_ket + sk) workspace                     */
+  double *S;                   /* output s_bra x s_ket, ld = s_bra                            */
   double *det;                 /* output scalar                                               */
   int ldb, ldk;
   int n_bra, n_ket;            /* sites                                                       */
   int mode, physical;
-  int rows, cols, k_always;    /* O is rows x cols                                            */
-  int phys_row;                /* row of O holding the physical orbital (-1: none)            */
+  int ka_bra, ka_ket;          /* always orbitals of each side                                */
+  int sb, sk;                  /* sometimes orbitals of each side (sb includes the physical)  */
   int pad_[4];
 } tmf_site_job;
 int64_t tmf_site_desc_bytes(int nsites);   /* size of desc_dev for the call below */

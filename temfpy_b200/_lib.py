@@ -24,7 +24,7 @@ c_u64_p = C.POINTER(C.c_uint64)
 class SitePlan(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "mode", "physical", "n_bra", "n_ket", "k_bra", "k_ket", "f_bra", "f_ket", "k_always",
-        "s_bra", "s_ket", "n_rows", "chi_bra", "chi_ket", "n_blocks", "qtotal")]
+        "s_bra", "s_ket", "n_rows", "chi_bra", "chi_ket", "n_blocks", "qtotal", "ka_bra", "ka_ket")]
 
 
 class GemmJob(C.Structure):
@@ -43,8 +43,8 @@ class SiteJob(C.Structure):
                 ("ket_cols", C.c_void_p), ("bra_sign", C.c_void_p), ("ket_sign", C.c_void_p),
                 ("O", C.c_void_p), ("S", C.c_void_p), ("det", C.c_void_p),
                 ("ldb", C.c_int), ("ldk", C.c_int), ("n_bra", C.c_int), ("n_ket", C.c_int),
-                ("mode", C.c_int), ("physical", C.c_int), ("rows", C.c_int), ("cols", C.c_int),
-                ("k_always", C.c_int), ("phys_row", C.c_int), ("pad_", C.c_int * 4)]
+                ("mode", C.c_int), ("physical", C.c_int), ("ka_bra", C.c_int), ("ka_ket", C.c_int),
+                ("sb", C.c_int), ("sk", C.c_int), ("pad_", C.c_int * 4)]
 
 
 class MinorBlock(C.Structure):

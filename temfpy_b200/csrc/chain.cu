@@ -266,7 +266,7 @@ int tmf_chain_enumerate(tmf_chain *c) {
     int64_t plan = 0;
     for (ChainSite &s : c->sites) {
       const tmf_site_plan &h = s.plan.h;
-      const int rows = h.k_always + h.s_bra, cols = h.k_always + h.s_ket;
+      const int rows = h.ka_bra + (h.s_bra - (h.ka_bra - h.k_always)), cols = h.ka_ket + (h.s_ket - (h.ka_ket - h.k_always));
       s.o_off = c->o_elems;
       c->o_elems += ((int64_t)rows * cols + 31) & ~int64_t(31);
       s.s_off = c->s_elems;
@@ -400,7 +400,8 @@ int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev,
     const tmf_site_plan &h = s.plan.h;
     const int side = s.mode == 1 ? TMF_SIDE_R : TMF_SIDE_L;
     const ChainSide &bs = c->bonds[s.bra_bond].side[side], &ks = c->bonds[s.ket_bond].side[side];
-    const int rows = h.k_always + h.s_bra, cols = h.k_always + h.s_ket;
+    const int sb0 = h.s_bra - (h.ka_bra - h.k_always), sk0 = h.s_ket - (h.ka_ket - h.k_always);
+    const int rows = h.ka_bra + sb0, cols = h.ka_ket + sk0;
     tmf_site_job &j = sj[u];
     std::memset(&j, 0, sizeof(j));
     j.Vb = V_dev + bs.v_off; j.Vk = V_dev + ks.v_off;
@@ -411,10 +412,7 @@ int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev,
     j.ket_sign = reinterpret_cast<const double *>(add(s.plan.ket_sign.data(), 8 * (size_t)cols));
     j.O = O_dev + s.o_off; j.S = S_dev + s.s_off; j.det = det_dev + u;
     j.n_bra = h.n_bra; j.n_ket = h.n_ket; j.mode = h.mode; j.physical = h.physical;
-    j.rows = rows; j.cols = cols; j.k_always = h.k_always;
-    j.phys_row = -1;
-    for (int r = 0; r < rows; ++r)
-      if (s.plan.bra_cols[r] < 0) j.phys_row = r;
+    j.ka_bra = h.ka_bra; j.ka_ket = h.ka_ket; j.sb = sb0; j.sk = sk0;
     const uint64_t *bm = reinterpret_cast<const uint64_t *>(add(s.plan.bra_masks.data(), 8 * (size_t)h.n_rows));
     const uint64_t *km = reinterpret_cast<const uint64_t *>(add(s.plan.ket_masks.data(), 8 * (size_t)h.chi_ket));
     for (int b = 0; b < h.n_blocks; ++b) {

@@ -294,11 +294,18 @@ void site_plan(int mode, int n_bra, int n_ket, int k_bra, int f_bra, int nferm_b
   if (br.size() > 64 || kr.size() > 64)
     throw std::invalid_argument("sometimes matrix larger than 64 rows/cols is not supported");
 
+  // device arrangement of O: [all always orbitals | sometimes orbitals]; which always orbitals form
+  // the square block is decided by pivoting on the device (any choice gives the same tensor up to a
+  // global sign), the surplus ones join the sometimes part as all-occupied rows / columns.
   out.bra_cols.clear(); out.bra_sign.clear(); out.ket_cols.clear(); out.ket_sign.clear();
-  for (auto &e : bb) { out.bra_cols.push_back(e.o.col); out.bra_sign.push_back(e.sign); }
-  for (auto &e : br) { out.bra_cols.push_back(e.o.col); out.bra_sign.push_back(e.sign); }
-  for (auto &e : kb_) { out.ket_cols.push_back(e.o.col); out.ket_sign.push_back(e.sign); }
-  for (auto &e : kr) { out.ket_cols.push_back(e.o.col); out.ket_sign.push_back(e.sign); }
+  for (auto &o : sb.always) { out.bra_cols.push_back(o.col); out.bra_sign.push_back(1.0); }
+  for (size_t i = 0; i < sb.sometimes.size(); ++i) {
+    out.bra_cols.push_back(sb.sometimes[i].col); out.bra_sign.push_back(sb.sometimes_sign[i]);
+  }
+  for (auto &o : sk.always) { out.ket_cols.push_back(o.col); out.ket_sign.push_back(1.0); }
+  for (size_t i = 0; i < sk.sometimes.size(); ++i) {
+    out.ket_cols.push_back(sk.sometimes[i].col); out.ket_sign.push_back(sk.sometimes_sign[i]);
+  }
 
   // occupation masks over the sometimes part
   auto row_mask = [&](const std::vector<Entry> &rest, uint64_t m, int p) {
@@ -366,6 +373,7 @@ void site_plan(int mode, int n_bra, int n_ket, int k_bra, int f_bra, int nferm_b
   h.s_bra = (int)br.size(); h.s_ket = (int)kr.size(); h.n_rows = n_rows;
   h.chi_bra = chi_bra; h.chi_ket = chi_ket; h.n_blocks = (int)out.blocks.size() / 6;
   h.qtotal = qtotal;
+  h.ka_bra = kb; h.ka_ket = kk;
 }
 
 }  // namespace tmf

@@ -19,9 +19,31 @@ int gemm_launch_uploaded(const tmf_gemm_job *jobs_dev, const int *prefix_dev, in
 constexpr int NB = 16;
 static_assert(sizeof(tmf_site_job) == 128, "site descriptor must be 128 bytes");
 
+// Frame of the elimination: the side with more always-occupied orbitals provides the rows, so that
+// the k = min(ka_bra, ka_ket) pivots can be chosen among all of its always orbitals.
+struct Frame {
+  int tr;            // 1: rows = ket orbitals, cols = bra orbitals (O is stored transposed)
+  int R, Cc;         // frame rows / cols
+  int ncand, k;      // candidate pivot rows, elimination steps
+  int s_r, s_c;      // sometimes orbitals of the row / column side
+};
+TMF_HD Frame make_frame(const tmf_site_job &jb) {
+  Frame f;
+  f.tr = jb.ka_ket > jb.ka_bra;
+  const int ka_r = f.tr ? jb.ka_ket : jb.ka_bra, ka_c = f.tr ? jb.ka_bra : jb.ka_ket;
+  f.s_r = f.tr ? jb.sk : jb.sb;
+  f.s_c = f.tr ? jb.sb : jb.sk;
+  f.R = ka_r + f.s_r;
+  f.Cc = ka_c + f.s_c;
+  f.ncand = ka_r;
+  f.k = ka_c;
+  return f;
+}
+
 TMF_GLOBAL schur_kernel(const tmf_site_job *jobs) {
   const tmf_site_job jb = jobs[BLOCK_ID];
-  const int rows = jb.rows, cols = jb.cols, k = jb.k_always, ld = jb.rows;
+  const Frame fr = make_frame(jb);
+  const int rows = fr.R, cols = fr.Cc, k = fr.k, ld = fr.R;
   double *O = jb.O;
   DYN_SMEM(double, sm);
   double *Lp = sm;                      // rows x NB  (column-major, ld = nr of the current panel)
@@ -33,13 +55,21 @@ TMF_GLOBAL schur_kernel(const tmf_site_job *jobs) {
     PAR_FOR(one, 1) *jb.det = 1.0;
     return;
   }
-  // physical orbital row: <n_i| overlaps = one row of the ket mode matrix (slater.py:1030-1051)
-  if (jb.physical && jb.phys_row >= 0) {
+  // physical orbital: <n_i| overlaps = one row of the ket mode matrix (slater.py:1030-1051)
+  if (jb.physical) {
     const int src = (jb.mode == 1) ? 0 : jb.n_bra;
-    PAR_FOR(n, cols) {
-      int c = jb.ket_cols[n];
-      double v = (c >= 0) ? jb.Vk[(int64_t)c * jb.ldk + src] : 0.0;
-      O[(int64_t)n * ld + jb.phys_row] = v * jb.bra_sign[jb.phys_row] * jb.ket_sign[n];
+    const int nb = jb.ka_bra + jb.sb, nk = jb.ka_ket + jb.sk;
+    int pb = -1;
+    for (int r = 0; r < nb; ++r)
+      if (jb.bra_cols[r] < 0) pb = r;
+    if (pb >= 0) {
+      PAR_FOR(n, nk) {
+        int c = jb.ket_cols[n];
+        double v = (c >= 0) ? jb.Vk[(int64_t)c * jb.ldk + src] : 0.0;
+        v *= jb.bra_sign[pb] * jb.ket_sign[n];
+        if (fr.tr) O[(int64_t)pb * ld + n] = v;
+        else O[(int64_t)n * ld + pb] = v;
+      }
     }
   }
   PAR_FOR(one, 1) red[36] = 1.0;  // running determinant
@@ -48,7 +78,7 @@ TMF_GLOBAL schur_kernel(const tmf_site_job *jobs) {
   for (int t0 = 0; t0 < k; t0 += NB) {
     const int w = (k - t0 < NB) ? (k - t0) : NB;
     const int nr = rows - t0;         // panel rows t0 .. rows-1
-    const int lim = k - t0;           // rows eligible as pivots (always block)
+    const int lim = fr.ncand - t0;    // rows eligible as pivots (always orbitals of the row side)
     PAR_FOR(idx, nr * w) {
       int c = idx / nr, r = idx - c * nr;
       Lp[c * nr + r] = O[(int64_t)(t0 + c) * ld + t0 + r];
@@ -142,10 +172,16 @@ TMF_GLOBAL schur_kernel(const tmf_site_job *jobs) {
     }
     CTA_SYNC();
   }
-  const int sr = rows - k, sc = cols - k;
-  PAR_FOR(idx, sr * sc) {
-    int c = idx / sr, r = idx - c * sr;
-    jb.S[(int64_t)c * sr + r] = O[(int64_t)(k + c) * ld + k + r];
+  // Schur complement -> S in the reference's row / column order (slater.py:1081-1090): the surplus
+  // always orbitals of the row side come first (left tensors) or last (right tensors).
+  const int nlo = fr.ncand - k, nfr = nlo + fr.s_r, nfc = fr.s_c;
+  const int s_bra = fr.tr ? nfc : nfr;
+  PAR_FOR(idx, nfr * nfc) {
+    int c = idx / nfr, r = idx - c * nfr;
+    int ref_r = (jb.mode == 0) ? r : (r < nlo ? fr.s_r + r : r - nlo);
+    double v = O[(int64_t)(k + c) * ld + k + r];
+    if (fr.tr) jb.S[(int64_t)ref_r * s_bra + c] = v;   // row side = ket -> column of S
+    else jb.S[(int64_t)c * s_bra + ref_r] = v;
   }
   PAR_FOR(one, 1) *jb.det = red[36];
 }
@@ -166,21 +202,26 @@ extern "C" int tmf_site_overlap_schur_batched(const tmf_site_job *jobs_host, int
   size_t smem = 0;
   for (int s = 0; s < nsites; ++s) {
     const tmf_site_job &sj = jobs_host[s];
+    const Frame fr = make_frame(sj);
     tmf_gemm_job &j = g[s];
     std::memset(&j, 0, sizeof(j));
-    j.A = sj.Vb; j.B = sj.Vk; j.C = sj.O;
-    j.a_idx = sj.bra_cols; j.b_idx = sj.ket_cols;
-    j.row_scale = sj.bra_sign; j.col_scale = sj.ket_sign;
-    j.M = sj.rows; j.N = sj.cols; j.K = sj.n_bra;
-    j.lda = sj.ldb; j.ldb = sj.ldk; j.ldc = sj.rows;
+    const int off = (sj.physical && sj.mode == 1) ? 1 : 0;  // right mode: ket site 0 is the new site
+    if (!fr.tr) {
+      j.A = sj.Vb; j.lda = sj.ldb; j.a_idx = sj.bra_cols; j.row_scale = sj.bra_sign; j.a_row_off = 0;
+      j.B = sj.Vk; j.ldb = sj.ldk; j.b_idx = sj.ket_cols; j.col_scale = sj.ket_sign; j.b_row_off = off;
+    } else {
+      j.A = sj.Vk; j.lda = sj.ldk; j.a_idx = sj.ket_cols; j.row_scale = sj.ket_sign; j.a_row_off = off;
+      j.B = sj.Vb; j.ldb = sj.ldb; j.b_idx = sj.bra_cols; j.col_scale = sj.bra_sign; j.b_row_off = 0;
+    }
+    j.C = sj.O;
+    j.M = fr.R; j.N = fr.Cc; j.K = sj.n_bra;
+    j.ldc = fr.R;
     j.transA = 1; j.transB = 0;
-    j.a_row_off = 0;
-    j.b_row_off = (sj.physical && sj.mode == 1) ? 1 : 0;  // right mode: ket site 0 is the new site
     j.alpha = 1.0; j.beta = 0.0;
     int tm = (j.M + 63) / 64, tn = (j.N + 63) / 64;
     if (j.M <= 0 || j.N <= 0) tm = tn = 0;
     prefix[s + 1] = prefix[s] + tm * tn;
-    smem = std::max(smem, schur_smem_bytes(sj.rows, sj.cols));
+    smem = std::max(smem, schur_smem_bytes(fr.R, fr.Cc));
   }
   if (smem > 220 * 1024) {
     set_error("site too large for the shared-memory LU panels (rows + cols > ~1700)");

@@ -37,7 +37,7 @@ def test_descriptor_struct_sizes():
     assert ctypes.sizeof(_lib.GemmJob) == 128
     assert ctypes.sizeof(_lib.SiteJob) == 128
     assert ctypes.sizeof(_lib.MinorBlock) == 64
-    assert ctypes.sizeof(_lib.SitePlan) == 64
+    assert ctypes.sizeof(_lib.SitePlan) == 72
 
 
 def test_no_cpu_fallback():

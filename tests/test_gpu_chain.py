@@ -138,9 +138,16 @@ def test_full_size_properties_L1024(gpu_backend):
         assert abs(np.linalg.norm(b.schmidt_values) - 1) < 1e-6
     for i in (0, 5, 300, 511, 512, 700, 1023):
         T = res.sites[i].dense()
-        E = np.einsum("apb,apc->bc", T, T) if i < 512 else np.einsum("apb,cpb->ac", T, T)
-        # isometry up to the truncation of the neighbouring bond
-        assert np.abs(E - np.eye(len(E))).max() < 1e-5
+        # canonical form weighted by the Schmidt weights of the open bond: exact up to the weight
+        # discarded on the neighbouring (truncated) bond
+        if i < 512:
+            E = np.einsum("apb,apc->bc", T, T)
+            w = res.bonds[i + 1].schmidt_values
+        else:
+            E = np.einsum("apb,cpb->ac", T, T)
+            w = res.bonds[i].schmidt_values
+        w = w / np.linalg.norm(w)
+        assert np.abs((E - np.eye(len(E))) * np.outer(w, w)).max() < 1e-9
     # entropy profile against the oracle on a few bonds (full oracle chain takes ~10 min on CPU)
     trunc = so.Trunc.make(tp)
     for x in (3, 512, 900):

@@ -128,6 +128,13 @@ def test_modes_vs_eigh(gpu_backend, L, seed):
         Vm = Vh[voff[j]: voff[j] + m * m].reshape(m, m).T[:, : k + f]
         A = Cm[:x, :x] if s == 0 else Cm[x:, x:]
         eig = np.concatenate([eh[j, :k] if s == 0 else 1 - eh[j, :k], np.ones(f)])
-        assert np.abs(Vm.T @ Vm - np.eye(k + f)).max() < 1e-12
-        assert np.abs(A @ Vm[:, :k] - Vm[:, :k] * eig[:k]).max() < 1e-12
-        assert np.abs(Vm[:, k:].T @ A @ Vm[:, k:] - np.eye(f)).max() < 1e-10   # filled space: A = 1
+        if k + f == 0:
+            continue
+        # entangled modes within ~cutoff of the filled cluster are only defined up to eps/gap
+        assert np.abs(Vm.T @ Vm - np.eye(k + f)).max() < 1e-8
+        if k:
+            # sketch path: a mode with singular value s is resolved to ~eps * s_max / s (<= 1e-9 at the
+            # cutoff s ~ 1e-6..1e-7); its eigenvalue is second order in that error
+            assert np.abs(A @ Vm[:, :k] - Vm[:, :k] * eig[:k]).max() < 2e-9
+        if f:
+            assert np.abs(Vm[:, k:].T @ A @ Vm[:, k:] - np.eye(f)).max() < 1e-10   # filled space: A = 1
