@@ -214,6 +214,9 @@ int tmf_chain_site(tmf_chain *c, int site, tmf_site_plan *plan, const int **bloc
                    const int64_t **block_off, const int **row_p, const int **row_alpha,
                    int64_t *offs /* O offset, S offset, det index */);
 int64_t tmf_chain_job_voff(tmf_chain *c, int job);
+/* algorithmic flops of the reference's algorithm for this shard:
+ * f[0] eigh, f[1] overlap GEMM, f[2] Schur, f[3] minors, f[4] number of minors */
+int tmf_chain_flops(tmf_chain *c, double *f);
 
 /* K14 -- Gutzwiller projection of one pair of fermion sites onto a spin-1/2 site.
  * replaces: the TeNPy arithmetic behind gutzwiller.py:227 (group_sites(2)) and :242 (iproject)
@@ -225,6 +228,12 @@ typedef struct tmf_gutz_job {
   int m, k, n, pad_;
 } tmf_gutz_job;
 int tmf_gutzwiller_site(const tmf_gutz_job *jobs_host, int njobs, void *desc_dev, void *stream);
+
+/* measurement hooks used by bench.py: kernel launch counter (always on) and per-kernel CUDA-event
+ * timing (off by default; enabled only in the profiling pass). */
+long long tmf_launch_count(int reset);
+int tmf_prof_enable(int on);
+int tmf_prof_report(char *buf, int cap);
 
 /* FP64 peak probe used by bench.py for the roofline denominator: runs `iters` dependent-free
  * DFMA chains on every SM and returns the elapsed ms through *ms_out (synchronises). */

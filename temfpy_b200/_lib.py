@@ -104,6 +104,10 @@ SIGNATURES = {
     "tmf_chain_site": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SitePlan), C.POINTER(c_int_p),
                                  C.POINTER(c_i64_p), C.POINTER(c_int_p), C.POINTER(c_int_p), c_i64_p]),
     "tmf_chain_job_voff": (C.c_int64, [C.c_void_p, C.c_int]),
+    "tmf_chain_flops": (C.c_int, [C.c_void_p, c_double_p]),
+    "tmf_launch_count": (C.c_longlong, [C.c_int]),
+    "tmf_prof_enable": (C.c_int, [C.c_int]),
+    "tmf_prof_report": (C.c_int, [C.c_char_p, C.c_int]),
     "tmf_gutzwiller_site": (C.c_int, [C.POINTER(GutzJob), C.c_int, C.c_void_p, C.c_void_p]),
     "tmf_fp64_peak_probe": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_float), c_double_p, C.c_void_p]),
 }

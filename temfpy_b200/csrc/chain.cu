@@ -468,4 +468,29 @@ int tmf_chain_site(tmf_chain *c, int site, tmf_site_plan *plan, const int **bloc
 
 int64_t tmf_chain_job_voff(tmf_chain *c, int job) { return c->v_off[job]; }
 
+// Algorithmic FP64 flop counts of the *reference's* algorithm for this shard:
+// f[0] eigh (10/3 n^3 per job), f[1] overlap GEMM 2 (n+1) c_b c_k, f[2] Schur (8/3) k^3,
+// f[3] minors sum nsb nsk (2/3) q^3, f[4] number of minors.
+int tmf_chain_flops(tmf_chain *c, double *f) {
+  if (!c->enumerated) return fail(TMF_ERR_VALUE, "tmf_chain_enumerate has not run");
+  for (int i = 0; i < 5; ++i) f[i] = 0.0;
+  for (size_t j = 0; j < c->job_x.size(); ++j) {
+    double n = (c->job_side[j] == TMF_SIDE_L) ? c->job_x[j] : c->L - c->job_x[j];
+    f[0] += 10.0 / 3.0 * n * n * n;
+  }
+  for (const ChainSite &s : c->sites) {
+    const tmf_site_plan &h = s.plan.h;
+    const double cb = h.ka_bra + (h.s_bra - (h.ka_bra - h.k_always));
+    const double ck = h.ka_ket + (h.s_ket - (h.ka_ket - h.k_always));
+    f[1] += 2.0 * (h.n_bra + 1.0) * cb * ck;
+    f[2] += 8.0 / 3.0 * (double)h.k_always * h.k_always * h.k_always;
+    for (int b = 0; b < h.n_blocks; ++b) {
+      const int *bl = &s.plan.blocks[6 * b];
+      f[3] += (double)bl[1] * bl[3] * (2.0 / 3.0) * bl[4] * bl[4] * bl[4];
+      f[4] += (double)bl[1] * bl[3];
+    }
+  }
+  return TMF_OK;
+}
+
 }  // extern "C"

@@ -39,8 +39,11 @@ extern thread_local unsigned char *smem;
 #define DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(tmfsim::smem)
 
 namespace tmf {
+void count_launch();
 template <class K, class... Args>
-inline int launch(K kernel, int grid, int block, size_t smem_bytes, void * /*stream*/, Args... args) {
+inline int launch_t(const char * /*tag*/, K kernel, int grid, int block, size_t smem_bytes, void * /*stream*/,
+                    Args... args) {
+  count_launch();
   std::vector<unsigned char> smem(smem_bytes + 64);
   tmfsim::n_threads = block;
   tmfsim::smem = smem.data();
@@ -49,6 +52,10 @@ inline int launch(K kernel, int grid, int block, size_t smem_bytes, void * /*str
     kernel(args...);
   }
   return TMF_OK;
+}
+template <class K, class... Args>
+inline int launch(K kernel, int grid, int block, size_t smem_bytes, void *stream, Args... args) {
+  return launch_t("other", kernel, grid, block, smem_bytes, stream, args...);
 }
 inline int copy_h2d(void *dst, const void *src, size_t bytes, void *) {
   std::memcpy(dst, src, bytes);
@@ -87,16 +94,32 @@ inline int check_cuda(cudaError_t e, const char *what) {
   set_error(std::string(what) + ": " + cudaGetErrorString(e));
   return TMF_ERR_RUNTIME;
 }
+// per-tag kernel timing (CUDA events around every launch) -- enabled only by bench.py's profiling
+// pass through tmf_prof_enable(); the launch counter is always on (bench "gpu_launches").
+void count_launch();
+bool prof_enabled();
+void prof_begin(const char *tag, void *stream);
+void prof_end(void *stream);
 template <class K, class... Args>
-inline int launch(K kernel, int grid, int block, size_t smem_bytes, void *stream, Args... args) {
+inline int launch_t(const char *tag, K kernel, int grid, int block, size_t smem_bytes, void *stream,
+                    Args... args) {
   if (grid <= 0) return TMF_OK;
   if (smem_bytes > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem_bytes);
+    // always opt in to the full 227 KB: the attribute is per function (not per launch), so concurrent
+    // launches from the pipeline threads must not lower each other's limit
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute");
   }
+  count_launch();
+  const bool prof = prof_enabled();
+  if (prof) prof_begin(tag, stream);
   kernel<<<grid, block, smem_bytes, (cudaStream_t)stream>>>(args...);
+  if (prof) prof_end(stream);
   return check_cuda(cudaGetLastError(), "kernel launch");
+}
+template <class K, class... Args>
+inline int launch(K kernel, int grid, int block, size_t smem_bytes, void *stream, Args... args) {
+  return launch_t("other", kernel, grid, block, smem_bytes, stream, args...);
 }
 inline int copy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
   if (bytes == 0) return TMF_OK;

@@ -80,82 +80,102 @@ __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
                : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256)
-gemm_grouped_kernel(const tmf_gemm_job *__restrict__ jobs, const int *__restrict__ prefix,
-                    int njobs) {
-  __shared__ double As[2][TM * LDS_STRIDE];
-  __shared__ double Bs[2][TN * LDS_STRIDE];
-  __shared__ tmf_gemm_job js;
-  const int tile = blockIdx.x;
-  const int jid = find_job(prefix, njobs, tile);
-  if (threadIdx.x < sizeof(tmf_gemm_job) / 8)
-    reinterpret_cast<uint64_t *>(&js)[threadIdx.x] =
-        reinterpret_cast<const uint64_t *>(&jobs[jid])[threadIdx.x];
-  __syncthreads();
-  const tmf_gemm_job &j = js;
-  const int t = tile - prefix[jid];
-  const int tiles_m = (j.M + TM - 1) / TM;
-  const int m0 = (t % tiles_m) * TM, n0 = (t / tiles_m) * TN;
+// Shared-memory layouts of an operand tile (64 rows x 16 k):
+//   KC  (k-contiguous in global): stored [row][k], row stride 20 doubles
+//   MC  (row-contiguous in global): stored [k][row], k stride 72 doubles
+// both make the DMMA fragment loads (8 rows x 4 k per warp) and the staging stores conflict-free.
+constexpr int KC_STRIDE = 20, MC_STRIDE = 72;
+constexpr int TILE_DOUBLES = 64 * KC_STRIDE;  // 1280 >= 16 * 72 = 1152
+
+template <bool KC>
+struct OperandLoader {
+  const double *p[4];   // per-thread source pointers at k-tile 0 (nullptr: outside the matrix)
+  int kk[4];            // k index inside the tile of each element
+  int so[4];            // shared-memory offset of each element
+  int64_t kstep;        // pointer increment per k-tile
+  // rows: index along the tile's row dimension (M for A, N for B); `cols` maps it to a column of the
+  // stored matrix when the operand is k-contiguous (optional gather), ld = leading dimension.
+  __device__ void init(const double *base, int ld, const int *idx, int row0, int nrows, int roff, int tid) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + 256 * i;
+      const int r = KC ? (e >> 4) : (e & 63);
+      kk[i] = KC ? (e & 15) : (e >> 6);
+      so[i] = KC ? r * KC_STRIDE + kk[i] : kk[i] * MC_STRIDE + r;
+      const int g = row0 + r;
+      p[i] = nullptr;
+      if (g < nrows) {
+        if (KC) {
+          const int col = idx ? idx[g] : g;
+          if (col >= 0) p[i] = base + (int64_t)col * ld + roff + kk[i];
+        } else {
+          p[i] = base + (int64_t)kk[i] * ld + g;
+        }
+      }
+    }
+    kstep = KC ? TK : (int64_t)TK * ld;
+  }
+  __device__ __forceinline__ void load(double (&r)[4], int k0, int K) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = (p[i] != nullptr && k0 + kk[i] < K) ? p[i][(int64_t)(k0 / TK) * kstep] : 0.0;
+  }
+  __device__ __forceinline__ void store(double *tile, const double (&r)[4]) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tile[so[i]] = r[i];
+  }
+  static __device__ __forceinline__ double frag(const double *tile, int row, int k) {
+    return KC ? tile[row * KC_STRIDE + k] : tile[k * MC_STRIDE + row];
+  }
+};
+
+template <bool AKC, bool BKC>
+__device__ __forceinline__ void gemm_tile(const tmf_gemm_job &j, int m0, int n0, double *As, double *Bs) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
-
-  // global -> register staging: 4 elements of each operand per thread and k-tile.
-  // k-contiguous operands: consecutive threads walk k; otherwise they walk the row index.
-  const bool a_kc = j.transA != 0, b_kc = j.transB == 0;
-  double ra[4], rb[4];
-  auto ldg = [&](int k0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int e = tid + 256 * i;
-      int r = a_kc ? (e >> 4) : (e & 63), kk = a_kc ? (e & 15) : (e >> 6);
-      ra[i] = load_a(j, m0 + r, k0 + kk);
-      r = b_kc ? (e >> 4) : (e & 63);
-      kk = b_kc ? (e & 15) : (e >> 6);
-      rb[i] = load_b(j, k0 + kk, n0 + r);
-    }
-  };
-  auto sts = [&](int buf) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int e = tid + 256 * i;
-      int r = a_kc ? (e >> 4) : (e & 63), kk = a_kc ? (e & 15) : (e >> 6);
-      As[buf][r * LDS_STRIDE + kk] = ra[i];
-      r = b_kc ? (e >> 4) : (e & 63);
-      kk = b_kc ? (e & 15) : (e >> 6);
-      Bs[buf][r * LDS_STRIDE + kk] = rb[i];
-    }
-  };
-
+  OperandLoader<AKC> la;
+  OperandLoader<BKC> lb;
+  // A: op(A) is M x K.  transA=1 -> stored K x M (k-contiguous, optional column gather a_idx)
+  la.init(j.A, j.lda, j.a_idx, m0, j.M, j.a_row_off, tid);
+  // B: op(B) is K x N.  transB=0 -> stored K x N (k-contiguous, optional column gather b_idx)
+  lb.init(j.B, j.ldb, j.b_idx, n0, j.N, j.b_row_off, tid);
   double acc[2][4][2];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-
   const int nk = (j.K + TK - 1) / TK;
+  double ra[4], rb[4];
   int buf = 0;
   if (nk > 0) {
-    ldg(0);
-    sts(0);
+    la.load(ra, 0, j.K);
+    lb.load(rb, 0, j.K);
+    la.store(As, ra);
+    lb.store(Bs, rb);
   }
   __syncthreads();
   const int fr = lane >> 2, fk = lane & 3;
   for (int kt = 0; kt < nk; ++kt) {
-    if (kt + 1 < nk) ldg((kt + 1) * TK);
-    const double *as = As[buf], *bs = Bs[buf];
+    if (kt + 1 < nk) {
+      la.load(ra, (kt + 1) * TK, j.K);
+      lb.load(rb, (kt + 1) * TK, j.K);
+    }
+    const double *as = As + buf * TILE_DOUBLES, *bs = Bs + buf * TILE_DOUBLES;
 #pragma unroll
     for (int ks = 0; ks < TK; ks += 4) {
       double fa[2], fb[4];
 #pragma unroll
-      for (int a = 0; a < 2; ++a) fa[a] = as[(wm + a * 8 + fr) * LDS_STRIDE + ks + fk];
+      for (int a = 0; a < 2; ++a) fa[a] = OperandLoader<AKC>::frag(as, wm + a * 8 + fr, ks + fk);
 #pragma unroll
-      for (int b = 0; b < 4; ++b) fb[b] = bs[(wn + b * 8 + fr) * LDS_STRIDE + ks + fk];
+      for (int b = 0; b < 4; ++b) fb[b] = OperandLoader<BKC>::frag(bs, wn + b * 8 + fr, ks + fk);
 #pragma unroll
       for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) dmma(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
     }
-    if (kt + 1 < nk) sts(buf ^ 1);
+    if (kt + 1 < nk) {
+      la.store(As + (buf ^ 1) * TILE_DOUBLES, ra);
+      lb.store(Bs + (buf ^ 1) * TILE_DOUBLES, rb);
+    }
     __syncthreads();
     buf ^= 1;
   }
@@ -168,6 +188,32 @@ gemm_grouped_kernel(const tmf_gemm_job *__restrict__ jobs, const int *__restrict
       store_c(j, m, n, acc[a][b][0]);
       store_c(j, m, n + 1, acc[a][b][1]);
     }
+}
+
+__global__ void __launch_bounds__(256, 2)
+gemm_grouped_kernel(const tmf_gemm_job *__restrict__ jobs, const int *__restrict__ prefix,
+                    int njobs) {
+  __shared__ double As[2 * TILE_DOUBLES];
+  __shared__ double Bs[2 * TILE_DOUBLES];
+  __shared__ tmf_gemm_job js;
+  const int tile = blockIdx.x;
+  const int jid = find_job(prefix, njobs, tile);
+  if (threadIdx.x < sizeof(tmf_gemm_job) / 8)
+    reinterpret_cast<uint64_t *>(&js)[threadIdx.x] =
+        reinterpret_cast<const uint64_t *>(&jobs[jid])[threadIdx.x];
+  __syncthreads();
+  const tmf_gemm_job &j = js;
+  const int t = tile - prefix[jid];
+  const int tiles_m = (j.M + TM - 1) / TM;
+  const int m0 = (t % tiles_m) * TM, n0 = (t / tiles_m) * TN;
+  const bool akc = j.transA != 0, bkc = j.transB == 0;
+  if (akc) {
+    if (bkc) gemm_tile<true, true>(j, m0, n0, As, Bs);
+    else gemm_tile<true, false>(j, m0, n0, As, Bs);
+  } else {
+    if (bkc) gemm_tile<false, true>(j, m0, n0, As, Bs);
+    else gemm_tile<false, false>(j, m0, n0, As, Bs);
+  }
 }
 #endif
 
@@ -188,14 +234,14 @@ int gemm_grouped(const tmf_gemm_job *jobs, int njobs, void *desc_dev, void *stre
   int *dprefix = reinterpret_cast<int *>(d + sizeof(tmf_gemm_job) * (size_t)njobs);
   rc = copy_h2d(dprefix, prefix.data(), sizeof(int) * (size_t)(njobs + 1), stream);
   if (rc) return rc;
-  return launch(gemm_grouped_kernel, ntiles, 256, 0, stream,
-                reinterpret_cast<const tmf_gemm_job *>(d), (const int *)dprefix, njobs);
+  return launch_t("gemm", gemm_grouped_kernel, ntiles, 256, 0, stream,
+                  reinterpret_cast<const tmf_gemm_job *>(d), (const int *)dprefix, njobs);
 }
 
 int gemm_launch_uploaded(const tmf_gemm_job *jobs_dev, const int *prefix_dev, int njobs, int ntiles,
-                         void *stream) {
+                         void *stream, const char *tag) {
   if (ntiles <= 0) return TMF_OK;
-  return launch(gemm_grouped_kernel, ntiles, 256, 0, stream, jobs_dev, prefix_dev, njobs);
+  return launch_t(tag, gemm_grouped_kernel, ntiles, 256, 0, stream, jobs_dev, prefix_dev, njobs);
 }
 
 int64_t gemm_desc_bytes(int njobs) {

@@ -101,14 +101,42 @@ void lowest_sums(const double *a, int k, double base, const TruncPar &tp, int fi
     order[i] = i;
   }
   std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return mag[x] < mag[y]; });
-  std::priority_queue<HeapItem, std::vector<HeapItem>, HeapCmp> heap;
+  // binary min-heap on (sum, seq) in a flat vector; "replace top" fuses the pop with the first push
+  std::vector<HeapItem> heap;
+  heap.reserve(tp.chi_max > 0 ? 2 * (size_t)tp.chi_max + 8 : 4096);
+  auto less = [](const HeapItem &x, const HeapItem &y) {
+    return x.sum < y.sum || (x.sum == y.sum && x.seq < y.seq);
+  };
+  auto sift_down = [&](size_t i) {
+    const size_t nh = heap.size();
+    HeapItem v = heap[i];
+    for (;;) {
+      size_t c = 2 * i + 1;
+      if (c >= nh) break;
+      if (c + 1 < nh && less(heap[c + 1], heap[c])) ++c;
+      if (!less(heap[c], v)) break;
+      heap[i] = heap[c];
+      i = c;
+    }
+    heap[i] = v;
+  };
+  auto push = [&](const HeapItem &v) {
+    size_t i = heap.size();
+    heap.push_back(v);
+    while (i > 0) {
+      size_t p = (i - 1) / 2;
+      if (!less(v, heap[p])) break;
+      heap[i] = heap[p];
+      i = p;
+    }
+    heap[i] = v;
+  };
   int64_t seq = 0;
-  heap.push({base + mag[order[0]], seq, 0, neg ^ (1ull << order[0])});  // :291-293
+  push({base + mag[order[0]], seq, 0, neg ^ (1ull << order[0])});  // :291-293
   int checked = 1;
   while (!heap.empty() && (sums.empty() || more_needed(sums, tp, max_logval))) {  // :297
     ++checked;
-    HeapItem it = heap.top();
-    heap.pop();
+    const HeapItem it = heap[0];
     if (tp.is_sector(charge_of(it.set, k, filled_left, filled_right))) {
       sums.push_back(it.sum);
       sets.push_back(it.set);
@@ -116,10 +144,15 @@ void lowest_sums(const double *a, int k, double base, const TruncPar &tp, int fi
     if (it.i < k - 1) {  // :304-315
       uint64_t c1 = it.set ^ (1ull << order[it.i + 1]);
       double s = it.sum + mag[order[it.i + 1]];
-      heap.push({s, ++seq, it.i + 1, c1});
+      heap[0] = {s, ++seq, it.i + 1, c1};   // heappop + first heappush
+      sift_down(0);
       uint64_t c2 = c1 ^ (1ull << order[it.i]);
       s = s - mag[order[it.i]];
-      heap.push({s, ++seq, it.i + 1, c2});
+      push({s, ++seq, it.i + 1, c2});
+    } else {
+      heap[0] = heap.back();
+      heap.pop_back();
+      if (!heap.empty()) sift_down(0);
     }
   }
   if (n_checked) *n_checked = checked;

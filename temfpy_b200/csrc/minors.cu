@@ -5,78 +5,50 @@
 // det_always scaling of :1137.
 //
 // Instead of one n x n LU per entry we share the elimination between all kets of a bra row:
-//   X = S[rows(alpha), :]   (n x s_ket)  is row-reduced once (Gauss-Jordan, complete pivoting)
+//   X = S[rows(alpha), :]   (n x s_ket)  is row-reduced once (Gauss-Jordan, pivoting along each row)
 //   to [I | Y] on a pivot column set C0(alpha);  for any column set C with |C| = n
 //      det X[:, C] = (prod of pivots) * sign * det Y[C0 \ C, C \ C0],
 //   a determinant of size d = |C \ C0| (d <= 5 at chi = 1024, mean 2.5, versus n = 11).
-// Complete pivoting keeps |Y| <= 1, so the small determinants are perfectly conditioned.
+// The pivot of row t is its largest entry among the unused columns (partial pivoting along the row).
 //
-// One CTA handles up to MB_ROWS bra rows of one block: the row reductions of SLOTS rows proceed in
-// lock-step through shared memory, then every thread evaluates one (alpha, beta) entry with the
-// d x d matrix in registers and stores it coalesced along beta.
+// One CTA handles up to MB_ROWS bra rows of one block.  Its warps work independently: a warp row-reduces
+// one bra row in a private shared-memory tile (lanes = columns, __syncwarp only), then every lane
+// evaluates one (alpha, beta) entry with the d x d matrix in registers; stores are coalesced along beta.
 #include "cta.hpp"
 
 namespace tmf {
 
-constexpr int SLOTS = 8;       // bra rows reduced concurrently by one CTA
 constexpr int MB_ROWS = 32;    // bra rows per CTA
-constexpr int DMAX = 6;        // register path for reduced determinants up to 6 x 6
 constexpr int DGEN = 16;       // generic local-memory path up to 16 x 16
 static_assert(sizeof(tmf_minor_block) == 64, "block descriptor must be 64 bytes");
 
-template <int D>
-TMF_DEVICE double det_small(double (&m)[DMAX][DMAX]) {
-  double det = 1.0;
-#pragma unroll
-  for (int j = 0; j < D; ++j) {
-    int p = j;
-    double best = fabs(m[j][j]);
-#pragma unroll
-    for (int i = j + 1; i < D; ++i) {
-      double a = fabs(m[i][j]);
-      if (a > best) { best = a; p = i; }
-    }
-    if (best == 0.0) return 0.0;
-    if (p != j) {
-      det = -det;
-#pragma unroll
-      for (int i = j + 1; i < D; ++i) {
-        if (i == p) {
-#pragma unroll
-          for (int c = j; c < D; ++c) { double t = m[j][c]; m[j][c] = m[i][c]; m[i][c] = t; }
-        }
-      }
-    }
-    const double piv = m[j][j];
-    det *= piv;
-    const double inv = 1.0 / piv;
-#pragma unroll
-    for (int i = j + 1; i < D; ++i) {
-      const double l = m[i][j] * inv;
-#pragma unroll
-      for (int c = j + 1; c < D; ++c) m[i][c] -= l * m[j][c];
-    }
-  }
-  return det;
-}
-
 // generic fallback (d > DMAX): in-place LU on a local array
-TMF_DEVICE double det_generic(double *m, int d, int ld) {
+#if !defined(TMF_HOSTSIM)
+__device__ __noinline__
+#else
+static
+#endif
+double det_generic(double *m, int d, int ld) {
   double det = 1.0;
+#pragma unroll 1
   for (int j = 0; j < d; ++j) {
     int p = j;
     double best = fabs(m[j * ld + j]);
+#pragma unroll 1
     for (int i = j + 1; i < d; ++i)
       if (fabs(m[i * ld + j]) > best) { best = fabs(m[i * ld + j]); p = i; }
     if (best == 0.0) return 0.0;
     if (p != j) {
       det = -det;
+#pragma unroll 1
       for (int c = 0; c < d; ++c) { double t = m[j * ld + c]; m[j * ld + c] = m[p * ld + c]; m[p * ld + c] = t; }
     }
     double piv = m[j * ld + j];
     det *= piv;
+#pragma unroll 1
     for (int i = j + 1; i < d; ++i) {
       double l = m[i * ld + j] / piv;
+#pragma unroll 1
       for (int c = j + 1; c < d; ++c) m[i * ld + c] -= l * m[j * ld + c];
     }
   }
@@ -98,16 +70,129 @@ TMF_DEVICE int ctz64(uint64_t x) {
 #endif
 }
 
-// smem per slot: X (nmax x smax), plus bookkeeping
-struct SlotMeta {
+// entry with more than 4 exchanged columns (rare): LU on a local-memory array
+#if !defined(TMF_HOSTSIM)
+__device__ __noinline__
+#else
+static
+#endif
+double entry_generic(const double *x, int smax, const int *colrow, uint64_t U, uint64_t mu,
+                                uint64_t de, int d, int &par) {
+  if (d > DGEN) return NAN;   // would need > 16 simultaneous column exchanges
+  double buf[DGEN * DGEN];
+  int rows_[DGEN], cols_[DGEN];
+#pragma unroll 1
+  for (int i = 0; i < d; ++i) {
+    const int m = ctz64(mu), e = ctz64(de);
+    mu &= mu - 1;
+    de &= de - 1;
+    const int a = m < e ? m : e, b = m < e ? e : m;
+    const uint64_t between = (b - a > 1) ? (((1ull << (b - a - 1)) - 1) << (a + 1)) : 0ull;
+    par += popc64(U & between);
+    rows_[i] = colrow[m];
+    cols_[i] = e;
+  }
+#pragma unroll 1
+  for (int i = 0; i < d; ++i)
+#pragma unroll 1
+    for (int j = 0; j < d; ++j) buf[i * DGEN + j] = x[rows_[i] * smax + cols_[j]];
+  return det_generic(buf, d, DGEN);
+}
+
+// Closed-form determinants for the reduced sizes that occur in practice (d <= 4 covers > 99.9 % of
+// the entries at chi = 1024).  Straight-line cofactor / 2x2-minor expansions keep the kernel small
+// enough for the instruction cache (an unrolled pivoted LU per size made it 340 KB of SASS and
+// stalled the warps on instruction fetch).
+TMF_DEVICE double det2(double a, double b, double c, double d) { return a * d - b * c; }
+TMF_DEVICE double det3(const double *m) {   // row-major 3 x 3
+  return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
+         m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+TMF_DEVICE double det4(const double *m) {   // row-major 4 x 4, complementary 2 x 2 minors of rows 01 | 23
+  const double s0 = m[0] * m[5] - m[1] * m[4], s1 = m[0] * m[6] - m[2] * m[4], s2 = m[0] * m[7] - m[3] * m[4];
+  const double s3 = m[1] * m[6] - m[2] * m[5], s4 = m[1] * m[7] - m[3] * m[5], s5 = m[2] * m[7] - m[3] * m[6];
+  const double c5 = m[10] * m[15] - m[11] * m[14], c4 = m[9] * m[15] - m[11] * m[13], c3 = m[9] * m[14] - m[10] * m[13];
+  const double c2 = m[8] * m[15] - m[11] * m[12], c1 = m[8] * m[14] - m[10] * m[12], c0 = m[8] * m[13] - m[9] * m[12];
+  return s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+}
+
+// One tensor entry: gathers Y[C0 \\ C, C \\ C0] (d x d) from the reduced matrix, accumulates the
+// permutation parity and returns the determinant.
+TMF_DEVICE double entry_value(const double *x, int smax, const int *colrow, uint64_t c0, uint64_t cm) {
+  const uint64_t U = cm & c0;
+  uint64_t mu = c0 & ~cm, de = cm & ~c0;
+  const int d = popc64(de);
+  if (d == 0) return 1.0;
+  int par = 0;
+  double val;
+  if (d <= 4) {
+    int rr[4] = {0, 0, 0, 0}, cc[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i < d) {
+        const int m = ctz64(mu), e = ctz64(de);
+        mu &= mu - 1;
+        de &= de - 1;
+        const int a = m < e ? m : e, b = m < e ? e : m;
+        const uint64_t between = (b - a > 1) ? (((1ull << (b - a - 1)) - 1) << (a + 1)) : 0ull;
+        par += popc64(U & between);
+        rr[i] = colrow[m] * smax;
+        cc[i] = e;
+      }
+    }
+    if (d == 1) {
+      val = x[rr[0] + cc[0]];
+    } else if (d == 2) {
+      val = det2(x[rr[0] + cc[0]], x[rr[0] + cc[1]], x[rr[1] + cc[0]], x[rr[1] + cc[1]]);
+    } else if (d == 3) {
+      double m[9];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) m[3 * i + j] = x[rr[i] + cc[j]];
+      val = det3(m);
+    } else {
+      double m[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[4 * i + j] = x[rr[i] + cc[j]];
+      val = det4(m);
+    }
+  } else {
+    val = entry_generic(x, smax, colrow, U, mu, de, d, par);
+  }
+  return (par & 1) ? -val : val;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-independent kernel: after the sometimes matrix is staged in shared memory (one CTA barrier)
+// every warp processes bra rows on its own -- row reduction with lanes = columns in a private
+// shared-memory tile, then one tensor entry per lane -- synchronising with __syncwarp only.
+// ---------------------------------------------------------------------------------------------
+#if defined(TMF_HOSTSIM)
+#define LANE_FOR(l) for (int l = 0; l < 32; ++l)
+#define WARP_FOR(w, W) for (int w = 0; w < (W); ++w)
+#define WSYNC() ((void)0)
+#else
+#define LANE_FOR(l) for (int l = (threadIdx.x & 31), l##_once = 1; l##_once; l##_once = 0)
+#define WARP_FOR(w, W) for (int w = (threadIdx.x >> 5), w##_once = 1; w##_once && w < (W); w##_once = 0)
+#define WSYNC() __syncwarp()
+#endif
+
+struct WarpMeta {
   uint64_t c0;        // pivot column set
   double scale;       // prod of pivots * sigma0 * det_always
+  double inv;         // 1 / current pivot
+  int pc, pad_;       // current pivot column
   int colrow[64];     // pivot row of every pivot column
+  double cand[64];    // simulator only: candidates of the pivot search
 };
+
+constexpr int MB_WARPS = 8;
 
 TMF_GLOBAL minors_kernel(const tmf_minor_block *blocks, const int *cta_prefix, int nblocks,
                          int nmax, int smax) {
-  // locate (block, first row) of this CTA
   int lo = 0, hi = nblocks;
   const int cta = BLOCK_ID;
   while (hi - lo > 1) {
@@ -120,13 +205,9 @@ TMF_GLOBAL minors_kernel(const tmf_minor_block *blocks, const int *cta_prefix, i
   const int n = blk.minor, sk = blk.s_ket, sb = blk.s_bra;
 
   DYN_SMEM(unsigned char, raw);
-  double *Ssm = reinterpret_cast<double *>(raw);             // sb * sk  (smax * smax)
-  double *X = Ssm + (size_t)smax * smax;                       // SLOTS * nmax * smax
-  double *red = X + (size_t)SLOTS * nmax * smax;               // SLOTS * 33
-  SlotMeta *meta = reinterpret_cast<SlotMeta *>(red + SLOTS * 33);
-  int *ired = reinterpret_cast<int *>(meta + SLOTS);           // SLOTS * 33 * 2
-  int *rowdone = ired + SLOTS * 33 * 2;                        // SLOTS * 64 (pivot step of row, -1)
-  int *pivrc = rowdone + SLOTS * 64;                           // SLOTS * 2
+  double *Ssm = reinterpret_cast<double *>(raw);                 // smax * smax
+  double *Xall = Ssm + (size_t)smax * smax;                      // MB_WARPS * nmax * smax
+  WarpMeta *metas = reinterpret_cast<WarpMeta *>(Xall + (size_t)MB_WARPS * nmax * smax);
 
   const double det_always = blk.det ? *blk.det : 1.0;
   PAR_FOR(idx, sb * sk) Ssm[idx] = blk.S[idx];
@@ -140,180 +221,123 @@ TMF_GLOBAL minors_kernel(const tmf_minor_block *blocks, const int *cta_prefix, i
     return;
   }
 
-  for (int g0 = 0; g0 < nrows; g0 += SLOTS) {
-    const int ns = (nrows - g0 < SLOTS) ? (nrows - g0) : SLOTS;
-    // ---- gather X = S[rows(alpha), :] for the ns slots -----------------------------------
-    PAR_FOR(idx, ns * sk) {
-      int s = idx / sk, c = idx - s * sk;
-      uint64_t rm = blk.bra_masks[row0 + g0 + s];
-      double *x = X + (size_t)s * nmax * smax;
-      int r = 0;
-      while (rm) {
-        int b = ctz64(rm);
-        rm &= rm - 1;
-        x[r * smax + c] = Ssm[(size_t)c * sb + b];
-        ++r;
-      }
-    }
-    PAR_FOR(idx, ns * 64) rowdone[idx] = -1;
-    PAR_FOR(s, ns) {
-      meta[s].c0 = 0;
-      meta[s].scale = det_always;
-    }
-    CTA_SYNC();
-    // ---- Gauss-Jordan with complete pivoting, n steps in lock-step -------------------------
-    for (int t = 0; t < n; ++t) {
-      PAR_FOR(item, ns * 32) {
-        int s = item >> 5, lane = item & 31;
-        const double *x = X + (size_t)s * nmax * smax;
-        const uint64_t c0 = meta[s].c0;
-        double best = -1.0;
-        int br = 0, bc = 0;
-        for (int e = lane; e < n * sk; e += 32) {
-          int r = e / sk, c = e - r * sk;
-          if (rowdone[s * 64 + r] >= 0 || ((c0 >> c) & 1)) continue;
-          double a = fabs(x[r * smax + c]);
-          if (a > best) { best = a; br = r; bc = c; }
-        }
-        red[s * 33 + lane] = best;
-        ired[(s * 33 + lane) * 2] = br;
-        ired[(s * 33 + lane) * 2 + 1] = bc;
-      }
-      CTA_SYNC();
-      PAR_FOR(s, ns) {
-        double best = red[s * 33];
-        int br = ired[(s * 33) * 2], bc = ired[(s * 33) * 2 + 1];
-        for (int l = 1; l < 32; ++l) {
-          double v = red[s * 33 + l];
-          int r = ired[(s * 33 + l) * 2], c = ired[(s * 33 + l) * 2 + 1];
-          if (v > best || (v == best && (r < br || (r == br && c < bc)))) { best = v; br = r; bc = c; }
-        }
-        pivrc[s * 2] = br;
-        pivrc[s * 2 + 1] = bc;
-        double *x = X + (size_t)s * nmax * smax;
-        double pv = (best >= 0.0) ? x[br * smax + bc] : 0.0;
-        meta[s].scale *= pv;
-        meta[s].c0 |= (1ull << bc);
-        meta[s].colrow[bc] = br;
-        rowdone[s * 64 + br] = t;
-        red[s * 33 + 32] = (pv != 0.0) ? 1.0 / pv : 0.0;
-      }
-      CTA_SYNC();
-      // normalise the pivot row
-      PAR_FOR(idx, ns * sk) {
-        int s = idx / sk, c = idx - s * sk;
-        double *x = X + (size_t)s * nmax * smax;
-        x[pivrc[s * 2] * smax + c] *= red[s * 33 + 32];
-      }
-      CTA_SYNC();
-      // eliminate the pivot column from every other row (column-parallel: one thread per column)
-      PAR_FOR(idx, ns * sk) {
-        int s = idx / sk, c = idx - s * sk;
-        double *x = X + (size_t)s * nmax * smax;
-        const int pr = pivrc[s * 2], pc = pivrc[s * 2 + 1];
-        if (c != pc) {
-          const double u = x[pr * smax + c];
-          for (int r = 0; r < n; ++r)
-            if (r != pr) x[r * smax + c] -= x[r * smax + pc] * u;
-        }
-      }
-      CTA_SYNC();
-      PAR_FOR(idx, ns * n) {  // the pivot column itself becomes a unit vector
-        int s = idx / n, r = idx - s * n;
-        double *x = X + (size_t)s * nmax * smax;
-        const int pr = pivrc[s * 2], pc = pivrc[s * 2 + 1];
-        x[r * smax + pc] = (r == pr) ? 1.0 : 0.0;
-      }
-      CTA_SYNC();
-    }
-    // sigma0: sign of the permutation (rank of pivot column) -> pivot row
-    PAR_FOR(s, ns) {
-      uint64_t c0 = meta[s].c0;
-      uint64_t seen = 0;
-      int inv = 0;
-      while (c0) {
-        int c = ctz64(c0);
-        c0 &= c0 - 1;
-        int r = meta[s].colrow[c];
-        inv += popc64(seen >> (r + 1));   // earlier columns mapped to larger rows
-        seen |= (1ull << r);
-      }
-      if (inv & 1) meta[s].scale = -meta[s].scale;
-    }
-    CTA_SYNC();
-    // ---- one thread per (alpha, beta) entry -------------------------------------------------
-    PAR_FOR(idx, ns * blk.n_ket) {
-      const int s = idx / blk.n_ket, c = idx - s * blk.n_ket;
-      const double *x = X + (size_t)s * nmax * smax;
-      const uint64_t c0 = meta[s].c0;
-      const uint64_t cm = blk.ket_masks[c];
-      const uint64_t U = cm & c0;
-      uint64_t mu = c0 & ~cm, de = cm & ~c0;
-      const int d = popc64(de);
-      int par = 0;
-      double val;
-      if (d <= DMAX) {
-        int rr[DMAX], cc[DMAX];
-#pragma unroll
-        for (int i = 0; i < DMAX; ++i) {
-          rr[i] = 0;
-          cc[i] = 0;
-          if (i < d) {
-            int m = ctz64(mu), e = ctz64(de);
-            mu &= mu - 1;
-            de &= de - 1;
-            int a = m < e ? m : e, b = m < e ? e : m;
-            uint64_t between = (b - a > 1) ? (((1ull << (b - a - 1)) - 1) << (a + 1)) : 0ull;
-            par += popc64(U & between);
-            rr[i] = meta[s].colrow[m];
-            cc[i] = e;
+  WARP_FOR(w, MB_WARPS) {
+    double *x = Xall + (size_t)w * nmax * smax;
+    WarpMeta *mt = metas + w;
+    for (int a = w; a < nrows; a += MB_WARPS) {
+      const uint64_t rmask = blk.bra_masks[row0 + a];
+      // ---- gather X = S[rows(alpha), :] (lane = column) -------------------------------------
+      LANE_FOR(l) {
+        for (int c = l; c < sk; c += 32) {
+          uint64_t rm = rmask;
+          int r = 0;
+          while (rm) {
+            const int bit = ctz64(rm);
+            rm &= rm - 1;
+            x[r * smax + c] = Ssm[(size_t)c * sb + bit];
+            ++r;
           }
         }
-        double m8[DMAX][DMAX];
-#pragma unroll
-        for (int i = 0; i < DMAX; ++i)
-#pragma unroll
-          for (int j = 0; j < DMAX; ++j)
-            m8[i][j] = (i < d && j < d) ? x[rr[i] * smax + cc[j]] : ((i == j) ? 1.0 : 0.0);
-        switch (d) {
-          case 0: val = 1.0; break;
-          case 1: val = m8[0][0]; break;
-          case 2: val = m8[0][0] * m8[1][1] - m8[0][1] * m8[1][0]; break;
-          case 3: val = det_small<3>(m8); break;
-          case 4: val = det_small<4>(m8); break;
-          case 5: val = det_small<5>(m8); break;
-          default: val = det_small<6>(m8); break;
-        }
-      } else if (d <= DGEN) {
-        double buf[DGEN * DGEN];
-        int rows_[DGEN], cols_[DGEN];
-        for (int i = 0; i < d; ++i) {
-          int m = ctz64(mu), e = ctz64(de);
-          mu &= mu - 1;
-          de &= de - 1;
-          int a = m < e ? m : e, b = m < e ? e : m;
-          uint64_t between = (b - a > 1) ? (((1ull << (b - a - 1)) - 1) << (a + 1)) : 0ull;
-          par += popc64(U & between);
-          rows_[i] = meta[s].colrow[m];
-          cols_[i] = e;
-        }
-        for (int i = 0; i < d; ++i)
-          for (int j = 0; j < d; ++j) buf[i * DGEN + j] = x[rows_[i] * smax + cols_[j]];
-        val = det_generic(buf, d, DGEN);
-      } else {
-        val = NAN;  // would need > 16 simultaneous column exchanges; not produced by Schmidt sets
+        if (l == 0) { mt->c0 = 0; mt->scale = det_always; }
       }
-      val *= meta[s].scale;
-      if (par & 1) val = -val;
-      blk.out[(int64_t)(row0 + g0 + s) * blk.n_ket + c] = val;
+      WSYNC();
+      // ---- Gauss-Jordan, pivoting along the row (largest entry among the unused columns) ------
+      for (int t = 0; t < n; ++t) {
+#if defined(TMF_HOSTSIM)
+        LANE_FOR(l) {
+          for (int c = l; c < sk; c += 32)
+            mt->cand[c] = ((mt->c0 >> c) & 1) ? -1.0 : fabs(x[t * smax + c]);
+        }
+        LANE_FOR(l) if (l == 0) {
+          double best = -1.0;
+          int bc = 0;
+          for (int c = 0; c < sk; ++c)
+            if (mt->cand[c] > best) { best = mt->cand[c]; bc = c; }
+          const double pv = x[t * smax + bc];
+          mt->pc = bc;
+          mt->inv = (pv != 0.0) ? 1.0 / pv : 0.0;
+          mt->scale *= pv;
+          mt->c0 |= (1ull << bc);
+          mt->colrow[bc] = t;
+        }
+#else
+        {
+          const int l = threadIdx.x & 31;
+          const uint64_t c0 = mt->c0;
+          double best = -1.0;
+          int bc = l;
+          for (int c = l; c < sk; c += 32) {
+            const double v = ((c0 >> c) & 1) ? -1.0 : fabs(x[t * smax + c]);
+            if (v > best) { best = v; bc = c; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+            if (ob > best || (ob == best && oc < bc)) { best = ob; bc = oc; }
+          }
+          __syncwarp();
+          if (l == 0) {
+            const double pv = x[t * smax + bc];
+            mt->pc = bc;
+            mt->inv = (pv != 0.0) ? 1.0 / pv : 0.0;
+            mt->scale *= pv;
+            mt->c0 = c0 | (1ull << bc);
+            mt->colrow[bc] = t;
+          }
+        }
+#endif
+        WSYNC();
+        LANE_FOR(l) {
+          const int pc = mt->pc;
+          const double inv = mt->inv;
+          for (int c = l; c < sk; c += 32) {
+            if (c == pc) continue;
+            const double u = x[t * smax + c] * inv;
+            x[t * smax + c] = u;
+#pragma unroll 4
+            for (int r = 0; r < n; ++r)
+              if (r != t) x[r * smax + c] -= x[r * smax + pc] * u;
+          }
+        }
+        WSYNC();
+        LANE_FOR(l) {   // the pivot column becomes a unit vector
+          const int pc = mt->pc;
+          for (int r = l; r < n; r += 32) x[r * smax + pc] = (r == t) ? 1.0 : 0.0;
+        }
+        WSYNC();
+      }
+      // sigma0: sign of the permutation (rank of pivot column) -> pivot row
+      LANE_FOR(l) if (l == 0) {
+        uint64_t c0 = mt->c0, seen = 0;
+        int inv = 0;
+        while (c0) {
+          const int c = ctz64(c0);
+          c0 &= c0 - 1;
+          const int r = mt->colrow[c];
+          inv += popc64(seen >> (r + 1));
+          seen |= (1ull << r);
+        }
+        if (inv & 1) mt->scale = -mt->scale;
+      }
+      WSYNC();
+      // ---- one tensor entry per lane ---------------------------------------------------------
+      LANE_FOR(l) {
+        const uint64_t c0 = mt->c0;
+        const double scale = mt->scale;
+        double *orow = blk.out + (int64_t)(row0 + a) * blk.n_ket;
+        for (int c = l; c < blk.n_ket; c += 32) {
+          const double val = scale * entry_value(x, smax, mt->colrow, c0, blk.ket_masks[c]);
+          orow[c] = val;
+        }
+      }
+      WSYNC();
     }
-    CTA_SYNC();
   }
 }
 
 static size_t minors_smem_bytes(int nmax, int smax) {
-  return sizeof(double) * ((size_t)smax * smax + (size_t)SLOTS * nmax * smax + SLOTS * 33) +
-         sizeof(SlotMeta) * SLOTS + sizeof(int) * (SLOTS * 33 * 2 + SLOTS * 64 + SLOTS * 2 + 8);
+  return sizeof(double) * ((size_t)smax * smax + (size_t)MB_WARPS * nmax * smax) + sizeof(WarpMeta) * MB_WARPS + 64;
 }
 
 }  // namespace tmf
@@ -346,7 +370,7 @@ extern "C" int tmf_minors_blocks(const tmf_minor_block *blocks_host, int nblocks
   if (rc) return rc;
   rc = copy_h2d(d + o_pref, prefix.data(), sizeof(int) * (size_t)(nblocks + 1), stream);
   if (rc) return rc;
-  return launch(minors_kernel, prefix[nblocks], 256, minors_smem_bytes(nmax, smax), stream,
+  return launch_t("minors", minors_kernel, prefix[nblocks], 32 * tmf::MB_WARPS, minors_smem_bytes(nmax, smax), stream,
                 reinterpret_cast<const tmf_minor_block *>(d), reinterpret_cast<const int *>(d + o_pref),
                 nblocks, nmax, smax);
 }

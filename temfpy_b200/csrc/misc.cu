@@ -9,6 +9,75 @@ thread_local unsigned char *smem = nullptr;
 }  // namespace tmfsim
 #endif
 
+#include <atomic>
+#include <map>
+#include <mutex>
+
+namespace tmf {
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+#if !defined(TMF_HOSTSIM)
+static bool g_prof = false;
+static std::mutex g_prof_mu;
+struct ProfRec { std::string tag; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_recs;
+bool prof_enabled() { return g_prof; }
+void prof_begin(const char *tag, void *stream) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  r.tag = tag;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, (cudaStream_t)stream);
+  g_recs.push_back(r);
+}
+void prof_end(void *stream) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_recs.back().b, (cudaStream_t)stream);
+}
+#endif
+}  // namespace tmf
+
+extern "C" long long tmf_launch_count(int reset) {
+  long long v = tmf::g_launches.load();
+  if (reset) tmf::g_launches.store(0);
+  return v;
+}
+
+extern "C" int tmf_prof_enable(int on) {
+#if !defined(TMF_HOSTSIM)
+  std::lock_guard<std::mutex> lk(tmf::g_prof_mu);
+  for (auto &r : tmf::g_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  tmf::g_recs.clear();
+  tmf::g_prof = on != 0;
+#else
+  (void)on;
+#endif
+  return TMF_OK;
+}
+
+// writes "tag total_ms launches\n" lines into buf (synchronises the device)
+extern "C" int tmf_prof_report(char *buf, int cap) {
+  std::string out;
+#if !defined(TMF_HOSTSIM)
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(tmf::g_prof_mu);
+  std::map<std::string, std::pair<double, int>> acc;
+  for (auto &r : tmf::g_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      acc[r.tag].first += ms;
+      acc[r.tag].second += 1;
+    }
+  }
+  for (auto &kv : acc)
+    out += kv.first + " " + std::to_string(kv.second.first) + " " + std::to_string(kv.second.second) + "\n";
+#endif
+  if ((int)out.size() + 1 > cap) return TMF_ERR_VALUE;
+  std::memcpy(buf, out.c_str(), out.size() + 1);
+  return TMF_OK;
+}
+
 extern "C" int tmf_version(void) { return 100; }
 
 extern "C" int tmf_is_cuda(void) {

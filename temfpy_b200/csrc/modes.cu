@@ -114,7 +114,7 @@ tmf_gemm_job mk_gemm(const double *A, int lda, int transA, const double *B, int 
 
 // defined in gemm.cu (kernel symbol shared through this launcher)
 int gemm_launch_uploaded(const tmf_gemm_job *jobs_dev, const int *prefix_dev, int njobs, int ntiles,
-                         void *stream);
+                         void *stream, const char *tag);
 
 static int64_t big_job_doubles(int n, int m, int rr) {
   // Y, Wt, Wt0, coef, Rw, Jsel, U0, AU, TE, Zsel, norm0y, norm0w, eside (+ ints)
@@ -361,18 +361,18 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
 
   // ---- launches ----------------------------------------------------------------------------
   if (!small.empty()) {
-    rc = launch(small_modes_kernel, (int)small.size(), 256, small_smem, stream, small_dev, cutoff);
+    rc = launch_t("small_modes", small_modes_kernel, (int)small.size(), 256, small_smem, stream, small_dev, cutoff);
     if (rc) return rc;
   }
   if (nb == 0) return TMF_OK;
-  rc = launch(omega_kernel, (int)(((int64_t)L * r_sketch + 1023) / 1024), 256, 0, stream, Om, L, r_sketch);
+  rc = launch_t("omega", omega_kernel, (int)(((int64_t)L * r_sketch + 1023) / 1024), 256, 0, stream, Om, L, r_sketch);
   if (rc) return rc;
   auto run = [&](const GemmLaunch &gl) {
     if (gl.ntiles == 0) return (int)TMF_OK;
-    return gemm_launch_uploaded(gl.jobs, gl.prefix, gl.njobs, gl.ntiles, stream);
+    return gemm_launch_uploaded(gl.jobs, gl.prefix, gl.njobs, gl.ntiles, stream, "gemm_modes");
   };
   auto run_orth = [&](OrthPlan &op) -> int {
-    int r2 = launch(colnorm_kernel, nb, 256, op.norm_smem, stream, op.norm);
+    int r2 = launch_t("colnorm", colnorm_kernel, nb, 256, op.norm_smem, stream, op.norm);
     if (r2) return r2;
     for (size_t p = 0; p < op.panel.size(); ++p) {
       if (op.panel_n[p] == 0) continue;
@@ -383,7 +383,7 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
           if ((r2 = run(op.coef[p]))) return r2;
           if ((r2 = run(op.upd[p]))) return r2;
         }
-        r2 = launch(panel_mgs2_kernel, op.panel_n[p], 256, op.panel_smem[p], stream, op.panel[p], 0.0);
+        r2 = launch_t("panel_mgs2", panel_mgs2_kernel, op.panel_n[p], 256, op.panel_smem[p], stream, op.panel[p], 0.0);
         if (r2) return r2;
       }
     }
@@ -399,14 +399,14 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
   if ((rc = run_orth(orthW))) return rc;
   if ((rc = run(L_rw[0]))) return rc;
   const double thr = cutoff * (1.0 - cutoff);
-  rc = launch(svd_select_kernel, nb, 256, svd_smem, stream, sj_dev, thr, 1e-26);
+  rc = launch_t("svd_select", svd_select_kernel, nb, 256, svd_smem, stream, sj_dev, thr, 1e-26);
   if (rc) return rc;
   if ((rc = run(L_u0[0]))) return rc;
   if ((rc = run(L_au[0]))) return rc;
   if ((rc = run(L_te[0]))) return rc;
-  rc = launch(ritz_kernel, nb, 256, ritz_smem, stream, rj_dev, cutoff);
+  rc = launch_t("ritz", ritz_kernel, nb, 256, ritz_smem, stream, rj_dev, cutoff);
   if (rc) return rc;
   if ((rc = run(L_out[0]))) return rc;
-  rc = launch(pivchol_kernel, nb, 256, chol_smem, stream, cj_dev, 1e-8);
+  rc = launch_t("pivchol", pivchol_kernel, nb, 1024, chol_smem, stream, cj_dev, 1e-8);
   return rc;
 }

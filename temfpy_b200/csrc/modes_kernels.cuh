@@ -4,6 +4,7 @@
 // style of cta.hpp so that the CPU simulator executes the very same source.
 #pragma once
 #include "cta.hpp"
+#include <cstdio>
 
 namespace tmf {
 
@@ -11,6 +12,7 @@ constexpr int PANEL_W = 16;        // panel width of the block Gram-Schmidt
 constexpr int JAC_MAX_SWEEPS = 40;
 constexpr int SMALL_N = 64;        // blocks up to this size are diagonalised directly
 constexpr int JAC_SMEM_J_MAX = 96; // above this the Jacobi rotation matrix lives in global memory
+constexpr int PIVCHOL_MAX_PARTS = 8;
 constexpr int R_SKETCH_MAX = 160;  // G (r x r) must fit in shared memory
 
 // ---------------------------------------------------------------------------------------------
@@ -131,15 +133,70 @@ inline size_t panel_smem_bytes(int rows, int ncols, bool use_smem) {
 // Parallel round-robin ordering; `rot` (n/2 * 2 doubles), `part` (n/2 * 33 * 3) and `flag` are
 // shared scratch.  n may be odd (a bye is inserted).
 // ---------------------------------------------------------------------------------------------
-TMF_DEVICE void jacobi_onesided(double *G, int ldg, double *J, int ldj, int n, double *rot,
-                                double *part, int *flag) {
-  if (n < 2) return;
+TMF_DEVICE int jacobi_onesided(double *G, int ldg, double *J, int ldj, int n, double *rot,
+                               double *part, int *flag) {
+  if (n < 2) return 0;
+  int sweeps_done = 0;
   const int np = (n + 1) & ~1;  // padded to even; index np-1 == n is a bye when n is odd
   const int half = np / 2;
   for (int sweep = 0; sweep < JAC_MAX_SWEEPS; ++sweep) {
     PAR_FOR(one, 1) *flag = 0;
     CTA_SYNC();
     for (int round = 0; round < np - 1; ++round) {
+#if !defined(TMF_HOSTSIM)
+      // CUDA path: one warp per column pair.  Pairs of a round touch disjoint columns, so the dot
+      // products (shuffle reductions), the rotation and the column updates of a pair need no CTA
+      // barrier; one __syncthreads per round separates the pairings.
+      {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+        for (int pr = warp; pr < half; pr += nwarp) {
+          int p = round + pr, q = round + np - 1 - pr;      // circle method without integer division
+          if (p >= np - 1) p -= np - 1;
+          if (q >= np - 1) q -= np - 1;
+          if (pr == 0) p = np - 1;
+          if (p >= n || q >= n) continue;
+          double *gp = G + (int64_t)p * ldg, *gq = G + (int64_t)q * ldg;
+          double a = 0.0, b = 0.0, c = 0.0;
+          for (int r = lane; r < n; r += 32) {
+            const double x = gp[r], y = gq[r];
+            a += x * x;
+            b += y * y;
+            c += x * y;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+          }
+          // a column with norm < 1e-15 (all our matrices have norm O(1)) is numerically null: rounding
+          // noise of the rotations with the other columns keeps changing it by O(1) of its own size, so
+          // pairs involving it would never meet the relative criterion -- skip them (as LAPACK's dgesvj)
+          if (c * c > 1e-30 * a * b && a > 1e-30 && b > 1e-30) {
+            const double zeta = (b - a) / (2.0 * c);
+            const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            const double cs = rsqrt(1.0 + t * t), sn = cs * t;
+            if (lane == 0) *flag = 1;
+            for (int r = lane; r < n; r += 32) {
+              const double x = gp[r], y = gq[r];
+              gp[r] = cs * x - sn * y;
+              gq[r] = sn * x + cs * y;
+            }
+            if (J != nullptr) {
+              double *jp = J + (int64_t)p * ldj, *jq = J + (int64_t)q * ldj;
+              for (int r = lane; r < n; r += 32) {
+                const double x = jp[r], y = jq[r];
+                jp[r] = cs * x - sn * y;
+                jq[r] = sn * x + cs * y;
+              }
+            }
+          }
+        }
+        __syncthreads();
+        continue;
+      }
+#endif
+      // simulator path (same arithmetic, shared-memory staging instead of shuffles)
       // circle method: position i of the top row meets position i of the bottom row
       PAR_FOR(item, half * 32) {
         int pr = item >> 5, lane = item & 31;
@@ -166,7 +223,7 @@ TMF_DEVICE void jacobi_onesided(double *G, int ldg, double *J, int ldj, int n, d
           a += pp[0]; b += pp[1]; c += pp[2];
         }
         double cs = 1.0, sn = 0.0;
-        if (c != 0.0 && fabs(c) > 1e-15 * sqrt(a) * sqrt(b)) {
+        if (c * c > 1e-30 * a * b && a > 1e-30 && b > 1e-30) {
           double zeta = (b - a) / (2.0 * c);
           double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
           cs = 1.0 / sqrt(1.0 + t * t);
@@ -187,32 +244,41 @@ TMF_DEVICE void jacobi_onesided(double *G, int ldg, double *J, int ldj, int n, d
           double x = *gp, y = *gq;
           *gp = cs * x - sn * y;
           *gq = sn * x + cs * y;
-          double *jp = J + (int64_t)p * ldj + r, *jq = J + (int64_t)q * ldj + r;
-          x = *jp; y = *jq;
-          *jp = cs * x - sn * y;
-          *jq = sn * x + cs * y;
+          if (J != nullptr) {
+            double *jp = J + (int64_t)p * ldj + r, *jq = J + (int64_t)q * ldj + r;
+            x = *jp; y = *jq;
+            *jp = cs * x - sn * y;
+            *jq = sn * x + cs * y;
+          }
         }
       }
       CTA_SYNC();
     }
     const int any = *flag;
+    sweeps_done = sweep + 1;
     CTA_SYNC();
+#if defined(TMF_HOSTSIM) && defined(TMF_DEBUG_SWEEPS)
+    if (!any || sweep == JAC_MAX_SWEEPS - 1) fprintf(stderr, "jacobi n=%d sweeps=%d\n", n, sweep + 1);
+#endif
     if (!any) break;
   }
   // the product of ~n * sweeps plane rotations drifts from orthonormality by ~1e-14: renormalise the
   // columns of J (first-order repair; the residual non-orthogonality only enters at second order)
-  PAR_FOR(c, n) {
-    double s = 0.0;
-    for (int r = 0; r < n; ++r) s += J[(int64_t)c * ldj + r] * J[(int64_t)c * ldj + r];
-    rot[c] = (s > 0.0) ? 1.0 / sqrt(s) : 1.0;
+  if (J != nullptr) {
+    PAR_FOR(c, n) {
+      double s = 0.0;
+      for (int r = 0; r < n; ++r) s += J[(int64_t)c * ldj + r] * J[(int64_t)c * ldj + r];
+      rot[c] = (s > 0.0) ? 1.0 / sqrt(s) : 1.0;
+    }
+    CTA_SYNC();
+    PAR_FOR(idx, n * n) {
+      int c = idx / n, r = idx - c * n;
+      J[(int64_t)c * ldj + r] *= rot[c];
+      G[(int64_t)c * ldg + r] *= rot[c];
+    }
+    CTA_SYNC();
   }
-  CTA_SYNC();
-  PAR_FOR(idx, n * n) {
-    int c = idx / n, r = idx - c * n;
-    J[(int64_t)c * ldj + r] *= rot[c];
-    G[(int64_t)c * ldg + r] *= rot[c];
-  }
-  CTA_SYNC();
+  return sweeps_done;
 }
 inline size_t jacobi_scratch_doubles(int n) {
   int half = ((n + 1) & ~1) / 2;
@@ -265,13 +331,16 @@ TMF_GLOBAL svd_select_kernel(const SvdSelJob *jobs, double thr, double floor2) {
   double *part = rot + ((n + 1) & ~1);
   int *iw = reinterpret_cast<int *>(part + (((n + 1) & ~1) / 2) * 33 * 3 + 2);
   int *flag = iw, *sel = iw + 2, *rank = sel + n, *cnt = rank + n;
-  double *J = (n > JAC_SMEM_J_MAX) ? jb.Jwork : reinterpret_cast<double *>(cnt + 6);
+  // One-sided Jacobi on the *transposed* triangular factor (Drmac-Veselic): G = Rw^T, G J = U S,
+  // so the normalised columns of the converged G are the right singular vectors of Rw, i.e. the
+  // left singular vectors of W = Q^T B that we need; J itself is never formed.
   PAR_FOR(idx, n * n) {
-    G[idx] = jb.Rw[idx];
-    J[idx] = ((idx / n) == (idx % n)) ? 1.0 : 0.0;
+    int c = idx / n, r = idx - c * n;
+    G[idx] = jb.Rw[(size_t)r * n + c];
   }
   CTA_SYNC();
-  jacobi_onesided(G, n, J, n, n, rot, part, flag);
+  const int sweeps = jacobi_onesided(G, n, nullptr, n, n, rot, part, flag);
+  PAR_FOR(one, 1) jb.info[3] = sweeps;   // diagnostics: Jacobi sweeps of the sketch SVD
   PAR_FOR(c, n) {
     double s = 0.0;
     for (int r = 0; r < n; ++r) s += G[c * n + r] * G[c * n + r];
@@ -284,7 +353,7 @@ TMF_GLOBAL svd_select_kernel(const SvdSelJob *jobs, double thr, double floor2) {
   CTA_SYNC();
   PAR_FOR(idx, n * n) {
     int c = idx / n, r = idx - c * n;
-    if (rank[c] >= 0) jb.Jsel[rank[c] * n + r] = J[idx];
+    if (rank[c] >= 0) jb.Jsel[rank[c] * n + r] = G[idx] / sqrt(s2[c]);
   }
   PAR_FOR(one, 1) {
     *jb.k0_out = *cnt;
@@ -298,7 +367,7 @@ TMF_GLOBAL svd_select_kernel(const SvdSelJob *jobs, double thr, double floor2) {
 }
 inline size_t svdsel_smem_bytes(int n) {
   int np = (n + 1) & ~1;
-  size_t nj = (n > JAC_SMEM_J_MAX) ? 0 : (size_t)n * n;
+  size_t nj = 0;   // the SVD use needs no rotation matrix
   return sizeof(double) * ((size_t)n * n + nj + n + np + (size_t)(np / 2) * 33 * 3 + 2) +
          sizeof(int) * ((size_t)2 * n + 12);
 }
@@ -399,7 +468,8 @@ TMF_GLOBAL pivchol_kernel(const CholJob *jobs, double tol) {
   const int k = jb.info[0];
   DYN_SMEM(double, sm);
   double *d = sm, *col = d + n, *lp = col + n, *red = lp + n + TMF_MAX_MODES;  // red: 64 + 64
-  int *ired = reinterpret_cast<int *>(red + 72);
+  double *psum = red + 72;                                                   // PIVCHOL_MAX_PARTS * n
+  int *ired = reinterpret_cast<int *>(psum + (size_t)PIVCHOL_MAX_PARTS * n);
   const double *U = jb.V;
   double *F = jb.V + (int64_t)k * n;
   PAR_FOR(i, n) {
@@ -435,11 +505,33 @@ TMF_GLOBAL pivchol_kernel(const CholJob *jobs, double tol) {
     if (!(dmax > tol)) break;
     PAR_FOR(m, k + f) lp[m] = (m < k) ? jb.w[m] * U[(int64_t)m * n + p] : F[(int64_t)(m - k) * n + p];
     CTA_SYNC();
-    PAR_FOR(i, n) {
-      double c = jb.A[(int64_t)p * jb.lda + i];
-      for (int m = 0; m < k; ++m) c -= U[(int64_t)m * n + i] * lp[m];
-      for (int m = 0; m < f; ++m) c -= F[(int64_t)m * n + i] * lp[k + m];
-      col[i] = c;
+    // column p of the remaining projector: A[:, p] - [U | F] * lp, the (k + f) columns split over
+    // `parts` thread groups (four independent accumulators each keep several L2 loads in flight)
+    {
+      const int K = k + f;
+      int parts = NTHREADS / ((n + 31) & ~31);
+      parts = parts < 1 ? 1 : (parts > PIVCHOL_MAX_PARTS ? PIVCHOL_MAX_PARTS : parts);
+      const int chunk = (K + parts - 1) / parts;
+      PAR_FOR(item, n * parts) {
+        const int part = item / n, i = item - part * n;
+        const int m0 = part * chunk, m1 = (m0 + chunk < K) ? m0 + chunk : K;
+        double c0 = (part == 0) ? jb.A[(int64_t)p * jb.lda + i] : 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+        int m = m0;
+        for (; m + 3 < m1; m += 4) {
+          c0 -= jb.V[(int64_t)m * n + i] * lp[m];
+          c1 -= jb.V[(int64_t)(m + 1) * n + i] * lp[m + 1];
+          c2 -= jb.V[(int64_t)(m + 2) * n + i] * lp[m + 2];
+          c3 -= jb.V[(int64_t)(m + 3) * n + i] * lp[m + 3];
+        }
+        for (; m < m1; ++m) c0 -= jb.V[(int64_t)m * n + i] * lp[m];
+        psum[part * n + i] = (c0 + c1) + (c2 + c3);
+      }
+      CTA_SYNC();
+      PAR_FOR(i, n) {
+        double c = 0.0;
+        for (int q = 0; q < parts; ++q) c += psum[q * n + i];
+        col[i] = c;
+      }
     }
     CTA_SYNC();
     const double piv = col[p];
@@ -455,7 +547,7 @@ TMF_GLOBAL pivchol_kernel(const CholJob *jobs, double tol) {
   PAR_FOR(one, 1) jb.info[1] = f;
 }
 inline size_t pivchol_smem_bytes(int n) {
-  return sizeof(double) * ((size_t)3 * n + TMF_MAX_MODES + 72) + sizeof(int) * 48;
+  return sizeof(double) * ((size_t)(3 + PIVCHOL_MAX_PARTS) * n + TMF_MAX_MODES + 72) + sizeof(int) * 48;
 }
 
 // ---------------------------------------------------------------------------------------------

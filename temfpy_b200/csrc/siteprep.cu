@@ -14,7 +14,7 @@
 namespace tmf {
 
 int gemm_launch_uploaded(const tmf_gemm_job *jobs_dev, const int *prefix_dev, int njobs, int ntiles,
-                         void *stream);
+                         void *stream, const char *tag);
 
 constexpr int NB = 16;
 static_assert(sizeof(tmf_site_job) == 128, "site descriptor must be 128 bytes");
@@ -237,9 +237,9 @@ extern "C" int tmf_site_overlap_schur_batched(const tmf_site_job *jobs_host, int
   rc = copy_h2d(d + o_pref, prefix.data(), sizeof(int) * (size_t)(nsites + 1), stream);
   if (rc) return rc;
   rc = gemm_launch_uploaded(reinterpret_cast<const tmf_gemm_job *>(d + o_gemm),
-                            reinterpret_cast<const int *>(d + o_pref), nsites, prefix[nsites], stream);
+                            reinterpret_cast<const int *>(d + o_pref), nsites, prefix[nsites], stream, "gemm_site");
   if (rc) return rc;
-  return launch(schur_kernel, nsites, 256, smem, stream,
+  return launch_t("schur", schur_kernel, nsites, 256, smem, stream,
                 reinterpret_cast<const tmf_site_job *>(d + o_site));
 }
 

@@ -28,6 +28,8 @@ class TorchBackend:
         self.torch = torch
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.lib = _lib.load()
+        self.h2d_bytes = 0       # traffic counters (bench.py reports them per step)
+        self.d2h_bytes = 0
 
     def empty(self, n, dtype):
         t = self.torch
@@ -36,12 +38,22 @@ class TorchBackend:
 
     def from_host(self, arr: np.ndarray):
         t = self.torch
-        return t.from_numpy(np.ascontiguousarray(arr)).to(self.device, non_blocking=False)
+        arr = np.ascontiguousarray(arr)
+        self.h2d_bytes += arr.nbytes
+        return t.from_numpy(arr).to(self.device, non_blocking=False)
 
     def to_host(self, buf, n=None) -> np.ndarray:
+        """Device -> pinned host copy.  The returned array aliases a pinned tensor owned by the
+        result (PyTorch's caching host allocator recycles it once the result is dropped)."""
         if n is not None:
             buf = buf[:n]
-        return buf.cpu().numpy()
+        t = self.torch
+        host = t.empty(buf.shape, dtype=buf.dtype, pin_memory=True)
+        host.copy_(buf, non_blocking=True)
+        self.sync()
+        arr = host.numpy()
+        self.d2h_bytes += arr.nbytes
+        return arr
 
     @staticmethod
     def ptr(buf) -> int:
@@ -53,6 +65,18 @@ class TorchBackend:
 
     def sync(self):
         self.torch.cuda.current_stream(self.device).synchronize()
+
+    # side streams for the chunk pipeline (one per worker thread; PyTorch's current stream is
+    # thread-local, so every native call of a worker is enqueued on that worker's stream)
+    def side_stream(self, i):
+        if not hasattr(self, "_streams"):
+            self._streams = {}
+        if i not in self._streams:
+            self._streams[i] = self.torch.cuda.Stream(device=self.device)
+        return self._streams[i]
+
+    def stream_context(self, stream):
+        return self.torch.cuda.stream(stream)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -252,22 +276,104 @@ class SlaterChain:
         return res
 
 
-def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_lo=0, site_hi=None,
-              r_sketch=64, n_threads=0, fetch_tensors=True) -> ChainResult:
-    """C (device) -> Schmidt data of every bond and block-sparse tensor of every site."""
+def _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch, n_threads,
+               fetch_tensors, lazy=False):
     last_err = None
     widths = [r for r in (64, 128, 160) if r > r_sketch]
     for r in [r_sketch] + widths:
-        chain = SlaterChain(backend, L, trunc, n_fermion, ortho_center, site_lo, site_hi, r, n_threads)
+        chain = SlaterChain(backend, L, trunc, n_fermion, ortho_center, lo, hi, r, n_threads)
+        ok = False
         try:
             chain.run_modes(C_dev, ldc)
             chain.run_enumerate()
             chain.run_tensors(C_dev, ldc)
+            if lazy:
+                backend.sync()
+                ok = True
+                return chain
             return chain.collect(fetch_tensors)
-        except ValueError as err:           # sketch too narrow -> widen once (cylinders)
+        except ValueError as err:           # sketch too narrow -> widen (cylinders)
             last_err = err
             if "r_sketch" not in str(err) or r == 160:
                 raise
         finally:
-            chain.close()
+            if not (lazy and ok):
+                chain.close()
     raise last_err
+
+
+class DeviceChainResult:
+    """Result of a conversion that stays resident on the device (tensors in ``chain._buffers['out']``
+    of every chunk, Schmidt tables in the native chain objects); nothing is wrapped until asked."""
+
+    def __init__(self, chains):
+        self.chains = chains
+
+    @property
+    def out_elems(self):
+        return sum(c.out_elems for c in self.chains)
+
+    def out_buffers(self):
+        return [(c._buffers["out"], c.out_elems) for c in self.chains]
+
+    def bond(self, x):
+        for c in self.chains:
+            if c.site_lo <= x <= c.site_hi:
+                return c.bond(x)
+        raise KeyError(x)
+
+    def flops(self):
+        tot = np.zeros(5)
+        for c in self.chains:
+            f = (C.c_double * 8)()
+            check(c.lib, c.lib.tmf_chain_flops(c.handle, f))
+            tot += np.array(f[:5])
+        return tot
+
+    def close(self):
+        for c in self.chains:
+            c.close()
+        self.chains = []
+
+
+def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_lo=0, site_hi=None,
+              r_sketch=64, n_threads=0, fetch_tensors=True, n_chunks=None, lazy=False):
+    """C (device) -> Schmidt data of every bond and block-sparse tensor of every site.
+
+    The site range is cut into cost-balanced chunks that run as a software pipeline: one worker
+    thread and one CUDA stream per chunk, so that the host stages of a chunk (enumeration,
+    planning; the native calls release the GIL) overlap with the kernels of the other chunks.
+    Chunks are independent (same decomposition as the multi-GPU shards, see ``dist.py``)."""
+    from .dist import partition
+    site_hi = L if site_hi is None else site_hi
+    nsites = site_hi - site_lo
+    if n_chunks is None:
+        n_chunks = 4 if (nsites >= 256 and hasattr(backend, "side_stream")) else 1
+    n_chunks = max(1, min(n_chunks, nsites))
+    if n_chunks == 1:
+        r = _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi, r_sketch,
+                       n_threads, fetch_tensors, lazy)
+        return DeviceChainResult([r]) if lazy else r
+    cuts = partition(L, n_chunks, trunc.chi_max, ortho_center, lo=site_lo, hi=site_hi)
+    backend.sync()                       # C_dev must be complete before the side streams read it
+
+    def work(i):
+        lo, hi = cuts[i]
+        with backend.stream_context(backend.side_stream(i)):
+            return _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch,
+                              n_threads, fetch_tensors, lazy)
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=n_chunks) as pool:
+        parts = list(pool.map(work, range(n_chunks)))
+    if lazy:
+        return DeviceChainResult(parts)
+    res = ChainResult(L=L, ortho_center=parts[0].ortho_center, site_lo=site_lo, site_hi=site_hi)
+    for p in parts:
+        res.bonds.update(p.bonds)
+        res.sites.update(p.sites)
+    res.stats = dict(out_elems=sum(p.stats["out_elems"] for p in parts),
+                     nblocks=sum(p.stats["nblocks"] for p in parts),
+                     max_chi=max(p.stats["max_chi"] for p in parts),
+                     njobs=sum(p.stats["njobs"] for p in parts), n_chunks=n_chunks)
+    return res

@@ -121,6 +121,8 @@ def compare_mps(ref: so.DenseMPS, got: so.DenseMPS, trunc, lam_abs=1e-8, noise=N
         a, b = ref.lams[x], got.lams[x]
         if x in amb:
             # everything clearly above the contested multiplet must agree as a multiset
+            # (relative to the largest value: the normalisation depends on which multiplet was kept)
+            a, b = a / a.max(), b / b.max()
             cutv = max(a.min(), b.min()) * (1 + 1e-3)
             sa, sb = np.sort(a[a > cutv])[::-1], np.sort(b[b > cutv])[::-1]
             assert len(sa) == len(sb) and np.all(np.abs(sa - sb) <= 1e-12 * sa + np.minimum(noise / (2 * sa), lam_abs)), \
