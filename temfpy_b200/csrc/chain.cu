@@ -12,8 +12,26 @@
 #include <stdexcept>
 #include <thread>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include "cta.hpp"
 #include "hostlogic.hpp"
+
+namespace {
+struct StageTimer {   // TMF_DEBUG_TIMING=1 prints host-side stage times to stderr
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  StageTimer() : on(std::getenv("TMF_DEBUG_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+  void lap(const char *what) {
+    if (!on) return;
+    auto n = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[tmf timing] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+}  // namespace
 
 namespace tmf {
 int gemm_grouped(const tmf_gemm_job *jobs, int njobs, void *desc_dev, void *stream);
@@ -220,6 +238,7 @@ int tmf_chain_modes(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, d
 // host: enumeration + planning.  Requires tmf_chain_modes to have completed.
 int tmf_chain_enumerate(tmf_chain *c) {
   try {
+    StageTimer tm;
     std::vector<int> used;
     for (int b = 0; b <= c->L; ++b)
       if (c->bonds[b].used) used.push_back(b);
@@ -242,6 +261,7 @@ int tmf_chain_enumerate(tmf_chain *c) {
       const int job = (B.side[TMF_SIDE_L].job >= 0) ? B.side[TMF_SIDE_L].job : B.side[TMF_SIDE_R].job;
       tmf::bond_vectors(c->e_host.data() + (size_t)job * TMF_MAX_MODES, B.k, B.filled_left, c->tp, B.bv);
     });
+    tm.lap("enumerate: bond vectors");
     c->sites.clear();
     for (int i = c->site_lo; i < c->site_hi; ++i) {
       ChainSite s;
@@ -259,6 +279,7 @@ int tmf_chain_enumerate(tmf_chain *c) {
                      bb.bv.masks.data(), bb.bv.charge.data(), kb.k, ks.f, c->nferm,
                      (int)kb.bv.masks.size(), kb.bv.masks.data(), kb.bv.charge.data(), s.plan);
     });
+    tm.lap("enumerate: site plans");
     // offsets
     c->o_elems = c->s_elems = c->out_elems = 0;
     c->nblocks = 0;
@@ -380,8 +401,10 @@ int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev,
   if (!c->enumerated) return fail(TMF_ERR_VALUE, "tmf_chain_enumerate has not run");
   if (plan_bytes < c->plan_bytes) return fail(TMF_ERR_VALUE, "plan workspace too small");
   tmf::Arena ar(plan_dev, plan_bytes);
+  StageTimer tm;
   int rc = centre_pairing(c, C_dev, ldc, V_dev, ar, stream);
   if (rc) return rc;
+  tm.lap("tensors: centre pairing");
   // ---- one blob with every per-site index / sign / mask array ------------------------------
   const int ns = (int)c->sites.size();
   unsigned char *blob_dev = ar.take<unsigned char>(0);
@@ -430,11 +453,16 @@ int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev,
   void *site_desc = ar.take<unsigned char>(tmf_site_desc_bytes(ns));
   void *minor_desc = ar.take<unsigned char>(tmf_minor_desc_bytes((int)mb.size()));
   if (!ar.ok()) return fail(TMF_ERR_VALUE, "plan workspace too small");
+  tm.lap("tensors: build blob");
   rc = tmf::copy_h2d(blob_dev, blob.data(), blob.size(), stream);
   if (rc) return rc;
+  tm.lap("tensors: upload blob");
   rc = tmf_site_overlap_schur_batched(sj.data(), ns, site_desc, stream);
   if (rc) return rc;
-  return tmf_minors_blocks(mb.data(), (int)mb.size(), minor_desc, stream);
+  tm.lap("tensors: enqueue site kernels");
+  rc = tmf_minors_blocks(mb.data(), (int)mb.size(), minor_desc, stream);
+  tm.lap("tensors: enqueue minors");
+  return rc;
 }
 
 // ---- result accessors (host pointers stay valid until tmf_chain_destroy) ----------------------
