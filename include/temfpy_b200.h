@@ -162,7 +162,11 @@ typedef struct tmf_site_job {
   int mode, physical;
   int ka_bra, ka_ket;          /* always orbitals of each side                                */
   int sb, sk;                  /* sometimes orbitals of each side (sb includes the physical)  */
-  int pad_[4];
+  int emb;                     /* 1: Pfaffian path -- rows are re/im-interleaved Majorana components
+                                  (4 per site); bra_cols -1..-4 = emb(w), J emb(w) of the physical
+                                  site's lower mode (c^+ row, pfaffian.py:1667-1688) and the same
+                                  for its upper mode (c row)                                  */
+  int pad_[3];
 } tmf_site_job;
 int64_t tmf_site_desc_bytes(int nsites);   /* size of desc_dev for the call below */
 int tmf_site_overlap_schur_batched(const tmf_site_job *jobs_host, int nsites, void *desc_dev,
@@ -185,6 +189,55 @@ typedef struct tmf_minor_block {
 int64_t tmf_minor_desc_bytes(int nblocks); /* size of desc_dev for the call below */
 int tmf_minors_blocks(const tmf_minor_block *blocks_host, int nblocks, void *desc_dev,
                       void *stream);
+
+
+/* ---- Pfaffian (Bogoliubov) path --------------------------------------------------------------
+ * The Majorana-basis Nambu correlation matrix C_M = 1/2 + iA (pfaffian.py:269-273) is handed to the
+ * library as its real representation P' (re/im interleaved, 4L x 4L real symmetric projector).  The
+ * per-bond eigenproblems (pfaffian.py:789) then run through tmf_slater_modes_batched on P' with the
+ * cuts at 4x; the overlap / Schur stage through tmf_site_overlap_schur_batched with `emb` = 1. */
+
+/* K4p -- complex modes out of the real eigenvectors of P'.  replaces: the complex eigenvectors that
+ * eigh returns at pfaffian.py:789 and the Nambu completion of :886/:891.
+ * For job j (one CTA): V (rows x >=k4, ld) holds the k4 = 4k raw entangled columns of
+ * tmf_slater_modes_batched (ordered by decreasing left eigenvalue, e_raw[k4]); on return columns
+ * 4a..4a+3 are emb(w_a), J emb(w_a), emb(conj w_a), J emb(conj w_a) for the k modes with block
+ * eigenvalue e_out[a] <= 1/2 (ascending).  Eigenvalues within half_tol of 1/2 (pfaffian.py:802-816,
+ * half_tol = degeneracy_tol) span the complexification of a real null space: a real orthonormal
+ * basis r_1..r_2kh is extracted and paired as w_j = (r_j + i r_{kh+j}) / sqrt 2 (pfaffian.py:884);
+ * which real vectors are paired is a gauge choice (the reference shuffles them with a fixed random
+ * orthogonal matrix, :867-874).  tmp: tmf_pair_tmp_doubles(rows) doubles of workspace.
+ * status: 0 ok, 2 bad k4, 3 odd multiplicity, 4 missing plane, 5 asymmetric 1/2 spectrum,
+ * 6 1/2 eigenvectors cannot be made real. */
+typedef struct tmf_pair_job {
+  double *V;
+  double *tmp;
+  const double *e_raw;
+  double *e_out;
+  int *status;
+  int *kh_out;                 /* number of modes with eigenvalue 1/2 (the last kh of the k modes) */
+  int rows, ld, k4, side;
+} tmf_pair_job;
+int64_t tmf_pair_tmp_doubles(int rows);
+int tmf_pfaffian_pair_modes(const tmf_pair_job *jobs_host, int njobs, double half_tol,
+                            void *desc_dev /* 64*njobs */, void *stream);
+
+/* K11 -- all Pfaffians of a (bra excitation number, ket excitation number) block.
+ * replaces: pfaffian.py:1429-1479 (_tensor_block: gather + one pfapack call per entry, :1425).
+ *   out[a * n_ket + c] = scale * Pf(N[idx, idx]),  idx = bits(ket_masks[c]) ++ bits(bra_masks[a])
+ * N: m x m complex128 (re, im interleaved), row-major, antisymmetric; bit t of a mask = index t of
+ * N (ket modes occupy the low indices, pfaffian.py:1400-1408); n1 / n2 = excitations per bra / ket
+ * mask; out is complex128 (interleaved), row-major n_bra x n_ket. */
+typedef struct tmf_pf_block {
+  const double *N;
+  const uint64_t *bra_masks;
+  const uint64_t *ket_masks;
+  double *out;
+  double scale;
+  int m, n_bra, n_ket, n1, n2, pad_;
+} tmf_pf_block;
+int64_t tmf_pf_desc_bytes(int nblocks);
+int tmf_pfaffians_blocks(const tmf_pf_block *blocks_host, int nblocks, void *desc_dev, void *stream);
 
 
 /* Chain driver -- replaces the per-site loop of slater.C_to_MPS (slater.py:1216-1353) for the

@@ -135,8 +135,71 @@ def dump_lowest_sums(ref):
     print("lowest_sums cases", len(cases))
 
 
+def dump_pfaffian_case(ref, name, H, trunc, basis="C"):
+    """Pfaffian path: every number below comes from the reference's own functions
+    (pfaffian.py: correlation_matrix :302, SchmidtVectors.from_correlation_matrix :1216,
+    MPSTensorData.from_schmidt_vectors :1578, _tensor_block :1429).  The pfapack routine
+    (pfaffian.py:1425, absent from the image) is bound to oracle/pfaffian_oracle.pfaffian."""
+    import pfaffian_oracle as po
+    rp = ref.pfaffian
+    rp.cpf = lambda A, **kw: po.pfaffian(A)
+    C = rp.correlation_matrix(H, basis=f"{basis}->{basis}")
+    L = len(C) // 2
+    oc = L // 2
+    data = dict(H=H, C=C, L=L, oc=oc, basis=basis,
+                chi_max=-1 if trunc.get("chi_max") is None else trunc["chi_max"],
+                svd_min=trunc.get("svd_min", 1e-6))
+
+    def put_bond(x, S):
+        data[f"bond{x}_e"] = S.modes.e
+        data[f"bond{x}_lam"] = S.schmidt_values
+        data[f"bond{x}_sets"] = S.left_sets if S.left_sets is not None else S.right_sets[:, ::-1]
+        data[f"bond{x}_pL"] = -1 if S.pL is None else S.pL
+        data[f"bond{x}_pR"] = -1 if S.pR is None else S.pR
+        q = np.zeros(S.n_schmidt, dtype=np.int64)
+        for par, slc in S.idx_parity.items():
+            q[slc] = (par + S.pL) % 2
+        data[f"bond{x}_charge"] = q
+
+    def put_site(i, td, chi_bra, chi_ket):
+        data[f"site{i}_N"] = td.pfaffian_matrix
+        data[f"site{i}_norm"] = td.norm
+        data[f"site{i}_qtotal"] = td.qtotal
+        M = np.zeros((2 * chi_bra, chi_ket), dtype=complex)
+        for n_bra, sb in td.idx_n_bra.items():          # the block loop of pfaffian.py:1766-1776
+            for n_ket, sk in td.idx_n_ket.items():
+                if (n_bra + n_ket) % 2 == 1:
+                    continue
+                M[td.leg_idx_bra[sb], sk] = td.norm * rp._tensor_block(td.pfaffian_matrix, td.new_sets_bra[sb],
+                                                                      td.new_sets_ket[sk])
+        data[f"site{i}_T"] = M.reshape(2, chi_bra, chi_ket)
+
+    centre = rp.SchmidtVectors.from_correlation_matrix(C, oc, trunc, basis=basis)
+    put_bond(oc, centre)
+    parity = centre.parity()
+    prev = centre
+    for i in range(oc, L):
+        new = rp.SchmidtVectors.from_correlation_matrix(C, i + 1, trunc, which="R", basis=basis, total_parity=parity)
+        put_bond(i + 1, new)
+        put_site(i, rp.MPSTensorData.from_schmidt_vectors(new, prev, "right"), new.n_schmidt, prev.n_schmidt)
+        prev = new
+    prev = centre
+    for i in reversed(range(oc)):
+        new = rp.SchmidtVectors.from_correlation_matrix(C, i, trunc, which="L", basis=basis, total_parity=parity)
+        put_bond(i, new)
+        put_site(i, rp.MPSTensorData.from_schmidt_vectors(new, prev, "left"), new.n_schmidt, prev.n_schmidt)
+        prev = new
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **data)
+    print(name, "L", L, "max chi", max(len(data[f"bond{x}_lam"]) for x in range(L + 1)))
+
+
 if __name__ == "__main__":
     ref = ref_shim.load("pass")
+    import pfaffian_oracle as _po
+    dump_pfaffian_case(ref, "pfaffian_random_L8", _po.random_bdg(8, 3, cplx=True), {"chi_max": 1000, "svd_min": 1e-7})
+    dump_pfaffian_case(ref, "pfaffian_random_L9_real", _po.random_bdg(9, 4, cplx=False), {"chi_max": 1000, "svd_min": 1e-7})
+    dump_pfaffian_case(ref, "pfaffian_random_L14_chi20", _po.random_bdg(14, 7, cplx=True), {"chi_max": 20})
+    dump_pfaffian_case(ref, "pfaffian_kitaev_L16", _po.bdg_chain(16, mu=0.0, delta=0.05), {"chi_max": 24})
     dump_case(ref, "slater_random_L12", random_hamiltonian(12, 1), {"chi_max": 1000, "svd_min": 1e-7})
     dump_case(ref, "slater_random_L20_chi24", random_hamiltonian(20, 2), {"chi_max": 24})
     dump_case(ref, "slater_random_L11_N4", random_hamiltonian(11, 3), {"chi_max": 64}, N=4)

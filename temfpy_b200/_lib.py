@@ -44,7 +44,7 @@ class SiteJob(C.Structure):
                 ("O", C.c_void_p), ("S", C.c_void_p), ("det", C.c_void_p),
                 ("ldb", C.c_int), ("ldk", C.c_int), ("n_bra", C.c_int), ("n_ket", C.c_int),
                 ("mode", C.c_int), ("physical", C.c_int), ("ka_bra", C.c_int), ("ka_ket", C.c_int),
-                ("sb", C.c_int), ("sk", C.c_int), ("pad_", C.c_int * 4)]
+                ("sb", C.c_int), ("sk", C.c_int), ("emb", C.c_int), ("pad_", C.c_int * 3)]
 
 
 class MinorBlock(C.Structure):
@@ -54,12 +54,26 @@ class MinorBlock(C.Structure):
                 ("minor", C.c_int), ("pad_", C.c_int)]
 
 
+class PairJob(C.Structure):
+    _fields_ = [("V", C.c_void_p), ("tmp", C.c_void_p), ("e_raw", C.c_void_p), ("e_out", C.c_void_p),
+                ("status", C.c_void_p), ("kh_out", C.c_void_p), ("rows", C.c_int), ("ld", C.c_int),
+                ("k4", C.c_int), ("side", C.c_int)]
+
+
+class PfBlock(C.Structure):
+    _fields_ = [("N", C.c_void_p), ("bra_masks", C.c_void_p), ("ket_masks", C.c_void_p),
+                ("out", C.c_void_p), ("scale", C.c_double),
+                ("m", C.c_int), ("n_bra", C.c_int), ("n_ket", C.c_int), ("n1", C.c_int),
+                ("n2", C.c_int), ("pad_", C.c_int)]
+
+
 class GutzJob(C.Structure):
     _fields_ = [("A", C.c_void_p), ("B", C.c_void_p), ("out", C.c_void_p),
                 ("m", C.c_int), ("k", C.c_int), ("n", C.c_int), ("pad_", C.c_int)]
 
 
 assert C.sizeof(GemmJob) == 128 and C.sizeof(SiteJob) == 128 and C.sizeof(MinorBlock) == 64
+assert C.sizeof(PairJob) == 64 and C.sizeof(PfBlock) == 64
 
 # name -> (restype, argtypes); this table is also what tests check against include/temfpy_b200.h
 SIGNATURES = {
@@ -108,6 +122,10 @@ SIGNATURES = {
     "tmf_launch_count": (C.c_longlong, [C.c_int]),
     "tmf_prof_enable": (C.c_int, [C.c_int]),
     "tmf_prof_report": (C.c_int, [C.c_char_p, C.c_int]),
+    "tmf_pair_tmp_doubles": (C.c_int64, [C.c_int]),
+    "tmf_pfaffian_pair_modes": (C.c_int, [C.POINTER(PairJob), C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
+    "tmf_pf_desc_bytes": (C.c_int64, [C.c_int]),
+    "tmf_pfaffians_blocks": (C.c_int, [C.POINTER(PfBlock), C.c_int, C.c_void_p, C.c_void_p]),
     "tmf_gutzwiller_site": (C.c_int, [C.POINTER(GutzJob), C.c_int, C.c_void_p, C.c_void_p]),
     "tmf_fp64_peak_probe": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_float), c_double_p, C.c_void_p]),
 }

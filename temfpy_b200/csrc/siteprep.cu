@@ -55,17 +55,33 @@ TMF_GLOBAL schur_kernel(const tmf_site_job *jobs) {
     PAR_FOR(one, 1) *jb.det = 1.0;
     return;
   }
-  // physical orbital: <n_i| overlaps = one row of the ket mode matrix (slater.py:1030-1051)
+  // physical orbital: <n_i| overlaps = one row of the ket mode matrix (slater.py:1030-1051); in the
+  // embedded Pfaffian frame (emb) the two physical modes (c^+ / c rows of pfaffian.py:1667-1688) are
+  // fixed combinations of the site's four Majorana components
   if (jb.physical) {
-    const int src = (jb.mode == 1) ? 0 : jb.n_bra;
+    const int unit = jb.emb ? 4 : 1;
+    const int src = ((jb.mode == 1) ? 0 : jb.n_bra) * unit;
     const int nb = jb.ka_bra + jb.sb, nk = jb.ka_ket + jb.sk;
-    int pb = -1;
-    for (int r = 0; r < nb; ++r)
-      if (jb.bra_cols[r] < 0) pb = r;
-    if (pb >= 0) {
+    const double h = 0.70710678118654752440;
+    for (int pb = 0; pb < nb; ++pb) {
+      const int code = jb.bra_cols[pb];
+      if (code >= 0) continue;
+      double cf[4] = {1.0, 0.0, 0.0, 0.0};
+      if (jb.emb) {
+        const int t = -1 - code;   // 0: emb(lo) 1: J emb(lo) 2: emb(up) 3: J emb(up)
+        cf[0] = (t == 0 || t == 2) ? h : 0.0;
+        cf[1] = (t == 1 || t == 3) ? h : 0.0;
+        cf[2] = (t == 1) ? -h : (t == 3 ? h : 0.0);
+        cf[3] = (t == 0) ? h : (t == 2 ? -h : 0.0);
+      }
       PAR_FOR(n, nk) {
         int c = jb.ket_cols[n];
-        double v = (c >= 0) ? jb.Vk[(int64_t)c * jb.ldk + src] : 0.0;
+        double v = 0.0;
+        if (c >= 0) {
+          const double *col = jb.Vk + (int64_t)c * jb.ldk + src;
+          v = cf[0] * col[0];
+          if (jb.emb) v += cf[1] * col[1] + cf[2] * col[2] + cf[3] * col[3];
+        }
         v *= jb.bra_sign[pb] * jb.ket_sign[n];
         if (fr.tr) O[(int64_t)pb * ld + n] = v;
         else O[(int64_t)n * ld + pb] = v;
@@ -205,7 +221,8 @@ extern "C" int tmf_site_overlap_schur_batched(const tmf_site_job *jobs_host, int
     const Frame fr = make_frame(sj);
     tmf_gemm_job &j = g[s];
     std::memset(&j, 0, sizeof(j));
-    const int off = (sj.physical && sj.mode == 1) ? 1 : 0;  // right mode: ket site 0 is the new site
+    const int unit = sj.emb ? 4 : 1;                         // rows per site (Pfaffian frame: 4)
+    const int off = (sj.physical && sj.mode == 1) ? unit : 0;  // right mode: ket site 0 is the new site
     if (!fr.tr) {
       j.A = sj.Vb; j.lda = sj.ldb; j.a_idx = sj.bra_cols; j.row_scale = sj.bra_sign; j.a_row_off = 0;
       j.B = sj.Vk; j.ldb = sj.ldk; j.b_idx = sj.ket_cols; j.col_scale = sj.ket_sign; j.b_row_off = off;
@@ -214,7 +231,7 @@ extern "C" int tmf_site_overlap_schur_batched(const tmf_site_job *jobs_host, int
       j.B = sj.Vb; j.ldb = sj.ldb; j.b_idx = sj.bra_cols; j.col_scale = sj.bra_sign; j.b_row_off = 0;
     }
     j.C = sj.O;
-    j.M = fr.R; j.N = fr.Cc; j.K = sj.n_bra;
+    j.M = fr.R; j.N = fr.Cc; j.K = sj.n_bra * unit;
     j.ldc = fr.R;
     j.transA = 1; j.transB = 0;
     j.alpha = 1.0; j.beta = 0.0;

@@ -151,3 +151,56 @@ def compare_mps(ref: so.DenseMPS, got: so.DenseMPS, trunc, lam_abs=1e-8, noise=N
         report["overlap"] = float(o)
         assert o >= 1 - ov_tol, report
     return report
+
+
+# ---------------------------------------------------------------------------------------------
+# Pfaffian path
+# ---------------------------------------------------------------------------------------------
+def block_mps_to_dense(m) -> so.DenseMPS:
+    """temfpy_b200.mps.BlockMPS -> the oracle's dense container."""
+    return so.DenseMPS(tensors=[m.get_B_dense(i) for i in range(m.L)], lams=list(m.lams), charges=list(m.charges),
+                       form=list(m.form), ortho_center=m.ortho_center)
+
+
+def golden_pf_mps(g) -> so.DenseMPS:
+    """Dense MPS assembled from the reference's own tensors stored in a Pfaffian fixture."""
+    L, oc = int(g["L"]), int(g["oc"])
+    lams = [g[f"bond{x}_lam"] / np.linalg.norm(g[f"bond{x}_lam"]) for x in range(L + 1)]
+    charges = [g[f"bond{x}_charge"] for x in range(L + 1)]
+    tensors = []
+    for i in range(L):
+        T = g[f"site{i}_T"]
+        tensors.append(np.transpose(T, (2, 0, 1)) if i >= oc else np.transpose(T, (1, 0, 2)))
+    return so.DenseMPS(tensors=tensors, lams=lams, charges=charges, form=["A"] * oc + ["B"] * (L - oc),
+                       ortho_center=oc)
+
+
+def compare_pf_mps(ref: so.DenseMPS, got: so.DenseMPS, half_bonds=(), ent_tol=1e-10, ov_tol=1e-10):
+    """Parity gate for the Pfaffian path: bond dimensions and parity sectors identical, Schmidt values within
+    the tolerance model of compare_mps, entropies, normalised overlap.  On bonds that carry modes with
+    eigenvalue exactly 1/2 the vacuum parity is a gauge choice (the reference fixes it through LAPACK's
+    arbitrary basis of the degenerate eigenspace and a random shuffle, pfaffian.py:807-816, :867-874), so
+    the charge table is compared as a multiset there."""
+    L = ref.L
+    noise = 4e-15 * np.sqrt(4 * L)
+    rep = dict(lam_rel=0.0, lam_abs=0.0, gauge_bonds=0)
+    for x in range(L + 1):
+        a, b = ref.lams[x], got.lams[x]
+        assert len(a) == len(b), f"bond {x}: chi {len(b)} != reference {len(a)}"
+        if x in half_bonds:
+            assert np.array_equal(np.sort(ref.charges[x]), np.sort(got.charges[x])), f"bond {x}: parity sectors differ"
+            rep["gauge_bonds"] += int(not np.array_equal(ref.charges[x], got.charges[x]))
+        else:
+            assert np.array_equal(ref.charges[x], got.charges[x]), f"bond {x}: parity sectors differ"
+        tol = 1e-12 * a + np.minimum(noise / (2 * a), 1e-8)
+        assert np.all(np.abs(a - b) <= tol), f"bond {x}: Schmidt values differ by {np.max(np.abs(a - b) / tol)} tol"
+        rep["lam_abs"] = max(rep["lam_abs"], float(np.max(np.abs(a - b))))
+        big = a > 0.05 * a.max()
+        rep["lam_rel"] = max(rep["lam_rel"], float(np.max(np.abs(a[big] - b[big]) / a[big])))
+    assert rep["lam_rel"] < 1e-12, rep
+    rep["entropy"] = float(np.abs(so.entropies(ref.lams) - so.entropies(got.lams)).max())
+    assert rep["entropy"] < ent_tol, rep
+    o = abs(so.mps_overlap(ref, got)) / np.sqrt(abs(so.mps_overlap(ref, ref) * so.mps_overlap(got, got)))
+    rep["overlap"] = float(o)
+    assert o >= 1 - ov_tol, rep
+    return rep
