@@ -210,7 +210,7 @@ def test_gpu_chain_vs_reference_fixture(gpu_backend, name):
 @pytest.mark.gpu
 @pytest.mark.parametrize("H,tp", [
     (po.random_bdg(11, 41), {"chi_max": 4096, "svd_min": 1e-7}),
-    (po.bdg_chain(48, mu=0.4, delta=0.3), {"chi_max": 64}),
+    (po.bdg_chain(48, mu=0.5, delta=0.2), {"chi_max": 64}),
     (po.bdg_chain(64, mu=0.0, delta=0.05), {"chi_max": 64}),
 ])
 def test_gpu_chain_vs_oracle(gpu_backend, H, tp):
