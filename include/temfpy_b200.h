@@ -83,9 +83,16 @@ int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int njobs, con
                              const int64_t *v_off, double *V_dev, double *e_dev, int *info_dev,
                              void *work_dev, int64_t work_bytes, void *stream);
 
-/* centre bond (K4): the pairing of left and right entangled modes -- utils.py:19-96 (block_svd) as
- * called from slater.py:407, and the odd-index sign flips of slater.py:410 -- is part of
- * tmf_chain_tensors (GEMMs V_L^T C_LR V_R on the device, SVD of the k x k degenerate groups). */
+/* K4 -- pairing of the left and right entangled modes of a bond whose two sides were both extracted.
+ * replaces: utils.py:19-96 (block_svd) as called from slater.py:407, and the odd-index sign flips of
+ * slater.py:410.  VL (x rows) / VR (L-x rows): stored mode matrices of the two jobs; their first k
+ * columns are rotated in place (GEMMs V_L^T C_LR V_R on the device, SVD of the degenerate k x k
+ * groups on the host -> one synchronisation).  e_host: the k left eigenvalues (host pointer).
+ * Called by tmf_chain_tensors for the centre bond and by the iMPS driver for its two cuts. */
+int64_t tmf_slater_pair_bond_workspace(int L, int k);
+int tmf_slater_pair_bond(const double *C_dev, int ldc, int L, int x, int k, const double *e_host,
+                         double degeneracy_tol, double *VL_dev, double *VR_dev, void *work_dev,
+                         int64_t work_bytes, void *stream);
 
 /* K6/K7 -- best-first enumeration of the most probable occupation subsets (HOST, multi-threaded
  * over bonds).  replaces: schmidt_utils.py:211-324 (lowest_sums), :99-185 (StoppingCondition

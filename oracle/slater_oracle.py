@@ -562,6 +562,96 @@ def entropies(lams):
     return np.array(out)
 
 
+
+# --------------------------------------------------------------------------------------------
+# infinite MPS from two finite chains (slater.py:1356-1565, iMPS.py:65-192)
+# --------------------------------------------------------------------------------------------
+def basis_rotation(Cm, q_bra, q_ket, S_bra, S_ket, mode="left", form="B"):
+    """iMPS.py:65-192 on a dense overlap ``Cm[bra, ket]`` whose charge blocks are q_bra == q_ket
+    (``npc.svd`` is block-wise: one SVD per charge sector).  Returns (rotation, unitary_error,
+    schmidt_error).  Only the branch used by the mean-field drivers (mode "left") is restated."""
+    assert mode == "left"
+    S_bra, S_ket = np.asarray(S_bra), np.asarray(S_ket)
+    C_Sk = Cm * S_ket[None, :]                                                     # :137
+    err2 = np.sum(S_ket ** 2) - np.sum(np.abs(C_Sk) ** 2)                          # :139
+    unitary_error = 0.0 if err2 < 0 else float(np.sqrt(err2))                      # :141-155
+    if (mode, form) in [("left", "A"), ("right", "B")]:
+        M = C_Sk * S_bra[:, None]                                                  # :168
+    else:
+        M = C_Sk * S_ket[None, :]                                                  # :172
+    R = np.zeros_like(Cm)
+    for q in np.intersect1d(np.unique(q_bra), np.unique(q_ket)):
+        r, c = np.flatnonzero(q_bra == q), np.flatnonzero(q_ket == q)
+        U, _, Vh = np.linalg.svd(M[np.ix_(r, c)], full_matrices=False)
+        R[np.ix_(r, c)] = U @ Vh                                                   # :173
+    if (mode, form) in [("left", "A"), ("right", "B")]:
+        Sb_C = R * S_bra[:, None]
+    else:
+        Sb_C = R * S_ket[None, :]                                                  # :182
+    return R, unitary_error, float(np.linalg.norm(Sb_C - C_Sk))                    # :184
+
+
+@dataclass
+class DenseIMPS:
+    tensors: list          # T[vL, p, vR], right-canonical ("B" form)
+    lams: list             # cell + 1 normalised Schmidt vectors (lams[i] left of site i)
+    charges: list          # cell + 1 int arrays (fermion number left of the bond, minus offset)
+    errors: tuple          # (left_unitary, left_schmidt, 0.0, 0.0)
+    qtotal: list           # charge carried by every tensor
+
+
+def C_to_iMPS(C_short, C_long, trunc, sites_per_cell, cut, spinful=None, offset="auto") -> DenseIMPS:
+    """slater.py:1356-1565 with dense tensors."""
+    trunc = Trunc.make(trunc)
+    if spinful == "simple":                                                        # :1456-1471
+        offset = 2 * round(np.trace(C_short[:cut, :cut]).real) if offset == "auto" else 2 * offset
+        C_short, C_long = spinful_correlation_matrix(C_short, False), spinful_correlation_matrix(C_long, False)
+        sites_per_cell, cut = 2 * sites_per_cell, 2 * cut
+    elif spinful == "PH":
+        C_short, C_long = spinful_correlation_matrix(C_short, True), spinful_correlation_matrix(C_long, True)
+        sites_per_cell, cut = 2 * sites_per_cell, 2 * cut
+    elif spinful is not None:
+        raise ValueError("`spinful` must be 'simple', 'PH', or `None`")
+    assert len(C_short) + sites_per_cell == len(C_long)
+    if offset == "auto":
+        offset = round(np.trace(C_short[:cut, :cut]).real)                         # :1491
+
+    def unit(v):
+        return v / np.linalg.norm(v)
+
+    short = bond_vectors_from_C(C_short, cut, trunc)                               # :1499-1505
+    long_ = bond_vectors_from_C(C_long, cut, trunc)
+    lams, tensors, charges, qtot = [unit(short.lam)], [], [long_.n_left - offset], []
+    prev = long_
+    for i in range(sites_per_cell):                                                # :1509-1537
+        if i == sites_per_cell - 1:
+            new = short
+            lams.append(lams[0])
+        else:
+            new = bond_vectors_from_C(C_long, cut + i + 1, trunc, "R")
+            lams.append(unit(new.lam))
+        td = tensor_data(new, prev, "right")
+        tensors.append(np.transpose(dense_tensor(td), (2, 0, 1)))
+        charges.append(new.n_left - offset)
+        qtot.append(td.qtotal)
+        prev = new
+    td = tensor_data(short, long_, "left")                                         # :1540 (no physical leg)
+    R, uerr, serr = basis_rotation(dense_tensor(td), short.n_left, long_.n_left, short.lam, long_.lam)
+    tensors[0] = np.tensordot(R, tensors[0], axes=(1, 0))                          # :1554
+    charges[0] = short.n_left - offset
+    return DenseIMPS(tensors=tensors, lams=lams, charges=charges, errors=(uerr, serr, 0.0, 0.0), qtotal=qtot)
+
+
+def imps_expectation(imps: DenseIMPS, ops):
+    """<prod_i O_i> over one unit cell of a right-canonical iMPS: ``ops`` = list of 2x2 matrices
+    (one per site; Jordan-Wigner strings are the caller's business)."""
+    lam0 = np.asarray(imps.lams[0])
+    E = np.diag(lam0 ** 2).astype(complex)
+    for T, O in zip(imps.tensors, ops):
+        E = np.einsum("ab,apc,pq,bqd->cd", E, T.conj(), O, T, optimize=True)
+    return np.trace(E)
+
+
 def hopping_chain(L, t=-1.0):
     H = np.zeros((L, L))
     i = np.arange(L - 1)

@@ -88,6 +88,9 @@ SIGNATURES = {
     "tmf_slater_modes_batched": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p,
                                            C.c_double, C.c_int, c_i64_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "tmf_slater_pair_bond_workspace": (C.c_int64, [C.c_int, C.c_int]),
+    "tmf_slater_pair_bond": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, C.c_double,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "tmf_lowest_sums": (C.c_int, [c_double_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double,
                                   c_int_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_u64_p,
                                   c_int_p, c_int_p]),

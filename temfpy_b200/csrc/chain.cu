@@ -304,8 +304,7 @@ int tmf_chain_enumerate(tmf_chain *c) {
               tmf::align256(8 * (int64_t)h.n_rows) + tmf::align256(8 * (int64_t)h.chi_ket);
     }
     const int kc = c->bonds[c->oc].used ? c->bonds[c->oc].k : 0;
-    const int64_t pair = tmf::align256(8 * (int64_t)c->L * (kc + 1)) * 3 + tmf::align256(8 * (int64_t)kc * kc) * 3 +
-                         tmf::gemm_desc_bytes(4) + 4096;
+    const int64_t pair = tmf_slater_pair_bond_workspace(c->L, kc) + 512;
     c->plan_bytes = plan + tmf_site_desc_bytes((int)c->sites.size()) + tmf_minor_desc_bytes(c->nblocks) +
                     pair + 4096;
     c->enumerated = true;
@@ -323,18 +322,27 @@ int tmf_chain_tensor_sizes(tmf_chain *c, int64_t *q) {
   return TMF_OK;
 }
 
-static int centre_pairing(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, tmf::Arena &ar,
-                          void *stream) {
-  ChainBond &B = c->bonds[c->oc];
-  if (!B.used || B.side[0].job < 0 || B.side[1].job < 0 || B.k == 0) return TMF_OK;
-  const int k = B.k, x = c->oc, nL = x, nR = c->L - x;
-  double *VL = V_dev + B.side[TMF_SIDE_L].v_off, *VR = V_dev + B.side[TMF_SIDE_R].v_off;
+int64_t tmf_slater_pair_bond_workspace(int L, int k) {
+  return tmf::align256(8 * (int64_t)L * (k + 1)) * 3 + tmf::align256(8 * (int64_t)k * k) * 3 +
+         tmf::gemm_desc_bytes(4) + 4096;
+}
+
+// K4: pairing of the left and right entangled modes of one bond (utils.py:19-96 as called from
+// slater.py:407, and the sign flips of :410).  Rotates the first k columns of VL (x rows) and VR
+// (L - x rows) in place.  Synchronises once (k x k matrix to the host for the small SVDs).
+int tmf_slater_pair_bond(const double *C_dev, int ldc, int L, int x, int k, const double *e_host,
+                         double degeneracy_tol, double *VL, double *VR, void *work_dev, int64_t work_bytes,
+                         void *stream) {
+  if (k <= 0) return TMF_OK;
+  if (x <= 0 || x >= L) return fail(TMF_ERR_VALUE, "tmf_slater_pair_bond: bond has an empty side");
+  tmf::Arena ar(work_dev, work_bytes);
+  const int nL = x, nR = L - x;
   double *T1 = ar.take<double>((int64_t)nL * k), *tmpL = ar.take<double>((int64_t)nL * k);
   double *tmpR = ar.take<double>((int64_t)nR * k);
   double *M = ar.take<double>((int64_t)k * k), *RotL = ar.take<double>((int64_t)k * k);
   double *RotR = ar.take<double>((int64_t)k * k);
   void *desc = ar.take<unsigned char>(tmf::gemm_desc_bytes(4));
-  if (!ar.ok()) return fail(TMF_ERR_VALUE, "plan workspace too small (pairing)");
+  if (!ar.ok()) return fail(TMF_ERR_VALUE, "workspace too small (pairing)");
   auto mk = [](const double *A, int lda, int tA, const double *Bm, int ldb, double *Cm, int ldc_, int Mm,
                int Nn, int Kk) {
     tmf_gemm_job j;
@@ -353,11 +361,11 @@ static int centre_pairing(tmf_chain *c, const double *C_dev, int ldc, double *V_
   std::vector<double> Mh((size_t)k * k), RL((size_t)k * k, 0.0), RR((size_t)k * k, 0.0);
   rc = tmf::copy_d2h_sync(Mh.data(), M, sizeof(double) * Mh.size(), stream);
   if (rc) return rc;
-  const double *e = c->e_host.data() + (size_t)B.side[TMF_SIDE_L].job * TMF_MAX_MODES;
+  const double *e = e_host;
   int a = 0;
   while (a < k) {  // groups of (nearly) degenerate eigenvalues (utils.py:71-78)
     int b = a + 1;
-    while (b < k && !(std::fabs(e[b] - e[b - 1]) > c->tp.degeneracy_tol)) ++b;
+    while (b < k && !(std::fabs(e[b] - e[b - 1]) > degeneracy_tol)) ++b;
     const int m = b - a;
     std::vector<double> G((size_t)m * m), U, V;
     for (int cc = 0; cc < m; ++cc)
@@ -393,6 +401,19 @@ static int centre_pairing(tmf_chain *c, const double *C_dev, int ldc, double *V_
   if (rc) return rc;
 #endif
   return TMF_OK;
+}
+
+static int centre_pairing(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, tmf::Arena &ar,
+                          void *stream) {
+  ChainBond &B = c->bonds[c->oc];
+  if (!B.used || B.side[0].job < 0 || B.side[1].job < 0 || B.k == 0) return TMF_OK;
+  const int64_t wb = tmf_slater_pair_bond_workspace(c->L, B.k);
+  void *work = ar.take<unsigned char>(wb);
+  if (!ar.ok()) return fail(TMF_ERR_VALUE, "plan workspace too small (pairing)");
+  return tmf_slater_pair_bond(C_dev, ldc, c->L, c->oc, B.k,
+                              c->e_host.data() + (size_t)B.side[TMF_SIDE_L].job * TMF_MAX_MODES,
+                              c->tp.degeneracy_tol, V_dev + B.side[TMF_SIDE_L].v_off,
+                              V_dev + B.side[TMF_SIDE_R].v_off, work, wb, stream);
 }
 
 int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, void *plan_dev,

@@ -1,0 +1,100 @@
+"""slater.C_to_iMPS (reference slater.py:1356-1565, iMPS.py:65-192): oracle known answers, the device
+driver on the CPU simulator and on the GPU."""
+import numpy as np
+import pytest
+
+import slater_oracle as so
+from temfpy_b200 import iMPS, slater
+
+
+def dimer_chain(L, t1=-1.0, t2=-1.5, tnn=0.0):
+    """examples/iMPS_slater.py:6-23 (BASELINE cfg5, iMPS half): dimerised hopping chain.  ``tnn`` adds a
+    next-nearest-neighbour hopping that breaks the particle-hole symmetry (and with it the exact degeneracies
+    of the Schmidt spectrum, see _compare)."""
+    H = np.zeros((L, L))
+    for i in range(L - 1):
+        H[i, i + 1] = H[i + 1, i] = t1 if i % 2 == 0 else t2
+    for i in range(L - 2):
+        H[i, i + 2] = H[i + 2, i] = tnn
+    return H
+
+
+def cell_transfer_eig(A, B):
+    """dominant eigenvalue of the mixed transfer matrix of two unit cells (lists of T[vL, p, vR])."""
+    E = None
+    for Ta, Tb in zip(A, B):
+        M = np.einsum("apc,bpd->abcd", Ta.conj(), Tb).reshape(Ta.shape[0] * Tb.shape[0], Ta.shape[2] * Tb.shape[2])
+        E = M if E is None else E @ M
+    w = np.linalg.eigvals(E)
+    return w[np.argmax(np.abs(w))]
+
+
+def _case(Ls, cell, cut, tp, spinful=None, tnn=0.2):
+    Cs, _ = so.correlation_matrix(dimer_chain(Ls, tnn=tnn))
+    Cl, _ = so.correlation_matrix(dimer_chain(Ls + cell, tnn=tnn))
+    return Cs, Cl, so.C_to_iMPS(Cs, Cl, tp, cell, cut, spinful=spinful)
+
+
+def test_oracle_imps_known_answers():
+    """the unit cell reproduces the bulk correlators of the long chain and is (nearly) unitary-gauged."""
+    Cs, Cl, im = _case(64, 2, 32, {"chi_max": 40}, tnn=0.0)
+    assert im.errors[0] < 1e-3 and im.errors[1] < 1e-3
+    n, I = np.diag([0, 1.0]), np.eye(2)
+    cd = np.array([[0, 0], [1, 0.0]])
+    assert abs(so.imps_expectation(im, [n, I]) - Cl[32, 32]) < 1e-6
+    assert abs(so.imps_expectation(im, [I, n]) - Cl[33, 33]) < 1e-6
+    assert abs(so.imps_expectation(im, [cd, cd.T]) - Cl[32, 33]) < 1e-5
+    assert abs(abs(cell_transfer_eig(im.tensors, im.tensors)) - 1) < 1e-5
+
+
+def _compare(im_ref, mps, err):
+    """NB the test chains break particle-hole symmetry (tnn) to keep the chi_max cut away from (near-)degenerate
+    Schmidt multiplets: there the kept set is
+    decided by the rounding noise of the weakest mode eigenvalues (e ~ 1e-12 known to ~1e-16 absolute),
+    in the reference as much as here, and the two chains of a pair may even truncate differently."""
+    got = [mps.get_B_dense(i) for i in range(mps.L)]
+    assert [len(l) for l in mps.lams] == [len(l) for l in im_ref.lams]
+    for a, b in zip(im_ref.lams, mps.lams):      # tolerance model of helpers.compare_mps
+        assert np.all(np.abs(a - b) <= 1e-12 * a + np.minimum(1e-13 / (2 * a), 1e-8)), np.abs(a - b).max()
+    for a, b in zip(im_ref.charges, mps.charges):
+        assert np.array_equal(a, b)
+    assert mps.meta["qtotal"] == im_ref.qtotal
+    # unitary_error^2 is a difference of O(1) numbers (iMPS.py:139): compare the squares at rounding level
+    assert abs(err.left_unitary ** 2 - im_ref.errors[0] ** 2) < 1e-13 and abs(err.left_schmidt - im_ref.errors[1]) < 1e-9
+    e_mix = cell_transfer_eig(im_ref.tensors, got)
+    e_ref, e_got = cell_transfer_eig(im_ref.tensors, im_ref.tensors), cell_transfer_eig(got, got)
+    fid = abs(e_mix) ** 2 / abs(e_ref * e_got)
+    assert fid >= 1 - 1e-10, fid
+    return fid
+
+
+@pytest.mark.parametrize("Ls,cell,cut,tp,spinful", [(32, 2, 16, {"chi_max": 40}, None),
+                                                    (40, 4, 20, {"chi_max": 64}, None),
+                                                    (20, 2, 10, {"chi_max": 48}, "simple"),
+                                                    (20, 2, 10, {"svd_min": 1e-3}, "PH")])
+def test_sim_imps_vs_oracle(sim_backend, Ls, cell, cut, tp, spinful):
+    Cs, Cl, ref = _case(Ls, cell, cut, tp, spinful)
+    mps, err = slater.C_to_iMPS(Cs, Cl, tp, cell, cut, spinful=spinful, _backend=sim_backend, as_tenpy=False)
+    assert mps.bc == "infinite" and mps.form == ["B"] * mps.L
+    _compare(ref, mps, err)
+
+
+def test_basis_rotation_matches_oracle():
+    rng = np.random.default_rng(3)
+    q = np.array([0, 0, 1, 1, 1, 2])
+    Cm = rng.normal(size=(6, 6)) * (q[:, None] == q[None, :])
+    S = np.sort(rng.uniform(size=6))[::-1]
+    S /= np.linalg.norm(S)
+    R1, u1, s1 = so.basis_rotation(Cm * 0.3, q, q, S, S)
+    R2, u2, s2 = iMPS.basis_rotation(Cm * 0.3, q, q, S, S, "left", unitary_tol=10, schmidt_tol=10)
+    assert np.allclose(R1, R2) and abs(u1 - u2) < 1e-14 and abs(s1 - s2) < 1e-14
+    assert np.allclose(R2 @ R2.T, np.eye(6))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Ls,cell,cut,tp", [(64, 2, 32, {"chi_max": 100}), (128, 2, 64, {"chi_max": 100})])
+def test_gpu_imps_vs_oracle(gpu_backend, Ls, cell, cut, tp):
+    Cs, Cl, ref = _case(Ls, cell, cut, tp)
+    mps, err = slater.C_to_iMPS(Cs, Cl, tp, cell, cut, _backend=gpu_backend, as_tenpy=False)
+    fid = _compare(ref, mps, err)
+    print("iMPS cell fidelity", fid, "errors", err)
