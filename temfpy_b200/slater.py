@@ -54,12 +54,12 @@ def _real_or_raise(M, what):
 
 
 #### High-level functions ####
-def correlation_matrix(H: np.ndarray, N: int | None = None) -> tuple[np.ndarray, int]:
+def correlation_matrix(H: np.ndarray, N: int | None = None, *, _backend=None) -> tuple[np.ndarray, int]:
     r"""Ground-state correlation matrix of a mean-field Hamiltonian (slater.py:1150-1180).
 
     The one-off ``eigh(H)`` (K1) stays on LAPACK like in the reference; the rank-N update
     ``C = Phi Phi^T`` (K2) runs on the DMMA GEMM (``tmf_corr_build``)."""
-    be = _be()
+    be = _backend or _be()
     H = _real_or_raise(H, "Hamiltonian")
     e, v = np.linalg.eigh(H)
     if N is None:
@@ -120,7 +120,7 @@ def _chain_to_mps(res: engine.ChainResult, unit_cell_width) -> BlockMPS:
 
 def C_to_MPS(C: np.ndarray, trunc_par: dict | StoppingCondition, *, diag_tol: float = _DIAG_TOL,
              ortho_center: int = None, spinful: Literal["simple", "PH", None] = None,
-             unit_cell_width: int | None = None, as_tenpy: bool | None = None):
+             unit_cell_width: int | None = None, as_tenpy: bool | None = None, _backend=None):
     r"""MPS representation of a Slater determinant from its correlation matrix
     (slater.py:1216-1353; same parameters)."""
     trunc_par = to_stopping_condition(trunc_par)
@@ -128,7 +128,7 @@ def C_to_MPS(C: np.ndarray, trunc_par: dict | StoppingCondition, *, diag_tol: fl
         unit_cell_width = len(C)
     elif len(C) % unit_cell_width != 0:
         raise ValueError(f"{unit_cell_width = } does not divide system size {len(C)}")
-    be = _be()
+    be = _backend or _be()
     C = _prepare_C(C, spinful)
     _check_projector(C)
     L = len(C)
@@ -142,12 +142,12 @@ def C_to_MPS(C: np.ndarray, trunc_par: dict | StoppingCondition, *, diag_tol: fl
 
 def H_to_MPS(H: np.ndarray, trunc_par: dict | StoppingCondition, *, diag_tol: float = _DIAG_TOL,
              ortho_center: int = None, spinful: Literal["simple", "PH", None] = None,
-             unit_cell_width: int | None = None, as_tenpy: bool | None = None):
+             unit_cell_width: int | None = None, as_tenpy: bool | None = None, _backend=None):
     r"""MPS representation of a Slater determinant from its single body Hamiltonian
     (slater.py:1568-1627)."""
-    C, _ = correlation_matrix(H)
+    C, _ = correlation_matrix(H, _backend=_backend)
     return C_to_MPS(C, trunc_par, diag_tol=diag_tol, ortho_center=ortho_center, spinful=spinful,
-                    unit_cell_width=unit_cell_width, as_tenpy=as_tenpy)
+                    unit_cell_width=unit_cell_width, as_tenpy=as_tenpy, _backend=_backend)
 
 
 #### Schmidt vectors of a single bond ####
@@ -202,6 +202,6 @@ def C_to_iMPS(C_short, C_long, trunc_par, sites_per_cell, cut, **kwargs):
 
 def H_to_iMPS(H_short, H_long, trunc_par, sites_per_cell, cut, **kwargs):
     r"""iMPS representation of a Slater determinant from Hamiltonians (slater.py:1630-1734)."""
-    C_short, _ = correlation_matrix(H_short)
-    C_long, _ = correlation_matrix(H_long)
+    C_short, _ = correlation_matrix(H_short, _backend=kwargs.get("_backend"))
+    C_long, _ = correlation_matrix(H_long, _backend=kwargs.get("_backend"))
     return C_to_iMPS(C_short, C_long, trunc_par, sites_per_cell, cut, **kwargs)

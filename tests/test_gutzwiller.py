@@ -1,0 +1,158 @@
+"""Gutzwiller projection (reference gutzwiller.py:95-486): brute-force known answers on the dense state,
+the device path on the CPU simulator and on the GPU."""
+import itertools
+
+import numpy as np
+import pytest
+
+import slater_oracle as so
+from temfpy_b200 import gutzwiller as gw, slater
+from tests import helpers
+
+
+def fermion_state(H, spinful, tp):
+    C_, _ = so.correlation_matrix(H)
+    return C_, so.mps_to_state(so.C_to_MPS(C_, tp, spinful=spinful))
+
+
+def brute_force(psi, kind):
+    """amplitudes of the fermion state restricted to the allowed pair occupations (gutzwiller.py:104-117 /
+    :294-303); spin index order as documented in temfpy_b200.gutzwiller."""
+    L = psi.ndim // 2
+    occ = {"simple": {0: (1, 0), 1: (0, 1)},      # abrikosov:    up, down
+           "PH": {0: (0, 0), 1: (1, 1)}}[kind]     # abrikosov_ph: down, up
+    out = np.zeros((2,) * L, dtype=complex)
+    for s in itertools.product((0, 1), repeat=L):
+        out[s] = psi[tuple(x for sj in s for x in occ[sj])]
+    return out
+
+
+def spin_ops(kind):
+    up, dn = (0, 1) if kind == "simple" else (1, 0)
+    Sz = np.zeros((2, 2)); Sz[up, up], Sz[dn, dn] = 0.5, -0.5
+    Sp = np.zeros((2, 2)); Sp[up, dn] = 1.0
+    return Sz, Sp, Sp.T
+
+
+def heisenberg_bonds(phi, kind):
+    L = phi.ndim
+    phi = phi / np.linalg.norm(phi)
+    Sz, Sp, Sm = spin_ops(kind)
+
+    def apply(op, i, v):
+        return np.moveaxis(np.tensordot(op, v, axes=(1, i)), 0, i)
+    out = []
+    for i in range(L - 1):
+        e = np.vdot(phi, apply(Sz, i, apply(Sz, i + 1, phi)))
+        e += 0.5 * np.vdot(phi, apply(Sp, i, apply(Sm, i + 1, phi)))
+        e += 0.5 * np.vdot(phi, apply(Sm, i, apply(Sp, i + 1, phi)))
+        out.append(e.real)
+    return np.array(out)
+
+
+def spin_state(m):
+    """dense state of a finite spin BlockMPS (right-canonical or bare)."""
+    psi = np.ones((1, 1), dtype=complex)
+    for i in range(m.L):
+        T = m.get_B_dense(i)
+        psi = np.tensordot(psi, T, axes=(1, 0)).reshape(-1, T.shape[2])
+    return psi.reshape((2,) * m.L)
+
+
+def test_brute_force_known_answers():
+    """both conventions give the same singlet with the listed bond energies."""
+    H = so.hopping_chain(6)
+    tp = {"chi_max": 4096, "svd_min": 1e-7}
+    want = np.array([-0.7024, -0.2055, -0.6640, -0.2055, -0.7024])
+    for kind in ("simple", "PH"):
+        _, psi = fermion_state(H, kind, tp)
+        phi = brute_force(psi, kind)
+        assert abs(np.linalg.norm(phi) ** 2 - 0.084184) < 1e-6
+        assert np.abs(heisenberg_bonds(phi, kind) - want).max() < 1e-4
+
+
+def _check(be, L, kind, tp, canonical):
+    H = so.hopping_chain(L)
+    C_, psi = fermion_state(H, kind, tp)
+    phi = brute_force(psi, kind)
+    fm = slater.C_to_MPS(C_, tp, spinful=kind, _backend=be, as_tenpy=False)
+    fn = gw.abrikosov if kind == "simple" else gw.abrikosov_ph
+    sm = fn(fm, return_canonical=canonical, _backend=be)
+    got = spin_state(sm)
+    ov = abs(np.vdot(phi, got)) / (np.linalg.norm(phi) * np.linalg.norm(got))
+    assert ov > 1 - 1e-10, ov
+    if canonical:
+        assert abs(np.linalg.norm(got) - 1) < 1e-12
+        for i in range(sm.L):       # right-canonical
+            T = sm.get_B_dense(i)
+            e = np.einsum("apc,bpc->ab", T, T.conj())
+            assert np.abs(e - np.eye(len(e))).max() < 1e-12
+        for lam in sm.lams:
+            assert abs(np.linalg.norm(lam) - 1) < 1e-12
+        if kind == "PH":            # 2Sz charges: q(vL) + q_p = q(vR), total Sz = 0
+            qp = np.array([-1, 1])
+            for i in range(sm.L):
+                T = sm.get_B_dense(i)
+                a, p, b = np.nonzero(np.abs(T) > 1e-14)
+                assert np.all(sm.charges[i][a] + qp[p] == sm.charges[i + 1][b])
+            assert np.all(sm.charges[0] == 0) and np.all(sm.charges[sm.L] == 0)
+    else:
+        assert abs(np.linalg.norm(got) - np.linalg.norm(phi)) < 1e-10 * np.linalg.norm(phi) + 1e-13
+    return sm
+
+
+@pytest.mark.parametrize("L,kind,canonical", [(6, "simple", True), (6, "PH", True), (8, "PH", False),
+                                              (8, "simple", False), (10, "PH", True)])
+def test_sim_projection_vs_brute_force(sim_backend, L, kind, canonical):
+    if L % 2 and kind == "simple":
+        pytest.skip("odd L has no half filling")
+    _check(sim_backend, L, kind, {"chi_max": 4096, "svd_min": 1e-7}, canonical)
+
+
+def test_sim_ortho_center_inside_pair(sim_backend):
+    """Schmidt values of the centre bond inside a pair (odd ortho_center)."""
+    H = so.hopping_chain(6)
+    tp = {"chi_max": 4096, "svd_min": 1e-7}
+    C_, psi = fermion_state(H, "PH", tp)
+    phi = brute_force(psi, "PH")
+    for oc in (5, 4, 7):
+        fm = slater.C_to_MPS(C_, tp, spinful="PH", ortho_center=oc, _backend=sim_backend, as_tenpy=False)
+        got = spin_state(gw.abrikosov_ph(fm, _backend=sim_backend))
+        assert abs(np.vdot(phi, got)) / np.linalg.norm(phi) > 1 - 1e-10
+
+
+def test_sim_validation(sim_backend):
+    C_, _ = so.correlation_matrix(so.hopping_chain(5))
+    fm = slater.C_to_MPS(C_, {"chi_max": 64}, _backend=sim_backend, as_tenpy=False)
+    with pytest.raises(AssertionError):
+        gw.abrikosov(fm, _backend=sim_backend)            # odd length
+    C_, n = so.correlation_matrix(so.hopping_chain(6), N=2)
+    fm = slater.C_to_MPS(C_, {"chi_max": 64}, _backend=sim_backend, as_tenpy=False)
+    with pytest.raises(AssertionError):
+        gw.abrikosov(fm, _backend=sim_backend)            # 2 fermions on 3 spin sites
+    with pytest.raises(NotImplementedError):
+        gw.abrikosov_ph(fm, inplace=True, _backend=sim_backend)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,kind", [(8, "simple"), (8, "PH"), (10, "PH")])
+def test_gpu_projection_vs_brute_force(gpu_backend, L, kind):
+    _check(gpu_backend, L, kind, {"chi_max": 4096, "svd_min": 1e-7}, True)
+
+
+@pytest.mark.gpu
+def test_gpu_cfg3_heisenberg_L64(gpu_backend):
+    """BASELINE configs[2] at reduced length (the dense brute force is impossible at L=256): Gutzwiller-projected
+    half-filled Fermi sea, both conventions must give the same spin state, a singlet."""
+    L, tp = 64, {"chi_max": 256}
+    H = so.hopping_chain(L)
+    C_, _ = so.correlation_matrix(H)
+    a = gw.abrikosov(slater.C_to_MPS(C_, tp, spinful="simple", _backend=gpu_backend, as_tenpy=False), _backend=gpu_backend)
+    b = gw.abrikosov_ph(slater.C_to_MPS(C_, tp, spinful="PH", _backend=gpu_backend, as_tenpy=False), _backend=gpu_backend)
+    # overlap of the two spin MPS; index maps: abrikosov 0 = up, abrikosov_ph 1 = up
+    E = np.ones((1, 1))
+    for i in range(L):
+        E = np.einsum("ab,apc,bpd->cd", E, a.get_B_dense(i), b.get_B_dense(i)[:, ::-1, :], optimize=True)
+    assert abs(abs(E[0, 0]) - 1) < 1e-6, E
+    assert max(a.chi) <= 256 and max(b.chi) <= 256
+    print("cfg3-like chi_proj:", max(a.chi), max(b.chi), "overlap", abs(E[0, 0]))
