@@ -179,6 +179,39 @@ static double numpy_sum(const double *v, int n) {
   return res;
 }
 
+// Mode weights a_i = log((1-e_i)/e_i)/2 amplify the rounding error of the eigenvalue by 1/(2 e (1-e)):
+// for weak modes (e or 1-e ~ 1e-8) two eigenvalues that are equal by symmetry (spin partners of a
+// spinful chain, particle-hole partners) come out with |a| differing by ~1e-8, far above
+// degeneracy_tol, and the chi_max cut may then split their Schmidt multiplet -- which side survives
+// is rounding noise (in the reference it is LAPACK's noise) and can leave neighbouring
+// bonds with incompatible vector sets.  Weights that are indistinguishable within the eigenvalue
+// accuracy (4e-15 absolute, the calibrated noise of the mode solver) are therefore set to their
+// common mean before the enumeration, so that `truncate` sees the multiplets as the exact
+// degeneracies they are.  Well-conditioned weights are untouched (tolerance 1.6e-14 at e = 1/2).
+void snap_degenerate(double *a, const double *e, int k) {
+  std::vector<int> ord(k);
+  for (int i = 0; i < k; ++i) ord[i] = i;
+  std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return std::fabs(a[x]) < std::fabs(a[y]); });
+  auto tol = [&](int i) {
+    const double w = e[i] * (1.0 - e[i]);
+    return (w > 0.0) ? 4e-15 / (2.0 * w) : 0.0;
+  };
+  int s0 = 0;
+  while (s0 < k) {
+    int s1 = s0 + 1;
+    while (s1 < k && std::fabs(a[ord[s1]]) - std::fabs(a[ord[s1 - 1]]) <=
+                         std::max(tol(ord[s1]), tol(ord[s1 - 1])))
+      ++s1;
+    if (s1 - s0 > 1) {
+      double mean = 0.0;
+      for (int t = s0; t < s1; ++t) mean += std::fabs(a[ord[t]]);
+      mean /= (s1 - s0);
+      for (int t = s0; t < s1; ++t) a[ord[t]] = (a[ord[t]] < 0) ? -mean : mean;
+    }
+    s0 = s1;
+  }
+}
+
 void bond_vectors(const double *e, int k, int filled_left, const TruncPar &tp, BondVectors &out) {
   out.k = k;
   out.filled_left = filled_left;
@@ -187,6 +220,10 @@ void bond_vectors(const double *e, int k, int filled_left, const TruncPar &tp, B
     a[i] = std::log((1.0 - e[i]) / e[i]) / 2;  // slater.py:428, :663
     if (a[i] < 0) negs.push_back(a[i]);
   }
+  snap_degenerate(a.data(), e, k);
+  negs.clear();
+  for (int i = 0; i < k; ++i)
+    if (a[i] < 0) negs.push_back(a[i]);
   double base = numpy_sum(negs.data(), (int)negs.size());
   std::vector<double> sums;
   std::vector<uint64_t> sets;

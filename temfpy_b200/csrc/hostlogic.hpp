@@ -34,6 +34,9 @@ struct BondVectors {
   std::vector<int> sec_q, sec_start;  // sector table (sec_start has one extra entry)
 };
 
+// symmetrises weights that are equal within the accuracy of the eigenvalues (see hostlogic.cpp)
+void snap_degenerate(double *a, const double *e, int k);
+
 // slater.py:633-700 on top of lowest_sums; e = left eigenvalues of the entangled modes.
 void bond_vectors(const double *e, int k, int filled_left, const TruncPar &tp, BondVectors &out);
 

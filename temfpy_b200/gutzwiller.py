@@ -173,6 +173,15 @@ def _project(mps: BlockMPS, rules, keep, be):
     return tensors, keepers, len(jobs)
 
 
+def _svd(M):
+    """LAPACK gesdd with the gesvd fallback (gesdd occasionally fails to converge on graded matrices)."""
+    try:
+        return np.linalg.svd(M, full_matrices=False)
+    except np.linalg.LinAlgError:
+        from scipy.linalg import svd
+        return svd(M, full_matrices=False, lapack_driver="gesvd")
+
+
 def _canonical_form_finite(tensors, qs, qp, cutoff):
     """Right-canonical form of a finite MPS given by bare tensors ``T[vL, p, vR]`` (the job of
     ``canonical_form_finite`` at gutzwiller.py:266 / :471), block-wise in the charges: ``qs[j]`` flat charges
@@ -204,7 +213,7 @@ def _canonical_form_finite(tensors, qs, qp, cutoff):
             Rf[o: o + w, c] = R
             o += w
         T[j] = Qf.reshape(a, d, k)
-        T[j + 1] = np.tensordot(Rf, T[j + 1], axes=(1, 0))
+        T[j + 1] = np.tensordot(Rf / np.linalg.norm(Rf), T[j + 1], axes=(1, 0))   # the norm is fixed at the end
         qs[j + 1] = np.array(newq, dtype=np.int64)
     # right-to-left SVD sweep -> right-canonical + Schmidt values
     lams = [None] * (L + 1)
@@ -220,7 +229,7 @@ def _canonical_form_finite(tensors, qs, qp, cutoff):
             r, c = np.flatnonzero(qs[j] == q), np.flatnonzero(colq == q)
             if c.size == 0:
                 continue
-            U, S, Vh = np.linalg.svd(M[np.ix_(r, c)], full_matrices=False)
+            U, S, Vh = _svd(M[np.ix_(r, c)])
             keep = S > cutoff
             parts.append((r, c, U[:, keep], S[keep], Vh[keep]))
             newq += [q] * int(keep.sum())

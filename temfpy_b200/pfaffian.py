@@ -46,7 +46,7 @@ import numpy as np
 from . import _lib, engine, iMPS as _iMPS
 from ._lib import check
 from .mps import BlockMPS
-from .schmidt_utils import StoppingCondition, lowest_sums, to_stopping_condition
+from .schmidt_utils import StoppingCondition, lowest_sums, snap_degenerate, to_stopping_condition
 from .testing import _DIAG_TOL, assert_allclose, assert_array_less
 from .utils import HT, normalize_SV
 
@@ -373,7 +373,7 @@ class _PfChain:
                 assert k == kr, "Unequal number of entangled modes"                          # pfaffian.py:842
                 assert_allclose(e, er, rtol=0, atol=max(self.tp.degeneracy_tol, 1e-13),
                                 err_msg="Eigenvalues of C_LL and C_RR do not match")         # :848-849
-            a = np.log((1 - e) / e) / 2                                                      # :925, :1189
+            a = snap_degenerate(np.log((1 - e) / e) / 2, e)                                  # :925, :1189
             _, sets = lowest_sums(a, self.tp, _lib_override=self.lib)
             if len(sets) == 0:
                 raise ValueError("No Schmidt vectors left after filtering by `trunc_par.sectors`!")

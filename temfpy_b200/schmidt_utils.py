@@ -130,3 +130,29 @@ def lowest_sums(a, trunc_par: StoppingCondition, *, filled_left=None, filled_rig
     m = sets[: n.value]
     bits = ((m[:, None] >> np.arange(k, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(bool)
     return sums[: n.value].copy(), bits.reshape(n.value, k)
+
+
+def snap_degenerate(a: np.ndarray, e: np.ndarray) -> np.ndarray:
+    """Mode weights that are equal within the accuracy of the eigenvalues ``e`` (4e-15 absolute, amplified
+    by ``1 / (2 e (1 - e))`` in ``a = log((1 - e) / e) / 2``) are set to their common mean, so that the
+    truncation sees symmetry-related Schmidt multiplets as exact degeneracies instead of splitting them by
+    rounding noise (same rule as ``tmf::snap_degenerate`` in csrc/hostlogic.cpp, which the Slater chain
+    driver applies; see DESIGN.md "Truncation at noise-level degeneracies")."""
+    a = np.array(a, dtype=np.float64)
+    e = np.asarray(e, dtype=np.float64)
+    k = a.size
+    if k < 2:
+        return a
+    w = e * (1.0 - e)
+    tol = np.where(w > 0, 4e-15 / (2.0 * np.where(w > 0, w, 1.0)), 0.0)
+    order = np.argsort(np.abs(a), kind="stable")
+    s0 = 0
+    while s0 < k:
+        s1 = s0 + 1
+        while s1 < k and abs(a[order[s1]]) - abs(a[order[s1 - 1]]) <= max(tol[order[s1]], tol[order[s1 - 1]]):
+            s1 += 1
+        if s1 - s0 > 1:
+            idx = order[s0:s1]
+            a[idx] = np.sign(a[idx]) * np.abs(a[idx]).mean()
+        s0 = s1
+    return a

@@ -47,6 +47,18 @@ def test_oracle_imps_known_answers():
     assert abs(abs(cell_transfer_eig(im.tensors, im.tensors)) - 1) < 1e-5
 
 
+def clean_chi(Cs, Cl, cell, cut, target, spinful=None):
+    """a chi_max near ``target`` whose cut falls into a clear gap (> 5 % in lambda) of the Schmidt spectrum of
+    every bond involved, so that the kept sets do not depend on rounding noise (see _compare)."""
+    big = so.C_to_iMPS(Cs, Cl, {"chi_max": target + 24}, cell, cut, spinful=spinful)
+    spectra = [np.sort(l)[::-1] for l in big.lams]
+    for d in range(0, 20):
+        for chi in (target + d, target - d):
+            if all(len(l) > chi and l[chi - 1] / l[chi] > 1.05 for l in spectra):
+                return chi
+    raise RuntimeError(f"no clean cut found near {target}: {[len(l) for l in spectra]}")
+
+
 def _compare(im_ref, mps, err):
     """NB the test chains break particle-hole symmetry (tnn) to keep the chi_max cut away from (near-)degenerate
     Schmidt multiplets: there the kept set is
@@ -68,11 +80,11 @@ def _compare(im_ref, mps, err):
     return fid
 
 
-@pytest.mark.parametrize("Ls,cell,cut,tp,spinful", [(32, 2, 16, {"chi_max": 40}, None),
-                                                    (40, 4, 20, {"chi_max": 64}, None),
-                                                    (20, 2, 10, {"chi_max": 48}, "simple"),
-                                                    (20, 2, 10, {"svd_min": 1e-3}, "PH")])
-def test_sim_imps_vs_oracle(sim_backend, Ls, cell, cut, tp, spinful):
+@pytest.mark.parametrize("Ls,cell,cut,target,spinful", [(32, 2, 16, 40, None), (40, 4, 20, 56, None),
+                                                        (20, 2, 10, 40, "simple"), (20, 2, 10, 40, "PH")])
+def test_sim_imps_vs_oracle(sim_backend, Ls, cell, cut, target, spinful):
+    Cs, Cl, _ = _case(Ls, cell, cut, {"chi_max": 8}, spinful)
+    tp = {"chi_max": clean_chi(Cs, Cl, cell, cut, target, spinful)}
     Cs, Cl, ref = _case(Ls, cell, cut, tp, spinful)
     mps, err = slater.C_to_iMPS(Cs, Cl, tp, cell, cut, spinful=spinful, _backend=sim_backend, as_tenpy=False)
     assert mps.bc == "infinite" and mps.form == ["B"] * mps.L
@@ -92,8 +104,10 @@ def test_basis_rotation_matches_oracle():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("Ls,cell,cut,tp", [(64, 2, 32, {"chi_max": 100}), (128, 2, 64, {"chi_max": 100})])
-def test_gpu_imps_vs_oracle(gpu_backend, Ls, cell, cut, tp):
+@pytest.mark.parametrize("Ls,cell,cut,target", [(64, 2, 32, 100), (128, 2, 64, 100)])
+def test_gpu_imps_vs_oracle(gpu_backend, Ls, cell, cut, target):
+    Cs, Cl, _ = _case(Ls, cell, cut, {"chi_max": 8})
+    tp = {"chi_max": clean_chi(Cs, Cl, cell, cut, target)}
     Cs, Cl, ref = _case(Ls, cell, cut, tp)
     mps, err = slater.C_to_iMPS(Cs, Cl, tp, cell, cut, _backend=gpu_backend, as_tenpy=False)
     fid = _compare(ref, mps, err)
