@@ -104,10 +104,11 @@ def test_basis_rotation_matches_oracle():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("Ls,cell,cut,target", [(64, 2, 32, 100), (128, 2, 64, 100)])
-def test_gpu_imps_vs_oracle(gpu_backend, Ls, cell, cut, target):
-    Cs, Cl, _ = _case(Ls, cell, cut, {"chi_max": 8})
-    tp = {"chi_max": clean_chi(Cs, Cl, cell, cut, target)}
+@pytest.mark.parametrize("Ls,cell,cut,tp", [(64, 2, 32, {"chi_max": 200}), (128, 2, 64, {"chi_max": 200}),
+                                            (96, 4, 48, {"chi_max": 200, "svd_min": 1e-5})])
+def test_gpu_imps_vs_oracle(gpu_backend, Ls, cell, cut, tp):
+    """chi_max does not bind here (the gapped chain has ~40 Schmidt values above svd_min): the cut is set by the
+    dynamic-range rule, away from the heavily degenerate multiplets of this spectrum."""
     Cs, Cl, ref = _case(Ls, cell, cut, tp)
     mps, err = slater.C_to_iMPS(Cs, Cl, tp, cell, cut, _backend=gpu_backend, as_tenpy=False)
     fid = _compare(ref, mps, err)
