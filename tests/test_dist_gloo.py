@@ -1,0 +1,66 @@
+"""N > 1 path on CPU: two processes, gloo backend, the kernels executed by the CPU simulator.
+Checks the plumbing of temfpy_b200.dist (partition, broadcast of C, gather of the block-sparse tensors)
+and that the sharded conversion equals the unsharded one bit for bit."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, L, chi, out_path):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import slater_oracle as so
+        from temfpy_b200 import dist as tdist, engine
+        from temfpy_b200.schmidt_utils import to_stopping_condition
+        from tests import helpers
+        from tests.hostsim import NumpyBackend
+        be = NumpyBackend()
+        tp = to_stopping_condition({"chi_max": chi})
+        Ct = torch.zeros(L * L, dtype=torch.float64)
+        n = torch.zeros(1, dtype=torch.int64)
+        if rank == 0:
+            Cm, nf = so.correlation_matrix(helpers.random_hamiltonian(L, 12))
+            Ct.copy_(torch.from_numpy(Cm.ravel()))
+            n[0] = nf
+        tdist.broadcast_C(Ct)                       # C to every rank
+        dist.broadcast(n, src=0)
+        lo, hi = tdist.partition(L, world, chi)[rank]
+        res = engine.run_chain(be, Ct.numpy(), L, L, tp, int(n[0]), site_lo=lo, site_hi=hi, n_chunks=1, lazy=True)
+        buf, elems = res.out_buffers()[0]
+        full, offs = tdist.gather_tensors(torch.from_numpy(buf), elems)       # tensors to rank 0
+        lam = [res.bond(x).schmidt_values for x in range(lo, hi + 1)]
+        if rank == 0:
+            ref = engine.run_chain(be, Ct.numpy(), L, L, tp, int(n[0]), n_chunks=1, lazy=True)
+            rbuf, relems = ref.out_buffers()[0]
+            ok = int(offs[-1]) == relems and np.array_equal(full.numpy(), rbuf[:relems])
+            ok = ok and all(np.array_equal(a, ref.bond(x).schmidt_values) for x, a in zip(range(lo, hi + 1), lam))
+            np.save(out_path, np.array([int(ok), int(offs[-1]), relems]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("L,chi", [(24, 16)])
+def test_two_rank_gloo_sharding(tmp_path, L, chi):
+    out = str(tmp_path / "ok.npy")
+    mp.spawn(_worker, args=(2, _free_port(), L, chi, out), nprocs=2, join=True)
+    ok, gathered, ref = np.load(out)
+    assert ok == 1 and gathered == ref > 0
