@@ -294,6 +294,7 @@ int tmf_gutzwiller_site(const tmf_gutz_job *jobs_host, int njobs, void *desc_dev
 long long tmf_launch_count(int reset);
 int tmf_prof_enable(int on);
 int tmf_prof_report(char *buf, int cap);
+int tmf_prof_timeline(char *buf, int cap);   /* "tag stream start_ms end_ms" per launch */
 
 /* FP64 peak probe used by bench.py for the roofline denominator: runs `iters` dependent-free
  * DFMA chains on every SM and returns the elapsed ms through *ms_out (synchronises). */

@@ -125,6 +125,7 @@ SIGNATURES = {
     "tmf_launch_count": (C.c_longlong, [C.c_int]),
     "tmf_prof_enable": (C.c_int, [C.c_int]),
     "tmf_prof_report": (C.c_int, [C.c_char_p, C.c_int]),
+    "tmf_prof_timeline": (C.c_int, [C.c_char_p, C.c_int]),
     "tmf_pair_tmp_doubles": (C.c_int64, [C.c_int]),
     "tmf_pfaffian_pair_modes": (C.c_int, [C.POINTER(PairJob), C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "tmf_pf_desc_bytes": (C.c_int64, [C.c_int]),

@@ -71,6 +71,7 @@ struct tmf_chain {
   int64_t o_elems = 0, s_elems = 0, out_elems = 0, plan_bytes = 0;
   int nblocks = 0, max_chi = 0;
   bool enumerated = false;
+  std::vector<unsigned char> blob;   // staging of the per-site plan arrays (reused across calls)
 };
 
 namespace {
@@ -427,55 +428,72 @@ int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev,
   if (rc) return rc;
   tm.lap("tensors: centre pairing");
   // ---- one blob with every per-site index / sign / mask array ------------------------------
+  // pass 1 (serial, cheap): offsets of every array; pass 2 (threads over sites): copy + descriptors
   const int ns = (int)c->sites.size();
   unsigned char *blob_dev = ar.take<unsigned char>(0);
-  std::vector<unsigned char> blob;
-  auto add = [&](const void *p, size_t bytes) {
-    size_t off = (blob.size() + 255) & ~size_t(255);
-    blob.resize(off + bytes);
-    if (bytes) std::memcpy(blob.data() + off, p, bytes);
-    return blob_dev + off;
+  struct SiteOff { size_t bc, kc, bs, ks, bm, km; int mb0; };
+  std::vector<SiteOff> so(ns);
+  size_t bsz = 0;
+  int nmb = 0;
+  auto reserve = [&](size_t bytes) {
+    size_t off = (bsz + 255) & ~size_t(255);
+    bsz = off + bytes;
+    return off;
   };
-  std::vector<tmf_site_job> sj(ns);
-  std::vector<tmf_minor_block> mb;
-  mb.reserve(c->nblocks);
   for (int u = 0; u < ns; ++u) {
+    const tmf_site_plan &h = c->sites[u].plan.h;
+    const int sb0 = h.s_bra - (h.ka_bra - h.k_always), sk0 = h.s_ket - (h.ka_ket - h.k_always);
+    const size_t rows = (size_t)(h.ka_bra + sb0), cols = (size_t)(h.ka_ket + sk0);
+    so[u].bc = reserve(4 * rows); so[u].kc = reserve(4 * cols);
+    so[u].bs = reserve(8 * rows); so[u].ks = reserve(8 * cols);
+    so[u].bm = reserve(8 * (size_t)h.n_rows); so[u].km = reserve(8 * (size_t)h.chi_ket);
+    so[u].mb0 = nmb;
+    nmb += h.n_blocks;
+  }
+  std::vector<unsigned char> &blob = c->blob;
+  if (blob.size() < bsz) blob.resize(bsz);
+  std::vector<tmf_site_job> sj(ns);
+  std::vector<tmf_minor_block> mb(nmb);
+  parallel_for(ns, c->n_threads, [&](int u) {
     ChainSite &s = c->sites[u];
     const tmf_site_plan &h = s.plan.h;
     const int side = s.mode == 1 ? TMF_SIDE_R : TMF_SIDE_L;
     const ChainSide &bs = c->bonds[s.bra_bond].side[side], &ks = c->bonds[s.ket_bond].side[side];
     const int sb0 = h.s_bra - (h.ka_bra - h.k_always), sk0 = h.s_ket - (h.ka_ket - h.k_always);
     const int rows = h.ka_bra + sb0, cols = h.ka_ket + sk0;
+    auto put = [&](size_t off, const void *p, size_t bytes) {
+      if (bytes) std::memcpy(blob.data() + off, p, bytes);
+      return blob_dev + off;
+    };
     tmf_site_job &j = sj[u];
     std::memset(&j, 0, sizeof(j));
     j.Vb = V_dev + bs.v_off; j.Vk = V_dev + ks.v_off;
     j.ldb = std::max(bs.n, 1); j.ldk = std::max(ks.n, 1);
-    j.bra_cols = reinterpret_cast<const int *>(add(s.plan.bra_cols.data(), 4 * (size_t)rows));
-    j.ket_cols = reinterpret_cast<const int *>(add(s.plan.ket_cols.data(), 4 * (size_t)cols));
-    j.bra_sign = reinterpret_cast<const double *>(add(s.plan.bra_sign.data(), 8 * (size_t)rows));
-    j.ket_sign = reinterpret_cast<const double *>(add(s.plan.ket_sign.data(), 8 * (size_t)cols));
+    j.bra_cols = reinterpret_cast<const int *>(put(so[u].bc, s.plan.bra_cols.data(), 4 * (size_t)rows));
+    j.ket_cols = reinterpret_cast<const int *>(put(so[u].kc, s.plan.ket_cols.data(), 4 * (size_t)cols));
+    j.bra_sign = reinterpret_cast<const double *>(put(so[u].bs, s.plan.bra_sign.data(), 8 * (size_t)rows));
+    j.ket_sign = reinterpret_cast<const double *>(put(so[u].ks, s.plan.ket_sign.data(), 8 * (size_t)cols));
     j.O = O_dev + s.o_off; j.S = S_dev + s.s_off; j.det = det_dev + u;
     j.n_bra = h.n_bra; j.n_ket = h.n_ket; j.mode = h.mode; j.physical = h.physical;
     j.ka_bra = h.ka_bra; j.ka_ket = h.ka_ket; j.sb = sb0; j.sk = sk0;
-    const uint64_t *bm = reinterpret_cast<const uint64_t *>(add(s.plan.bra_masks.data(), 8 * (size_t)h.n_rows));
-    const uint64_t *km = reinterpret_cast<const uint64_t *>(add(s.plan.ket_masks.data(), 8 * (size_t)h.chi_ket));
+    const uint64_t *bm = reinterpret_cast<const uint64_t *>(put(so[u].bm, s.plan.bra_masks.data(), 8 * (size_t)h.n_rows));
+    const uint64_t *km = reinterpret_cast<const uint64_t *>(put(so[u].km, s.plan.ket_masks.data(), 8 * (size_t)h.chi_ket));
     for (int b = 0; b < h.n_blocks; ++b) {
       const int *bl = &s.plan.blocks[6 * b];
-      tmf_minor_block k;
+      tmf_minor_block &k = mb[so[u].mb0 + b];
       std::memset(&k, 0, sizeof(k));
       k.S = j.S; k.det = j.det;
       k.bra_masks = bm + bl[0]; k.ket_masks = km + bl[2];
       k.out = out_dev + s.block_off[b];
       k.s_bra = h.s_bra; k.s_ket = h.s_ket; k.n_bra = bl[1]; k.n_ket = bl[3]; k.minor = bl[4];
-      mb.push_back(k);
     }
-  }
-  ar.take<unsigned char>((int64_t)blob.size());
+  });
+  ar.take<unsigned char>((int64_t)bsz);
   void *site_desc = ar.take<unsigned char>(tmf_site_desc_bytes(ns));
   void *minor_desc = ar.take<unsigned char>(tmf_minor_desc_bytes((int)mb.size()));
   if (!ar.ok()) return fail(TMF_ERR_VALUE, "plan workspace too small");
   tm.lap("tensors: build blob");
-  rc = tmf::copy_h2d(blob_dev, blob.data(), blob.size(), stream);
+  rc = tmf::copy_h2d(blob_dev, blob.data(), bsz, stream);
   if (rc) return rc;
   tm.lap("tensors: upload blob");
   rc = tmf_site_overlap_schur_batched(sj.data(), ns, site_desc, stream);

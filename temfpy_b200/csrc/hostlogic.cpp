@@ -377,31 +377,63 @@ void site_plan(int mode, int n_bra, int n_ket, int k_bra, int f_bra, int nferm_b
     out.ket_cols.push_back(sk.sometimes[i].col); out.ket_sign.push_back(sk.sometimes_sign[i]);
   }
 
-  // occupation masks over the sometimes part
-  auto row_mask = [&](const std::vector<Entry> &rest, uint64_t m, int p) {
-    uint64_t r = 0;
+  // occupation masks over the sometimes part.  Row t of `rest` is occupied if it is a filled orbital,
+  // the physical orbital with p = 1, or an entangled mode whose bit in the Schmidt vector's mask says
+  // so (left vectors: bit set, right vectors: bit clear).  Evaluated through byte lookup tables of the
+  // (possibly complemented) mask: three loads per row instead of a loop over the orbitals.
+  struct MaskMap {
+    uint64_t constant = 0, phys = 0;
+    std::vector<uint64_t> tab;   // 8 x 256
+    int nbytes = 0;
+    bool complement = false;
+    uint64_t operator()(uint64_t m, int p) const {
+      if (complement) m = ~m;
+      uint64_t r = constant | (p == 1 ? phys : 0);
+      for (int b = 0; b < nbytes; ++b) r |= tab[(size_t)b * 256 + ((m >> (8 * b)) & 255)];
+      return r;
+    }
+  };
+  auto make_map = [&](const std::vector<Entry> &rest) {
+    MaskMap mm;
+    mm.complement = (mode != 0);
+    uint64_t bit_of[64];
+    for (int i = 0; i < 64; ++i) bit_of[i] = 0;
+    int top = -1;
     for (size_t t = 0; t < rest.size(); ++t) {
       const Orb &o = rest[t].o;
-      bool occ;
-      if (o.kind == PHYS) occ = (p == 1);
-      else if (o.kind == FILLED) occ = true;
-      else occ = (mode == 0) ? ((m >> o.idx) & 1) : !((m >> o.idx) & 1);
-      if (occ) r |= (1ull << t);
+      if (o.kind == PHYS) mm.phys |= (1ull << t);
+      else if (o.kind == FILLED) mm.constant |= (1ull << t);
+      else { bit_of[o.idx] |= (1ull << t); top = std::max(top, o.idx); }
     }
-    return r;
+    mm.nbytes = (top + 8) / 8;
+    mm.tab.assign((size_t)std::max(mm.nbytes, 1) * 256, 0);
+    for (int b = 0; b < mm.nbytes; ++b)
+      for (int v = 1; v < 256; ++v) {
+        const int low = __builtin_ctz(v);
+        mm.tab[(size_t)b * 256 + v] = mm.tab[(size_t)b * 256 + (v & (v - 1))] | bit_of[8 * b + low];
+      }
+    return mm;
   };
+  const MaskMap map_bra = make_map(br), map_ket = make_map(kr);
   const int qc = (mode == 0) ? 1 : -1;                       // slater.py:1111
   const int qtotal = (mode == 0) ? 0 : nferm_ket - nferm_bra;  // :1092
   const int n_rows = physical ? 2 * chi_bra : chi_bra;
   std::vector<int> rp(n_rows), ra(n_rows), rq(n_rows), ord(n_rows);
+  int qmin = 1 << 30, qmax = -(1 << 30);
   for (int r = 0; r < n_rows; ++r) {
     rp[r] = physical ? r / chi_bra : -1;
     ra[r] = physical ? r % chi_bra : r;
     int p = physical ? rp[r] : 0;
     rq[r] = charge_bra[ra[r]] + (mode == 0 ? p : -p);  // charge left of the combined leg
-    ord[r] = r;
+    qmin = std::min(qmin, rq[r]);
+    qmax = std::max(qmax, rq[r]);
   }
-  std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return rq[x] < rq[y]; });  // :1053-1058
+  {  // stable counting sort by the pipe charge (slater.py:1053-1058)
+    std::vector<int> start((size_t)(qmax - qmin + 2), 0);
+    for (int r = 0; r < n_rows; ++r) ++start[rq[r] - qmin + 1];
+    for (size_t q = 1; q < start.size(); ++q) start[q] += start[q - 1];
+    for (int r = 0; r < n_rows; ++r) ord[start[rq[r] - qmin]++] = r;
+  }
   out.row_p.resize(n_rows); out.row_alpha.resize(n_rows); out.bra_masks.resize(n_rows);
   std::vector<int> q_sorted(n_rows);
   for (int r = 0; r < n_rows; ++r) {
@@ -409,10 +441,10 @@ void site_plan(int mode, int n_bra, int n_ket, int k_bra, int f_bra, int nferm_b
     out.row_p[r] = rp[s];
     out.row_alpha[r] = ra[s];
     q_sorted[r] = rq[s];
-    out.bra_masks[r] = row_mask(br, masks_bra[ra[s]], physical ? rp[s] : 0);
+    out.bra_masks[r] = map_bra(masks_bra[ra[s]], physical ? rp[s] : 0);
   }
   out.ket_masks.resize(chi_ket);
-  for (int c = 0; c < chi_ket; ++c) out.ket_masks[c] = row_mask(kr, masks_ket[c], 0);
+  for (int c = 0; c < chi_ket; ++c) out.ket_masks[c] = map_ket(masks_ket[c], 0);
 
   // charge blocks (slater.py:1132-1141)
   out.blocks.clear();

@@ -262,22 +262,25 @@ TMF_GLOBAL minors_kernel(const tmf_minor_block *blocks, const int *cta_prefix, i
         }
 #else
         {
+          // pivot = largest |x[t][c]| among the unused columns.  The magnitudes are compared as
+          // float bit patterns (monotone for non-negative values) with the column index packed in
+          // the low 6 bits, so that one 32-bit warp reduction (REDUX) replaces five shuffle rounds;
+          // 18 bits of mantissa are ample for choosing a pivot.
           const int l = threadIdx.x & 31;
           const uint64_t c0 = mt->c0;
-          double best = -1.0;
-          int bc = l;
+          unsigned key = 0u;
           for (int c = l; c < sk; c += 32) {
-            const double v = ((c0 >> c) & 1) ? -1.0 : fabs(x[t * smax + c]);
-            if (v > best) { best = v; bc = c; }
+            if ((c0 >> c) & 1) continue;
+            const unsigned k2 = (__float_as_uint(fabsf((float)x[t * smax + c])) & ~63u) | (unsigned)(63 - c);
+            key = k2 > key ? k2 : key;
           }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
-            if (ob > best || (ob == best && oc < bc)) { best = ob; bc = oc; }
-          }
-          __syncwarp();
+          key = __reduce_max_sync(0xffffffffu, key);
           if (l == 0) {
+            int bc = 63 - (int)(key & 63u);
+            if (key == 0u) {   // every unused entry is zero (or no column left): singular minor
+              bc = 0;
+              while (bc < sk - 1 && ((c0 >> bc) & 1)) ++bc;
+            }
             const double pv = x[t * smax + bc];
             mt->pc = bc;
             mt->inv = (pv != 0.0) ? 1.0 / pv : 0.0;
@@ -301,11 +304,8 @@ TMF_GLOBAL minors_kernel(const tmf_minor_block *blocks, const int *cta_prefix, i
           }
         }
         WSYNC();
-        LANE_FOR(l) {   // the pivot column becomes a unit vector
-          const int pc = mt->pc;
-          for (int r = l; r < n; r += 32) x[r * smax + pc] = (r == t) ? 1.0 : 0.0;
-        }
-        WSYNC();
+        // (pivot columns are never read again: later pivots are searched among the unused columns and
+        //  the entries only gather columns outside the pivot set, so they are not reset to unit vectors)
       }
       // sigma0: sign of the permutation (rank of pivot column) -> pivot row
       LANE_FOR(l) if (l == 0) {

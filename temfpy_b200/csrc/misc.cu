@@ -19,7 +19,8 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 #if !defined(TMF_HOSTSIM)
 static bool g_prof = false;
 static std::mutex g_prof_mu;
-struct ProfRec { std::string tag; cudaEvent_t a, b; };
+struct ProfRec { std::string tag; cudaEvent_t a, b; void *stream; };
+static thread_local size_t t_last = 0;   // launches are issued from several pipeline threads
 static std::vector<ProfRec> g_recs;
 bool prof_enabled() { return g_prof; }
 void prof_begin(const char *tag, void *stream) {
@@ -28,12 +29,14 @@ void prof_begin(const char *tag, void *stream) {
   r.tag = tag;
   cudaEventCreate(&r.a);
   cudaEventCreate(&r.b);
+  r.stream = stream;
   cudaEventRecord(r.a, (cudaStream_t)stream);
+  t_last = g_recs.size();
   g_recs.push_back(r);
 }
 void prof_end(void *stream) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  cudaEventRecord(g_recs.back().b, (cudaStream_t)stream);
+  cudaEventRecord(g_recs[t_last].b, (cudaStream_t)stream);
 }
 #endif
 }  // namespace tmf
@@ -143,4 +146,28 @@ extern "C" int tmf_fp64_peak_probe(int iters, double *sink_dev, float *ms_out, d
   *flops_out = 2.0 * 8.0 * (double)iters * 256.0 * (double)grid;
   return tmf::check_cuda(err, "fp64 probe");
 #endif
+}
+
+// timeline of the recorded launches: "tag stream start_ms end_ms" per line, relative to the first
+// recorded launch (profiling pass of bench.py / scratch tools; synchronises the device)
+extern "C" int tmf_prof_timeline(char *buf, int cap) {
+  std::string out;
+#if !defined(TMF_HOSTSIM)
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(tmf::g_prof_mu);
+  if (!tmf::g_recs.empty()) {
+    std::map<void *, int> sid;
+    cudaEvent_t base = tmf::g_recs[0].a;
+    for (auto &r : tmf::g_recs) {
+      float t0 = 0.f, t1 = 0.f;
+      if (cudaEventElapsedTime(&t0, base, r.a) != cudaSuccess) continue;
+      if (cudaEventElapsedTime(&t1, base, r.b) != cudaSuccess) continue;
+      if (!sid.count(r.stream)) { int n = (int)sid.size(); sid[r.stream] = n; }
+      out += r.tag + " " + std::to_string(sid[r.stream]) + " " + std::to_string(t0) + " " + std::to_string(t1) + "\n";
+    }
+  }
+#endif
+  if ((int)out.size() + 1 > cap) return TMF_ERR_VALUE;
+  std::memcpy(buf, out.c_str(), out.size() + 1);
+  return TMF_OK;
 }

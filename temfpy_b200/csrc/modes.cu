@@ -130,6 +130,36 @@ static void job_geometry(int L, int x, int side, int &n, int &m) {
 
 }  // namespace tmf
 
+namespace tmf {
+// fork / join of an auxiliary stream around independent work (events only; nothing synchronises the host)
+struct ForkedStream {
+#if defined(TMF_HOSTSIM)
+  void *open(void *parent) { return parent; }
+  int join(void *) { return TMF_OK; }
+#else
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev = nullptr;
+  void *open(void *parent) {
+    if (cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking) != cudaSuccess) { aux = nullptr; return parent; }
+    cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    cudaEventRecord(ev, (cudaStream_t)parent);
+    cudaStreamWaitEvent(aux, ev, 0);
+    return aux;
+  }
+  int join(void *parent) {
+    if (!aux) return TMF_OK;
+    cudaEventRecord(ev, aux);
+    cudaError_t e = cudaStreamWaitEvent((cudaStream_t)parent, ev, 0);
+    return check_cuda(e, "stream join");
+  }
+  ~ForkedStream() {   // destruction is deferred by the runtime until the enqueued work has finished
+    if (ev) cudaEventDestroy(ev);
+    if (aux) cudaStreamDestroy(aux);
+  }
+#endif
+};
+}  // namespace tmf
+
 extern "C" int64_t tmf_slater_modes_workspace(int L, int njobs, const int *job_x,
                                               const int *job_side, int r_sketch) {
   using namespace tmf;
@@ -360,8 +390,12 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
   if (rc) return rc;
 
   // ---- launches ----------------------------------------------------------------------------
+  // The direct solver of the small blocks (<= 65 latency-bound CTAs) runs on a forked stream next to
+  // the sketch path of the large blocks and is joined at the end.
+  ForkedStream fork;
   if (!small.empty()) {
-    rc = launch_t("small_modes", small_modes_kernel, (int)small.size(), 256, small_smem, stream, small_dev, cutoff);
+    void *sstream = (nb > 0) ? fork.open(stream) : stream;
+    rc = launch_t("small_modes", small_modes_kernel, (int)small.size(), 256, small_smem, sstream, small_dev, cutoff);
     if (rc) return rc;
   }
   if (nb == 0) return TMF_OK;
@@ -408,5 +442,6 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
   if (rc) return rc;
   if ((rc = run(L_out[0]))) return rc;
   rc = launch_t("pivchol", pivchol_kernel, nb, 1024, chol_smem, stream, cj_dev, 1e-8);
-  return rc;
+  if (rc) return rc;
+  return fork.join(stream);
 }

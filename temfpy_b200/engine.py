@@ -69,10 +69,16 @@ class TorchBackend:
     # side streams for the chunk pipeline (one per worker thread; PyTorch's current stream is
     # thread-local, so every native call of a worker is enqueued on that worker's stream)
     def side_stream(self, i):
+        """Stream of pipeline chunk i.  Earlier chunks get a higher CUDA priority: when the chunks
+        compete for SMs in the mode-extraction phase the first one finishes first and its host stage
+        (enumeration / planning) runs while the kernels of the later chunks still keep the GPU busy,
+        instead of all chunks reaching their host stage at the same moment."""
         if not hasattr(self, "_streams"):
             self._streams = {}
         if i not in self._streams:
-            self._streams[i] = self.torch.cuda.Stream(device=self.device)
+            import os
+            lo = -5 if not os.environ.get("TMF_FLAT_PRIORITY") else 0
+            self._streams[i] = self.torch.cuda.Stream(device=self.device, priority=min(0, lo + i))
         return self._streams[i]
 
     def stream_context(self, stream):
