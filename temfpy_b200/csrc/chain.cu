@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <stdexcept>
+#include <mutex>
 #include <thread>
 
 #include <chrono>
@@ -71,8 +72,54 @@ struct tmf_chain {
   int64_t o_elems = 0, s_elems = 0, out_elems = 0, plan_bytes = 0;
   int nblocks = 0, max_chi = 0;
   bool enumerated = false;
-  std::vector<unsigned char> blob;   // staging of the per-site plan arrays (reused across calls)
+  unsigned char *blob = nullptr;     // pinned staging of the per-site plan arrays (from the pool below)
+  size_t blob_cap = 0;
+  ~tmf_chain();
 };
+
+namespace {
+// Process-wide pool of pinned host buffers: the plan blob (tens of MB per chain) is uploaded with one
+// asynchronous copy; pageable memory would make that copy synchronous and ~5x slower, and pinning a
+// fresh buffer per conversion would cost more than the copy.
+struct PinnedPool {
+  std::mutex mu;
+  std::vector<std::pair<unsigned char *, size_t>> free_list;
+  unsigned char *acquire(size_t bytes, size_t &cap) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (size_t i = 0; i < free_list.size(); ++i)
+        if (free_list[i].second >= bytes) {
+          auto r = free_list[i];
+          free_list.erase(free_list.begin() + i);
+          cap = r.second;
+          return r.first;
+        }
+    }
+    cap = std::max<size_t>(bytes + bytes / 4, 1 << 20);
+    unsigned char *p = nullptr;
+#if defined(TMF_HOSTSIM)
+    p = static_cast<unsigned char *>(std::malloc(cap));
+#else
+    if (cudaHostAlloc(reinterpret_cast<void **>(&p), cap, cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+#endif
+    return p;
+  }
+  void release(unsigned char *p, size_t cap) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(mu);
+    if (free_list.size() < 16) { free_list.emplace_back(p, cap); return; }
+#if defined(TMF_HOSTSIM)
+    std::free(p);
+#else
+    cudaFreeHost(p);
+#endif
+  }
+};
+PinnedPool g_pinned;
+}  // namespace
+
+tmf_chain::~tmf_chain() { g_pinned.release(blob, blob_cap); }
+
 
 namespace {
 
@@ -450,8 +497,12 @@ int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev,
     so[u].mb0 = nmb;
     nmb += h.n_blocks;
   }
-  std::vector<unsigned char> &blob = c->blob;
-  if (blob.size() < bsz) blob.resize(bsz);
+  if (c->blob_cap < bsz) {
+    g_pinned.release(c->blob, c->blob_cap);
+    c->blob = g_pinned.acquire(bsz, c->blob_cap);
+    if (!c->blob) { c->blob_cap = 0; return fail(TMF_ERR_RUNTIME, "cannot allocate pinned staging memory"); }
+  }
+  unsigned char *blob = c->blob;
   std::vector<tmf_site_job> sj(ns);
   std::vector<tmf_minor_block> mb(nmb);
   parallel_for(ns, c->n_threads, [&](int u) {
@@ -462,7 +513,7 @@ int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev,
     const int sb0 = h.s_bra - (h.ka_bra - h.k_always), sk0 = h.s_ket - (h.ka_ket - h.k_always);
     const int rows = h.ka_bra + sb0, cols = h.ka_ket + sk0;
     auto put = [&](size_t off, const void *p, size_t bytes) {
-      if (bytes) std::memcpy(blob.data() + off, p, bytes);
+      if (bytes) std::memcpy(blob + off, p, bytes);
       return blob_dev + off;
     };
     tmf_site_job &j = sj[u];
@@ -493,7 +544,7 @@ int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev,
   void *minor_desc = ar.take<unsigned char>(tmf_minor_desc_bytes((int)mb.size()));
   if (!ar.ok()) return fail(TMF_ERR_VALUE, "plan workspace too small");
   tm.lap("tensors: build blob");
-  rc = tmf::copy_h2d(blob_dev, blob.data(), bsz, stream);
+  rc = tmf::copy_h2d(blob_dev, blob, bsz, stream);
   if (rc) return rc;
   tm.lap("tensors: upload blob");
   rc = tmf_site_overlap_schur_batched(sj.data(), ns, site_desc, stream);

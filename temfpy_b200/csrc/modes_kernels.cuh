@@ -461,15 +461,31 @@ struct CholJob {
   int *info;           // reads info[0] = k, writes info[1] = f
   int n, lda, max_cols, pad_;
 };
+constexpr int PIVCHOL_B = 8;         // pivots per pass over the factor
+constexpr int PIVCHOL_THREADS = 1024;
+
+// Blocked left-looking variant.  The unblocked algorithm re-reads the whole factor [U | F] (n x K, in
+// L2) for every pivot column -- sum_f n K 8 B ~ 34 GB at L = 1024, which made the kernel L2-bandwidth
+// bound.  Here PIVCHOL_B candidate pivots (the largest residual diagonals) are advanced together: one
+// pass over the factor produces all their columns (8 FMAs per L2 load), then the B x B coupling between
+// them is resolved in shared memory.  A candidate whose residual diagonal collapses once its
+// predecessors in the block are accounted for (it was nearly dependent on them) is skipped; its
+// diagonal entry is exact, so the next selection simply does not pick it again.
 TMF_GLOBAL pivchol_kernel(const CholJob *jobs, double tol) {
   const CholJob jb = jobs[BLOCK_ID];
   const int n = jb.n;
   if (n <= 0) return;
   const int k = jb.info[0];
+  constexpr int B = PIVCHOL_B;
   DYN_SMEM(double, sm);
-  double *d = sm, *col = d + n, *lp = col + n, *red = lp + n + TMF_MAX_MODES;  // red: 64 + 64
-  double *psum = red + 72;                                                   // PIVCHOL_MAX_PARTS * n
-  int *ired = reinterpret_cast<int *>(psum + (size_t)PIVCHOL_MAX_PARTS * n);
+  double *d = sm;                        // n      residual diagonal (-1: already a pivot)
+  double *dd = d + n;                    // n      scratch copy for the candidate selection
+  double *cand = dd + n;                 // B * n  candidate columns, cand[b * n + i]
+  double *lpb = cand + (size_t)B * n;    // B * n  rows p_b of the factor (scaled by w for U), lpb[m * B + b]
+  double *psum = lpb + (size_t)B * n;    // B * PIVCHOL_THREADS partial sums
+  double *red = psum + (size_t)B * PIVCHOL_THREADS;   // 72
+  int *ired = reinterpret_cast<int *>(red + 72);      // 48: [0,32) lane results, [32, 32 + B) pivots, 44 count
+  int *pidx = ired + 32;
   const double *U = jb.V;
   double *F = jb.V + (int64_t)k * n;
   PAR_FOR(i, n) {
@@ -480,74 +496,111 @@ TMF_GLOBAL pivchol_kernel(const CholJob *jobs, double tol) {
   CTA_SYNC();
   int f = 0;
   const int fmax = jb.max_cols - k;
-  for (; f < fmax; ++f) {
-    // argmax of d (two-level)
-    PAR_FOR(lane, 32) {
-      double best = -1.0;
-      int bi = 0;
-      for (int i = lane; i < n; i += 32)
-        if (d[i] > best) { best = d[i]; bi = i; }
-      red[lane] = best;
-      ired[lane] = bi;
+  bool done = false;
+  while (f < fmax && !done) {
+    // ---- candidate selection: the nb largest residual diagonals above tol ---------------------
+    const int want = (fmax - f < B) ? (fmax - f) : B;
+    PAR_FOR(i, n) dd[i] = d[i];
+    CTA_SYNC();
+    int nb = 0;
+    for (int b = 0; b < want; ++b) {
+      PAR_FOR(lane, 32) {
+        double best = -1.0;
+        int bi = 0;
+        for (int i = lane; i < n; i += 32)
+          if (dd[i] > best) { best = dd[i]; bi = i; }
+        red[lane] = best;
+        ired[lane] = bi;
+      }
+      CTA_SYNC();
+      PAR_FOR(one, 1) {
+        double best = red[0];
+        int bi = ired[0];
+        for (int l = 1; l < 32; ++l)
+          if (red[l] > best || (red[l] == best && ired[l] < bi)) { best = red[l]; bi = ired[l]; }
+        red[40] = best;
+        red[48 + b] = best;      // residual diagonal at selection time
+        pidx[b] = bi;
+        if (best > tol) dd[bi] = -1.0;
+      }
+      CTA_SYNC();
+      if (!(red[40] > tol)) break;
+      ++nb;
+    }
+    if (nb == 0) break;
+    const int K = k + f;
+    // ---- rows p_b of the current factor --------------------------------------------------------
+    PAR_FOR(item, K * B) {
+      const int m = item / B, b = item - m * B;
+      double v = 0.0;
+      if (b < nb) {
+        const int p = pidx[b];
+        v = (m < k) ? jb.w[m] * U[(int64_t)m * n + p] : F[(int64_t)(m - k) * n + p];
+      }
+      lpb[item] = v;
     }
     CTA_SYNC();
-    PAR_FOR(one, 1) {
-      double best = red[0];
-      int bi = ired[0];
-      for (int l = 1; l < 32; ++l)
-        if (red[l] > best || (red[l] == best && ired[l] < bi)) { best = red[l]; bi = ired[l]; }
-      red[40] = best;
-      ired[40] = bi;
-    }
-    CTA_SYNC();
-    const double dmax = red[40];
-    const int p = ired[40];
-    if (!(dmax > tol)) break;
-    PAR_FOR(m, k + f) lp[m] = (m < k) ? jb.w[m] * U[(int64_t)m * n + p] : F[(int64_t)(m - k) * n + p];
-    CTA_SYNC();
-    // column p of the remaining projector: A[:, p] - [U | F] * lp, the (k + f) columns split over
-    // `parts` thread groups (four independent accumulators each keep several L2 loads in flight)
+    // ---- candidate columns: A[:, p_b] - [U | F] lp_b, one pass over the factor for all b -------
     {
-      const int K = k + f;
       int parts = NTHREADS / ((n + 31) & ~31);
       parts = parts < 1 ? 1 : (parts > PIVCHOL_MAX_PARTS ? PIVCHOL_MAX_PARTS : parts);
       const int chunk = (K + parts - 1) / parts;
       PAR_FOR(item, n * parts) {
         const int part = item / n, i = item - part * n;
         const int m0 = part * chunk, m1 = (m0 + chunk < K) ? m0 + chunk : K;
-        double c0 = (part == 0) ? jb.A[(int64_t)p * jb.lda + i] : 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
-        int m = m0;
-        for (; m + 3 < m1; m += 4) {
-          c0 -= jb.V[(int64_t)m * n + i] * lp[m];
-          c1 -= jb.V[(int64_t)(m + 1) * n + i] * lp[m + 1];
-          c2 -= jb.V[(int64_t)(m + 2) * n + i] * lp[m + 2];
-          c3 -= jb.V[(int64_t)(m + 3) * n + i] * lp[m + 3];
+        double acc[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) acc[b] = (part == 0 && b < nb) ? jb.A[(int64_t)pidx[b] * jb.lda + i] : 0.0;
+        for (int m = m0; m < m1; ++m) {
+          const double v = jb.V[(int64_t)m * n + i];
+          const double *l = lpb + (size_t)m * B;
+#pragma unroll
+          for (int b = 0; b < B; ++b) acc[b] -= v * l[b];
         }
-        for (; m < m1; ++m) c0 -= jb.V[(int64_t)m * n + i] * lp[m];
-        psum[part * n + i] = (c0 + c1) + (c2 + c3);
+#pragma unroll
+        for (int b = 0; b < B; ++b) psum[(size_t)item * B + b] = acc[b];
       }
       CTA_SYNC();
-      PAR_FOR(i, n) {
+      PAR_FOR(item, n * nb) {
+        const int b = item / n, i = item - b * n;
         double c = 0.0;
-        for (int q = 0; q < parts; ++q) c += psum[q * n + i];
-        col[i] = c;
+        for (int q = 0; q < parts; ++q) c += psum[(size_t)(q * n + i) * B + b];
+        cand[(size_t)b * n + i] = c;
       }
+      CTA_SYNC();
     }
-    CTA_SYNC();
-    const double piv = col[p];
-    if (!(piv > 0.0)) break;
-    const double inv = 1.0 / sqrt(piv);
-    PAR_FOR(i, n) {
-      double l = col[i] * inv;
-      F[(int64_t)f * n + i] = l;
-      d[i] = (i == p) ? -1.0 : d[i] - l * l;
+    // ---- resolve the coupling inside the block ---------------------------------------------------
+    for (int b = 0; b < nb && f < fmax; ++b) {
+      const int p = pidx[b];
+      const double piv = cand[(size_t)b * n + p];
+      // a pivot that collapsed below a quarter of its value at selection time was nearly dependent on its
+      // predecessors in this block: leave it to a later selection (d[p] already reflects the collapse)
+      if (!(piv > tol) || piv < 0.25 * red[48 + b]) continue;
+      const double inv = 1.0 / sqrt(piv);
+      double *col = cand + (size_t)b * n;
+      PAR_FOR(i, n) {
+        const double l = col[i] * inv;
+        col[i] = l;
+        F[(int64_t)f * n + i] = l;
+        d[i] = (i == p) ? -1.0 : d[i] - l * l;
+      }
+      CTA_SYNC();
+      const int rest = nb - b - 1;
+      if (rest > 0) {
+        PAR_FOR(item, n * rest) {
+          const int bb = b + 1 + item / n, i = item % n;
+          cand[(size_t)bb * n + i] -= col[i] * col[pidx[bb]];
+        }
+        CTA_SYNC();
+      }
+      ++f;
     }
-    CTA_SYNC();
   }
   PAR_FOR(one, 1) jb.info[1] = f;
 }
 inline size_t pivchol_smem_bytes(int n) {
-  return sizeof(double) * ((size_t)(3 + PIVCHOL_MAX_PARTS) * n + TMF_MAX_MODES + 72) + sizeof(int) * 48;
+  return sizeof(double) * ((size_t)(2 + 2 * PIVCHOL_B) * n + (size_t)PIVCHOL_B * PIVCHOL_THREADS + 72) +
+         sizeof(int) * 64;
 }
 
 // ---------------------------------------------------------------------------------------------
