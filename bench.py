@@ -350,7 +350,7 @@ def main():
     ap.add_argument("--L", type=int, default=1024)
     ap.add_argument("--chi", type=int, default=1024)
     ap.add_argument("--svd-min", type=float, default=1e-7)
-    ap.add_argument("--r-sketch", type=int, default=64)
+    ap.add_argument("--r-sketch", type=int, default=48)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--chunks", type=int, default=4, help="pipeline chunks per GPU (streams + host threads)")
     ap.add_argument("--cpu-sites", type=int, default=16)

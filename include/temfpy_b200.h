@@ -273,6 +273,16 @@ int tmf_chain_bond(tmf_chain *c, int bond, int *q /* chi, k, filled_left, n_sect
 int tmf_chain_site(tmf_chain *c, int site, tmf_site_plan *plan, const int **blocks,
                    const int64_t **block_off, const int **row_p, const int **row_alpha,
                    int64_t *offs /* O offset, S offset, det index */);
+/* Bulk export of the host-side results of a shard (one call instead of one per bond / site).
+ * Replaces the attribute reads of SchmidtVectors (slater.py:494-543) and MPSTensorData (:872-973) that
+ * C_to_MPS performs for every bond and site (:1296-1346). */
+int tmf_chain_bonds_sizes(tmf_chain *c, int64_t *q /* first bond, bonds, sum chi, sum sectors */);
+int tmf_chain_bonds_export(tmf_chain *c, int64_t *chi_off, int *head /* k, filled_left, fL, fR */,
+                           double *lam, int *charge, uint64_t *masks, int64_t *sec_off, int *sec_q,
+                           int *sec_start, double *e);
+int tmf_chain_sites_sizes(tmf_chain *c, int64_t *q /* sites, sum n_blocks, sum n_rows */);
+int tmf_chain_sites_export(tmf_chain *c, tmf_site_plan *plans, int64_t *blk_off, int *blocks,
+                           int64_t *block_off, int64_t *row_off, int *row_p, int *row_alpha);
 int64_t tmf_chain_job_voff(tmf_chain *c, int job);
 /* algorithmic flops of the reference's algorithm for this shard:
  * f[0] eigh, f[1] overlap GEMM, f[2] Schur, f[3] minors, f[4] number of minors */

@@ -120,6 +120,10 @@ SIGNATURES = {
                                  C.POINTER(c_int_p), C.POINTER(c_double_p)]),
     "tmf_chain_site": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SitePlan), C.POINTER(c_int_p),
                                  C.POINTER(c_i64_p), C.POINTER(c_int_p), C.POINTER(c_int_p), c_i64_p]),
+    "tmf_chain_bonds_sizes": (C.c_int, [C.c_void_p, c_i64_p]),
+    "tmf_chain_bonds_export": (C.c_int, [C.c_void_p] * 10),
+    "tmf_chain_sites_sizes": (C.c_int, [C.c_void_p, c_i64_p]),
+    "tmf_chain_sites_export": (C.c_int, [C.c_void_p] * 8),
     "tmf_chain_job_voff": (C.c_int64, [C.c_void_p, C.c_int]),
     "tmf_chain_flops": (C.c_int, [C.c_void_p, c_double_p]),
     "tmf_launch_count": (C.c_longlong, [C.c_int]),

@@ -584,6 +584,99 @@ int tmf_chain_site(tmf_chain *c, int site, tmf_site_plan *plan, const int **bloc
   return TMF_OK;
 }
 
+// ---- bulk export: every bond / site table of the shard in one call each (the per-object accessors
+// above cost one FFI round trip per bond / site, which dominated the end-to-end time at L = 1024) ----
+// q = {first bond, number of bonds, sum of chi, sum of sector counts}
+int tmf_chain_bonds_sizes(tmf_chain *c, int64_t *q) {
+  if (!c->enumerated) return fail(TMF_ERR_VALUE, "tmf_chain_enumerate has not run");
+  int first = -1, last = -1;
+  int64_t chi = 0, nsec = 0;
+  for (int b = 0; b <= c->L; ++b)
+    if (c->bonds[b].used) {
+      if (first < 0) first = b;
+      last = b;
+      chi += (int64_t)c->bonds[b].bv.masks.size();
+      nsec += (int64_t)c->bonds[b].bv.sec_q.size();
+    }
+  // bonds of a shard are contiguous except for the centre bond pulled in by the pairing
+  q[0] = first; q[1] = (first < 0) ? 0 : last - first + 1; q[2] = chi; q[3] = nsec;
+  return TMF_OK;
+}
+
+// Arrays are indexed by (bond - first); unused bonds in the range get chi = 0.
+//   chi_off[nb + 1], head[4 nb] = {k, filled_left, fL, fR}, lam / charge / masks [sum chi],
+//   sec_off[nb + 1], sec_q[sum nsec], sec_start[sum nsec + nb] (nsec + 1 entries per bond), e[64 nb]
+int tmf_chain_bonds_export(tmf_chain *c, int64_t *chi_off, int *head, double *lam, int *charge,
+                           uint64_t *masks, int64_t *sec_off, int *sec_q, int *sec_start, double *e) {
+  int64_t q[4];
+  int rc = tmf_chain_bonds_sizes(c, q);
+  if (rc) return rc;
+  const int first = (int)q[0], nb = (int)q[1];
+  int64_t co = 0, so = 0;
+  for (int i = 0; i < nb; ++i) {
+    const ChainBond &B = c->bonds[first + i];
+    chi_off[i] = co;
+    sec_off[i] = so;
+    int *h = head + 4 * i;
+    h[0] = h[1] = h[2] = h[3] = 0;
+    double *ei = e + (size_t)i * TMF_MAX_MODES;
+    std::memset(ei, 0, sizeof(double) * TMF_MAX_MODES);
+    if (!B.used) { sec_start[so + i] = 0; continue; }
+    const size_t chi = B.bv.masks.size(), ns = B.bv.sec_q.size();
+    h[0] = B.k; h[1] = B.filled_left; h[2] = B.side[0].f; h[3] = B.side[1].f;
+    if (chi) {
+      std::memcpy(lam + co, B.bv.lam.data(), sizeof(double) * chi);
+      std::memcpy(charge + co, B.bv.charge.data(), sizeof(int) * chi);
+      std::memcpy(masks + co, B.bv.masks.data(), sizeof(uint64_t) * chi);
+    }
+    if (ns) std::memcpy(sec_q + so, B.bv.sec_q.data(), sizeof(int) * ns);
+    if (B.bv.sec_start.size() == ns + 1) std::memcpy(sec_start + so + i, B.bv.sec_start.data(), sizeof(int) * (ns + 1));
+    else sec_start[so + i] = 0;
+    const int job = (B.side[0].job >= 0) ? B.side[0].job : B.side[1].job;
+    if (job >= 0 && B.k > 0) std::memcpy(ei, c->e_host.data() + (size_t)job * TMF_MAX_MODES, sizeof(double) * std::min(B.k, (int)TMF_MAX_MODES));
+    co += (int64_t)chi;
+    so += (int64_t)ns;
+  }
+  chi_off[nb] = co;
+  sec_off[nb] = so;
+  return TMF_OK;
+}
+
+// q = {number of sites, sum of n_blocks, sum of n_rows}
+int tmf_chain_sites_sizes(tmf_chain *c, int64_t *q) {
+  if (!c->enumerated) return fail(TMF_ERR_VALUE, "tmf_chain_enumerate has not run");
+  int64_t nbk = 0, nr = 0;
+  for (const ChainSite &s : c->sites) { nbk += s.plan.h.n_blocks; nr += s.plan.h.n_rows; }
+  q[0] = (int64_t)c->sites.size(); q[1] = nbk; q[2] = nr;
+  return TMF_OK;
+}
+
+//   plans[ns], blk_off[ns + 1], blocks[6 sum n_blocks], block_off[sum n_blocks] (element offsets into the
+//   shard's tensor buffer), row_off[ns + 1], row_p / row_alpha [sum n_rows]
+int tmf_chain_sites_export(tmf_chain *c, tmf_site_plan *plans, int64_t *blk_off, int *blocks,
+                           int64_t *block_off, int64_t *row_off, int *row_p, int *row_alpha) {
+  if (!c->enumerated) return fail(TMF_ERR_VALUE, "tmf_chain_enumerate has not run");
+  const int ns = (int)c->sites.size();
+  int64_t bo = 0, ro = 0;
+  for (int u = 0; u < ns; ++u) { blk_off[u] = bo; row_off[u] = ro; bo += c->sites[u].plan.h.n_blocks; ro += c->sites[u].plan.h.n_rows; }
+  blk_off[ns] = bo;
+  row_off[ns] = ro;
+  parallel_for(ns, c->n_threads > 0 ? c->n_threads : 4, [&](int u) {
+    const ChainSite &s = c->sites[u];
+    const tmf_site_plan &h = s.plan.h;
+    plans[u] = h;
+    if (h.n_blocks) {
+      std::memcpy(blocks + 6 * blk_off[u], s.plan.blocks.data(), sizeof(int) * 6 * (size_t)h.n_blocks);
+      std::memcpy(block_off + blk_off[u], s.block_off.data(), sizeof(int64_t) * (size_t)h.n_blocks);
+    }
+    if (h.n_rows) {
+      std::memcpy(row_p + row_off[u], s.plan.row_p.data(), sizeof(int) * (size_t)h.n_rows);
+      std::memcpy(row_alpha + row_off[u], s.plan.row_alpha.data(), sizeof(int) * (size_t)h.n_rows);
+    }
+  });
+  return TMF_OK;
+}
+
 int64_t tmf_chain_job_voff(tmf_chain *c, int job) { return c->v_off[job]; }
 
 // Algorithmic FP64 flop counts of the *reference's* algorithm for this shard:

@@ -395,7 +395,7 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
   ForkedStream fork;
   if (!small.empty()) {
     void *sstream = (nb > 0) ? fork.open(stream) : stream;
-    rc = launch_t("small_modes", small_modes_kernel, (int)small.size(), 256, small_smem, sstream, small_dev, cutoff);
+    rc = launch_t("small_modes", small_modes_kernel, (int)small.size(), 1024, small_smem, sstream, small_dev, cutoff);
     if (rc) return rc;
   }
   if (nb == 0) return TMF_OK;
@@ -433,12 +433,14 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
   if ((rc = run_orth(orthW))) return rc;
   if ((rc = run(L_rw[0]))) return rc;
   const double thr = cutoff * (1.0 - cutoff);
-  rc = launch_t("svd_select", svd_select_kernel, nb, 256, svd_smem, stream, sj_dev, thr, 1e-26);
+  // one warp per column pair of a Jacobi round (latency-bound: more warps per CTA, not more CTAs)
+  const int jac_threads = std::min(1024, 32 * std::max(4, (r_sketch + 1) / 2));
+  rc = launch_t("svd_select", svd_select_kernel, nb, jac_threads, svd_smem, stream, sj_dev, thr, 1e-26);
   if (rc) return rc;
   if ((rc = run(L_u0[0]))) return rc;
   if ((rc = run(L_au[0]))) return rc;
   if ((rc = run(L_te[0]))) return rc;
-  rc = launch_t("ritz", ritz_kernel, nb, 256, ritz_smem, stream, rj_dev, cutoff);
+  rc = launch_t("ritz", ritz_kernel, nb, jac_threads, ritz_smem, stream, rj_dev, cutoff);
   if (rc) return rc;
   if ((rc = run(L_out[0]))) return rc;
   rc = launch_t("pivchol", pivchol_kernel, nb, 1024, chol_smem, stream, cj_dev, 1e-8);

@@ -42,18 +42,24 @@ class TorchBackend:
         self.h2d_bytes += arr.nbytes
         return t.from_numpy(arr).to(self.device, non_blocking=False)
 
-    def to_host(self, buf, n=None) -> np.ndarray:
-        """Device -> pinned host copy.  The returned array aliases a pinned tensor owned by the
-        result (PyTorch's caching host allocator recycles it once the result is dropped)."""
+    def to_host_async(self, buf, n=None):
+        """Enqueues a device -> pinned host copy on the current stream and returns the pinned tensor
+        (valid after the stream has been synchronised).  PyTorch's caching host allocator recycles the
+        pinned block once the result is dropped."""
         if n is not None:
             buf = buf[:n]
         t = self.torch
         host = t.empty(buf.shape, dtype=buf.dtype, pin_memory=True)
         host.copy_(buf, non_blocking=True)
+        self.d2h_bytes += host.numel() * host.element_size()
+        return host
+
+    def to_host(self, buf, n=None) -> np.ndarray:
+        """Device -> pinned host copy.  The returned array aliases a pinned tensor owned by the
+        result."""
+        host = self.to_host_async(buf, n)
         self.sync()
-        arr = host.numpy()
-        self.d2h_bytes += arr.nbytes
-        return arr
+        return host.numpy()
 
     @staticmethod
     def ptr(buf) -> int:
@@ -135,14 +141,168 @@ class SiteTensor:
         return np.transpose(T, (1, 0, 2)) if self.mode == "left" else np.transpose(T, (2, 0, 1))
 
 
+class LazyMap:
+    """Mapping whose values are wrapped on first access (``factory(key)``) and then cached.  Wrapping
+    all 2 L + 1 bond / site objects of a long chain eagerly cost more than the conversion itself."""
+
+    def __init__(self):
+        self._made = {}
+        self._factory = {}
+
+    def add(self, keys, factory):
+        for k in keys:
+            self._factory[k] = factory
+            self._made.pop(k, None)
+
+    def __getitem__(self, k):
+        try:
+            return self._made[k]
+        except KeyError:
+            v = self._made[k] = self._factory[k](k)
+            return v
+
+    def __setitem__(self, k, v):
+        self._made[k] = v
+        self._factory.setdefault(k, None)
+
+    def get(self, k, default=None):
+        return self[k] if k in self._factory else default
+
+    def __contains__(self, k):
+        return k in self._factory
+
+    def __iter__(self):
+        return iter(self._factory)
+
+    def __len__(self):
+        return len(self._factory)
+
+    def keys(self):
+        return self._factory.keys()
+
+    def values(self):
+        return (self[k] for k in self._factory)
+
+    def items(self):
+        return ((k, self[k]) for k in self._factory)
+
+    def update(self, other):
+        if isinstance(other, LazyMap):
+            self._factory.update(other._factory)
+            for k in other._factory:
+                self._made.pop(k, None)
+            self._made.update(other._made)
+        else:
+            for k, v in dict(other).items():
+                self[k] = v
+
+
+class ShardTables:
+    """Host-side results of one shard in bulk arrays (``tmf_chain_bonds_export`` / ``_sites_export``);
+    the per-bond and per-site objects are views into them."""
+
+    def __init__(self, chain, out_host):
+        lib, h = chain.lib, chain.handle
+        q = (C.c_int64 * 4)()
+        check(lib, lib.tmf_chain_bonds_sizes(h, q))
+        self.first_bond, nb, nchi, nsec = (int(v) for v in q)
+        self.n_bonds = nb
+        self.chi_off = np.empty(nb + 1, np.int64)
+        self.head = np.empty((max(nb, 1), 4), np.int32)
+        self.lam = np.empty(nchi, np.float64)
+        self.charge = np.empty(nchi, np.int32)
+        self.masks = np.empty(nchi, np.uint64)
+        self.sec_off = np.empty(nb + 1, np.int64)
+        self.sec_q = np.empty(nsec, np.int32)
+        self.sec_start = np.empty(nsec + nb, np.int32)
+        self.e = np.empty((max(nb, 1), _lib.TMF_MAX_MODES), np.float64)
+        p = lambda a: a.ctypes.data
+        check(lib, lib.tmf_chain_bonds_export(h, p(self.chi_off), p(self.head), p(self.lam), p(self.charge),
+                                              p(self.masks), p(self.sec_off), p(self.sec_q), p(self.sec_start),
+                                              p(self.e)))
+        self.charge = self.charge.astype(np.int64)
+        self.out_host = out_host
+        self.site_lo = chain.site_lo
+        if out_host is not None:
+            check(lib, lib.tmf_chain_sites_sizes(h, q))
+            ns, nblk, nrows = int(q[0]), int(q[1]), int(q[2])
+            self.plans = (SitePlan * max(ns, 1))()
+            self.blk_off = np.empty(ns + 1, np.int64)
+            self.blocks = np.empty((nblk, 6), np.int32)
+            self.block_off = np.empty(nblk, np.int64)
+            self.row_off = np.empty(ns + 1, np.int64)
+            self.row_p = np.empty(nrows, np.int32)
+            self.row_alpha = np.empty(nrows, np.int32)
+            check(lib, lib.tmf_chain_sites_export(h, C.addressof(self.plans), p(self.blk_off), p(self.blocks),
+                                                  p(self.block_off), p(self.row_off), p(self.row_p),
+                                                  p(self.row_alpha)))
+
+    def bond(self, x) -> "BondData":
+        i = x - self.first_bond
+        a, b = int(self.chi_off[i]), int(self.chi_off[i + 1])
+        s0, s1 = int(self.sec_off[i]), int(self.sec_off[i + 1])
+        k, fl = int(self.head[i, 0]), int(self.head[i, 1])
+        sq = self.sec_q[s0:s1]
+        ss = self.sec_start[s0 + i: s1 + i + 1]
+        idx_L = {int(sq[j]): slice(int(ss[j]), int(ss[j + 1])) for j in range(s1 - s0)}
+        return BondData(x=int(x), k=k, filled_left=fl, e=self.e[i, :k], masks=self.masks[a:b],
+                        schmidt_values=self.lam[a:b], charge=self.charge[a:b], idx_L=idx_L)
+
+    def site(self, i) -> "SiteTensor":
+        u = i - self.site_lo
+        plan = self.plans[u]
+        b0, b1 = int(self.blk_off[u]), int(self.blk_off[u + 1])
+        r0_, r1_ = int(self.row_off[u]), int(self.row_off[u + 1])
+        out = []
+        for b in range(b0, b1):
+            r0, nr, c0, nc, _, qk = (int(v) for v in self.blocks[b])
+            o = int(self.block_off[b])
+            out.append((qk, r0, nr, c0, nc, self.out_host[o: o + nr * nc].reshape(nr, nc)))
+        return SiteTensor(site=int(i), mode="left" if plan.mode == 0 else "right", plan=plan, blocks=out,
+                          row_p=self.row_p[r0_:r1_], row_alpha=self.row_alpha[r0_:r1_], qtotal=plan.qtotal)
+
+
 @dataclass
 class ChainResult:
     L: int
     ortho_center: int
     site_lo: int
     site_hi: int
-    bonds: dict = field(default_factory=dict)    # x -> BondData
-    sites: dict = field(default_factory=dict)    # i -> SiteTensor
+    bonds: LazyMap = field(default_factory=LazyMap)    # x -> BondData   (wrapped on first access)
+    sites: LazyMap = field(default_factory=LazyMap)    # i -> SiteTensor
+    tables: list = field(default_factory=list)         # ShardTables of every chunk
+
+    def lam_charge(self, x):
+        """(Schmidt values, charges) of bond x without wrapping a BondData."""
+        for t in self.tables:
+            i = x - t.first_bond
+            if 0 <= i < t.n_bonds and t.chi_off[i + 1] > t.chi_off[i]:
+                a, b = int(t.chi_off[i]), int(t.chi_off[i + 1])
+                return t.lam[a:b], t.charge[a:b]
+        b = self.bonds[x]
+        return b.schmidt_values, b.charge
+
+
+class LazySeq:
+    """Read-only sequence view of a LazyMap over range(n) (the site tensors of an MPS)."""
+
+    def __init__(self, mapping, n):
+        self._m, self._n = mapping, n
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._m[j] for j in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        return self._m[i]
+
+    def __iter__(self):
+        return (self._m[i] for i in range(self._n))
     timings: dict = field(default_factory=dict)
     stats: dict = field(default_factory=dict)
 
@@ -160,7 +320,7 @@ class SlaterChain:
     """One chain conversion on one device for the sites [site_lo, site_hi)."""
 
     def __init__(self, backend, L, trunc, n_fermion, ortho_center=None, site_lo=0, site_hi=None,
-                 r_sketch=64, n_threads=0):
+                 r_sketch=48, n_threads=0):
         self.be = backend
         self.lib = backend.lib
         self.L = int(L)
@@ -268,15 +428,30 @@ class SlaterChain:
                           row_alpha=_ptr_array(row_a, plan.n_rows, np.int64), qtotal=plan.qtotal)
 
     def collect(self, fetch_tensors=True) -> ChainResult:
-        """Synchronises and wraps everything into host objects."""
-        self.be.sync()
+        """Brings the tensors to the host (one pinned copy) and exports the host-side tables in bulk;
+        the per-bond / per-site objects are wrapped lazily from those."""
+        import time
+        t0 = time.perf_counter()
         res = ChainResult(L=self.L, ortho_center=self.oc, site_lo=self.site_lo, site_hi=self.site_hi)
-        for x in range(self.site_lo, self.site_hi + 1):
-            res.bonds[x] = self.bond(x)
-        if fetch_tensors:
+        host = None
+        if fetch_tensors and hasattr(self.be, "to_host_async"):
+            host = self.be.to_host_async(self._buffers["out"], self.out_elems)   # overlaps the table export
+        t1 = time.perf_counter()
+        if fetch_tensors and host is None:
             out_host = self.be.to_host(self._buffers["out"], self.out_elems)
-            for i in range(self.site_lo, self.site_hi):
-                res.sites[i] = self.site(i, out_host)
+        else:
+            out_host = host.numpy() if host is not None else None
+        tab = ShardTables(self, out_host)
+        tab._pinned = host
+        t2 = time.perf_counter()
+        self.be.sync()
+        t3 = time.perf_counter()
+        res.tables = [tab]
+        res.bonds.add([x for x in range(tab.first_bond, tab.first_bond + tab.n_bonds)
+                       if self.site_lo <= x <= self.site_hi or x == self.oc], tab.bond)
+        if fetch_tensors:
+            res.sites.add(range(self.site_lo, self.site_hi), tab.site)
+        res.timings = dict(d2h_enqueue=t1 - t0, tables=t2 - t1, sync=t3 - t2)
         res.stats = dict(out_elems=self.out_elems, nblocks=self.nblocks, max_chi=self.max_chi,
                          njobs=self.njobs)
         return res
@@ -343,7 +518,7 @@ class DeviceChainResult:
 
 
 def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_lo=0, site_hi=None,
-              r_sketch=64, n_threads=0, fetch_tensors=True, n_chunks=None, lazy=False):
+              r_sketch=48, n_threads=0, fetch_tensors=True, n_chunks=None, lazy=False):
     """C (device) -> Schmidt data of every bond and block-sparse tensor of every site.
 
     The site range is cut into cost-balanced chunks that run as a software pipeline: one worker
@@ -378,6 +553,8 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
     for p in parts:
         res.bonds.update(p.bonds)
         res.sites.update(p.sites)
+    res.timings = dict(chunks=[p.timings for p in parts])
+    res.tables = [t for p in parts for t in p.tables]
     res.stats = dict(out_elems=sum(p.stats["out_elems"] for p in parts),
                      nblocks=sum(p.stats["nblocks"] for p in parts),
                      max_chi=max(p.stats["max_chi"] for p in parts),

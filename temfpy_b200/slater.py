@@ -110,10 +110,11 @@ def _check_projector(C, tol=1e-8):
 
 def _chain_to_mps(res: engine.ChainResult, unit_cell_width) -> BlockMPS:
     L = res.L
-    lams = [normalize_SV(res.bonds[x].schmidt_values, logger) for x in range(L + 1)]   # slater.py:1296
+    lc = [res.lam_charge(x) for x in range(L + 1)]
+    lams = [normalize_SV(l, logger) for l, _ in lc]                                     # slater.py:1296
     oc = res.ortho_center
-    return BlockMPS(L=L, tensors=[res.sites[i] for i in range(L)], lams=lams,
-                    charges=[res.bonds[x].charge for x in range(L + 1)],
+    return BlockMPS(L=L, tensors=engine.LazySeq(res.sites, L), lams=lams,
+                    charges=[c for _, c in lc],
                     form=["A"] * oc + ["B"] * (L - oc), unit_cell_width=unit_cell_width,     # slater.py:1348
                     ortho_center=oc, meta=dict(stats=res.stats, bonds=res.bonds))
 

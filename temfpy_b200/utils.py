@@ -39,5 +39,5 @@ def block_svd(CLR, vL, vR, e, degeneracy_tol: float = 1e-12, overwrite: bool = T
 def normalize_SV(λ: np.ndarray, logger: logging.Logger) -> np.ndarray:
     """Normalises the input array and prints the norm in the logs (utils.py:99-103)."""
     norm = np.linalg.norm(λ)
-    logger.info(f"Norm of Schmidt values: {norm}")
+    logger.info("Norm of Schmidt values: %s", norm)
     return λ / norm
