@@ -261,6 +261,10 @@ void tmf_chain_destroy(tmf_chain *c);
 int tmf_chain_modes_sizes(tmf_chain *c, int64_t *q /* njobs, V doubles, workspace bytes */);
 int tmf_chain_modes(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, double *e_dev,
                     int *info_dev, void *work_dev, int64_t work_bytes, void *stream);
+/* The same in two halves: enqueue all kernels (no host wait) / fetch the spectra (waits). */
+int tmf_chain_modes_enqueue(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, double *e_dev,
+                            int *info_dev, void *work_dev, int64_t work_bytes, void *stream);
+int tmf_chain_modes_finish(tmf_chain *c, const double *e_dev, const int *info_dev, void *stream);
 int tmf_chain_enumerate(tmf_chain *c);
 int tmf_chain_tensor_sizes(tmf_chain *c, int64_t *q /* plan bytes, O, S doubles, sites, blocks,
                                                        out doubles, max chi */);

@@ -1,23 +1,30 @@
+"""Device time and end-to-end time of one conversion vs number of pipeline chunks / stage gate."""
 import os, sys, time
 sys.path.insert(0, "/root/repo")
 import numpy as np, torch
 from bench import ground_state_C
-from temfpy_b200 import engine
+from temfpy_b200 import engine, slater
 from temfpy_b200.schmidt_utils import to_stopping_condition
+be = engine.TorchBackend("cuda:0")
+slater._backend = be
 L = 1024
 Cm, N = ground_state_C(L)
+Cd = be.from_host(Cm.ravel())
 tp = to_stopping_condition({"chi_max": 1024, "svd_min": 1e-7})
-print(torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else "n/a")
-for flat in (0, 1):
-    if flat: os.environ["TMF_FLAT_PRIORITY"] = "1"
-    else: os.environ.pop("TMF_FLAT_PRIORITY", None)
-    be = engine.TorchBackend("cuda:0")
-    Cd = be.from_host(Cm.ravel())
-    for nc in [3, 4, 6, 8]:
+for gate in (1, 0):
+    if gate: os.environ.pop("TMF_NO_STAGE_GATE", None)
+    else: os.environ["TMF_NO_STAGE_GATE"] = "1"
+    for nc in (2, 4, 6, 8, 12):
+        for _ in range(2):
+            engine.run_chain(be, Cd, L, L, tp, N, n_chunks=nc, lazy=True).close()
         ts = []
-        for it in range(6):
+        for _ in range(5):
             torch.cuda.synchronize(); t0 = time.perf_counter()
             r = engine.run_chain(be, Cd, L, L, tp, N, n_chunks=nc, lazy=True)
-            torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
-            r.close()
-        print("flat", flat, "n_chunks", nc, "ms", [round(1e3 * t, 1) for t in ts[1:]], flush=True)
+            torch.cuda.synchronize(); ts.append(1e3 * (time.perf_counter() - t0)); r.close()
+        te = []
+        for _ in range(3):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            r = engine.run_chain(be, Cd, L, L, tp, N, n_chunks=nc)
+            torch.cuda.synchronize(); te.append(1e3 * (time.perf_counter() - t0)); del r
+        print("gate", gate, "n_chunks", nc, "device ms", [round(t, 1) for t in ts], "with D2H+tables ms", [round(t, 1) for t in te], flush=True)

@@ -110,6 +110,9 @@ SIGNATURES = {
     "tmf_chain_modes_sizes": (C.c_int, [C.c_void_p, c_i64_p]),
     "tmf_chain_modes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "tmf_chain_modes_enqueue": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "tmf_chain_modes_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tmf_chain_enumerate": (C.c_int, [C.c_void_p]),
     "tmf_chain_tensor_sizes": (C.c_int, [C.c_void_p, c_i64_p]),
     "tmf_chain_tensors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,

@@ -259,17 +259,23 @@ int tmf_chain_modes_sizes(tmf_chain *c, int64_t *q) {
   return TMF_OK;
 }
 
-int tmf_chain_modes(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, double *e_dev,
-                    int *info_dev, void *work_dev, int64_t work_bytes, void *stream) {
+// Enqueues every mode-extraction kernel of the shard on `stream` and returns without waiting
+// (tmf_chain_modes_finish brings the spectra to the host).  The split lets a pipeline driver record
+// an event between the two and order the mode stages of consecutive chunks on the device.
+int tmf_chain_modes_enqueue(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, double *e_dev,
+                            int *info_dev, void *work_dev, int64_t work_bytes, void *stream) {
   const int nj = (int)c->job_x.size();
   const double cutoff = c->tp.svd_min * c->tp.svd_min;  // slater.py:318
-  int rc = tmf_slater_modes_batched(C_dev, c->L, ldc, nj, c->job_x.data(), c->job_side.data(), cutoff,
-                                    c->r_sketch, c->v_off.data(), V_dev, e_dev, info_dev, work_dev,
-                                    work_bytes, stream);
-  if (rc) return rc;
+  return tmf_slater_modes_batched(C_dev, c->L, ldc, nj, c->job_x.data(), c->job_side.data(), cutoff,
+                                  c->r_sketch, c->v_off.data(), V_dev, e_dev, info_dev, work_dev,
+                                  work_bytes, stream);
+}
+
+int tmf_chain_modes_finish(tmf_chain *c, const double *e_dev, const int *info_dev, void *stream) {
+  const int nj = (int)c->job_x.size();
   c->e_host.resize((size_t)nj * TMF_MAX_MODES);
   c->info_host.resize((size_t)nj * 4);
-  rc = tmf::copy_d2h_sync(c->info_host.data(), info_dev, sizeof(int) * 4 * (size_t)nj, stream);
+  int rc = tmf::copy_d2h_async(c->info_host.data(), info_dev, sizeof(int) * 4 * (size_t)nj, stream);
   if (rc) return rc;
   rc = tmf::copy_d2h_sync(c->e_host.data(), e_dev, sizeof(double) * TMF_MAX_MODES * (size_t)nj, stream);
   if (rc) return rc;
@@ -281,6 +287,13 @@ int tmf_chain_modes(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, d
                   "range sketch too narrow for this entanglement spectrum: rerun with a larger r_sketch");
   }
   return TMF_OK;
+}
+
+int tmf_chain_modes(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, double *e_dev,
+                    int *info_dev, void *work_dev, int64_t work_bytes, void *stream) {
+  int rc = tmf_chain_modes_enqueue(c, C_dev, ldc, V_dev, e_dev, info_dev, work_dev, work_bytes, stream);
+  if (rc) return rc;
+  return tmf_chain_modes_finish(c, e_dev, info_dev, stream);
 }
 
 // host: enumeration + planning.  Requires tmf_chain_modes to have completed.

@@ -65,6 +65,10 @@ inline int copy_d2h_sync(void *dst, const void *src, size_t bytes, void *) {
   std::memcpy(dst, src, bytes);
   return TMF_OK;
 }
+inline int copy_d2h_async(void *dst, const void *src, size_t bytes, void *) {
+  std::memcpy(dst, src, bytes);
+  return TMF_OK;
+}
 inline int memset_dev(void *dst, int v, size_t bytes, void *) {
   std::memset(dst, v, bytes);
   return TMF_OK;
@@ -125,6 +129,11 @@ inline int copy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
   if (bytes == 0) return TMF_OK;
   return check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream),
                     "cudaMemcpyAsync H2D");
+}
+inline int copy_d2h_async(void *dst, const void *src, size_t bytes, void *stream) {
+  if (bytes == 0) return TMF_OK;
+  return check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream),
+                    "cudaMemcpyAsync D2H");
 }
 inline int copy_d2h_sync(void *dst, const void *src, size_t bytes, void *stream) {
   if (bytes) {

@@ -116,59 +116,100 @@ TMF_DEVICE double det4(const double *m) {   // row-major 4 x 4, complementary 2 
   return s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
 }
 
-// One tensor entry: gathers Y[C0 \\ C, C \\ C0] (d x d) from the reduced matrix, accumulates the
-// permutation parity and returns the determinant.
-TMF_DEVICE double entry_value(const double *x, int smax, const int *colrow, uint64_t c0, uint64_t cm) {
-  const uint64_t U = cm & c0;
-  uint64_t mu = c0 & ~cm, de = cm & ~c0;
-  const int d = popc64(de);
-  if (d == 0) return 1.0;
-  int par = 0;
+// Exclusive prefix parity of a mask: bit j = parity of the number of set bits below j.  With it the
+// sign of the column exchange C0 -> C (the permutation that sorts U + E after the columns M of C0 were
+// replaced in place by E) is  popc(M & pp(C0)) + popc(E & pp(C))  mod 2  -- two ANDs and two POPCs per
+// entry instead of one masked popcount per exchanged column.
+template <typename MT>
+TMF_DEVICE MT prefix_parity(MT x) {
+  MT p = (MT)(x << 1);
+  p ^= (MT)(p << 1);
+  p ^= (MT)(p << 2);
+  p ^= (MT)(p << 4);
+  p ^= (MT)(p << 8);
+  p ^= (MT)(p << 16);
+  if (sizeof(MT) == 8) p ^= (MT)((uint64_t)p << 32);
+  return p;
+}
+TMF_DEVICE int popcm(uint32_t x) {
+#if defined(TMF_HOSTSIM)
+  return __builtin_popcount(x);
+#else
+  return __popc(x);
+#endif
+}
+TMF_DEVICE int popcm(uint64_t x) { return popc64(x); }
+TMF_DEVICE int ctzm(uint32_t x) {
+#if defined(TMF_HOSTSIM)
+  return __builtin_ctz(x);
+#else
+  return __ffs((int)x) - 1;
+#endif
+}
+TMF_DEVICE int ctzm(uint64_t x) { return ctz64(x); }
+
+// One tensor entry with exactly D exchanged columns (D = 1..4): gathers Y[C0 \ C, C \ C0] (D x D) from
+// the reduced matrix and returns the signed determinant.  D is a compile-time constant: the entries of a
+// bra row are binned by D first (see the kernel), so every lane of a warp runs the same straight-line code.
+template <int D, typename MT>
+TMF_DEVICE double entry_d(const double *x, int smax, const int *colrow, MT c0, MT pp0, MT cm, MT ppk) {
+  MT mu = c0 & ~cm, de = cm & ~c0;
+  const int par = popcm((MT)(mu & pp0)) ^ popcm((MT)(de & ppk));
+  int rr[D], cc[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const int m = ctzm(mu), e = ctzm(de);
+    mu &= (MT)(mu - 1);
+    de &= (MT)(de - 1);
+    rr[i] = colrow[m] * smax;
+    cc[i] = e;
+  }
   double val;
-  if (d <= 4) {
-    int rr[4] = {0, 0, 0, 0}, cc[4] = {0, 0, 0, 0};
+  if constexpr (D == 1) {
+    val = x[rr[0] + cc[0]];
+  } else if constexpr (D == 2) {
+    val = det2(x[rr[0] + cc[0]], x[rr[0] + cc[1]], x[rr[1] + cc[0]], x[rr[1] + cc[1]]);
+  } else if constexpr (D == 3) {
+    double m[9];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (i < d) {
-        const int m = ctz64(mu), e = ctz64(de);
-        mu &= mu - 1;
-        de &= de - 1;
-        const int a = m < e ? m : e, b = m < e ? e : m;
-        const uint64_t between = (b - a > 1) ? (((1ull << (b - a - 1)) - 1) << (a + 1)) : 0ull;
-        par += popc64(U & between);
-        rr[i] = colrow[m] * smax;
-        cc[i] = e;
-      }
-    }
-    if (d == 1) {
-      val = x[rr[0] + cc[0]];
-    } else if (d == 2) {
-      val = det2(x[rr[0] + cc[0]], x[rr[0] + cc[1]], x[rr[1] + cc[0]], x[rr[1] + cc[1]]);
-    } else if (d == 3) {
-      double m[9];
+    for (int i = 0; i < 3; ++i)
 #pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) m[3 * i + j] = x[rr[i] + cc[j]];
-      val = det3(m);
-    } else {
-      double m[16];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) m[4 * i + j] = x[rr[i] + cc[j]];
-      val = det4(m);
-    }
+      for (int j = 0; j < 3; ++j) m[3 * i + j] = x[rr[i] + cc[j]];
+    val = det3(m);
   } else {
-    val = entry_generic(x, smax, colrow, U, mu, de, d, par);
+    double m[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) m[4 * i + j] = x[rr[i] + cc[j]];
+    val = det4(m);
   }
   return (par & 1) ? -val : val;
 }
 
+// any number of exchanged columns (dispatch on d; used by the simulator path and for d > 4)
+template <typename MT>
+TMF_DEVICE double entry_any(const double *x, int smax, const int *colrow, MT c0, MT pp0, MT cm, MT ppk) {
+  const MT de = cm & ~c0;
+  const int d = popcm(de);
+  switch (d) {
+    case 0: return 1.0;
+    case 1: return entry_d<1, MT>(x, smax, colrow, c0, pp0, cm, ppk);
+    case 2: return entry_d<2, MT>(x, smax, colrow, c0, pp0, cm, ppk);
+    case 3: return entry_d<3, MT>(x, smax, colrow, c0, pp0, cm, ppk);
+    case 4: return entry_d<4, MT>(x, smax, colrow, c0, pp0, cm, ppk);
+    default: break;
+  }
+  int par = 0;
+  const double val = entry_generic(x, smax, colrow, (uint64_t)(cm & c0), (uint64_t)(c0 & ~cm), (uint64_t)de, d, par);
+  return (par & 1) ? -val : val;
+}
+
 // ---------------------------------------------------------------------------------------------
-// Warp-independent kernel: after the sometimes matrix is staged in shared memory (one CTA barrier)
-// every warp processes bra rows on its own -- row reduction with lanes = columns in a private
-// shared-memory tile, then one tensor entry per lane -- synchronising with __syncwarp only.
+// Warp-independent kernel: after the sometimes matrix and the ket masks are staged in shared memory (one
+// CTA barrier) every warp processes bra rows on its own -- row reduction with lanes = columns in a
+// private shared-memory tile, then the entries of the row, binned by their number of exchanged columns
+// so that each bin runs divergence-free -- synchronising with __syncwarp only.
 // ---------------------------------------------------------------------------------------------
 #if defined(TMF_HOSTSIM)
 #define LANE_FOR(l) for (int l = 0; l < 32; ++l)
@@ -182,6 +223,7 @@ TMF_DEVICE double entry_value(const double *x, int smax, const int *colrow, uint
 
 struct WarpMeta {
   uint64_t c0;        // pivot column set
+  uint64_t pp0;       // its exclusive prefix parity
   double scale;       // prod of pivots * sigma0 * det_always
   double inv;         // 1 / current pivot
   int pc, pad_;       // current pivot column
@@ -190,9 +232,100 @@ struct WarpMeta {
 };
 
 constexpr int MB_WARPS = 8;
+constexpr int NCLS = 5;        // bins: 1, 2, 3, 4 exchanged columns, more
+constexpr int QCAP = 64;       // a bin is flushed as soon as it holds a full warp of entries
 
+#if !defined(TMF_HOSTSIM)
+// processes the entries q[i0 .. i0 + cnt) (cnt <= 32) of one bin
+template <int D, typename MT>
+__device__ __forceinline__ void flush_bin(const unsigned short *q, int i0, int cnt, int lane, const double *x, int smax,
+                                          const int *colrow, MT c0, MT pp0, const MT *kmask, const MT *kpp,
+                                          double scale, double *orow) {
+  if (lane < cnt) {
+    const int c = q[i0 + lane];
+    double v;
+    if constexpr (D <= 4) v = entry_d<D, MT>(x, smax, colrow, c0, pp0, kmask[c], kpp[c]);
+    else v = entry_any<MT>(x, smax, colrow, c0, pp0, kmask[c], kpp[c]);
+    orow[c] = scale * v;
+  }
+}
+#endif
+
+#if !defined(TMF_HOSTSIM)
+// Register-resident Gauss-Jordan of one bra row for sometimes matrices of up to 32 columns and minors
+// of up to NR rows: lane c keeps column c of X in registers, the pivot column is broadcast through NR
+// doubles of shared memory, the pivot search is one REDUX.  Every lane tracks the pivot set, the
+// permutation parity and the pivot product redundantly (uniform registers), so no lane-0 section and no
+// shared-memory round trip of the matrix remain; the reduced matrix is written to the warp's tile once,
+// for the entry gathers.  Same pivoting rule and arithmetic as the shared-memory path below.
+template <int NR>
+__device__ __forceinline__ void reduce_row_regs(const double *Ssm, int ldS, int sk, int n, uint64_t rmask,
+                                                int lane, double *x, int smax, int *colrow, double *bcast,
+                                                double det_always, uint32_t &c0_out, double &scale_out) {
+  double xr[NR];
+  {
+    uint64_t rm = rmask;
+    const double *col = Ssm + (size_t)(lane < sk ? lane : 0) * ldS;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      double v = 0.0;
+      if (r < n) {
+        const int bit = ctz64(rm);
+        rm &= rm - 1;
+        if (lane < sk) v = col[bit];
+      }
+      xr[r] = v;
+    }
+  }
+  uint32_t c0 = 0u;
+  double scale = det_always;
+  int invs = 0;
+#pragma unroll
+  for (int t = 0; t < NR; ++t) {
+    if (t < n) {
+      const double v = xr[t];
+      // largest |v| among the unused columns: float bit pattern (monotone), bit 5 marks a candidate,
+      // bits 0-4 carry 31 - column so that ties go to the lowest column
+      unsigned key = 0u;
+      if (lane < sk && !((c0 >> lane) & 1u))
+        key = (__float_as_uint(fabsf((float)v)) & ~63u) | 32u | (unsigned)(31 - lane);
+      key = __reduce_max_sync(0xffffffffu, key);
+      const int pc = 31 - (int)(key & 31u);
+      const double pv = __shfl_sync(0xffffffffu, v, pc);
+      const double inv = (pv != 0.0) ? 1.0 / pv : 0.0;
+      scale *= pv;
+      invs += __popc((unsigned)((uint64_t)c0 >> (pc + 1)));
+      c0 |= 1u << pc;
+      if (lane == pc) {
+        colrow[pc] = t;
+#pragma unroll
+        for (int r = 0; r < NR; r += 2) *reinterpret_cast<double2 *>(bcast + r) = make_double2(xr[r], xr[r + 1]);
+      }
+      __syncwarp();
+      const double u = (lane == pc) ? 0.0 : v * inv;
+#pragma unroll
+      for (int r = 0; r < NR; r += 2) {
+        const double2 b = *reinterpret_cast<const double2 *>(bcast + r);
+        if (r != t) xr[r] -= b.x * u;
+        if (r + 1 != t) xr[r + 1] -= b.y * u;
+      }
+      xr[t] = u;
+      __syncwarp();
+    }
+  }
+  if (lane < sk) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+      if (r < n) x[r * smax + lane] = xr[r];
+  }
+  c0_out = c0;
+  scale_out = (invs & 1) ? -scale : scale;
+}
+#endif
+
+template <typename MT>
 TMF_GLOBAL minors_kernel(const tmf_minor_block *blocks, const int *cta_prefix, int nblocks,
-                         int nmax, int smax) {
+                         int nmax, int smax, int nkmax) {
   int lo = 0, hi = nblocks;
   const int cta = BLOCK_ID;
   while (hi - lo > 1) {
@@ -205,12 +338,25 @@ TMF_GLOBAL minors_kernel(const tmf_minor_block *blocks, const int *cta_prefix, i
   const int n = blk.minor, sk = blk.s_ket, sb = blk.s_bra;
 
   DYN_SMEM(unsigned char, raw);
-  double *Ssm = reinterpret_cast<double *>(raw);                 // smax * smax
-  double *Xall = Ssm + (size_t)smax * smax;                      // MB_WARPS * nmax * smax
-  WarpMeta *metas = reinterpret_cast<WarpMeta *>(Xall + (size_t)MB_WARPS * nmax * smax);
+  const int ldS = sb | 1;                                        // odd leading dimension: conflict-free column gathers
+  double *Ssm = reinterpret_cast<double *>(raw);                 // smax * (smax | 1)
+  double *Xall = Ssm + (size_t)smax * (smax | 1);                // MB_WARPS * nmax * smax
+  double *bcast_all = Ssm + ((((size_t)smax * (smax | 1) + (size_t)MB_WARPS * nmax * smax) + 1) & ~(size_t)1);   // MB_WARPS * 16, 16-byte aligned
+  WarpMeta *metas = reinterpret_cast<WarpMeta *>(bcast_all + MB_WARPS * 16);
+  MT *kmask = reinterpret_cast<MT *>(metas + MB_WARPS);          // nkmax
+  MT *kpp = kmask + nkmax;                                       // nkmax
+  unsigned short *queues = reinterpret_cast<unsigned short *>(kpp + nkmax);   // MB_WARPS * NCLS * QCAP
 
   const double det_always = blk.det ? *blk.det : 1.0;
-  PAR_FOR(idx, sb * sk) Ssm[idx] = blk.S[idx];
+  PAR_FOR(idx, sb * sk) {
+    const int c = idx / sb, r = idx - c * sb;
+    Ssm[c * ldS + r] = blk.S[idx];
+  }
+  PAR_FOR(c, blk.n_ket) {
+    const MT km = (MT)blk.ket_masks[c];
+    kmask[c] = km;
+    kpp[c] = prefix_parity<MT>(km);
+  }
   CTA_SYNC();
 
   if (n == 0) {  // empty minors: det of a 0 x 0 matrix is 1
@@ -226,6 +372,23 @@ TMF_GLOBAL minors_kernel(const tmf_minor_block *blocks, const int *cta_prefix, i
     WarpMeta *mt = metas + w;
     for (int a = w; a < nrows; a += MB_WARPS) {
       const uint64_t rmask = blk.bra_masks[row0 + a];
+#if !defined(TMF_HOSTSIM)
+      if (sizeof(MT) == 4 && n <= 16) {   // (uniform) register-resident reduction
+        const int lane = threadIdx.x & 31;
+        uint32_t c0r;
+        double sc;
+        double *bc = bcast_all + w * 16;
+        if (n <= 8) reduce_row_regs<8>(Ssm, ldS, sk, n, rmask, lane, x, smax, mt->colrow, bc, det_always, c0r, sc);
+        else if (n <= 12) reduce_row_regs<12>(Ssm, ldS, sk, n, rmask, lane, x, smax, mt->colrow, bc, det_always, c0r, sc);
+        else reduce_row_regs<16>(Ssm, ldS, sk, n, rmask, lane, x, smax, mt->colrow, bc, det_always, c0r, sc);
+        if (lane == 0) {
+          mt->c0 = c0r;
+          mt->pp0 = prefix_parity<uint32_t>(c0r);
+          mt->scale = sc;
+        }
+        __syncwarp();
+      } else {
+#endif
       // ---- gather X = S[rows(alpha), :] (lane = column) -------------------------------------
       LANE_FOR(l) {
         for (int c = l; c < sk; c += 32) {
@@ -234,7 +397,7 @@ TMF_GLOBAL minors_kernel(const tmf_minor_block *blocks, const int *cta_prefix, i
           while (rm) {
             const int bit = ctz64(rm);
             rm &= rm - 1;
-            x[r * smax + c] = Ssm[(size_t)c * sb + bit];
+            x[r * smax + c] = Ssm[(size_t)c * ldS + bit];
             ++r;
           }
         }
@@ -307,7 +470,7 @@ TMF_GLOBAL minors_kernel(const tmf_minor_block *blocks, const int *cta_prefix, i
         // (pivot columns are never read again: later pivots are searched among the unused columns and
         //  the entries only gather columns outside the pivot set, so they are not reset to unit vectors)
       }
-      // sigma0: sign of the permutation (rank of pivot column) -> pivot row
+      // sigma0: sign of the permutation (rank of pivot column) -> pivot row; prefix parity of C0
       LANE_FOR(l) if (l == 0) {
         uint64_t c0 = mt->c0, seen = 0;
         int inv = 0;
@@ -319,25 +482,69 @@ TMF_GLOBAL minors_kernel(const tmf_minor_block *blocks, const int *cta_prefix, i
           seen |= (1ull << r);
         }
         if (inv & 1) mt->scale = -mt->scale;
+        mt->pp0 = prefix_parity<uint64_t>(mt->c0);
       }
       WSYNC();
-      // ---- one tensor entry per lane ---------------------------------------------------------
-      LANE_FOR(l) {
-        const uint64_t c0 = mt->c0;
-        const double scale = mt->scale;
-        double *orow = blk.out + (int64_t)(row0 + a) * blk.n_ket;
-        for (int c = l; c < blk.n_ket; c += 32) {
-          const double val = scale * entry_value(x, smax, mt->colrow, c0, blk.ket_masks[c]);
-          orow[c] = val;
-        }
+#if !defined(TMF_HOSTSIM)
       }
+#endif
+      // ---- the entries of the row -------------------------------------------------------------
+      double *orow = blk.out + (int64_t)(row0 + a) * blk.n_ket;
+#if defined(TMF_HOSTSIM)
+      LANE_FOR(l) {
+        const MT c0 = (MT)mt->c0, pp0 = (MT)mt->pp0;
+        for (int c = l; c < blk.n_ket; c += 32)
+          orow[c] = mt->scale * entry_any<MT>(x, smax, mt->colrow, c0, pp0, kmask[c], kpp[c]);
+      }
+#else
+      {
+        const int lane = threadIdx.x & 31;
+        const unsigned lt = (1u << lane) - 1u;
+        const MT c0 = (MT)mt->c0, pp0 = (MT)mt->pp0;
+        const double scale = mt->scale;
+        const int *colrow = mt->colrow;
+        unsigned short *q = queues + (size_t)w * NCLS * QCAP;
+        int cnt[NCLS];
+#pragma unroll
+        for (int k = 0; k < NCLS; ++k) cnt[k] = 0;
+        for (int cb = 0; cb < blk.n_ket; cb += 32) {
+          const int c = cb + lane;
+          int cls = 0;
+          if (c < blk.n_ket) {
+            const int d = popcm((MT)(kmask[c] & ~c0));
+            if (d == 0) orow[c] = scale;
+            cls = d < NCLS ? d : NCLS;
+          }
+#pragma unroll
+          for (int k = 0; k < NCLS; ++k) {
+            const unsigned bal = __ballot_sync(0xffffffffu, cls == k + 1);
+            if (cls == k + 1) q[k * QCAP + cnt[k] + __popc(bal & lt)] = (unsigned short)c;
+            cnt[k] += __popc(bal);
+          }
+          __syncwarp();
+          if (cnt[0] >= 32) { cnt[0] -= 32; flush_bin<1, MT>(q + 0 * QCAP, cnt[0], 32, lane, x, smax, colrow, c0, pp0, kmask, kpp, scale, orow); }
+          if (cnt[1] >= 32) { cnt[1] -= 32; flush_bin<2, MT>(q + 1 * QCAP, cnt[1], 32, lane, x, smax, colrow, c0, pp0, kmask, kpp, scale, orow); }
+          if (cnt[2] >= 32) { cnt[2] -= 32; flush_bin<3, MT>(q + 2 * QCAP, cnt[2], 32, lane, x, smax, colrow, c0, pp0, kmask, kpp, scale, orow); }
+          if (cnt[3] >= 32) { cnt[3] -= 32; flush_bin<4, MT>(q + 3 * QCAP, cnt[3], 32, lane, x, smax, colrow, c0, pp0, kmask, kpp, scale, orow); }
+          if (cnt[4] >= 32) { cnt[4] -= 32; flush_bin<5, MT>(q + 4 * QCAP, cnt[4], 32, lane, x, smax, colrow, c0, pp0, kmask, kpp, scale, orow); }
+          __syncwarp();
+        }
+        if (cnt[0]) flush_bin<1, MT>(q + 0 * QCAP, 0, cnt[0], lane, x, smax, colrow, c0, pp0, kmask, kpp, scale, orow);
+        if (cnt[1]) flush_bin<2, MT>(q + 1 * QCAP, 0, cnt[1], lane, x, smax, colrow, c0, pp0, kmask, kpp, scale, orow);
+        if (cnt[2]) flush_bin<3, MT>(q + 2 * QCAP, 0, cnt[2], lane, x, smax, colrow, c0, pp0, kmask, kpp, scale, orow);
+        if (cnt[3]) flush_bin<4, MT>(q + 3 * QCAP, 0, cnt[3], lane, x, smax, colrow, c0, pp0, kmask, kpp, scale, orow);
+        if (cnt[4]) flush_bin<5, MT>(q + 4 * QCAP, 0, cnt[4], lane, x, smax, colrow, c0, pp0, kmask, kpp, scale, orow);
+      }
+#endif
       WSYNC();
     }
   }
 }
 
-static size_t minors_smem_bytes(int nmax, int smax) {
-  return sizeof(double) * ((size_t)smax * smax + (size_t)MB_WARPS * nmax * smax) + sizeof(WarpMeta) * MB_WARPS + 64;
+static size_t minors_smem_bytes(int nmax, int smax, int nkmax, size_t mask_bytes) {
+  return sizeof(double) * ((size_t)smax * (smax | 1) + (size_t)MB_WARPS * nmax * smax + MB_WARPS * 16 + 2) +
+         sizeof(WarpMeta) * MB_WARPS +
+         2 * mask_bytes * (size_t)nkmax + sizeof(unsigned short) * MB_WARPS * NCLS * QCAP + 64;
 }
 
 }  // namespace tmf
@@ -351,7 +558,7 @@ extern "C" int tmf_minors_blocks(const tmf_minor_block *blocks_host, int nblocks
   using namespace tmf;
   if (nblocks <= 0) return TMF_OK;
   std::vector<int> prefix(nblocks + 1, 0);
-  int nmax = 1, smax = 1;
+  int nmax = 1, smax = 1, nkmax = 1;
   for (int b = 0; b < nblocks; ++b) {
     const tmf_minor_block &k = blocks_host[b];
     if (k.s_bra > 64 || k.s_ket > 64 || k.minor > 32 || k.minor > k.s_ket || k.minor > k.s_bra) {
@@ -362,6 +569,12 @@ extern "C" int tmf_minors_blocks(const tmf_minor_block *blocks_host, int nblocks
     prefix[b + 1] = prefix[b] + ctas;
     nmax = std::max(nmax, k.minor);
     smax = std::max(smax, std::max(k.s_bra, k.s_ket));
+    nkmax = std::max(nkmax, k.n_ket);
+  }
+  nkmax = (nkmax + 3) & ~3;
+  if (nkmax > 65535) {
+    set_error("tmf_minors_blocks: more than 65535 Schmidt vectors in one charge sector");
+    return TMF_ERR_VALUE;
   }
   if (prefix[nblocks] == 0) return TMF_OK;
   unsigned char *d = static_cast<unsigned char *>(desc_dev);
@@ -370,7 +583,12 @@ extern "C" int tmf_minors_blocks(const tmf_minor_block *blocks_host, int nblocks
   if (rc) return rc;
   rc = copy_h2d(d + o_pref, prefix.data(), sizeof(int) * (size_t)(nblocks + 1), stream);
   if (rc) return rc;
-  return launch_t("minors", minors_kernel, prefix[nblocks], 32 * tmf::MB_WARPS, minors_smem_bytes(nmax, smax), stream,
-                reinterpret_cast<const tmf_minor_block *>(d), reinterpret_cast<const int *>(d + o_pref),
-                nblocks, nmax, smax);
+  // occupation masks fit 32 bits for the usual sometimes matrices (<= 32 columns): half the integer work
+  if (smax <= 32)
+    return launch_t("minors", minors_kernel<uint32_t>, prefix[nblocks], 32 * tmf::MB_WARPS,
+                    minors_smem_bytes(nmax, smax, nkmax, 4), stream, reinterpret_cast<const tmf_minor_block *>(d),
+                    reinterpret_cast<const int *>(d + o_pref), nblocks, nmax, smax, nkmax);
+  return launch_t("minors", minors_kernel<uint64_t>, prefix[nblocks], 32 * tmf::MB_WARPS,
+                  minors_smem_bytes(nmax, smax, nkmax, 8), stream, reinterpret_cast<const tmf_minor_block *>(d),
+                  reinterpret_cast<const int *>(d + o_pref), nblocks, nmax, smax, nkmax);
 }

@@ -355,7 +355,8 @@ class SlaterChain:
             pass
 
     # -- stage A: modes, enumeration, planning ------------------------------------------------
-    def run_modes(self, C_dev, ldc):
+    def enqueue_modes(self, C_dev, ldc):
+        """Enqueues the mode extraction of every (bond, side) of the shard; does not wait."""
         be, lib = self.be, self.lib
         q = (C.c_int64 * 8)()
         check(lib, lib.tmf_chain_modes_sizes(self.handle, q))
@@ -365,9 +366,20 @@ class SlaterChain:
         b["e"] = be.empty(njobs * _lib.TMF_MAX_MODES, np.float64)
         b["info"] = be.empty(njobs * 4, np.int32)
         b["work"] = be.empty(work_bytes, np.uint8)
-        check(lib, lib.tmf_chain_modes(self.handle, be.ptr(C_dev), int(ldc), be.ptr(b["V"]), be.ptr(b["e"]),
-                                       be.ptr(b["info"]), be.ptr(b["work"]), work_bytes, be.stream))
+        check(lib, lib.tmf_chain_modes_enqueue(self.handle, be.ptr(C_dev), int(ldc), be.ptr(b["V"]),
+                                               be.ptr(b["e"]), be.ptr(b["info"]), be.ptr(b["work"]),
+                                               work_bytes, be.stream))
         self.njobs = njobs
+
+    def finish_modes(self):
+        """Spectra to the host (waits for the stream)."""
+        b = self._buffers
+        check(self.lib, self.lib.tmf_chain_modes_finish(self.handle, self.be.ptr(b["e"]), self.be.ptr(b["info"]),
+                                                        self.be.stream))
+
+    def run_modes(self, C_dev, ldc):
+        self.enqueue_modes(C_dev, ldc)
+        self.finish_modes()
 
     def run_enumerate(self):
         check(self.lib, self.lib.tmf_chain_enumerate(self.handle))
@@ -457,15 +469,29 @@ class SlaterChain:
         return res
 
 
+class _NoGate:
+    def before(self):
+        pass
+
+    def after(self):
+        pass
+
+
 def _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch, n_threads,
-               fetch_tensors, lazy=False):
+               fetch_tensors, lazy=False, gate=None):
     last_err = None
+    gate = gate or _NoGate()
     widths = [r for r in (64, 128, 160) if r > r_sketch]
     for r in [r_sketch] + widths:
         chain = SlaterChain(backend, L, trunc, n_fermion, ortho_center, lo, hi, r, n_threads)
         ok = False
         try:
-            chain.run_modes(C_dev, ldc)
+            try:
+                gate.before()
+                chain.enqueue_modes(C_dev, ldc)
+            finally:
+                gate.after()
+            chain.finish_modes()
             chain.run_enumerate()
             chain.run_tensors(C_dev, ldc)
             if lazy:
@@ -481,6 +507,46 @@ def _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r
             if not (lazy and ok):
                 chain.close()
     raise last_err
+
+
+class _StageGate:
+    """Orders the mode-extraction stages of consecutive pipeline chunks on the device: chunk i's first
+    kernel waits for chunk i-1's last mode kernel (an event; the host never blocks on the GPU).  Run
+    all at once, the stages share the SMs, finish together and leave the GPU idle while every chunk is in
+    its host stage; run one after the other, the host stage and the tensor kernels of chunk i overlap the
+    mode kernels of chunk i+1."""
+
+    def __init__(self, backend, n):
+        import threading
+        self.be = backend
+        self.enqueued = [threading.Event() for _ in range(n)]
+        self.done = [None] * n
+
+    def gate(self, i):
+        outer = self
+
+        class G:
+            used = False
+
+            def before(self):
+                if self.used or i == 0:
+                    return
+                outer.enqueued[i - 1].wait()
+                ev = outer.done[i - 1]
+                if ev is not None:
+                    outer.be.torch.cuda.current_stream(outer.be.device).wait_event(ev)
+
+            def after(self):
+                if self.used:
+                    return
+                self.used = True
+                try:
+                    ev = outer.be.torch.cuda.Event()
+                    ev.record(outer.be.torch.cuda.current_stream(outer.be.device))
+                    outer.done[i] = ev
+                finally:
+                    outer.enqueued[i].set()
+        return G()
 
 
 class DeviceChainResult:
@@ -538,11 +604,14 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
     cuts = partition(L, n_chunks, trunc.chi_max, ortho_center, lo=site_lo, hi=site_hi)
     backend.sync()                       # C_dev must be complete before the side streams read it
 
+    import os
+    stages = _StageGate(backend, n_chunks) if not os.environ.get("TMF_NO_STAGE_GATE") else None
+
     def work(i):
         lo, hi = cuts[i]
         with backend.stream_context(backend.side_stream(i)):
             return _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch,
-                              n_threads, fetch_tensors, lazy)
+                              n_threads, fetch_tensors, lazy, gate=stages.gate(i) if stages else None)
 
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=n_chunks) as pool:
