@@ -23,6 +23,7 @@ void set_error(const std::string &msg);
 #if defined(TMF_HOSTSIM)
 // ------------------------------------------------------------------------------------------
 #define TMF_GLOBAL static void
+#define TMF_GLOBAL_LB(threads, blocks) static void
 #define TMF_DEVICE static inline
 #define TMF_HD static inline
 #define TMF_RESTRICT
@@ -80,6 +81,7 @@ inline int stream_sync(void *) { return TMF_OK; }
 // ------------------------------------------------------------------------------------------
 #include <cuda_runtime.h>
 #define TMF_GLOBAL __global__ void
+#define TMF_GLOBAL_LB(threads, blocks) __global__ void __launch_bounds__(threads, blocks)
 #define TMF_DEVICE __device__ __forceinline__
 #define TMF_HD __host__ __device__ __forceinline__
 #define TMF_RESTRICT __restrict__
@@ -101,6 +103,7 @@ inline int check_cuda(cudaError_t e, const char *what) {
 // per-tag kernel timing (CUDA events around every launch) -- enabled only by bench.py's profiling
 // pass through tmf_prof_enable(); the launch counter is always on (bench "gpu_launches").
 void count_launch();
+void prefer_shared_carveout(const void *kernel);   // once per kernel: ask for the largest shared-memory carve-out
 bool prof_enabled();
 void prof_begin(const char *tag, void *stream);
 void prof_end(void *stream);

@@ -22,6 +22,17 @@ static std::mutex g_prof_mu;
 struct ProfRec { std::string tag; cudaEvent_t a, b; void *stream; };
 static thread_local size_t t_last = 0;   // launches are issued from several pipeline threads
 static std::vector<ProfRec> g_recs;
+#if !defined(TMF_HOSTSIM)
+void prefer_shared_carveout(const void *kernel) {
+  static std::mutex mu;
+  static std::vector<const void *> done;
+  std::lock_guard<std::mutex> lk(mu);
+  for (const void *k : done)
+    if (k == kernel) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  done.push_back(kernel);
+}
+#endif
 bool prof_enabled() { return g_prof; }
 void prof_begin(const char *tag, void *stream) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
