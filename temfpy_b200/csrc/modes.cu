@@ -16,6 +16,7 @@
 //   5. pivoted Cholesky of the remaining projector A - U diag(e) U^T -> filled-space basis.
 // Blocks with n <= 64 are diagonalised directly by Jacobi.  All bonds of the chain run in the
 // same launches (grids of hundreds of CTAs), descriptors are uploaded once up front.
+#include <cstdlib>
 #include "modes_kernels.cuh"
 
 namespace tmf {
@@ -405,6 +406,7 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
     if (gl.ntiles == 0) return (int)TMF_OK;
     return gemm_launch_uploaded(gl.jobs, gl.prefix, gl.njobs, gl.ntiles, stream, "gemm_modes");
   };
+  static const bool use_mgs = std::getenv("TMF_PANEL_MGS") != nullptr;   // debugging switch: column-by-column MGS2 panels
   auto run_orth = [&](OrthPlan &op) -> int {
     int r2 = launch_t("colnorm", colnorm_kernel, nb, 256, op.norm_smem, stream, op.norm);
     if (r2) return r2;
@@ -417,7 +419,10 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
           if ((r2 = run(op.coef[p]))) return r2;
           if ((r2 = run(op.upd[p]))) return r2;
         }
-        r2 = launch_t("panel_mgs2", panel_mgs2_kernel, op.panel_n[p], 256, op.panel_smem[p], stream, op.panel[p], 0.0);
+        if (use_mgs)
+          r2 = launch_t("panel_mgs2", panel_mgs2_kernel, op.panel_n[p], 256, op.panel_smem[p], stream, op.panel[p], 0.0);
+        else
+          r2 = launch_t("panel_cholqr", panel_cholqr_kernel, op.panel_n[p], 256, panel_cholqr_smem_bytes(), stream, op.panel[p], 0.0);
         if (r2) return r2;
       }
     }

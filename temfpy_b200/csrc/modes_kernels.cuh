@@ -52,10 +52,7 @@ struct PanelJob {
   int rows, ld, ncols, use_smem;
 };
 
-TMF_GLOBAL panel_mgs2_kernel(const PanelJob *jobs, double rel_tol2) {
-  const PanelJob jb = jobs[BLOCK_ID];
-  if (jb.rows <= 0 || jb.ncols <= 0) return;
-  DYN_SMEM(double, sm);
+TMF_DEVICE void panel_mgs2_body(const PanelJob &jb, double rel_tol2, double *sm) {
   double *part = sm;                        // PANEL_W * 33
   double *coef = part + PANEL_W * 33;       // PANEL_W
   double *red = coef + PANEL_W;             // 32 + 2
@@ -120,6 +117,183 @@ TMF_GLOBAL panel_mgs2_kernel(const PanelJob *jobs, double rel_tol2) {
       jb.P[(int64_t)c * jb.ld + r] = panel[idx];
     }
   }
+}
+TMF_GLOBAL panel_mgs2_kernel(const PanelJob *jobs, double rel_tol2) {
+  const PanelJob jb = jobs[BLOCK_ID];
+  if (jb.rows <= 0 || jb.ncols <= 0) return;
+  DYN_SMEM(double, sm);
+  panel_mgs2_body(jb, rel_tol2, sm);
+}
+
+// ---------------------------------------------------------------------------------------------
+// panel Cholesky-QR: G = P^T P (w x w), G = R^T R, P <- P R^-1.  Everything is parallel over the rows
+// (the MGS2 kernel above walks the columns one by one: ~100 dependent CTA phases per panel), so a panel
+// costs a few microseconds.  A sketch panel after the projection on the previous panels has a condition
+// number ~1e5 (16 columns of a geometrically decaying spectrum): one pass leaves ~kappa^2 eps of
+// non-orthogonality, which the second round of the block Gram-Schmidt driver removes (CholQR2).  If a pivot
+// of the Cholesky factorisation collapses (kappa > ~1e6, dependent or zero columns) the CTA falls back to
+// the MGS2 body on the panel in global memory.
+// ---------------------------------------------------------------------------------------------
+constexpr double CHOLQR_PIVOT_TOL = 1e-12;
+TMF_GLOBAL_LB(256, 3) panel_cholqr_kernel(const PanelJob *jobs, double rel_tol2) {
+  const PanelJob jb0 = jobs[BLOCK_ID];
+  if (jb0.rows <= 0 || jb0.ncols <= 0) return;
+  const int w = jb0.ncols, rows = jb0.rows, ld = jb0.ld;
+  double *P = jb0.P;
+  DYN_SMEM(double, sm);
+  double *G = sm;                      // PANEL_W * PANEL_W
+  double *Ri = G + PANEL_W * PANEL_W;  // inverse of R (upper triangular), Ri[k * PANEL_W + j]
+  int *flag = reinterpret_cast<int *>(Ri + PANEL_W * PANEL_W);
+  double *scratch = Ri + PANEL_W * PANEL_W + 2;   // MGS2 fallback scratch
+#if !defined(TMF_HOSTSIM)
+  {
+    // Gram matrix: warp -> 4 x 4 blocks of column pairs (register tile), lanes -> rows, shuffle reduction
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nbk = (w + 3) / 4;
+    for (int blk = wid; blk < nbk * nbk; blk += nw) {
+      const int bi = blk / nbk, bj = blk - bi * nbk;
+      if (bj < bi) continue;             // symmetric: upper blocks only
+      double acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+      for (int r = lane; r < rows; r += 32) {
+        double pi[4], pj[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          pi[a] = (4 * bi + a < w) ? P[(int64_t)(4 * bi + a) * ld + r] : 0.0;
+          pj[a] = (4 * bj + a < w) ? P[(int64_t)(4 * bj + a) * ld + r] : 0.0;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] += pi[a] * pj[b];
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          double v = acc[a][b];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0 && 4 * bi + a < w && 4 * bj + b < w) {
+            G[(4 * bi + a) * PANEL_W + 4 * bj + b] = v;
+            G[(4 * bj + b) * PANEL_W + 4 * bi + a] = v;
+          }
+        }
+    }
+  }
+#else
+  PAR_FOR(idx, w * w) {
+    const int i = idx / w, j = idx - i * w;
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += P[(int64_t)i * ld + r] * P[(int64_t)j * ld + r];
+    G[i * PANEL_W + j] = s;
+  }
+#endif
+  CTA_SYNC();
+#if !defined(TMF_HOSTSIM)
+  // Cholesky G = L L^T (R = L^T) by warp 0: lane i keeps row i of the lower triangle in registers, the
+  // pivot row is broadcast by shuffles (left-looking, one column per step); then lane j inverts column j.
+  if (threadIdx.x < 32) {
+    const int i = threadIdx.x;
+    double g[PANEL_W];
+#pragma unroll
+    for (int q = 0; q < PANEL_W; ++q) g[q] = (i < w && q < w) ? G[i * PANEL_W + q] : ((i == q) ? 1.0 : 0.0);
+    double diag0 = 0.0;
+#pragma unroll
+    for (int q = 0; q < PANEL_W; ++q) if (q == i) diag0 = g[q];
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < PANEL_W; ++k) {
+      double v = g[k];
+#pragma unroll
+      for (int q = 0; q < k; ++q) v -= g[q] * __shfl_sync(0xffffffffu, g[q], k);
+      const double d = __shfl_sync(0xffffffffu, v, k), d0 = __shfl_sync(0xffffffffu, diag0, k);
+      if (k < w && (!(d > CHOLQR_PIVOT_TOL * d0) || !(d0 > 0.0))) bad = 1;
+      const double lkk = (d > 0.0) ? sqrt(d) : 1.0;
+      g[k] = (i == k) ? lkk : v / lkk;
+    }
+    if (i < PANEL_W) {
+#pragma unroll
+      for (int q = 0; q < PANEL_W; ++q) G[i * PANEL_W + q] = g[q];   // L in the lower triangle (q <= i)
+    }
+    __syncwarp();
+    if (!bad && i < w) {
+      // column j = i of M = L^-1 (forward substitution); Ri[k][j] = R^-1[k][j] = M[j][k]
+      const int j = i;
+      double m[PANEL_W];
+#pragma unroll
+      for (int r = 0; r < PANEL_W; ++r) {
+        double v = (r == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int q = 0; q < r; ++q) v -= G[r * PANEL_W + q] * ((q >= j) ? m[q] : 0.0);
+        m[r] = (r >= j && r < w) ? v / G[r * PANEL_W + r] : 0.0;
+      }
+#pragma unroll
+      for (int r = 0; r < PANEL_W; ++r) Ri[j * PANEL_W + r] = m[r];   // M[r][j] -> Ri[j][r]
+    }
+    if (i == 0) *flag = bad;
+  }
+#else
+  // Cholesky G = L L^T (R = L^T) and Ri = R^-1 (simulator: one thread)
+  PAR_FOR(one, 1) {
+    int bad = 0;
+    for (int k = 0; k < w && !bad; ++k) {
+      double d = G[k * PANEL_W + k];
+      const double d0 = d;
+      for (int q = 0; q < k; ++q) d -= G[k * PANEL_W + q] * G[k * PANEL_W + q];   // L stored in the lower triangle
+      if (!(d > CHOLQR_PIVOT_TOL * d0) || !(d0 > 0.0)) { bad = 1; break; }
+      const double lkk = sqrt(d);
+      G[k * PANEL_W + k] = lkk;
+      for (int i = k + 1; i < w; ++i) {
+        double v = G[i * PANEL_W + k];
+        for (int q = 0; q < k; ++q) v -= G[i * PANEL_W + q] * G[k * PANEL_W + q];
+        G[i * PANEL_W + k] = v / lkk;
+      }
+    }
+    if (!bad) {
+      // Ri = R^-1 with R[k][j] = L[j][k] (k <= j): back substitution column by column
+      for (int j = 0; j < w; ++j) {
+        for (int k = j; k >= 0; --k) {
+          double v = (k == j) ? 1.0 : 0.0;
+          for (int q = k + 1; q <= j; ++q) v -= G[q * PANEL_W + k] * Ri[q * PANEL_W + j];   // R[k][q] = L[q][k]
+          Ri[k * PANEL_W + j] = v / G[k * PANEL_W + k];
+        }
+      }
+    }
+    *flag = bad;
+  }
+#endif
+  CTA_SYNC();
+  if (*flag) {
+    PanelJob jb = jb0;
+    jb.use_smem = 0;
+    CTA_SYNC();
+    panel_mgs2_body(jb, rel_tol2, scratch);
+    return;
+  }
+  // Q = P Ri, one row per thread; q_j only needs p_k with k <= j, so the row is transformed in place from
+  // the last column down
+  PAR_FOR(r, rows) {
+    double p[PANEL_W];
+#pragma unroll
+    for (int k = 0; k < PANEL_W; ++k) p[k] = (k < w) ? P[(int64_t)k * ld + r] : 0.0;
+#pragma unroll
+    for (int j = PANEL_W - 1; j >= 0; --j) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k <= j; ++k) v += p[k] * Ri[k * PANEL_W + j];
+      p[j] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < PANEL_W; ++j)
+      if (j < w) P[(int64_t)j * ld + r] = p[j];
+  }
+}
+inline size_t panel_cholqr_smem_bytes() {
+  return sizeof(double) * (size_t)(2 * PANEL_W * PANEL_W + 2 + PANEL_W * 33 + PANEL_W + 40 + 8);
 }
 inline size_t panel_smem_bytes(int rows, int ncols, bool use_smem) {
   return sizeof(double) * (size_t)(PANEL_W * 33 + PANEL_W + 40 + (use_smem ? (size_t)rows * ncols : 0));
