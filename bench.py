@@ -141,7 +141,25 @@ def run_native(args):
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        # NCCL announces its version on stdout when the first communicator comes up; the contract is ONE
+        # JSON line on stdout, so fd 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+        if not args.threads:      # the ranks share the host cores
+            try:
+                ncpu = len(os.sched_getaffinity(0))
+            except AttributeError:
+                ncpu = os.cpu_count() or 8
+            args.threads = max(2, ncpu // world)
     be = engine.TorchBackend(f"cuda:{local}")
     slater._backend = be
     lib = be.lib
@@ -269,14 +287,22 @@ def run_native(args):
     else:
         # every rank converts its shard from host C and brings its tensors back to its host
         import torch.distributed as dist
+        res = engine.run_chain(be, be.from_host(C_host.ravel()), L, L, tp, N, site_lo=lo, site_hi=hi,
+                               r_sketch=args.r_sketch, n_threads=args.threads)      # warm-up (pinned allocations)
+        del res
         be.h2d_bytes = be.d2h_bytes = 0
+        n_e2e = max(1, min(args.steps, 3))
         barrier()
         t0 = time.perf_counter()
-        Cd = be.from_host(C_host.ravel())
-        res = engine.run_chain(be, Cd, L, L, tp, N, site_lo=lo, site_hi=hi, r_sketch=args.r_sketch)
-        del res
+        for _ in range(n_e2e):
+            Cd = be.from_host(C_host.ravel())
+            res = engine.run_chain(be, Cd, L, L, tp, N, site_lo=lo, site_hi=hi, r_sketch=args.r_sketch,
+                                   n_threads=args.threads)
+            del res
         barrier()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=be.device)
+        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=be.device)
+        be.h2d_bytes //= n_e2e
+        be.d2h_bytes //= n_e2e
         by = torch.tensor([be.h2d_bytes, be.d2h_bytes], dtype=torch.float64, device=be.device)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dist.all_reduce(by)

@@ -72,6 +72,99 @@ int truncate(const std::vector<double> &lv, const TruncPar &tp) {
 
 }  // namespace
 
+namespace {
+// Monotone priority queue for the best-first enumeration.  Popped sums never decrease (a child is never
+// smaller than its parent, up to one rounding) and only the window [base, base + max_logval] matters, so
+// the items are binned by sum into a few thousand buckets: a pop takes the (sum, seq)-minimum of the lowest
+// non-empty bucket (a scan of one or two items), a push is an index computation.  The order of the pops --
+// and with it every result -- is exactly that of the reference's binary heap; it is just ~4x cheaper than
+// sifting through a 1000-entry heap.  Items beyond the window go to a small binary heap.
+struct BucketQueue {
+  static constexpr int NB = 8192;
+  std::vector<int32_t> head, next;
+  std::vector<uint64_t> bits;
+  std::vector<HeapItem> pool, over;
+  double base = 0.0, scale = 0.0;
+  int cur = NB;
+  static bool less(const HeapItem &x, const HeapItem &y) {
+    return (x.sum < y.sum) | ((x.sum == y.sum) & (x.seq < y.seq));
+  }
+  void reset(double base_, double window) {
+    head.assign(NB, -1);
+    bits.assign(NB / 64, 0);
+    pool.clear();
+    next.clear();
+    over.clear();
+    base = base_;
+    scale = NB / (window * 1.0001);
+    cur = NB;
+  }
+  void push(const HeapItem &v) {
+    const double t = (v.sum - base) * scale;
+    if (!(t < (double)NB)) {          // beyond the window (or NaN): overflow heap
+      size_t i = over.size();
+      over.push_back(v);
+      while (i > 0) {
+        size_t p = (i - 1) / 2;
+        if (!less(v, over[p])) break;
+        over[i] = over[p];
+        i = p;
+      }
+      over[i] = v;
+      return;
+    }
+    const int b = t > 0.0 ? (int)t : 0;
+    const int32_t id = (int32_t)pool.size();
+    pool.push_back(v);
+    next.push_back(head[b]);
+    head[b] = id;
+    bits[b >> 6] |= (1ull << (b & 63));
+    if (b < cur) cur = b;
+  }
+  bool empty() {
+    if (cur < NB && head[cur] >= 0) return false;
+    int w = cur >> 6;
+    if (cur < NB) {
+      uint64_t m = bits[w] & (~0ull << (cur & 63));
+      for (;;) {
+        if (m) { cur = (w << 6) + __builtin_ctzll(m); return false; }
+        if (++w >= NB / 64) break;
+        m = bits[w];
+      }
+      cur = NB;
+    }
+    return over.empty();
+  }
+  HeapItem pop() {   // precondition: !empty()
+    if (cur < NB) {
+      int32_t best = head[cur], bprev = -1, prev = head[cur];
+      for (int32_t it = next[prev]; it >= 0; prev = it, it = next[it])
+        if (less(pool[it], pool[best])) { best = it; bprev = prev; }
+      if (bprev < 0) head[cur] = next[best]; else next[bprev] = next[best];
+      if (head[cur] < 0) bits[cur >> 6] &= ~(1ull << (cur & 63));
+      return pool[best];
+    }
+    const HeapItem top = over[0];
+    const HeapItem v = over.back();
+    over.pop_back();
+    const size_t nh = over.size();
+    if (nh) {
+      size_t i = 0;
+      for (;;) {
+        size_t c = 2 * i + 1;
+        if (c >= nh) break;
+        if (c + 1 < nh && less(over[c + 1], over[c])) ++c;
+        if (!less(over[c], v)) break;
+        over[i] = over[c];
+        i = c;
+      }
+      over[i] = v;
+    }
+    return top;
+  }
+};
+}  // namespace
+
 void lowest_sums(const double *a, int k, double base, const TruncPar &tp, int filled_left,
                  int filled_right, std::vector<double> &sums, std::vector<uint64_t> &sets,
                  int *n_checked) {
@@ -104,16 +197,19 @@ void lowest_sums(const double *a, int k, double base, const TruncPar &tp, int fi
   // binary min-heap on (sum, seq) in a flat vector; "replace top" fuses the pop with the first push
   std::vector<HeapItem> heap;
   heap.reserve(tp.chi_max > 0 ? 2 * (size_t)tp.chi_max + 8 : 4096);
+  // (sum, seq) order without short-circuit branches: the comparison outcomes along a sift are unpredictable
   auto less = [](const HeapItem &x, const HeapItem &y) {
-    return x.sum < y.sum || (x.sum == y.sum && x.seq < y.seq);
+    return (x.sum < y.sum) | ((x.sum == y.sum) & (x.seq < y.seq));
   };
+  // Replacing the root: the new item is a child of the popped one (a larger sum), so it belongs near the
+  // bottom -- walk the hole down along the smaller children without comparing against it, then sift it up.
   auto sift_down = [&](size_t i) {
     const size_t nh = heap.size();
-    HeapItem v = heap[i];
+    const HeapItem v = heap[i];
     for (;;) {
       size_t c = 2 * i + 1;
       if (c >= nh) break;
-      if (c + 1 < nh && less(heap[c + 1], heap[c])) ++c;
+      if (c + 1 < nh) c += (size_t)less(heap[c + 1], heap[c]);
       if (!less(heap[c], v)) break;
       heap[i] = heap[c];
       i = c;
@@ -132,8 +228,30 @@ void lowest_sums(const double *a, int k, double base, const TruncPar &tp, int fi
     heap[i] = v;
   };
   int64_t seq = 0;
-  push({base + mag[order[0]], seq, 0, neg ^ (1ull << order[0])});  // :291-293
   int checked = 1;
+  if (max_logval > 0.0 && max_logval < 64.0) {
+    // fast path: bucket queue over the window of admissible sums
+    static thread_local BucketQueue q;
+    q.reset(base, max_logval);
+    q.push({base + mag[order[0]], seq, 0, neg ^ (1ull << order[0])});  // :291-293
+    while (!q.empty() && (sums.empty() || more_needed(sums, tp, max_logval))) {  // :297
+      ++checked;
+      const HeapItem it = q.pop();
+      if (tp.is_sector(charge_of(it.set, k, filled_left, filled_right))) {
+        sums.push_back(it.sum);
+        sets.push_back(it.set);
+      }
+      if (it.i < k - 1) {  // :304-315
+        const uint64_t c1 = it.set ^ (1ull << order[it.i + 1]);
+        double s = it.sum + mag[order[it.i + 1]];
+        q.push({s, ++seq, it.i + 1, c1});
+        const uint64_t c2 = c1 ^ (1ull << order[it.i]);
+        s = s - mag[order[it.i]];
+        q.push({s, ++seq, it.i + 1, c2});
+      }
+    }
+  } else {
+  push({base + mag[order[0]], seq, 0, neg ^ (1ull << order[0])});  // :291-293
   while (!heap.empty() && (sums.empty() || more_needed(sums, tp, max_logval))) {  // :297
     ++checked;
     const HeapItem it = heap[0];
@@ -154,6 +272,7 @@ void lowest_sums(const double *a, int k, double base, const TruncPar &tp, int fi
       heap.pop_back();
       if (!heap.empty()) sift_down(0);
     }
+  }
   }
   if (n_checked) *n_checked = checked;
   if (sums.empty()) return;
@@ -236,24 +355,49 @@ void bond_vectors(const double *e, int k, int filled_left, const TruncPar &tp, B
     idx[i] = i;
     nl[i] = filled_left + __builtin_popcountll(sets[i]);  // slater.py:673
   }
-  std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return nl[x] < nl[y]; });  // :676
+  {  // stable sort by n_L (slater.py:676): counting sort, the charges span at most k + 1 values
+    std::vector<int> start((size_t)k + 2, 0);
+    for (int i = 0; i < chi; ++i) ++start[nl[i] - filled_left + 1];
+    for (int q = 1; q <= k + 1; ++q) start[q] += start[q - 1];
+    for (int i = 0; i < chi; ++i) idx[start[nl[i] - filled_left]++] = i;
+  }
   out.masks.resize(chi);
   out.lam.resize(chi);
   out.charge.resize(chi);
   out.sec_q.clear();
   out.sec_start.clear();
+  // slater.py:489: lambda^2 = prod_i (e_i if occupied else 1 - e_i), multiplied in mode order.  Table lookup
+  // instead of a branch per mode, four vectors at a time to overlap the multiply latencies.
+  std::vector<double> tab(2 * (size_t)std::max(k, 1));
+  for (int i = 0; i < k; ++i) { tab[2 * i] = 1.0 - e[i]; tab[2 * i + 1] = e[i]; }
   for (int r = 0; r < chi; ++r) {
-    const uint64_t m = sets[idx[r]];
-    out.masks[r] = m;
+    out.masks[r] = sets[idx[r]];
     out.charge[r] = nl[idx[r]];
+  }
+  int r4 = 0;
+  for (; r4 + 4 <= chi; r4 += 4) {
+    const uint64_t m0 = out.masks[r4], m1 = out.masks[r4 + 1], m2 = out.masks[r4 + 2], m3 = out.masks[r4 + 3];
+    double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
+    for (int i = 0; i < k; ++i) {
+      p0 *= tab[2 * i + ((m0 >> i) & 1)];
+      p1 *= tab[2 * i + ((m1 >> i) & 1)];
+      p2 *= tab[2 * i + ((m2 >> i) & 1)];
+      p3 *= tab[2 * i + ((m3 >> i) & 1)];
+    }
+    out.lam[r4] = std::sqrt(p0); out.lam[r4 + 1] = std::sqrt(p1);
+    out.lam[r4 + 2] = std::sqrt(p2); out.lam[r4 + 3] = std::sqrt(p3);
+  }
+  for (; r4 < chi; ++r4) {
+    const uint64_t m = out.masks[r4];
     double p = 1.0;
-    for (int i = 0; i < k; ++i) p *= ((m >> i) & 1) ? e[i] : (1.0 - e[i]);  // slater.py:489
-    out.lam[r] = std::sqrt(p);
+    for (int i = 0; i < k; ++i) p *= tab[2 * i + ((m >> i) & 1)];
+    out.lam[r4] = std::sqrt(p);
+  }
+  for (int r = 0; r < chi; ++r)
     if (r == 0 || out.charge[r] != out.charge[r - 1]) {
       out.sec_q.push_back(out.charge[r]);
       out.sec_start.push_back(r);
     }
-  }
   out.sec_start.push_back(chi);
 }
 

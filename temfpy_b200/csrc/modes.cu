@@ -39,6 +39,51 @@ TMF_GLOBAL omega_kernel(double *om, int rows, int cols) {
   }
 }
 
+// Range sketch Y_x = B_x Omega for every bond x at once.  With the same test matrix for all bonds
+// (rows of Omega indexed by the global site) the sketches of consecutive bonds are prefix / suffix sums,
+//     right block at x:  Y_x[g - x, c] = sum_{j <  x} C[g, j] Omega[j, c]   (g >= x)
+//     left  block at x:  Y_x[g,     c] = sum_{j >= x} C[g, j] Omega[j, c]   (g <  x)
+// so one pass over C per sketch column (L^2 r multiply-adds in total) replaces the batched GEMM
+// (sum_x 2 n m r, ~2e10 flop at L = 1024).  Thread = (site g, sketch column c), lanes along g: the reads of
+// C (symmetric, so C[g, j] = C[j, g]) and the writes of Y coalesce.
+struct SketchEntry {
+  double *Y;   // n x rr sketch of the job at this bond (nullptr: no job)
+  int n, rr;
+};
+TMF_GLOBAL sketch_scan_kernel(const double *C, int ldc, int L, const double *Om, int r, const SketchEntry *tabR,
+                              const SketchEntry *tabL, int xloR, int xhiR, int xloL, int xhiL) {
+  const int gblocks = (L + 31) / 32;
+  const int gb = BLOCK_ID % gblocks, cb = BLOCK_ID / gblocks;
+  PAR_FOR(t, 256) {
+    const int g = gb * 32 + (t & 31), c = cb * 8 + (t >> 5);
+    if (g < L && c < r) {
+      const double *om = Om + (int64_t)c * L;
+      if (xhiR >= xloR) {
+        double s = 0.0;
+        const int jend = g < xhiR ? g : xhiR;
+        for (int j = 0; j <= jend; ++j) {
+          if (j >= xloR) {
+            const SketchEntry e = tabR[j];
+            if (e.Y != nullptr && c < e.rr) e.Y[(int64_t)c * e.n + (g - j)] = s;
+          }
+          s += C[(int64_t)j * ldc + g] * om[j];
+        }
+      }
+      if (xhiL >= xloL) {
+        double s = 0.0;
+        const int jbeg = (g + 1 > xloL) ? g + 1 : xloL;
+        for (int j = L - 1; j >= jbeg; --j) {
+          s += C[(int64_t)j * ldc + g] * om[j];
+          if (j <= xhiL) {
+            const SketchEntry e = tabL[j];
+            if (e.Y != nullptr && c < e.rr) e.Y[(int64_t)c * e.n + g] = s;
+          }
+        }
+      }
+    }
+  }
+}
+
 #if defined(TMF_HOSTSIM)
 static int copy_d2d(void *dst, const void *src, size_t bytes, void *) {
   std::memcpy(dst, src, bytes);
@@ -179,7 +224,7 @@ extern "C" int64_t tmf_slater_modes_workspace(int L, int njobs, const int *job_x
   }
   // descriptor blob: ~ (14 + 8 * panels) launches of nbig descriptors of 128 bytes
   const int panels = (r_sketch + PANEL_W - 1) / PANEL_W;
-  bytes += align256((int64_t)(nbig + 1) * 128 * (16 + 10 * panels) + (int64_t)(nsmall + 1) * 64 + 65536);
+  bytes += align256((int64_t)(nbig + 1) * 128 * (16 + 10 * panels) + (int64_t)(nsmall + 1) * 64 + (int64_t)(L + 1) * 32 + 65536);
   return bytes;
 }
 
@@ -322,10 +367,25 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
     }
   };
 
-  // 1. Y = B * Omega
+  // 1. Y = B * Omega: prefix / suffix scan over all bonds (the batched GEMM is kept as a debugging switch)
+  static const bool sketch_gemm = std::getenv("TMF_SKETCH_GEMM") != nullptr;
   g.clear();
-  for (auto &b : big) g.push_back(mk_gemm(b.B, ldc, 0, b.Om, L, 0, b.Y, b.n, b.n, b.rr, b.m));
+  if (sketch_gemm)
+    for (auto &b : big) g.push_back(mk_gemm(b.B, ldc, 0, b.Om, L, 0, b.Y, b.n, b.n, b.rr, b.m));
   L_sketch[0] = add_gemm(blob, g);
+  std::vector<SketchEntry> tabR((size_t)L + 1, SketchEntry{nullptr, 0, 0}), tabL((size_t)L + 1, SketchEntry{nullptr, 0, 0});
+  int xloR = L + 1, xhiR = -1, xloL = L + 1, xhiL = -1;
+  for (auto &b : big) {
+    const int x = job_x[b.job];
+    if (b.side == TMF_SIDE_R) {
+      tabR[x] = SketchEntry{b.Y, b.n, b.rr};
+      xloR = std::min(xloR, x); xhiR = std::max(xhiR, x);
+    } else {
+      tabL[x] = SketchEntry{b.Y, b.n, b.rr};
+      xloL = std::min(xloL, x); xhiL = std::max(xhiL, x);
+    }
+  }
+  const SketchEntry *tabR_dev = blob.add(tabR), *tabL_dev = blob.add(tabL);
   build_orth(orthY, false);
   // 4. Wt = B^T Q
   g.clear();
@@ -430,7 +490,13 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
   };
   rc = memset_dev(counters, 0, sizeof(int) * 4 * (size_t)nb, stream);
   if (rc) return rc;
-  if ((rc = run(L_sketch[0]))) return rc;
+  if (sketch_gemm) {
+    if ((rc = run(L_sketch[0]))) return rc;
+  } else {
+    rc = launch_t("sketch_scan", sketch_scan_kernel, ((L + 31) / 32) * ((r_sketch + 7) / 8), 256, 0, stream, C_dev, ldc, L,
+                  (const double *)Om, r_sketch, tabR_dev, tabL_dev, xloR, xhiR, xloL, xhiL);
+    if (rc) return rc;
+  }
   if ((rc = run_orth(orthY))) return rc;
   if ((rc = run(L_wt[0]))) return rc;
   rc = copy_d2d(wt_begin + wt_bytes, wt_begin, wt_bytes, stream);
