@@ -176,7 +176,7 @@ def run_native(args):
         if world > 1:
             tdist.broadcast_C(C_dev)
         res = engine.run_chain(be, C_dev, L, L, tp, N, site_lo=lo, site_hi=hi, r_sketch=args.r_sketch,
-                               n_threads=args.threads, n_chunks=n_chunks if n_chunks else args.chunks, lazy=True)
+                               n_threads=args.threads, n_chunks=n_chunks if n_chunks else (args.chunks or None), lazy=True)
         if world > 1:
             bufs = res.out_buffers()
             local = bufs[0][0][: bufs[0][1]] if len(bufs) == 1 else torch.cat([b[:n] for b, n in bufs])
@@ -359,7 +359,7 @@ def run_native(args):
                                    "all site tensors + Schmidt data resident in HBM",
                        "l2": f"working set {(8 * state['out_elems'] + 6e8) / 1e9:.1f} GB per step >> 126 MB L2",
                        "parallelism": (f"sites sharded over {world} GPU(s), broadcast(C) + gather(tensors) over NCCL"
-                                       if world > 1 else "1 GPU") + f"; {args.chunks} pipeline chunks per GPU"},
+                                       if world > 1 else "1 GPU") + f"; {args.chunks or 'auto (6 at >= 512 sites per GPU)'} pipeline chunks per GPU"},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roof,
             "whole_step": whole, "cpu_baseline": cpu}
     print(json.dumps(line))
@@ -378,7 +378,7 @@ def main():
     ap.add_argument("--svd-min", type=float, default=1e-7)
     ap.add_argument("--r-sketch", type=int, default=48)
     ap.add_argument("--threads", type=int, default=0)
-    ap.add_argument("--chunks", type=int, default=4, help="pipeline chunks per GPU (streams + host threads)")
+    ap.add_argument("--chunks", type=int, default=0, help="pipeline chunks per GPU (streams + host threads)")
     ap.add_argument("--cpu-sites", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

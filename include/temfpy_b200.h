@@ -266,6 +266,10 @@ int tmf_chain_modes_enqueue(tmf_chain *c, const double *C_dev, int ldc, double *
                             int *info_dev, void *work_dev, int64_t work_bytes, void *stream);
 int tmf_chain_modes_finish(tmf_chain *c, const double *e_dev, const int *info_dev, void *stream);
 int tmf_chain_enumerate(tmf_chain *c);
+/* The same with the subset enumeration (schmidt_utils.py:211-324, slater.py:633-700) on the device:
+ * one warp per bond; work_dev holds tmf_chain_enum_workspace(c) bytes.  Bit-identical tables. */
+int64_t tmf_chain_enum_workspace(tmf_chain *c);
+int tmf_chain_enumerate_dev(tmf_chain *c, void *work_dev, int64_t work_bytes, void *stream);
 int tmf_chain_tensor_sizes(tmf_chain *c, int64_t *q /* plan bytes, O, S doubles, sites, blocks,
                                                        out doubles, max chi */);
 int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, void *plan_dev,

@@ -114,6 +114,8 @@ SIGNATURES = {
                                           C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "tmf_chain_modes_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tmf_chain_enumerate": (C.c_int, [C.c_void_p]),
+    "tmf_chain_enum_workspace": (C.c_int64, [C.c_void_p]),
+    "tmf_chain_enumerate_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "tmf_chain_tensor_sizes": (C.c_int, [C.c_void_p, c_i64_p]),
     "tmf_chain_tensors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

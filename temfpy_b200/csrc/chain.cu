@@ -39,6 +39,13 @@ int gemm_grouped(const tmf_gemm_job *jobs, int njobs, void *desc_dev, void *stre
 int64_t gemm_desc_bytes(int njobs);
 }  // namespace tmf
 
+namespace tmf {
+int64_t enum_workspace_bytes(int nb, int chi_max);
+int enumerate_device(int nb, const double *const *e_ptr, const int *k, const int *filled_left, const TruncPar &tp,
+                     std::vector<BondVectors *> &out, void *work_dev, int64_t work_bytes, void *stream,
+                     unsigned char *stage, size_t stage_bytes, int n_threads);
+}  // namespace tmf
+
 extern "C" int64_t tmf_site_desc_bytes(int nsites);
 extern "C" int64_t tmf_minor_desc_bytes(int nblocks);
 
@@ -296,8 +303,20 @@ int tmf_chain_modes(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, d
   return tmf_chain_modes_finish(c, e_dev, info_dev, stream);
 }
 
-// host: enumeration + planning.  Requires tmf_chain_modes to have completed.
-int tmf_chain_enumerate(tmf_chain *c) {
+// enumeration (device kernel when a workspace is given, host otherwise) + planning (host).  Requires
+// tmf_chain_modes to have completed.
+static int chain_enumerate_impl(tmf_chain *c, void *work_dev, int64_t work_bytes, void *stream);
+int tmf_chain_enumerate(tmf_chain *c) { return chain_enumerate_impl(c, nullptr, 0, nullptr); }
+int64_t tmf_chain_enum_workspace(tmf_chain *c) {
+  int nb = 0;
+  for (int b = 0; b <= c->L; ++b)
+    if (c->bonds[b].used) ++nb;
+  return tmf::enum_workspace_bytes(nb, c->tp.chi_max);
+}
+int tmf_chain_enumerate_dev(tmf_chain *c, void *work_dev, int64_t work_bytes, void *stream) {
+  return chain_enumerate_impl(c, work_dev, work_bytes, stream);
+}
+static int chain_enumerate_impl(tmf_chain *c, void *work_dev, int64_t work_bytes, void *stream) {
   try {
     StageTimer tm;
     std::vector<int> used;
@@ -317,11 +336,34 @@ int tmf_chain_enumerate(tmf_chain *c) {
       // slater.py:145-174: filled-left count, inferred from n_fermion when only vR is known
       B.filled_left = (Ls.job >= 0) ? Ls.f : c->nferm - B.k - Rs.f;
     }
+    if (work_dev != nullptr) {
+      const int nbu = (int)used.size();
+      std::vector<const double *> ep(nbu);
+      std::vector<int> kk(nbu), fl(nbu);
+      std::vector<tmf::BondVectors *> outp(nbu);
+      for (int u = 0; u < nbu; ++u) {
+        ChainBond &B = c->bonds[used[u]];
+        const int job = (B.side[TMF_SIDE_L].job >= 0) ? B.side[TMF_SIDE_L].job : B.side[TMF_SIDE_R].job;
+        ep[u] = c->e_host.data() + (size_t)job * TMF_MAX_MODES;
+        kk[u] = B.k; fl[u] = B.filled_left; outp[u] = &B.bv;
+      }
+      // pinned staging for the job upload and the table download (shared with the plan blob later)
+      const size_t need = (size_t)nbu * (2048 + (size_t)(std::max(c->tp.chi_max, 0) + 2) * 20 + 1024) + 4096;
+      if (c->blob_cap < need) {
+        g_pinned.release(c->blob, c->blob_cap);
+        c->blob = g_pinned.acquire(need, c->blob_cap);
+        if (!c->blob) c->blob_cap = 0;
+      }
+      int rc = tmf::enumerate_device(nbu, ep.data(), kk.data(), fl.data(), c->tp, outp, work_dev, work_bytes, stream,
+                                     c->blob, c->blob_cap, c->n_threads > 0 ? c->n_threads : 8);
+      if (rc) return rc;
+    } else {
     parallel_for((int)used.size(), c->n_threads, [&](int u) {
       ChainBond &B = c->bonds[used[u]];
       const int job = (B.side[TMF_SIDE_L].job >= 0) ? B.side[TMF_SIDE_L].job : B.side[TMF_SIDE_R].job;
       tmf::bond_vectors(c->e_host.data() + (size_t)job * TMF_MAX_MODES, B.k, B.filled_left, c->tp, B.bv);
     });
+    }
     tm.lap("enumerate: bond vectors");
     c->sites.clear();
     for (int i = c->site_lo; i < c->site_hi; ++i) {

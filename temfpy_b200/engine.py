@@ -382,7 +382,17 @@ class SlaterChain:
         self.finish_modes()
 
     def run_enumerate(self):
-        check(self.lib, self.lib.tmf_chain_enumerate(self.handle))
+        """Subset enumeration on the device (one warp per bond), planning on the host."""
+        import os
+        if os.environ.get("TMF_HOST_ENUMERATE"):
+            check(self.lib, self.lib.tmf_chain_enumerate(self.handle))
+            return
+        be, lib = self.be, self.lib
+        nbytes = int(lib.tmf_chain_enum_workspace(self.handle))
+        work = self._buffers.get("work")
+        if work is None or work.nbytes < nbytes:
+            work = self._buffers["work"] = be.empty(nbytes, np.uint8)     # the mode workspace is dead by now
+        check(lib, lib.tmf_chain_enumerate_dev(self.handle, be.ptr(work), nbytes, be.stream))
 
     # -- stage B: tensors -----------------------------------------------------------------------
     def run_tensors(self, C_dev, ldc, out=None):
@@ -519,8 +529,10 @@ class _StageGate:
     def __init__(self, backend, n):
         import threading
         self.be = backend
+        import os
         self.enqueued = [threading.Event() for _ in range(n)]
         self.done = [None] * n
+        self.depth = max(1, int(os.environ.get("TMF_GATE_DEPTH", "2")))
 
     def gate(self, i):
         outer = self
@@ -529,10 +541,11 @@ class _StageGate:
             used = False
 
             def before(self):
-                if self.used or i == 0:
+                j = i - outer.depth        # `depth` mode stages may be in flight at once
+                if self.used or j < 0:
                     return
-                outer.enqueued[i - 1].wait()
-                ev = outer.done[i - 1]
+                outer.enqueued[j].wait()
+                ev = outer.done[j]
                 if ev is not None:
                     outer.be.torch.cuda.current_stream(outer.be.device).wait_event(ev)
 
@@ -595,7 +608,7 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
     site_hi = L if site_hi is None else site_hi
     nsites = site_hi - site_lo
     if n_chunks is None:
-        n_chunks = 4 if (nsites >= 256 and hasattr(backend, "side_stream")) else 1
+        n_chunks = (6 if nsites >= 512 else 4 if nsites >= 192 else 2 if nsites >= 64 else 1) if hasattr(backend, "side_stream") else 1
     n_chunks = max(1, min(n_chunks, nsites))
     if n_chunks == 1:
         r = _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi, r_sketch,

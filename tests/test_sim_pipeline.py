@@ -102,3 +102,22 @@ def test_gemm_grouped_semantics(sim_backend):
     desc = np.zeros(lib.tmf_gemm_desc_bytes(1), np.uint8)
     _lib.check(lib, lib.tmf_gemm_grouped((_lib.GemmJob * 1)(j), 1, desc.ctypes.data, None))
     assert np.allclose(Cc, 2 * A @ B - C0, atol=1e-12)
+
+
+@pytest.mark.parametrize("tp", [{"chi_max": 64}, {"chi_max": 200, "svd_min": 1e-5}, {"chi_max": 7},
+                                {"chi_max": 64, "sectors": [q for q in range(31) if q not in (14, 17)]}])
+def test_device_enumeration_equals_host_enumeration(sim_backend, monkeypatch, tp):
+    """The enumeration kernel (bucket queue, one warp per bond) reproduces the host implementation of
+    schmidt_utils.lowest_sums / SchmidtVectors.from_schmidt_modes bit for bit: masks in the same order,
+    identical Schmidt values, charges and sector tables."""
+    L = 30
+    Cm, n = so.correlation_matrix(helpers.random_hamiltonian(L, 21))
+    dev = helpers.run_native(sim_backend, Cm, tp, n)
+    monkeypatch.setenv("TMF_HOST_ENUMERATE", "1")
+    host = helpers.run_native(sim_backend, Cm, tp, n)
+    for x in range(L + 1):
+        a, b = dev.bonds[x], host.bonds[x]
+        assert np.array_equal(a.masks, b.masks)
+        assert np.array_equal(a.schmidt_values, b.schmidt_values)
+        assert np.array_equal(a.charge, b.charge)
+        assert a.idx_L == b.idx_L
