@@ -15,9 +15,10 @@ for _ in range(2):
     slater.C_to_MPS(C, tpd, as_tenpy=False)
 for it in range(3):
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    Cp = slater._prepare_C(C, None); slater._check_projector(Cp)
+    Cp = slater._prepare_C(C, None)
     t1 = time.perf_counter()
     Cd = be.from_host(Cp.ravel())
+    slater._check_projector(Cp, be=be, Cd=Cd)
     t2 = time.perf_counter()
     res = engine.run_chain(be, Cd, L, L, tp, N)
     t3 = time.perf_counter()
