@@ -178,9 +178,7 @@ def run_native(args):
         res = engine.run_chain(be, C_dev, L, L, tp, N, site_lo=lo, site_hi=hi, r_sketch=args.r_sketch,
                                n_threads=args.threads, n_chunks=n_chunks if n_chunks else (args.chunks or None), lazy=True)
         if world > 1:
-            bufs = res.out_buffers()
-            local = bufs[0][0][: bufs[0][1]] if len(bufs) == 1 else torch.cat([b[:n] for b, n in bufs])
-            full, offs = tdist.gather_tensors(local, int(local.numel()))
+            full, offs = tdist.gather_tensors(res.out_buffers())
             state["gathered"] = None if full is None else int(full.numel())
         if collect_stats:
             state["flops"] = [float(x) for x in res.flops()]

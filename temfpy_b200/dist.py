@@ -48,29 +48,48 @@ def broadcast_C(C_dev, src=0):
     dist.broadcast(C_dev, src=src)
 
 
-def gather_tensors(out_dev, out_elems: int, dst=0):
+MAX_PARTS = 16
+
+
+def gather_tensors(parts, dst=0):
     """Gathers the ranks' block-sparse tensor buffers on ``dst`` (variable sizes -> grouped
-    point-to-point sends over NVLink).  Returns (buffer, offsets) on dst, (None, None) elsewhere."""
+    point-to-point sends over NVLink).  ``parts``: list of (device buffer, n_elements) in site order (the
+    pipeline chunks of this rank; sent one by one, no concatenation copy).  Returns (buffer, offsets per
+    rank) on dst, (None, None) elsewhere."""
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(), dist.get_rank()
-    sizes = torch.zeros(world, dtype=torch.int64, device=out_dev.device)
-    sizes[rank] = out_elems
+    if not isinstance(parts, (list, tuple)):
+        raise TypeError("parts must be a list of (buffer, n_elements)")
+    if len(parts) > MAX_PARTS:
+        raise ValueError("too many pipeline chunks for one gather")
+    dev = parts[0][0].device
+    sizes_h = np.zeros((world, MAX_PARTS), dtype=np.int64)
+    for i, (_, n) in enumerate(parts):
+        sizes_h[rank, i] = int(n)
+    sizes = torch.from_numpy(sizes_h).to(dev)
     dist.all_reduce(sizes)
-    sizes = sizes.cpu().tolist()
-    offs = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+    sizes = sizes.cpu().numpy()
+    per_rank = sizes.sum(axis=1)
+    offs = np.concatenate(([0], np.cumsum(per_rank))).astype(np.int64)
     if rank == dst:
-        full = torch.empty(int(offs[-1]), dtype=out_dev.dtype, device=out_dev.device)
+        full = torch.empty(int(offs[-1]), dtype=parts[0][0].dtype, device=dev)
         ops = []
         for r in range(world):
-            if r == dst:
-                full[offs[r]: offs[r + 1]].copy_(out_dev[:out_elems])
-            elif sizes[r]:
-                ops.append(dist.P2POp(dist.irecv, full[offs[r]: offs[r + 1]], r))
+            o = int(offs[r])
+            for i in range(MAX_PARTS):
+                n = int(sizes[r, i])
+                if n == 0:
+                    continue
+                if r == dst:
+                    full[o: o + n].copy_(parts[i][0][:n])
+                else:
+                    ops.append(dist.P2POp(dist.irecv, full[o: o + n], r))
+                o += n
         for w in (dist.batch_isend_irecv(ops) if ops else []):
             w.wait()
         return full, offs
-    if out_elems:
-        for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, out_dev[:out_elems], dst)]):
-            w.wait()
+    ops = [dist.P2POp(dist.isend, buf[:n], dst) for buf, n in parts if n]
+    for w in (dist.batch_isend_irecv(ops) if ops else []):
+        w.wait()
     return None, None

@@ -608,7 +608,7 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
     site_hi = L if site_hi is None else site_hi
     nsites = site_hi - site_lo
     if n_chunks is None:
-        n_chunks = (6 if nsites >= 512 else 4 if nsites >= 192 else 2 if nsites >= 64 else 1) if hasattr(backend, "side_stream") else 1
+        n_chunks = (6 if nsites >= 768 else 4 if nsites >= 384 else 2 if nsites >= 192 else 1) if hasattr(backend, "side_stream") else 1
     n_chunks = max(1, min(n_chunks, nsites))
     if n_chunks == 1:
         r = _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi, r_sketch,

@@ -46,7 +46,7 @@ def _worker(rank, world, port, L, chi, out_path):
         lo, hi = tdist.partition(L, world, chi)[rank]
         res = engine.run_chain(be, Ct.numpy(), L, L, tp, int(n[0]), site_lo=lo, site_hi=hi, n_chunks=1, lazy=True)
         buf, elems = res.out_buffers()[0]
-        full, offs = tdist.gather_tensors(torch.from_numpy(buf), elems)       # tensors to rank 0
+        full, offs = tdist.gather_tensors([(torch.from_numpy(buf), elems)])       # tensors to rank 0
         lam = [res.bond(x).schmidt_values for x in range(lo, hi + 1)]
         if rank == 0:
             ref = engine.run_chain(be, Ct.numpy(), L, L, tp, int(n[0]), n_chunks=1, lazy=True)
