@@ -347,8 +347,25 @@ TMF_DEVICE int jacobi_onesided(double *G, int ldg, double *J, int ldj, int n, do
           // noise of the rotations with the other columns keeps changing it by O(1) of its own size, so
           // pairs involving it would never meet the relative criterion -- skip them (as LAPACK's dgesvj)
           if (c * c > 1e-30 * a * b && a > 1e-30 && b > 1e-30) {
-            const double zeta = (b - a) / (2.0 * c);
-            const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b - a) / (2 c), written without the
+            // two IEEE divisions and the IEEE square root: every lane of the warp computes the same scalars
+            // and those three emulated operations (~25 FP64 instructions each) were the bulk of the FP64-pipe
+            // time of a Jacobi round.  rsqrt and a Newton-refined reciprocal are accurate to a few ulp, ample
+            // for a rotation angle (cs^2 + sn^2 = 1 holds to the same few ulp; J is renormalised at the end).
+            const double d = b - a, h = 2.0 * c;
+            const double q2 = d * d + h * h;
+            const double rs = rsqrt(q2);
+            const double den = fabs(d) + q2 * rs;            // |d| + sqrt(d^2 + h^2)
+            double rc;
+            if (den > 1e-30 && den < 1e30) {
+              rc = (double)__frcp_rn((float)den);
+              rc = rc * (2.0 - den * rc);
+              rc = rc * (2.0 - den * rc);
+              rc = rc * (2.0 - den * rc);
+            } else {
+              rc = 1.0 / den;
+            }
+            const double t = ((d >= 0.0) == (h >= 0.0) ? fabs(h) : -fabs(h)) * rc;
             const double cs = rsqrt(1.0 + t * t), sn = cs * t;
             if (lane == 0) *flag = 1;
             for (int r = lane; r < n; r += 32) {

@@ -12,15 +12,17 @@ import numpy as np
 
 
 def site_costs(L: int, chi_max: int | None, ortho_center: int | None = None) -> np.ndarray:
-    """Relative cost model per site: mode extraction ~ n^3 of the block that is decomposed plus the
-    tensor entries ~ chi_bra * chi_ket (chi saturates at chi_max, 2^distance near the ends)."""
+    """Relative cost model per site, fitted to measured shard times on B200 (8 ranks, L = 1024): the mode
+    extraction of a block of n sites costs ~ (150 + n) (sketch + skinny GEMMs + latency-bound panels, no
+    O(n^3) eigen-solver any more), the tensor entries ~ chi_bra * chi_ket (chi saturates at chi_max,
+    2^distance near the ends)."""
     oc = ortho_center or L // 2
     i = np.arange(L)
     n = np.where(i >= oc, L - i, i + 1).astype(float)
     dist = np.minimum(i + 1, L - i).astype(float)
     cap = float(chi_max) if chi_max else 1024.0
     chi = np.minimum(cap, 2.0 ** np.minimum(dist, 40))
-    return 1.2e-2 * n ** 3 + 2.0 * chi * chi + 5e4
+    return (150.0 + n) * (0.35 + 0.65 * (chi / cap) ** 2)
 
 
 def partition(L: int, world: int, chi_max: int | None = None, ortho_center: int | None = None,
