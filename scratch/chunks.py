@@ -11,10 +11,10 @@ L = 1024
 Cm, N = ground_state_C(L)
 Cd = be.from_host(Cm.ravel())
 tp = to_stopping_condition({"chi_max": 1024, "svd_min": 1e-7})
-for gate in (1, 2, 3, 0):
+for gate in (2,):
     if gate: os.environ.pop("TMF_NO_STAGE_GATE", None); os.environ["TMF_GATE_DEPTH"] = str(gate)
     else: os.environ["TMF_NO_STAGE_GATE"] = "1"
-    for nc in (4, 6, 8):
+    for nc in (6, 8, 10):
         for _ in range(2):
             engine.run_chain(be, Cd, L, L, tp, N, n_chunks=nc, lazy=True).close()
         ts = []

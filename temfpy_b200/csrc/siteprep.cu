@@ -9,6 +9,7 @@
 //
 // O is produced by the grouped DMMA GEMM (column gathers + sign scalings in the epilogue); the LU
 // runs one CTA per site with 16-wide panels staged in shared memory.
+#include <cstdlib>
 #include "cta.hpp"
 
 namespace tmf {
@@ -256,7 +257,8 @@ extern "C" int tmf_site_overlap_schur_batched(const tmf_site_job *jobs_host, int
   rc = gemm_launch_uploaded(reinterpret_cast<const tmf_gemm_job *>(d + o_gemm),
                             reinterpret_cast<const int *>(d + o_pref), nsites, prefix[nsites], stream, "gemm_site");
   if (rc) return rc;
-  return launch_t("schur", schur_kernel, nsites, 256, smem, stream,
+  static const int schur_threads = std::getenv("TMF_SCHUR_THREADS") ? std::atoi(std::getenv("TMF_SCHUR_THREADS")) : 256;
+  return launch_t("schur", schur_kernel, nsites, schur_threads, smem, stream,
                 reinterpret_cast<const tmf_site_job *>(d + o_site));
 }
 
