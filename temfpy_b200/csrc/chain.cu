@@ -114,7 +114,7 @@ struct PinnedPool {
   void release(unsigned char *p, size_t cap) {
     if (!p) return;
     std::lock_guard<std::mutex> lk(mu);
-    if (free_list.size() < 16) { free_list.emplace_back(p, cap); return; }
+    if (free_list.size() < 32) { free_list.emplace_back(p, cap); return; }
 #if defined(TMF_HOSTSIM)
     std::free(p);
 #else
