@@ -321,6 +321,7 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
     size_t norm_smem;
   } orthY, orthW;
 
+  static const bool use_mgs = std::getenv("TMF_PANEL_MGS") != nullptr;   // debugging switch: column-by-column MGS2 panels + GEMM projections
   auto build_orth = [&](OrthPlan &op, bool forW) {
     int rmax = 0;
     for (auto &b : big) rmax = std::max(rmax, b.rr);
@@ -347,13 +348,15 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
         double *M = forW ? b.Wt : b.Y;
         const int rows = forW ? b.m : b.n;
         double *P = M + (int64_t)c0 * rows;
-        if (c0 > 0) {
-          // coef (c0 x w) = Qprev^T P ;  P -= Qprev coef
+        if (c0 > 0 && use_mgs) {
+          // coef (c0 x w) = Qprev^T P ;  P -= Qprev coef   (the Cholesky-QR panel kernel does this itself)
           gc.push_back(mk_gemm(M, rows, 1, P, rows, 0, b.coef, c0, c0, w, rows));
           gu.push_back(mk_gemm(M, rows, 0, b.coef, c0, 0, P, rows, rows, w, c0, -1.0, 1.0));
         }
         PanelJob q;
+        std::memset(&q, 0, sizeof(q));
         q.P = P; q.norm0 = (forW ? b.norm0w : b.norm0y) + c0; q.nzero = forW ? b.nzw : b.nzy;
+        q.Qprev = (c0 > 0 && !use_mgs) ? M : nullptr; q.c0 = c0;
         q.rows = rows; q.ld = rows; q.ncols = w;
         q.use_smem = (panel_smem_bytes(rows, w, true) <= 200 * 1024) ? 1 : 0;
         smem = std::max(smem, panel_smem_bytes(rows, w, q.use_smem != 0));
@@ -466,7 +469,6 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
     if (gl.ntiles == 0) return (int)TMF_OK;
     return gemm_launch_uploaded(gl.jobs, gl.prefix, gl.njobs, gl.ntiles, stream, "gemm_modes");
   };
-  static const bool use_mgs = std::getenv("TMF_PANEL_MGS") != nullptr;   // debugging switch: column-by-column MGS2 panels
   auto run_orth = [&](OrthPlan &op) -> int {
     int r2 = launch_t("colnorm", colnorm_kernel, nb, 256, op.norm_smem, stream, op.norm);
     if (r2) return r2;
@@ -482,7 +484,7 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
         if (use_mgs)
           r2 = launch_t("panel_mgs2", panel_mgs2_kernel, op.panel_n[p], 256, op.panel_smem[p], stream, op.panel[p], 0.0);
         else
-          r2 = launch_t("panel_cholqr", panel_cholqr_kernel, op.panel_n[p], 256, panel_cholqr_smem_bytes(), stream, op.panel[p], 0.0);
+          r2 = launch_t("panel_cholqr", panel_cholqr_kernel, op.panel_n[p], 256, panel_cholqr_smem_bytes((int)p * PANEL_W), stream, op.panel[p], 0.0);
         if (r2) return r2;
       }
     }

@@ -49,7 +49,9 @@ struct PanelJob {
   double *P;            // rows x ncols, column-major, ld
   const double *norm0;  // squared norms of the original columns (ncols)
   int *nzero;           // incremented for every zeroed column (may be null)
+  const double *Qprev;  // previous (orthonormal) panels, rows x c0, same ld (fused projection; may be null)
   int rows, ld, ncols, use_smem;
+  int c0, pad_;         // number of previous columns to project out before the panel step (0: none)
 };
 
 TMF_DEVICE void panel_mgs2_body(const PanelJob &jb, double rel_tol2, double *sm) {
@@ -145,6 +147,73 @@ TMF_GLOBAL_LB(256, 3) panel_cholqr_kernel(const PanelJob *jobs, double rel_tol2)
   double *Ri = G + PANEL_W * PANEL_W;  // inverse of R (upper triangular), Ri[k * PANEL_W + j]
   int *flag = reinterpret_cast<int *>(Ri + PANEL_W * PANEL_W);
   double *scratch = Ri + PANEL_W * PANEL_W + 2;   // MGS2 fallback scratch
+  // ---- fused block Gram-Schmidt projection: P -= Qprev (Qprev^T P) ---------------------------------
+  // (two skinny GEMMs per panel and round in the previous version: 64 x 64 DMMA tiles of which a 16- or
+  // 32-row by 16-column corner was useful, and two more launches in the dependent chain)
+  const int c0 = (jb0.Qprev != nullptr) ? jb0.c0 : 0;
+  if (c0 > 0) {
+    double *coef = scratch + PANEL_W * 33 + PANEL_W + 40 + 8;   // c0 x PANEL_W, coef[i * PANEL_W + j]
+    const double *Q = jb0.Qprev;
+#if !defined(TMF_HOSTSIM)
+    {
+      const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+      const int nbi = (c0 + 3) / 4, nbj = (w + 3) / 4;
+      for (int blk = wid; blk < nbi * nbj; blk += nw) {
+        const int bi = blk / nbj, bj = blk - bi * nbj;
+        double acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+        for (int r = lane; r < rows; r += 32) {
+          double qi[4], pj[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            qi[a] = (4 * bi + a < c0) ? Q[(int64_t)(4 * bi + a) * ld + r] : 0.0;
+            pj[a] = (4 * bj + a < w) ? P[(int64_t)(4 * bj + a) * ld + r] : 0.0;
+          }
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] += qi[a] * pj[b];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            double v = acc[a][b];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && 4 * bi + a < c0) coef[(4 * bi + a) * PANEL_W + 4 * bj + b] = (4 * bj + b < w) ? v : 0.0;
+          }
+      }
+    }
+#else
+    PAR_FOR(idx, c0 * PANEL_W) {
+      const int i = idx / PANEL_W, j = idx - i * PANEL_W;
+      double sacc = 0.0;
+      if (j < w)
+        for (int r = 0; r < rows; ++r) sacc += Q[(int64_t)i * ld + r] * P[(int64_t)j * ld + r];
+      coef[idx] = sacc;
+    }
+#endif
+    CTA_SYNC();
+    PAR_FOR(r, rows) {
+      double p[PANEL_W];
+#pragma unroll
+      for (int j = 0; j < PANEL_W; ++j) p[j] = (j < w) ? P[(int64_t)j * ld + r] : 0.0;
+      for (int i = 0; i < c0; ++i) {
+        const double q = Q[(int64_t)i * ld + r];
+        const double *ci = coef + i * PANEL_W;
+#pragma unroll
+        for (int j = 0; j < PANEL_W; ++j) p[j] -= q * ci[j];
+      }
+#pragma unroll
+      for (int j = 0; j < PANEL_W; ++j)
+        if (j < w) P[(int64_t)j * ld + r] = p[j];
+    }
+    CTA_SYNC();
+  }
 #if !defined(TMF_HOSTSIM)
   {
     // Gram matrix: warp -> 4 x 4 blocks of column pairs (register tile), lanes -> rows, shuffle reduction
@@ -292,8 +361,8 @@ TMF_GLOBAL_LB(256, 3) panel_cholqr_kernel(const PanelJob *jobs, double rel_tol2)
       if (j < w) P[(int64_t)j * ld + r] = p[j];
   }
 }
-inline size_t panel_cholqr_smem_bytes() {
-  return sizeof(double) * (size_t)(2 * PANEL_W * PANEL_W + 2 + PANEL_W * 33 + PANEL_W + 40 + 8);
+inline size_t panel_cholqr_smem_bytes(int c0_max = 0) {
+  return sizeof(double) * (size_t)(2 * PANEL_W * PANEL_W + 2 + PANEL_W * 33 + PANEL_W + 40 + 8 + (size_t)c0_max * PANEL_W);
 }
 inline size_t panel_smem_bytes(int rows, int ncols, bool use_smem) {
   return sizeof(double) * (size_t)(PANEL_W * 33 + PANEL_W + 40 + (use_smem ? (size_t)rows * ncols : 0));
