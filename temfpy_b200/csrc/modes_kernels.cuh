@@ -763,6 +763,45 @@ TMF_GLOBAL pivchol_kernel(const CholJob *jobs, double tol) {
     PAR_FOR(i, n) dd[i] = d[i];
     CTA_SYNC();
     int nb = 0;
+#if !defined(TMF_HOSTSIM)
+    {
+      // CTA-wide argmax per candidate with shuffles: thread-strided scan, warp reduction, one barrier,
+      // then every warp reduces the 32 warp results redundantly (no second barrier, no single-thread
+      // section).  The two-barrier / one-thread version below spent half of the kernel's time here.
+      const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+      for (int b = 0; b < want; ++b) {
+        double best = -1.0;
+        int bi = 0x7fffffff;
+        for (int i = tid; i < n; i += blockDim.x) {
+          const double v = dd[i];
+          if (v > best) { best = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        double *wr = psum + (b & 1) * 32;                          // psum is free during the selection
+        int *wi = reinterpret_cast<int *>(psum + 64) + (b & 1) * 32;
+        if (lane == 0) { wr[wid] = best; wi[wid] = bi; }
+        __syncthreads();
+        double fb = (lane < nw) ? wr[lane] : -1.0;
+        int fi = (lane < nw) ? wi[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ob = __shfl_xor_sync(0xffffffffu, fb, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, fi, o);
+          if (ob > fb || (ob == fb && oi < fi)) { fb = ob; fi = oi; }
+        }
+        if (tid == 0) { red[40] = fb; red[48 + b] = fb; pidx[b] = fi; }
+        if (!(fb > tol)) break;
+        if (fi % (int)blockDim.x == tid) dd[fi] = -1.0;              // the owner re-reads it next round
+        ++nb;
+      }
+      __syncthreads();
+    }
+#else
     for (int b = 0; b < want; ++b) {
       PAR_FOR(lane, 32) {
         double best = -1.0;
@@ -787,6 +826,7 @@ TMF_GLOBAL pivchol_kernel(const CholJob *jobs, double tol) {
       if (!(red[40] > tol)) break;
       ++nb;
     }
+#endif
     if (nb == 0) break;
     const int K = k + f;
     // ---- rows p_b of the current factor --------------------------------------------------------
