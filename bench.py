@@ -121,7 +121,8 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"1D tight-binding chain L={args.L}, half filling, chi_max={args.chi}, "
-                                   f"svd_min={args.svd_min:g}"},
+                                   f"svd_min={args.svd_min:g} (BASELINE configs[4]); finite MPS; host arrays in, "
+                                   "host arrays out (reference's NumPy path)"},
             "cpu_baseline": {"value": value, "unit": "sites/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
