@@ -14,11 +14,11 @@ tp = to_stopping_condition({"chi_max": 1024, "svd_min": 1e-7})
 for gate in (2,):
     if gate: os.environ.pop("TMF_NO_STAGE_GATE", None); os.environ["TMF_GATE_DEPTH"] = str(gate)
     else: os.environ["TMF_NO_STAGE_GATE"] = "1"
-    for nc in (6, 8, 10):
+    for nc in (6,):
         for _ in range(2):
             engine.run_chain(be, Cd, L, L, tp, N, n_chunks=nc, lazy=True).close()
         ts = []
-        for _ in range(5):
+        for _ in range(9):
             torch.cuda.synchronize(); t0 = time.perf_counter()
             r = engine.run_chain(be, Cd, L, L, tp, N, n_chunks=nc, lazy=True)
             torch.cuda.synchronize(); ts.append(1e3 * (time.perf_counter() - t0)); r.close()

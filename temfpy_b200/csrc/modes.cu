@@ -456,10 +456,11 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
   // ---- launches ----------------------------------------------------------------------------
   // The direct solver of the small blocks (<= 65 latency-bound CTAs) runs on a forked stream next to
   // the sketch path of the large blocks and is joined at the end.
+  static const int small_threads = std::getenv("TMF_SMALL_THREADS") ? std::atoi(std::getenv("TMF_SMALL_THREADS")) : 1024;
   ForkedStream fork;
   if (!small.empty()) {
     void *sstream = (nb > 0) ? fork.open(stream) : stream;
-    rc = launch_t("small_modes", small_modes_kernel, (int)small.size(), 1024, small_smem, sstream, small_dev, cutoff);
+    rc = launch_t("small_modes", small_modes_kernel, (int)small.size(), small_threads, small_smem, sstream, small_dev, cutoff);
     if (rc) return rc;
   }
   if (nb == 0) return TMF_OK;
@@ -507,7 +508,8 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
   if ((rc = run(L_rw[0]))) return rc;
   const double thr = cutoff * (1.0 - cutoff);
   // one warp per column pair of a Jacobi round (latency-bound: more warps per CTA, not more CTAs)
-  const int jac_threads = std::min(1024, 32 * std::max(4, (r_sketch + 1) / 2));
+  static const int jac_env = std::getenv("TMF_JAC_THREADS") ? std::atoi(std::getenv("TMF_JAC_THREADS")) : 0;
+  const int jac_threads = jac_env > 0 ? jac_env : std::min(1024, 32 * std::max(4, (r_sketch + 1) / 2));
   rc = launch_t("svd_select", svd_select_kernel, nb, jac_threads, svd_smem, stream, sj_dev, thr, 1e-26);
   if (rc) return rc;
   if ((rc = run(L_u0[0]))) return rc;

@@ -26,15 +26,21 @@ def site_costs(L: int, chi_max: int | None, ortho_center: int | None = None) -> 
 
 
 def partition(L: int, world: int, chi_max: int | None = None, ortho_center: int | None = None,
-              lo: int = 0, hi: int | None = None):
-    """Contiguous ranges covering [lo, hi) with (nearly) equal summed cost."""
+              lo: int = 0, hi: int | None = None, weights=None):
+    """Contiguous ranges covering [lo, hi) with (nearly) equal summed cost, or with costs proportional to
+    ``weights`` (one per range)."""
     hi = L if hi is None else hi
     c = np.cumsum(site_costs(L, chi_max, ortho_center)[lo:hi])
     n = hi - lo
     world = max(1, min(world, n))
+    if weights is None or len(weights) != world:
+        targets = np.arange(1, world) / world
+    else:
+        w = np.asarray(weights, dtype=float)
+        targets = np.cumsum(w)[:-1] / w.sum()
     cuts = [0]
-    for r in range(1, world):
-        cuts.append(int(np.searchsorted(c, c[-1] * r / world)))
+    for t in targets:
+        cuts.append(int(np.searchsorted(c, c[-1] * t)))
     cuts.append(n)
     for r in range(1, world + 1):           # every rank gets at least one site
         cuts[r] = max(cuts[r], cuts[r - 1] + 1)

@@ -283,6 +283,31 @@ class ChainResult:
         return b.schmidt_values, b.charge
 
 
+def bulk_normalized(res: "ChainResult", L: int, log=None):
+    """Normalised Schmidt vectors (slater.py:1296, utils.normalize_SV) and charges of all L + 1 bonds from
+    the shard tables: one vectorised pass per shard instead of 2 L small NumPy calls."""
+    lams, charges = [None] * (L + 1), [None] * (L + 1)
+    for t in res.tables:
+        off = t.chi_off
+        lens = np.diff(off)
+        valid = lens > 0
+        if not valid.any():
+            continue
+        starts = off[:-1][valid]
+        norms = np.sqrt(np.add.reduceat(t.lam * t.lam, starts))
+        lam_n = t.lam / np.repeat(norms, lens[valid])
+        if log is not None and log.isEnabledFor(20):
+            for nv in norms:
+                log.info("Norm of Schmidt values: %s", nv)
+        for i in np.flatnonzero(valid):
+            x = t.first_bond + int(i)
+            if 0 <= x <= L:
+                a, b = int(off[i]), int(off[i + 1])
+                lams[x] = lam_n[a:b]
+                charges[x] = t.charge[a:b]
+    return lams, charges
+
+
 class LazySeq:
     """Read-only sequence view of a LazyMap over range(n) (the site tensors of an MPS)."""
 
@@ -639,7 +664,10 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
         r = _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi, r_sketch,
                        n_threads, fetch_tensors, lazy)
         return DeviceChainResult([r]) if lazy else r
-    cuts = partition(L, n_chunks, trunc.chi_max, ortho_center, lo=site_lo, hi=site_hi)
+    # a short first chunk fills the pipeline quickly: its tensors (and their copy to the host) start while the
+    # mode kernels of the later chunks run
+    weights = [0.4] + [1.0] * (n_chunks - 1) if n_chunks >= 4 else None
+    cuts = partition(L, n_chunks, trunc.chi_max, ortho_center, lo=site_lo, hi=site_hi, weights=weights)
     backend.sync()                       # C_dev must be complete before the side streams read it
 
     import os

@@ -129,11 +129,14 @@ def _check_projector(C, tol=1e-8, be=None, Cd=None):
 
 def _chain_to_mps(res: engine.ChainResult, unit_cell_width) -> BlockMPS:
     L = res.L
-    lc = [res.lam_charge(x) for x in range(L + 1)]
-    lams = [normalize_SV(l, logger) for l, _ in lc]                                     # slater.py:1296
+    lams, charges = engine.bulk_normalized(res, L, logger)                             # slater.py:1296
+    for x in range(L + 1):
+        if lams[x] is None:      # (results assembled without shard tables)
+            l, c = res.lam_charge(x)
+            lams[x], charges[x] = normalize_SV(l, logger), c
     oc = res.ortho_center
     return BlockMPS(L=L, tensors=engine.LazySeq(res.sites, L), lams=lams,
-                    charges=[c for _, c in lc],
+                    charges=charges,
                     form=["A"] * oc + ["B"] * (L - oc), unit_cell_width=unit_cell_width,     # slater.py:1348
                     ortho_center=oc, meta=dict(stats=res.stats, bonds=res.bonds))
 
