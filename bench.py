@@ -200,7 +200,8 @@ def run_native(args):
     # ---- timed region ----------------------------------------------------------------------------
     sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    if rank == 0:          # one sampler per job: eight nvidia-smi processes every 100 ms compete with the host stages
+        sampler.start()
     lib.tmf_launch_count(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -332,8 +333,15 @@ def run_native(args):
         else:                     # any kernel of the mode extraction: the reference's eigh flops
             a_fl = alg["eigh"]
         achieved = a_fl / world / (dms * 1e-3) / 1e12
+        traffic = None          # DRAM bytes per launch of this kernel from the committed ncu full-set capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+            if tj and tj["launches_per_step"] == dcnt and tj["n_gpus"] == world and L == 1024 and args.chi == 1024:
+                traffic = tj["dram_bytes_per_launch"]
+        except (OSError, ValueError, KeyError):
+            pass
         roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "launches_per_step": dcnt, "ms_per_step": dms,
+                "frac": achieved / peak, "traffic": traffic, "launches_per_step": dcnt, "ms_per_step": dms,
                 "algorithmic_flops_per_step": a_fl,
                 "peak_source": f"measured in this run: FP64 DFMA probe {dfma_tflops:.1f} TF/s, cuBLAS DGEMM 4096^3 "
                                f"{dgemm_tflops:.1f} TF/s (MEASURED_PEAKS.json has no FP64 figure)"}

@@ -13,5 +13,5 @@ C, N = ground_state_C(L)
 Cd = be.from_host(C.ravel())
 tp = to_stopping_condition({"chi_max": 1024, "svd_min": 1e-7})
 for _ in range(reps):
-    res = engine.run_chain(be, Cd, L, L, tp, N, fetch_tensors=False)
+    res = engine.run_chain(be, Cd, L, L, tp, N, fetch_tensors=False, n_chunks=int(os.environ.get('TMF_RUN_CHUNKS', '0')) or None)
 print("ok", res.stats)
