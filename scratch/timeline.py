@@ -14,10 +14,22 @@ Cd = be.from_host(Cm.ravel())
 tp = to_stopping_condition({"chi_max": 1024, "svd_min": 1e-7})
 for _ in range(3):
     engine.run_chain(be, Cd, L, L, tp, N, n_chunks=nc, lazy=True).close()
+os.environ["TMF_DEBUG_TIMING"] = "1"
+torch.cuda.synchronize(); t0 = time.perf_counter()
+r0 = engine.run_chain(be, Cd, L, L, tp, N, n_chunks=nc, lazy=True)
+torch.cuda.synchronize(); print("unprofiled wall ms", 1e3 * (time.perf_counter() - t0))
+for c in r0.chains:
+    tt = c.stage_times
+    print("unprofiled chunk", (c.site_lo, c.site_hi), "start %.1f" % (1e3 * (tt[0] - t0)), "stages ms:", [round(1e3 * (b - a), 2) for a, b in zip(tt[:-1], tt[1:])])
+r0.close()
+os.environ.pop("TMF_DEBUG_TIMING", None)
 lib.tmf_prof_enable(1)
 torch.cuda.synchronize(); t0 = time.perf_counter()
 r = engine.run_chain(be, Cd, L, L, tp, N, n_chunks=nc, lazy=True)
 torch.cuda.synchronize(); print("wall ms", 1e3 * (time.perf_counter() - t0))
+for c in r.chains:
+    tt = c.stage_times
+    print("chunk", (c.site_lo, c.site_hi), "start %.1f" % (1e3 * (tt[0] - t0)), "stages ms:", [round(1e3 * (b - a), 2) for a, b in zip(tt[:-1], tt[1:])], "(gate wait, enqueue, modes, enumerate+plan, tensors enqueue, drain)")
 buf = C.create_string_buffer(1 << 20)
 lib.tmf_prof_timeline(buf, len(buf))
 rows = [ln.split() for ln in buf.value.decode().strip().splitlines()]

@@ -132,27 +132,18 @@ namespace {
 
 template <class F>
 void parallel_for(int n, int n_threads, F f) {
-  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
-  n_threads = std::max(1, std::min(n_threads, n));
-  std::vector<std::thread> th;
-  std::vector<std::string> err(n_threads);
-  std::vector<int> code(n_threads, 0);
-  auto body = [&](int t) {
-    try {
-      for (int i = t; i < n; i += n_threads) f(i);
-    } catch (const std::invalid_argument &e) {
-      code[t] = TMF_ERR_VALUE;
-      err[t] = e.what();
-    } catch (const std::exception &e) {
-      code[t] = TMF_ERR_ASSERT;
-      err[t] = e.what();
-    }
-  };
-  for (int t = 1; t < n_threads; ++t) th.emplace_back(body, t);
-  body(0);
-  for (auto &x : th) x.join();
-  for (int t = 0; t < n_threads; ++t)
-    if (code[t]) throw std::runtime_error(std::to_string(code[t]) + "|" + err[t]);
+  // exceptions keep their class through the pool: invalid_argument -> ValueError, others -> AssertionError
+  try {
+    tmf::pool_for(n, n_threads, [&](int i) { f(i); });
+  } catch (const std::invalid_argument &e) {
+    throw std::runtime_error(std::to_string(TMF_ERR_VALUE) + "|" + e.what());
+  } catch (const std::runtime_error &e) {
+    const std::string w = e.what();
+    if (!w.empty() && w[0] == '-' && w.find('|') != std::string::npos) throw;
+    throw std::runtime_error(std::to_string(TMF_ERR_ASSERT) + "|" + w);
+  } catch (const std::exception &e) {
+    throw std::runtime_error(std::to_string(TMF_ERR_ASSERT) + "|" + e.what());
+  }
 }
 
 // one-sided Jacobi SVD of a small m x m matrix (column-major): M = U diag(s) V^T
@@ -282,10 +273,23 @@ int tmf_chain_modes_finish(tmf_chain *c, const double *e_dev, const int *info_de
   const int nj = (int)c->job_x.size();
   c->e_host.resize((size_t)nj * TMF_MAX_MODES);
   c->info_host.resize((size_t)nj * 4);
-  int rc = tmf::copy_d2h_async(c->info_host.data(), info_dev, sizeof(int) * 4 * (size_t)nj, stream);
+  // through pinned staging: a device -> pageable copy is executed synchronously inside the driver (it waits
+  // there for the whole mode stage of this chunk), which stalled the kernel launches of the other pipeline
+  // threads for milliseconds; cudaStreamSynchronize does not
+  const size_t e_bytes = sizeof(double) * TMF_MAX_MODES * (size_t)nj, i_bytes = sizeof(int) * 4 * (size_t)nj;
+  const size_t need = e_bytes + i_bytes + 512;
+  if (c->blob_cap < need) {
+    g_pinned.release(c->blob, c->blob_cap);
+    c->blob = g_pinned.acquire(need, c->blob_cap);
+    if (!c->blob) { c->blob_cap = 0; return fail(TMF_ERR_RUNTIME, "cannot allocate pinned staging memory"); }
+  }
+  unsigned char *st_e = c->blob, *st_i = c->blob + ((e_bytes + 255) & ~size_t(255));
+  int rc = tmf::copy_d2h_async(st_i, info_dev, i_bytes, stream);
   if (rc) return rc;
-  rc = tmf::copy_d2h_sync(c->e_host.data(), e_dev, sizeof(double) * TMF_MAX_MODES * (size_t)nj, stream);
+  rc = tmf::copy_d2h_sync(st_e, e_dev, e_bytes, stream);
   if (rc) return rc;
+  std::memcpy(c->e_host.data(), st_e, e_bytes);
+  std::memcpy(c->info_host.data(), st_i, i_bytes);
   for (int j = 0; j < nj; ++j) {
     const int st = c->info_host[4 * j + 2];
     if (st & 2) return fail(TMF_ERR_VALUE, "more than 64 entangled modes on one bond");

@@ -80,6 +80,9 @@ inline int stream_sync(void *) { return TMF_OK; }
 #else
 // ------------------------------------------------------------------------------------------
 #include <cuda_runtime.h>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #define TMF_GLOBAL __global__ void
 #define TMF_GLOBAL_LB(threads, blocks) __global__ void __launch_bounds__(threads, blocks)
 #define TMF_DEVICE __device__ __forceinline__
@@ -104,6 +107,7 @@ inline int check_cuda(cudaError_t e, const char *what) {
 // pass through tmf_prof_enable(); the launch counter is always on (bench "gpu_launches").
 void count_launch();
 void prefer_shared_carveout(const void *kernel);   // once per kernel: ask for the largest shared-memory carve-out
+int ensure_max_dynamic_smem(const void *kernel);    // once per kernel: cudaFuncAttributeMaxDynamicSharedMemorySize = 227 KB
 bool prof_enabled();
 void prof_begin(const char *tag, void *stream);
 void prof_end(void *stream);
@@ -112,15 +116,23 @@ inline int launch_t(const char *tag, K kernel, int grid, int block, size_t smem_
                     Args... args) {
   if (grid <= 0) return TMF_OK;
   if (smem_bytes > 48 * 1024) {
-    // always opt in to the full 227 KB: the attribute is per function (not per launch), so concurrent
-    // launches from the pipeline threads must not lower each other's limit
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute");
+    // opt in to the full 227 KB once per kernel function (the attribute is per function, not per launch; the
+    // call takes a context-wide lock, and with six pipeline threads launching it showed up as millisecond
+    // stalls of unrelated launches)
+    int rc = ensure_max_dynamic_smem(reinterpret_cast<const void *>(kernel));
+    if (rc) return rc;
   }
   count_launch();
   const bool prof = prof_enabled();
   if (prof) prof_begin(tag, stream);
+  static const bool dbg = std::getenv("TMF_DEBUG_LAUNCH") != nullptr;
+  std::chrono::steady_clock::time_point t0;
+  if (dbg) t0 = std::chrono::steady_clock::now();
   kernel<<<grid, block, smem_bytes, (cudaStream_t)stream>>>(args...);
+  if (dbg) {
+    const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    if (us > 40.0) std::fprintf(stderr, "[tmf launch] %-14s grid %6d block %4d smem %6zu : %8.1f us\n", tag, grid, block, smem_bytes, us);
+  }
   if (prof) prof_end(stream);
   return check_cuda(cudaGetLastError(), "kernel launch");
 }
@@ -128,11 +140,11 @@ template <class K, class... Args>
 inline int launch(K kernel, int grid, int block, size_t smem_bytes, void *stream, Args... args) {
   return launch_t("other", kernel, grid, block, smem_bytes, stream, args...);
 }
-inline int copy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
-  if (bytes == 0) return TMF_OK;
-  return check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream),
-                    "cudaMemcpyAsync H2D");
-}
+// Host -> device copy that never blocks the calling thread on the stream: pinned sources are copied
+// directly; pageable sources (descriptor vectors) are first copied into a reusable pinned staging ring of
+// the calling thread.  (cudaMemcpyAsync from pageable memory waits for all prior work of the stream -- with
+// the event-gated pipeline that turned every descriptor upload into a wait for the previous chunks' kernels.)
+int copy_h2d(void *dst, const void *src, size_t bytes, void *stream);
 inline int copy_d2h_async(void *dst, const void *src, size_t bytes, void *stream) {
   if (bytes == 0) return TMF_OK;
   return check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream),

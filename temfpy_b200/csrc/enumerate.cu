@@ -361,20 +361,7 @@ int enumerate_device(int nb, const double *const *e_ptr, const int *k, const int
   EnumJob *jobs = reinterpret_cast<EnumJob *>(stage);
   if (n_threads <= 0) n_threads = 4;
   n_threads = std::max(1, std::min(n_threads, nb));
-  auto run_threads = [&](const std::function<void(int)> &f) {
-    std::vector<std::thread> th;
-    std::vector<std::string> msg(n_threads);
-    auto body = [&](int t) {
-      try {
-        for (int b = t; b < nb; b += n_threads) f(b);
-      } catch (const std::exception &ex) { msg[t] = ex.what(); }
-    };
-    for (int t = 1; t < n_threads; ++t) th.emplace_back(body, t);
-    body(0);
-    for (auto &x : th) x.join();
-    for (auto &m : msg)
-      if (!m.empty()) throw std::runtime_error(m);
-  };
+  auto run_threads = [&](const std::function<void(int)> &f) { pool_for(nb, n_threads, f); };
   run_threads([&](int b) {
     EnumJob &j = jobs[b];
     std::memset(&j, 0, sizeof(j));

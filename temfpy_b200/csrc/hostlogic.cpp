@@ -9,6 +9,12 @@
 #include <queue>
 #include <stdexcept>
 #include <thread>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <exception>
+#include <memory>
+#include <mutex>
 
 namespace tmf {
 
@@ -19,6 +25,98 @@ void set_error(const std::string &msg) {
   g_error_shared = msg;
 }
 const char *last_error_cstr() { return g_error.empty() ? g_error_shared.c_str() : g_error.c_str(); }
+
+// -------------------------------------------------------------------------------------------
+// persistent host thread pool
+// -------------------------------------------------------------------------------------------
+namespace {
+struct PoolJob {
+  std::atomic<int> next{0}, finished{0};
+  int n = 0;
+  const std::function<void(int)> *f = nullptr;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::exception_ptr err;
+  void work() {
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= n) break;
+      try {
+        (*f)(i);
+      } catch (...) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!err) err = std::current_exception();
+      }
+      if (finished.fetch_add(1) + 1 == n) {
+        std::lock_guard<std::mutex> lk(mu);
+        cv.notify_all();
+      }
+    }
+  }
+};
+struct Pool {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<std::shared_ptr<PoolJob>> q;
+  std::vector<std::thread> workers;
+  bool stop = false;
+  int size = 0;
+  Pool() {
+    size = (int)std::max(1u, std::thread::hardware_concurrency());
+    for (int t = 0; t < size; ++t)
+      workers.emplace_back([this] {
+        for (;;) {
+          std::shared_ptr<PoolJob> job;
+          {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [this] { return stop || !q.empty(); });
+            if (stop && q.empty()) return;
+            job = q.front();
+            q.pop_front();
+          }
+          job->work();
+        }
+      });
+  }
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stop = true;
+    }
+    cv.notify_all();
+    for (auto &w : workers) w.join();
+  }
+};
+Pool &pool() {
+  static Pool *p = new Pool();   // intentionally leaked: worker threads must outlive static destruction order
+  return *p;
+}
+}  // namespace
+
+void pool_for(int n, int max_threads, const std::function<void(int)> &f) {
+  if (n <= 0) return;
+  if (max_threads <= 0) max_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  if (n == 1 || max_threads == 1) {
+    for (int i = 0; i < n; ++i) f(i);
+    return;
+  }
+  Pool &p = pool();
+  auto job = std::make_shared<PoolJob>();
+  job->n = n;
+  job->f = &f;
+  const int helpers = std::min(std::min(max_threads, n), p.size) - 1;
+  {
+    std::lock_guard<std::mutex> lk(p.mu);
+    for (int h = 0; h < helpers; ++h) p.q.push_back(job);
+  }
+  if (helpers > 0) p.cv.notify_all();
+  job->work();
+  {
+    std::unique_lock<std::mutex> lk(job->mu);
+    job->cv.wait(lk, [&] { return job->finished.load() >= n; });
+  }
+  if (job->err) std::rethrow_exception(job->err);
+}
 
 bool TruncPar::is_sector(int q) const {
   if (!filter) return true;

@@ -5,6 +5,7 @@
 // kernels.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -56,5 +57,10 @@ void site_plan(int mode, int n_bra, int n_ket, int k_bra, int f_bra, int nferm_b
                SitePlan &out);
 
 void set_error(const std::string &msg);
+
+// Runs f(0) .. f(n-1) on a persistent pool of host threads (at most max_threads of them plus the caller,
+// dynamic scheduling); rethrows the first exception.  Spawning fresh threads for every stage of every
+// pipeline chunk cost more than the stages themselves.
+void pool_for(int n, int max_threads, const std::function<void(int)> &f);
 
 }  // namespace tmf

@@ -9,6 +9,7 @@ thread_local unsigned char *smem = nullptr;
 }  // namespace tmfsim
 #endif
 
+#include <algorithm>
 #include <atomic>
 #include <map>
 #include <mutex>
@@ -22,6 +23,82 @@ static std::mutex g_prof_mu;
 struct ProfRec { std::string tag; cudaEvent_t a, b; void *stream; };
 static thread_local size_t t_last = 0;   // launches are issued from several pipeline threads
 static std::vector<ProfRec> g_recs;
+#if !defined(TMF_HOSTSIM)
+namespace {
+struct StagingRing {
+  unsigned char *p = nullptr;
+  size_t cap = 0, off = 0;
+  cudaEvent_t ev = nullptr;
+  bool pending = false;
+  std::mutex mu;
+  ~StagingRing() {
+    if (ev) cudaEventDestroy(ev);
+    if (p) cudaFreeHost(p);
+  }
+  // returns pinned space for `bytes` (nullptr: use the pageable path)
+  unsigned char *take(size_t bytes) {
+    const size_t need = (bytes + 255) & ~size_t(255);
+    if (need > (size_t(8) << 20)) return nullptr;
+    if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (off + need > cap) {
+      if (pending) { cudaEventSynchronize(ev); pending = false; }   // every earlier copy from the ring is done
+      off = 0;
+      if (need > cap) {
+        if (p) cudaFreeHost(p);
+        cap = std::max(need * 2, size_t(4) << 20);
+        if (cudaHostAlloc(reinterpret_cast<void **>(&p), cap, cudaHostAllocDefault) != cudaSuccess) { p = nullptr; cap = 0; return nullptr; }
+      }
+    }
+    unsigned char *r = p + off;
+    off += need;
+    return r;
+  }
+};
+// one ring per stream (the pipeline's streams are persistent; its worker threads are not), never freed
+std::mutex g_ring_mu;
+std::map<void *, StagingRing *> g_rings;
+StagingRing *ring_of(void *stream) {
+  std::lock_guard<std::mutex> lk(g_ring_mu);
+  StagingRing *&r = g_rings[stream];
+  if (!r) r = new StagingRing();
+  return r;
+}
+}  // namespace
+
+int copy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
+  if (bytes == 0) return TMF_OK;
+  cudaPointerAttributes attr;
+  const bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  if (!pinned) {
+    cudaGetLastError();   // (older drivers flag unregistered pointers as an error)
+    StagingRing *ring = ring_of(stream);
+    std::lock_guard<std::mutex> lk(ring->mu);
+    if (unsigned char *st = ring->take(bytes)) {
+      std::memcpy(st, src, bytes);
+      int rc = check_cuda(cudaMemcpyAsync(dst, st, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream), "cudaMemcpyAsync H2D");
+      if (rc) return rc;
+      cudaEventRecord(ring->ev, (cudaStream_t)stream);
+      ring->pending = true;
+      return TMF_OK;
+    }
+  }
+  return check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream), "cudaMemcpyAsync H2D");
+}
+#endif
+
+#if !defined(TMF_HOSTSIM)
+int ensure_max_dynamic_smem(const void *kernel) {
+  static std::mutex mu;
+  static std::vector<const void *> done;
+  std::lock_guard<std::mutex> lk(mu);
+  for (const void *k : done)
+    if (k == kernel) return TMF_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute");
+  done.push_back(kernel);
+  return TMF_OK;
+}
+#endif
 #if !defined(TMF_HOSTSIM)
 void prefer_shared_carveout(const void *kernel) {
   static std::mutex mu;

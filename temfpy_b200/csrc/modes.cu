@@ -16,8 +16,25 @@
 //   5. pivoted Cholesky of the remaining projector A - U diag(e) U^T -> filled-space basis.
 // Blocks with n <= 64 are diagonalised directly by Jacobi.  All bonds of the chain run in the
 // same launches (grids of hundreds of CTAs), descriptors are uploaded once up front.
+#include <chrono>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include "modes_kernels.cuh"
+
+namespace {
+struct ModesTimer {   // TMF_DEBUG_TIMING=1 prints host-side stage times to stderr
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  ModesTimer() : on(std::getenv("TMF_DEBUG_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+  void lap(const char *what, int n) {
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[tmf timing] %-28s %8.3f ms  (%d jobs)\n", what, std::chrono::duration<double, std::milli>(now - t).count(), n);
+    t = now;
+  }
+};
+}  // namespace
 
 namespace tmf {
 
@@ -183,24 +200,33 @@ struct ForkedStream {
   void *open(void *parent) { return parent; }
   int join(void *) { return TMF_OK; }
 #else
-  cudaStream_t aux = nullptr;
-  cudaEvent_t ev = nullptr;
+  // one auxiliary stream + event per parent stream, created once and kept (stream creation / destruction
+  // takes context-wide locks: per-call streams stalled the launches of the other pipeline threads)
+  struct Aux { cudaStream_t s = nullptr; cudaEvent_t ev = nullptr; };
+  Aux aux;
+  static Aux lookup(void *parent) {
+    static std::mutex mu;
+    static std::map<void *, Aux> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    Aux &a = cache[parent];
+    if (!a.s) {
+      if (cudaStreamCreateWithFlags(&a.s, cudaStreamNonBlocking) != cudaSuccess) { a.s = nullptr; return a; }
+      if (cudaEventCreateWithFlags(&a.ev, cudaEventDisableTiming) != cudaSuccess) { a.ev = nullptr; a.s = nullptr; }
+    }
+    return a;
+  }
   void *open(void *parent) {
-    if (cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking) != cudaSuccess) { aux = nullptr; return parent; }
-    cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    cudaEventRecord(ev, (cudaStream_t)parent);
-    cudaStreamWaitEvent(aux, ev, 0);
-    return aux;
+    aux = lookup(parent);
+    if (!aux.s) return parent;
+    cudaEventRecord(aux.ev, (cudaStream_t)parent);
+    cudaStreamWaitEvent(aux.s, aux.ev, 0);
+    return aux.s;
   }
   int join(void *parent) {
-    if (!aux) return TMF_OK;
-    cudaEventRecord(ev, aux);
-    cudaError_t e = cudaStreamWaitEvent((cudaStream_t)parent, ev, 0);
+    if (!aux.s) return TMF_OK;
+    cudaEventRecord(aux.ev, aux.s);
+    cudaError_t e = cudaStreamWaitEvent((cudaStream_t)parent, aux.ev, 0);
     return check_cuda(e, "stream join");
-  }
-  ~ForkedStream() {   // destruction is deferred by the runtime until the enqueued work has finished
-    if (ev) cudaEventDestroy(ev);
-    if (aux) cudaStreamDestroy(aux);
   }
 #endif
 };
@@ -242,8 +268,10 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
     set_error("tmf_slater_modes_batched: workspace too small");
     return TMF_ERR_VALUE;
   }
+  ModesTimer tm;
   int rc = memset_dev(info_dev, 0, sizeof(int) * 4 * (size_t)njobs, stream);
   if (rc) return rc;
+  tm.lap("modes: memset", njobs);
   Arena arena(work_dev, work_bytes);
   double *Om = arena.take<double>((int64_t)L * r_sketch);
 
@@ -450,8 +478,10 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
     set_error("modes: descriptor blob does not fit the workspace");
     return TMF_ERR_VALUE;
   }
+  tm.lap("modes: build descriptors", njobs);
   rc = copy_h2d(blob_dev, blob.host.data(), blob.host.size(), stream);
   if (rc) return rc;
+  tm.lap("modes: upload descriptors", njobs);
 
   // ---- launches ----------------------------------------------------------------------------
   // The direct solver of the small blocks (<= 65 latency-bound CTAs) runs on a forked stream next to
@@ -520,5 +550,6 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
   if ((rc = run(L_out[0]))) return rc;
   rc = launch_t("pivchol", pivchol_kernel, nb, 1024, chol_smem, stream, cj_dev, 1e-8);
   if (rc) return rc;
+  tm.lap("modes: launches", njobs);
   return fork.join(stream);
 }

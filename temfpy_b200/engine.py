@@ -546,16 +546,25 @@ def _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r
         chain = SlaterChain(backend, L, trunc, n_fermion, ortho_center, lo, hi, r, n_threads)
         ok = False
         try:
+            import time
+            tt = [time.perf_counter()]
             try:
                 gate.before()
+                tt.append(time.perf_counter())
                 chain.enqueue_modes(C_dev, ldc)
             finally:
                 gate.after()
+            tt.append(time.perf_counter())
             chain.finish_modes()
+            tt.append(time.perf_counter())
             chain.run_enumerate()
+            tt.append(time.perf_counter())
             chain.run_tensors(C_dev, ldc)
+            tt.append(time.perf_counter())
             if lazy:
                 backend.sync()
+                tt.append(time.perf_counter())
+                chain.stage_times = tt      # gate wait, enqueue, modes, enumerate + plan, tensors enqueue, drain
                 ok = True
                 return chain
             return chain.collect(fetch_tensors)
@@ -582,7 +591,7 @@ class _StageGate:
         import os
         self.enqueued = [threading.Event() for _ in range(n)]
         self.done = [None] * n
-        self.depth = max(1, int(os.environ.get("TMF_GATE_DEPTH", "2")))
+        self.depth = max(1, int(os.environ.get("TMF_GATE_DEPTH", "3")))
 
     def gate(self, i):
         outer = self
@@ -664,24 +673,32 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
         r = _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi, r_sketch,
                        n_threads, fetch_tensors, lazy)
         return DeviceChainResult([r]) if lazy else r
-    # a short first chunk fills the pipeline quickly: its tensors (and their copy to the host) start while the
-    # mode kernels of the later chunks run
-    weights = [0.4] + [1.0] * (n_chunks - 1) if n_chunks >= 4 else None
+    weights = None      # equal-cost chunks
     cuts = partition(L, n_chunks, trunc.chi_max, ortho_center, lo=site_lo, hi=site_hi, weights=weights)
     backend.sync()                       # C_dev must be complete before the side streams read it
 
     import os
     stages = _StageGate(backend, n_chunks) if not os.environ.get("TMF_NO_STAGE_GATE") else None
 
-    def work(i):
-        lo, hi = cuts[i]
-        with backend.stream_context(backend.side_stream(i)):
+    # pipeline order: natural (left to right) unless TMF_CHUNK_ORDER=ends asks for "chain ends first, centre
+    # last"; measured within noise of each other on B200, the natural order brings the tensors to the host sooner
+    order = list(range(n_chunks))
+    if os.environ.get("TMF_CHUNK_ORDER") == "ends":
+        oc_ = ortho_center or L // 2
+        order = sorted(range(n_chunks), key=lambda i: -abs(0.5 * (cuts[i][0] + cuts[i][1]) - oc_))
+
+    def work(pos):
+        lo, hi = cuts[order[pos]]
+        with backend.stream_context(backend.side_stream(pos)):
             return _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch,
-                              n_threads, fetch_tensors, lazy, gate=stages.gate(i) if stages else None)
+                              n_threads, fetch_tensors, lazy, gate=stages.gate(pos) if stages else None)
 
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=n_chunks) as pool:
-        parts = list(pool.map(work, range(n_chunks)))
+        done = list(pool.map(work, range(n_chunks)))
+    parts = [None] * n_chunks
+    for pos, r in enumerate(done):
+        parts[order[pos]] = r
     if lazy:
         return DeviceChainResult(parts)
     res = ChainResult(L=L, ortho_center=parts[0].ortho_center, site_lo=site_lo, site_hi=site_hi)
