@@ -673,11 +673,15 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
         r = _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi, r_sketch,
                        n_threads, fetch_tensors, lazy)
         return DeviceChainResult([r]) if lazy else r
-    weights = None      # equal-cost chunks
+    import os
+    # equal-cost chunks with a short last one: after the last mode stage only its host stage and tensor
+    # kernels remain, and those scale with its number of sites
+    weights = [1.0] * (n_chunks - 1) + [0.4] if n_chunks >= 4 else None
+    if os.environ.get("TMF_CHUNK_WEIGHTS"):
+        weights = [float(v) for v in os.environ["TMF_CHUNK_WEIGHTS"].split(",")]
     cuts = partition(L, n_chunks, trunc.chi_max, ortho_center, lo=site_lo, hi=site_hi, weights=weights)
     backend.sync()                       # C_dev must be complete before the side streams read it
 
-    import os
     stages = _StageGate(backend, n_chunks) if not os.environ.get("TMF_NO_STAGE_GATE") else None
 
     # pipeline order: natural (left to right) unless TMF_CHUNK_ORDER=ends asks for "chain ends first, centre
