@@ -11,11 +11,11 @@ L = 1024
 Cm, N = ground_state_C(L)
 Cd = be.from_host(Cm.ravel())
 tp = to_stopping_condition({"chi_max": 1024, "svd_min": 1e-7})
-for order in ("ends", "natural"):
+for order in ("natural",):
     os.environ["TMF_CHUNK_ORDER"] = order
-    for gate in (2, 3):
+    for gate in (3,):
         os.environ.pop("TMF_NO_STAGE_GATE", None); os.environ["TMF_GATE_DEPTH"] = str(gate)
-        for nc in (6, 8):
+        for nc in (6,):
             for _ in range(2):
                 engine.run_chain(be, Cd, L, L, tp, N, n_chunks=nc, lazy=True).close()
             ts = []

@@ -548,7 +548,8 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
   rc = launch_t("ritz", ritz_kernel, nb, jac_threads, ritz_smem, stream, rj_dev, cutoff);
   if (rc) return rc;
   if ((rc = run(L_out[0]))) return rc;
-  rc = launch_t("pivchol", pivchol_kernel, nb, 1024, chol_smem, stream, cj_dev, 1e-8);
+  static const int pivchol_threads = std::getenv("TMF_PIVCHOL_THREADS") ? std::atoi(std::getenv("TMF_PIVCHOL_THREADS")) : 1024;
+  rc = launch_t("pivchol", pivchol_kernel, nb, pivchol_threads, chol_smem, stream, cj_dev, 1e-8);
   if (rc) return rc;
   tm.lap("modes: launches", njobs);
   return fork.join(stream);

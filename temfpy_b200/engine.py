@@ -237,6 +237,20 @@ class ShardTables:
                                                   p(self.block_off), p(self.row_off), p(self.row_p),
                                                   p(self.row_alpha)))
 
+    def normalized(self):
+        """(norms, normalised Schmidt values) of all bonds of the shard in one vectorised pass; computed once
+        (by the chunk's worker thread, next to the device -> host copy of its tensors)."""
+        if not hasattr(self, "_lam_n"):
+            off = self.chi_off
+            lens = np.diff(off)
+            valid = lens > 0
+            if not valid.any():
+                self._norms, self._lam_n = None, None
+            else:
+                self._norms = np.sqrt(np.add.reduceat(self.lam * self.lam, off[:-1][valid]))
+                self._lam_n = self.lam / np.repeat(self._norms, lens[valid])
+        return self._norms, self._lam_n
+
     def bond(self, x) -> "BondData":
         i = x - self.first_bond
         a, b = int(self.chi_off[i]), int(self.chi_off[i + 1])
@@ -288,18 +302,14 @@ def bulk_normalized(res: "ChainResult", L: int, log=None):
     the shard tables: one vectorised pass per shard instead of 2 L small NumPy calls."""
     lams, charges = [None] * (L + 1), [None] * (L + 1)
     for t in res.tables:
-        off = t.chi_off
-        lens = np.diff(off)
-        valid = lens > 0
-        if not valid.any():
+        norms, lam_n = t.normalized()
+        if lam_n is None:
             continue
-        starts = off[:-1][valid]
-        norms = np.sqrt(np.add.reduceat(t.lam * t.lam, starts))
-        lam_n = t.lam / np.repeat(norms, lens[valid])
         if log is not None and log.isEnabledFor(20):
             for nv in norms:
                 log.info("Norm of Schmidt values: %s", nv)
-        for i in np.flatnonzero(valid):
+        off = t.chi_off
+        for i in np.flatnonzero(np.diff(off) > 0):
             x = t.first_bond + int(i)
             if 0 <= x <= L:
                 a, b = int(off[i]), int(off[i + 1])
@@ -515,6 +525,7 @@ class SlaterChain:
             out_host = host.numpy() if host is not None else None
         tab = ShardTables(self, out_host)
         tab._pinned = host
+        tab.normalized()
         t2 = time.perf_counter()
         self.be.sync()
         t3 = time.perf_counter()
