@@ -537,10 +537,11 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
   if ((rc = run_orth(orthW))) return rc;
   if ((rc = run(L_rw[0]))) return rc;
   const double thr = cutoff * (1.0 - cutoff);
+  static const double sketch_floor = std::getenv("TMF_SKETCH_FLOOR") ? std::atof(std::getenv("TMF_SKETCH_FLOOR")) : 1e-26;
   // one warp per column pair of a Jacobi round (latency-bound: more warps per CTA, not more CTAs)
   static const int jac_env = std::getenv("TMF_JAC_THREADS") ? std::atoi(std::getenv("TMF_JAC_THREADS")) : 0;
   const int jac_threads = jac_env > 0 ? jac_env : std::min(1024, 32 * std::max(4, (r_sketch + 1) / 2));
-  rc = launch_t("svd_select", svd_select_kernel, nb, jac_threads, svd_smem, stream, sj_dev, thr, 1e-26);
+  rc = launch_t("svd_select", svd_select_kernel, nb, jac_threads, svd_smem, stream, sj_dev, thr, sketch_floor);
   if (rc) return rc;
   if ((rc = run(L_u0[0]))) return rc;
   if ((rc = run(L_au[0]))) return rc;
