@@ -106,7 +106,6 @@ inline int check_cuda(cudaError_t e, const char *what) {
 // per-tag kernel timing (CUDA events around every launch) -- enabled only by bench.py's profiling
 // pass through tmf_prof_enable(); the launch counter is always on (bench "gpu_launches").
 void count_launch();
-void prefer_shared_carveout(const void *kernel);   // once per kernel: ask for the largest shared-memory carve-out
 int ensure_max_dynamic_smem(const void *kernel);    // once per kernel: cudaFuncAttributeMaxDynamicSharedMemorySize = 227 KB
 bool prof_enabled();
 void prof_begin(const char *tag, void *stream);

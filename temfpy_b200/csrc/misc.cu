@@ -99,17 +99,6 @@ int ensure_max_dynamic_smem(const void *kernel) {
   return TMF_OK;
 }
 #endif
-#if !defined(TMF_HOSTSIM)
-void prefer_shared_carveout(const void *kernel) {
-  static std::mutex mu;
-  static std::vector<const void *> done;
-  std::lock_guard<std::mutex> lk(mu);
-  for (const void *k : done)
-    if (k == kernel) return;
-  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  done.push_back(kernel);
-}
-#endif
 bool prof_enabled() { return g_prof; }
 void prof_begin(const char *tag, void *stream) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
