@@ -39,25 +39,49 @@ def ground_state_C(L):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons during the timed region: NVML in-process (the library behind
+    nvidia-smi; a query costs microseconds) or, when pynvml is missing, the nvidia-smi CLI (whose process
+    start-up takes ~100 ms and perturbs the host stages of a 25 ms step)."""
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        act = lambda bit: "Active" if (r & bit) else "Not Active"
+        return [str(sm), str(mx), act(0x8), act(0x40), act(0x20), act(0x4)]   # hw, hw_thermal, sw_thermal, sw_power_cap
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                f = [x.strip() for x in out.stdout.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
+                if self.nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                    f = [x.strip() for x in out.stdout.strip().split(",")]
+                    if len(f) >= 6:
+                        self.samples.append(f)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05 if self.nvml is not None else 0.1)
 
     def summary(self):
         if not self.samples:
@@ -68,7 +92,7 @@ class ClockSampler(threading.Thread):
             if any(s[col].lower().startswith("active") for s in self.samples):
                 reasons.append(name)
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------
