@@ -1,5 +1,6 @@
 """Where the end-to-end time of slater.C_to_MPS(C_host) goes (host buffers in, host objects out)."""
-import sys, time
+import os, sys, time
+os.environ['TMF_PY_TIMING'] = '1'
 sys.path.insert(0, "/root/repo")
 import numpy as np, torch
 from bench import ground_state_C
@@ -26,5 +27,5 @@ for it in range(3):
     t4 = time.perf_counter()
     print(f"prepare {1e3*(t1-t0):.1f}  h2d {1e3*(t2-t1):.1f}  run_chain {1e3*(t3-t2):.1f}  to_mps {1e3*(t4-t3):.1f}  total {1e3*(t4-t0):.1f} ms")
     for ch in res.timings.get("chunks", []):
-        print("    chunk", {k: round(1e3 * v, 1) for k, v in ch.items()})
+        print("    chunk", {k: (round(1e3 * (v - t2), 1) if k == "t_done" else round(v, 1) if k.startswith("d2h_") and k != "d2h_enqueue" else round(1e3 * v, 1)) for k, v in ch.items()})
     del mps, res

@@ -516,8 +516,16 @@ class SlaterChain:
         t0 = time.perf_counter()
         res = ChainResult(L=self.L, ortho_center=self.oc, site_lo=self.site_lo, site_hi=self.site_hi)
         host = None
+        evs = None
         if fetch_tensors and hasattr(self.be, "to_host_async"):
+            import os
+            if os.environ.get("TMF_PY_TIMING"):
+                tc = self.be.torch.cuda
+                evs = (tc.Event(enable_timing=True), tc.Event(enable_timing=True))
+                evs[0].record(tc.current_stream(self.be.device))
             host = self.be.to_host_async(self._buffers["out"], self.out_elems)   # overlaps the table export
+            if evs:
+                evs[1].record(self.be.torch.cuda.current_stream(self.be.device))
         t1 = time.perf_counter()
         if fetch_tensors and host is None:
             out_host = self.be.to_host(self._buffers["out"], self.out_elems)
@@ -535,6 +543,10 @@ class SlaterChain:
         if fetch_tensors:
             res.sites.add(range(self.site_lo, self.site_hi), tab.site)
         res.timings = dict(d2h_enqueue=t1 - t0, tables=t2 - t1, sync=t3 - t2)
+        if evs:
+            res.timings["d2h_ms"] = evs[0].elapsed_time(evs[1])
+            res.timings["d2h_GBps"] = 8e-6 * self.out_elems / max(res.timings["d2h_ms"], 1e-9)
+            res.timings["t_done"] = time.perf_counter()
         res.stats = dict(out_elems=self.out_elems, nblocks=self.nblocks, max_chi=self.max_chi,
                          njobs=self.njobs)
         return res
