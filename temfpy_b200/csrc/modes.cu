@@ -349,6 +349,9 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
     size_t norm_smem;
   } orthY, orthW;
 
+  // squared norm (relative to the original sketch column) below which an orthogonalised column is rounding
+  // noise: a real direction at the sketch's noise floor (s^2 = 1e-26 s_max^2) keeps ~1e-26, noise is ~1e-31
+  constexpr double SKETCH_NOISE2 = 1e-28;
   static const bool use_mgs = std::getenv("TMF_PANEL_MGS") != nullptr;   // debugging switch: column-by-column MGS2 panels + GEMM projections
   auto build_orth = [&](OrthPlan &op, bool forW) {
     int rmax = 0;
@@ -513,9 +516,9 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
           if ((r2 = run(op.upd[p]))) return r2;
         }
         if (use_mgs)
-          r2 = launch_t("panel_mgs2", panel_mgs2_kernel, op.panel_n[p], 256, op.panel_smem[p], stream, op.panel[p], 0.0);
+          r2 = launch_t("panel_mgs2", panel_mgs2_kernel, op.panel_n[p], 256, op.panel_smem[p], stream, op.panel[p], SKETCH_NOISE2);
         else
-          r2 = launch_t("panel_cholqr", panel_cholqr_kernel, op.panel_n[p], 256, panel_cholqr_smem_bytes((int)p * PANEL_W), stream, op.panel[p], 0.0);
+          r2 = launch_t("panel_cholqr", panel_cholqr_kernel, op.panel_n[p], 256, panel_cholqr_smem_bytes((int)p * PANEL_W), stream, op.panel[p], SKETCH_NOISE2);
         if (r2) return r2;
       }
     }

@@ -273,6 +273,19 @@ TMF_GLOBAL_LB(256, 3) panel_cholqr_kernel(const PanelJob *jobs, double rel_tol2)
     double diag0 = 0.0;
 #pragma unroll
     for (int q = 0; q < PANEL_W; ++q) if (q == i) diag0 = g[q];
+    // a column whose norm after the projection is below the rounding noise of the original sketch column
+    // carries no direction of its own (the range of B is exhausted: normalising it would put a copy of
+    // directions already in Q back into the basis).  Such columns are zeroed: their row / column of G
+    // becomes that of the identity, so the factorisation passes over them.
+    const double noise0 = (i < w) ? rel_tol2 * jb0.norm0[i] : 0.0;
+    const unsigned zmask = __ballot_sync(0xffffffffu, i < w && !(diag0 > noise0));
+    if (zmask) {
+      const bool zi = (zmask >> i) & 1u;
+#pragma unroll
+      for (int q = 0; q < PANEL_W; ++q)
+        if (zi || ((zmask >> q) & 1u)) g[q] = (i == q) ? 1.0 : 0.0;
+      if (zi) diag0 = 1.0;
+    }
     int bad = 0;
 #pragma unroll
     for (int k = 0; k < PANEL_W; ++k) {
@@ -303,12 +316,26 @@ TMF_GLOBAL_LB(256, 3) panel_cholqr_kernel(const PanelJob *jobs, double rel_tol2)
 #pragma unroll
       for (int r = 0; r < PANEL_W; ++r) Ri[j * PANEL_W + r] = m[r];   // M[r][j] -> Ri[j][r]
     }
-    if (i == 0) *flag = bad;
+    if (i == 0) {
+      *flag = bad;
+      flag[1] = (int)zmask;
+      if (!bad && zmask && jb0.nzero) *jb0.nzero += __popc(zmask);
+    }
   }
 #else
   // Cholesky G = L L^T (R = L^T) and Ri = R^-1 (simulator: one thread)
   PAR_FOR(one, 1) {
     int bad = 0;
+    unsigned zm = 0u;
+    for (int k = 0; k < w; ++k)
+      if (!(G[k * PANEL_W + k] > rel_tol2 * jb0.norm0[k])) zm |= (1u << k);
+    for (int k = 0; k < w; ++k)
+      if ((zm >> k) & 1u)
+        for (int q = 0; q < w; ++q) {
+          G[k * PANEL_W + q] = (q == k) ? 1.0 : 0.0;
+          G[q * PANEL_W + k] = (q == k) ? 1.0 : 0.0;
+        }
+    flag[1] = (int)zm;
     for (int k = 0; k < w && !bad; ++k) {
       double d = G[k * PANEL_W + k];
       const double d0 = d;
@@ -333,6 +360,7 @@ TMF_GLOBAL_LB(256, 3) panel_cholqr_kernel(const PanelJob *jobs, double rel_tol2)
       }
     }
     *flag = bad;
+    if (!bad && zm && jb0.nzero) *jb0.nzero += __builtin_popcount(zm);
   }
 #endif
   CTA_SYNC();
@@ -347,8 +375,9 @@ TMF_GLOBAL_LB(256, 3) panel_cholqr_kernel(const PanelJob *jobs, double rel_tol2)
   // the last column down
   PAR_FOR(r, rows) {
     double p[PANEL_W];
+    const unsigned zm = (unsigned)flag[1];
 #pragma unroll
-    for (int k = 0; k < PANEL_W; ++k) p[k] = (k < w) ? P[(int64_t)k * ld + r] : 0.0;
+    for (int k = 0; k < PANEL_W; ++k) p[k] = (k < w && !((zm >> k) & 1u)) ? P[(int64_t)k * ld + r] : 0.0;
 #pragma unroll
     for (int j = PANEL_W - 1; j >= 0; --j) {
       double v = 0.0;

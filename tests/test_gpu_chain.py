@@ -197,3 +197,18 @@ def test_full_size_properties_cylinder_cfg4(gpu_backend):
         assert abs(len(a) - len(b)) <= 16
         m = min(len(a), len(b)) - 16
         assert np.allclose(a[:m] / a[0], b[:m] / b[0], rtol=1e-9, atol=1e-13)
+
+
+def test_decoupled_blocks_rank_deficient_sketch(gpu_backend):
+    """Rank-deficient off-diagonal blocks (two decoupled subsystems): dependent sketch columns send the
+    Cholesky-QR panels to their MGS2 fallback; k = 0 at the decoupled bond."""
+    La, Lb = 160, 140
+    H = np.zeros((La + Lb, La + Lb))
+    H[:La, :La] = helpers.random_hamiltonian(La, 1)
+    H[La:, La:] = helpers.random_hamiltonian(Lb, 2)
+    Cm, n = so.correlation_matrix(H)
+    tp = {"chi_max": 48}
+    res = helpers.run_native(gpu_backend, Cm, tp, n, ortho_center=150)
+    assert res.bonds[La].k == 0 and res.bonds[La].chi == 1
+    rep = helpers.compare_mps(so.C_to_MPS(Cm, tp, ortho_center=150), helpers.chain_to_dense(res), tp)
+    assert rep["ambiguous"] == []

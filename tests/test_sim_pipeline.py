@@ -121,3 +121,19 @@ def test_device_enumeration_equals_host_enumeration(sim_backend, monkeypatch, tp
         assert np.array_equal(a.schmidt_values, b.schmidt_values)
         assert np.array_equal(a.charge, b.charge)
         assert a.idx_L == b.idx_L
+
+
+def test_decoupled_blocks_rank_deficient_sketch(sim_backend):
+    """Two decoupled subsystems: at and near the cut between them the off-diagonal block of C has rank
+    0 ... few, far below the sketch width -- the Cholesky-QR panels meet exactly dependent / zero columns and
+    must hand over to the MGS2 body, the mode count drops to zero at the decoupled bond."""
+    La, Lb = 80, 70
+    H = np.zeros((La + Lb, La + Lb))
+    H[:La, :La] = helpers.random_hamiltonian(La, 1)
+    H[La:, La:] = helpers.random_hamiltonian(Lb, 2)
+    Cm, n = so.correlation_matrix(H)
+    tp = {"chi_max": 32}
+    res = helpers.run_native(sim_backend, Cm, tp, n, ortho_center=70)
+    assert res.bonds[La].k == 0 and res.bonds[La].chi == 1
+    rep = helpers.compare_mps(so.C_to_MPS(Cm, tp, ortho_center=70), helpers.chain_to_dense(res), tp)
+    assert rep["ambiguous"] == []
