@@ -342,7 +342,8 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
   std::vector<GemmLaunch> L_sketch(1), L_wt(1), L_rw(1), L_u0(1), L_au(1), L_te(1), L_out(1);
   struct OrthPlan {
     std::vector<GemmLaunch> coef, upd;   // per panel (index 0 unused)
-    std::vector<const PanelJob *> panel;
+    std::vector<const PanelJob *> panel;    // first round: zero test against the original sketch column norms
+    std::vector<const PanelJob *> panel2;   // second round: zero test against the (unit) norms before the re-projection
     std::vector<size_t> panel_smem;
     std::vector<int> panel_n;
     const NormJob *norm;
@@ -352,6 +353,13 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
   // squared norm (relative to the original sketch column) below which an orthogonalised column is rounding
   // noise: a real direction at the sketch's noise floor (s^2 = 1e-26 s_max^2) keeps ~1e-26, noise is ~1e-31
   constexpr double SKETCH_NOISE2 = 1e-28;
+  // "twice is enough": in the second round every column enters with unit norm; one that loses more than half
+  // of it in the re-projection was rounding noise inside the span of the earlier panels (its first-round
+  // normalisation amplified that noise) and is zeroed -- otherwise Q picks up copies of earlier directions
+  // (seen as an O(1) loss of orthogonality for spectra that fall below the noise within one panel)
+  constexpr double REPROJECT_KEEP2 = 0.25;
+  const double *ones_dev = blob.add(std::vector<double>(PANEL_W, 1.0));
+  static const bool proj_gemm = std::getenv("TMF_PROJ_GEMM") != nullptr;   // debugging switch: projections as separate GEMMs
   static const bool use_mgs = std::getenv("TMF_PANEL_MGS") != nullptr;   // debugging switch: column-by-column MGS2 panels + GEMM projections
   auto build_orth = [&](OrthPlan &op, bool forW) {
     int rmax = 0;
@@ -366,7 +374,7 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
     }
     op.norm = blob.add(nj);
     op.norm_smem = sizeof(double) * (size_t)std::max(rmax, 1) * 33;
-    op.coef.resize(panels); op.upd.resize(panels); op.panel.resize(panels);
+    op.coef.resize(panels); op.upd.resize(panels); op.panel.resize(panels); op.panel2.resize(panels);
     op.panel_smem.assign(panels, 0); op.panel_n.assign(panels, 0);
     for (int p = 0; p < panels; ++p) {
       std::vector<tmf_gemm_job> gc, gu;
@@ -379,7 +387,7 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
         double *M = forW ? b.Wt : b.Y;
         const int rows = forW ? b.m : b.n;
         double *P = M + (int64_t)c0 * rows;
-        if (c0 > 0 && use_mgs) {
+        if (c0 > 0 && (use_mgs || proj_gemm)) {
           // coef (c0 x w) = Qprev^T P ;  P -= Qprev coef   (the Cholesky-QR panel kernel does this itself)
           gc.push_back(mk_gemm(M, rows, 1, P, rows, 0, b.coef, c0, c0, w, rows));
           gu.push_back(mk_gemm(M, rows, 0, b.coef, c0, 0, P, rows, rows, w, c0, -1.0, 1.0));
@@ -387,7 +395,7 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
         PanelJob q;
         std::memset(&q, 0, sizeof(q));
         q.P = P; q.norm0 = (forW ? b.norm0w : b.norm0y) + c0; q.nzero = forW ? b.nzw : b.nzy;
-        q.Qprev = (c0 > 0 && !use_mgs) ? M : nullptr; q.c0 = c0;
+        q.Qprev = (c0 > 0 && !use_mgs && !proj_gemm) ? M : nullptr; q.c0 = c0;
         q.rows = rows; q.ld = rows; q.ncols = w;
         q.use_smem = (panel_smem_bytes(rows, w, true) <= 200 * 1024) ? 1 : 0;
         smem = std::max(smem, panel_smem_bytes(rows, w, q.use_smem != 0));
@@ -396,6 +404,8 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
       op.coef[p] = add_gemm(blob, gc);
       op.upd[p] = add_gemm(blob, gu);
       op.panel[p] = blob.add(pj);
+      for (auto &q2 : pj) q2.norm0 = ones_dev;
+      op.panel2[p] = blob.add(pj);
       op.panel_n[p] = (int)pj.size();
       op.panel_smem[p] = smem;
     }
@@ -516,9 +526,11 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
           if ((r2 = run(op.upd[p]))) return r2;
         }
         if (use_mgs)
-          r2 = launch_t("panel_mgs2", panel_mgs2_kernel, op.panel_n[p], 256, op.panel_smem[p], stream, op.panel[p], SKETCH_NOISE2);
+          r2 = launch_t("panel_mgs2", panel_mgs2_kernel, op.panel_n[p], 256, op.panel_smem[p], stream,
+                        round == 0 ? op.panel[p] : op.panel2[p], round == 0 ? SKETCH_NOISE2 : REPROJECT_KEEP2);
         else
-          r2 = launch_t("panel_cholqr", panel_cholqr_kernel, op.panel_n[p], 256, panel_cholqr_smem_bytes((int)p * PANEL_W), stream, op.panel[p], SKETCH_NOISE2);
+          r2 = launch_t("panel_cholqr", panel_cholqr_kernel, op.panel_n[p], 256, panel_cholqr_smem_bytes((int)p * PANEL_W), stream,
+                        round == 0 ? op.panel[p] : op.panel2[p], round == 0 ? SKETCH_NOISE2 : REPROJECT_KEEP2);
         if (r2) return r2;
       }
     }
@@ -553,7 +565,13 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
   if (rc) return rc;
   if ((rc = run(L_out[0]))) return rc;
   static const int pivchol_threads = std::getenv("TMF_PIVCHOL_THREADS") ? std::atoi(std::getenv("TMF_PIVCHOL_THREADS")) : 1024;
-  rc = launch_t("pivchol", pivchol_kernel, nb, pivchol_threads, chol_smem, stream, cj_dev, 1e-8);
+  // rank tolerance of the pivoted Cholesky: the remaining projector still carries the near-empty modes
+  // (0 < e < cutoff, not selected as entangled) as eigenvalues up to `cutoff`, so the residual diagonal that
+  // ends the factorisation has to sit above them -- and below 1 / n, the smallest pivot of a true rank
+  int n_big = 1;
+  for (auto &b : big) n_big = std::max(n_big, b.n);
+  const double chol_tol = std::min(std::max(1e-8, 30.0 * cutoff), 0.25 / n_big);
+  rc = launch_t("pivchol", pivchol_kernel, nb, pivchol_threads, chol_smem, stream, cj_dev, chol_tol);
   if (rc) return rc;
   tm.lap("modes: launches", njobs);
   return fork.join(stream);

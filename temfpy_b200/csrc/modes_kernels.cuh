@@ -5,6 +5,7 @@
 #pragma once
 #include "cta.hpp"
 #include <cstdio>
+#include <cstdlib>
 
 namespace tmf {
 
@@ -136,7 +137,11 @@ TMF_GLOBAL panel_mgs2_kernel(const PanelJob *jobs, double rel_tol2) {
 // of the Cholesky factorisation collapses (kappa > ~1e6, dependent or zero columns) the CTA falls back to
 // the MGS2 body on the panel in global memory.
 // ---------------------------------------------------------------------------------------------
+#if defined(TMF_HOSTSIM)
+static const double CHOLQR_PIVOT_TOL = std::getenv("TMF_CHOLQR_TOL") ? std::atof(std::getenv("TMF_CHOLQR_TOL")) : 1e-12;
+#else
 constexpr double CHOLQR_PIVOT_TOL = 1e-12;
+#endif
 TMF_GLOBAL_LB(256, 3) panel_cholqr_kernel(const PanelJob *jobs, double rel_tol2) {
   const PanelJob jb0 = jobs[BLOCK_ID];
   if (jb0.rows <= 0 || jb0.ncols <= 0) return;
@@ -360,6 +365,11 @@ TMF_GLOBAL_LB(256, 3) panel_cholqr_kernel(const PanelJob *jobs, double rel_tol2)
       }
     }
     *flag = bad;
+    if (std::getenv("TMF_DEBUG_PANEL")) {
+      double rmin = 1e300;
+      for (int k = 0; k < w; ++k) rmin = std::min(rmin, G[k * PANEL_W + k]);
+      std::fprintf(stderr, "[panel] rows %d c0 %d w %d bad %d zmask %x min L_kk %.3e\n", rows, c0, w, bad, zm, rmin);
+    }
     if (!bad && zm && jb0.nzero) *jb0.nzero += __builtin_popcount(zm);
   }
 #endif

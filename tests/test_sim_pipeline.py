@@ -137,3 +137,27 @@ def test_decoupled_blocks_rank_deficient_sketch(sim_backend):
     assert res.bonds[La].k == 0 and res.bonds[La].chi == 1
     rep = helpers.compare_mps(so.C_to_MPS(Cm, tp, ortho_center=70), helpers.chain_to_dense(res), tp)
     assert rep["ambiguous"] == []
+
+
+@pytest.mark.parametrize("case", ["anderson", "svd_min_1e-3"])
+def test_structured_inputs_vs_oracle(sim_backend, case):
+    """Regression tests of two robustness bugs: (1) localised (Anderson) states -- the singular values of the
+    off-diagonal block fall below the rounding noise within one sketch panel; normalised noise columns used to
+    re-enter Q and entangled modes were lost; (2) svd_min = 1e-3 -- near-empty modes (e < svd_min^2) stay in
+    the filled-space projector and the rank tolerance of the pivoted Cholesky has to sit above them."""
+    rng = np.random.default_rng(5)
+    L = 130
+    H = np.zeros((L, L))
+    i = np.arange(L - 1)
+    H[i, i + 1] = H[i + 1, i] = -1.0
+    if case == "anderson":
+        H += np.diag(2.0 * rng.standard_normal(L))
+        tp = {"chi_max": 32}
+    else:
+        H += np.diag(0.1 * rng.standard_normal(L))
+        tp = {"svd_min": 1e-3}
+    Cm, n = so.correlation_matrix(H)
+    res = helpers.run_native(sim_backend, Cm, tp, n)
+    rep = helpers.compare_mps(so.C_to_MPS(Cm, tp), helpers.chain_to_dense(res), tp)
+    # (with an svd_min-limited cut a near-degenerate multiplet may straddle the cut: compare_mps audits it)
+    assert rep["ambiguous"] == [] or "svd_min" in case
