@@ -1,0 +1,29 @@
+"""Wall time of the other BASELINE configurations through the public API (host in, host out)."""
+import sys, time
+sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/oracle")
+import numpy as np, torch
+import slater_oracle as so
+import pfaffian_oracle as po
+from tests import helpers
+from temfpy_b200 import slater, pfaffian as pf, gutzwiller, engine
+be = engine.TorchBackend("cuda:0")
+slater._backend = be
+def timed(f, n=3):
+    f(); ts = []
+    for _ in range(n):
+        torch.cuda.synchronize(); t0 = time.perf_counter(); r = f(); torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
+    return min(ts), r
+C1, _ = so.correlation_matrix(so.hopping_chain(64))
+t, m = timed(lambda: slater.C_to_MPS(C1, {"chi_max": 64}, as_tenpy=False)); print("cfg1 chain L=64 chi=64: %.1f ms (%.0f sites/s)" % (1e3 * t, 64 / t))
+H2 = po.bdg_chain(128, t=1.0, mu=0.0, delta=0.05)
+t, m = timed(lambda: pf.H_to_MPS(H2, {"chi_max": 128}, basis="C", _backend=be, as_tenpy=False)); print("cfg2 Kitaev L=128 chi=128: %.1f ms (%.0f sites/s)" % (1e3 * t, 128 / t))
+C3, _ = so.correlation_matrix(so.hopping_chain(256))
+def cfg3():
+    mps = slater.C_to_MPS(C3, {"chi_max": 256}, spinful="PH", as_tenpy=False)
+    return gutzwiller.abrikosov_ph(mps, as_tenpy=False) if "as_tenpy" in gutzwiller.abrikosov_ph.__code__.co_varnames else gutzwiller.abrikosov_ph(mps)
+try:
+    t, m = timed(cfg3); print("cfg3 Gutzwiller L=256 (512 fermion sites) chi=256: %.1f ms (%.0f spin sites/s)" % (1e3 * t, 256 / t))
+except Exception as e:
+    print("cfg3 failed:", type(e).__name__, str(e)[:200])
+C4, _ = so.correlation_matrix(helpers.cylinder_hamiltonian(64, 6))
+t, m = timed(lambda: slater.C_to_MPS(C4, {"chi_max": 1024}, unit_cell_width=64 if False else None, as_tenpy=False)); print("cfg4 cylinder 6x64 chi=1024: %.1f ms (%.0f sites/s)" % (1e3 * t, 384 / t))
