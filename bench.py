@@ -197,14 +197,22 @@ def run_native(args):
 
     state = {}
 
+    gather = tdist.StreamingGather(be.device) if world > 1 and not os.environ.get("TMF_SIMPLE_GATHER") else None
+
     def step(collect_stats=False, n_chunks=None):
         if world > 1:
+            if gather is not None:
+                gather.begin()
             tdist.broadcast_C(C_dev)
         res = engine.run_chain(be, C_dev, L, L, tp, N, site_lo=lo, site_hi=hi, r_sketch=args.r_sketch,
                                n_threads=args.threads, n_chunks=n_chunks if n_chunks else (args.chunks or None), lazy=True)
         if world > 1:
-            full, offs = tdist.gather_tensors(res.out_buffers())
-            state["gathered"] = None if full is None else int(full.numel())
+            if gather is not None:
+                got = gather.finish(res.out_buffers())
+                state["gathered"] = None if got is None else int(sum(b.numel() for b in got.values()))
+            else:
+                full, offs = tdist.gather_tensors(res.out_buffers())
+                state["gathered"] = None if full is None else int(full.numel())
         if collect_stats:
             state["flops"] = [float(x) for x in res.flops()]
             state["out_elems"] = res.out_elems

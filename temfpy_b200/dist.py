@@ -101,3 +101,92 @@ def gather_tensors(parts, dst=0):
     for w in (dist.batch_isend_irecv(ops) if ops else []):
         w.wait()
     return None, None
+
+
+class StreamingGather:
+    """Gather of the ranks' tensor buffers on rank ``dst`` that does not wait for the slowest rank before
+    the first byte moves: every (dst, r) pair has its own two-rank NCCL communicator, a helper thread on
+    ``dst`` receives rank r's sizes and posts the matching receives as soon as *that* rank is done, so the
+    transfers of the early ranks overlap the kernels of the late ones (the all-reduce of the sizes in
+    ``gather_tensors`` made every transfer start after the slowest rank; at 8 GPUs that cost ~2 ms of a
+    15 ms step).  ``begin()`` at the start of a step, ``finish(parts)`` after the local conversion."""
+
+    def __init__(self, device, dst=0):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world, self.rank, self.dst, self.device = dist.get_world_size(), dist.get_rank(), dst, device
+        self.groups = {}
+        for r in range(self.world):          # new_group is collective: every rank creates every pair group
+            if r != dst:
+                self.groups[r] = dist.new_group(ranks=sorted((dst, r)))
+        self.stream = torch.cuda.Stream(device=device) if self.rank == dst else None
+        self.thread = None
+        self.result = None
+        self.error = None
+
+    def begin(self):
+        if self.rank != self.dst:
+            return
+        import threading
+        self.result, self.error = {}, None
+
+        def serve():
+            t, d = self.torch, self.dist
+            try:
+                with t.cuda.stream(self.stream):
+                    pending = []
+                    sizes = {}
+                    for r in self.groups:                      # one tiny message per rank: its chunk sizes
+                        st = t.zeros(MAX_PARTS, dtype=t.int64, device=self.device)
+                        w = d.irecv(st, src=r, group=self.groups[r])
+                        sizes[r] = (st, w)
+                    waiting = list(self.groups)
+                    while waiting:                               # whichever rank reports first is served first
+                        for r in list(waiting):
+                            st, w = sizes[r]
+                            if w.is_completed():
+                                w.wait()
+                                n = st.cpu().numpy()
+                                buf = t.empty(int(n.sum()), dtype=t.float64, device=self.device)
+                                o = 0
+                                for k in n:
+                                    if k:
+                                        pending.append(d.irecv(buf[o: o + int(k)], src=r, group=self.groups[r]))
+                                        o += int(k)
+                                self.result[r] = buf
+                                waiting.remove(r)
+                        if waiting:
+                            import time
+                            time.sleep(0.0001)
+                    for w in pending:
+                        w.wait()
+                    self.stream.synchronize()
+            except Exception as e:       # surfaced by finish()
+                self.error = e
+
+        self.thread = threading.Thread(target=serve, name="tmf-gather", daemon=True)
+        self.thread.start()
+
+    def finish(self, parts):
+        """parts: list of (device buffer, n_elements) of this rank.  Returns {rank: buffer} on dst, None elsewhere."""
+        t, d = self.torch, self.dist
+        if self.rank != self.dst:
+            if len(parts) > MAX_PARTS:
+                raise ValueError("too many pipeline chunks for one gather")
+            n = np.zeros(MAX_PARTS, dtype=np.int64)
+            for i, (_, k) in enumerate(parts):
+                n[i] = int(k)
+            g = self.groups[self.rank]
+            ws = [d.isend(t.from_numpy(n).to(self.device), dst=self.dst, group=g)]
+            ws += [d.isend(buf[:k], dst=self.dst, group=g) for buf, k in parts if k]
+            for w in ws:
+                w.wait()
+            return None
+        own = t.cat([b[:k] for b, k in parts]) if len(parts) > 1 else parts[0][0][: parts[0][1]]
+        self.thread.join()
+        if self.error is not None:
+            raise self.error
+        out = dict(self.result)
+        out[self.dst] = own
+        return out
