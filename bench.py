@@ -375,6 +375,8 @@ def run_native(args):
         roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic, "launches_per_step": dcnt, "ms_per_step": dms,
                 "algorithmic_flops_per_step": a_fl,
+                "note": "FP64 pipe roofline (vector DFMA and tensor DMMA peak coincide on B200); achieved counts the "
+                        "reference algorithm's flops for this stage (SURVEY 8d), the kernel itself needs far fewer",
                 "peak_source": f"measured in this run: FP64 DFMA probe {dfma_tflops:.1f} TF/s, cuBLAS DGEMM 4096^3 "
                                f"{dgemm_tflops:.1f} TF/s (MEASURED_PEAKS.json has no FP64 figure)"}
     total_alg = sum(alg.values())
