@@ -16,6 +16,7 @@
 //   5. pivoted Cholesky of the remaining projector A - U diag(e) U^T -> filled-space basis.
 // Blocks with n <= 64 are diagonalised directly by Jacobi.  All bonds of the chain run in the
 // same launches (grids of hundreds of CTAs), descriptors are uploaded once up front.
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <map>
@@ -303,6 +304,8 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
     b.info = info_dev + 4 * j;
     big.push_back(b);
   }
+  // largest blocks first: the one-CTA-per-job kernels take longest on them, so they should not start last
+  std::stable_sort(big.begin(), big.end(), [](const BigJob &a, const BigJob &b) { return a.n > b.n; });
   const int nb = (int)big.size();
   // sub-buffers are grouped by kind so that Wt -> Wt0 is one device copy and the counters one memset
   for (auto &b : big) b.Y = arena.take<double>((int64_t)b.n * b.rr);
