@@ -83,6 +83,19 @@ int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int njobs, con
                              const int64_t *v_off, double *V_dev, double *e_dev, int *info_dev,
                              void *work_dev, int64_t work_bytes, void *stream);
 
+/* Nested form used by the chain driver: no basis of the filled space.  Column k of a job's V slot
+ * receives the *edge vector* g = P_F e_edge / |P_F e_edge| (P_F = projector onto the filled space of the
+ * block, e_edge = unit vector of the block's site next to the cut) -- the one direction by which the filled
+ * space grows when the block grows by a site; info[1] = f = round(tr A - sum of the entangled
+ * eigenvalues); edge_dev[2 j] = |P_F e_edge|^2, edge_dev[2 j + 1] = rounding remainder of f.
+ * V slots need tmf_slater_modes_slot_cols() columns (ld = n).  replaces: slater.py:347-370 as above;
+ * the filled eigenvectors the reference keeps (:355-368) are never needed, see tmf_site_nested_batched. */
+int64_t tmf_slater_modes_slot_cols(int L, int x, int side, int r_sketch, int nested);
+int tmf_slater_modes_nested(const double *C_dev, int L, int ldc, int njobs, const int *job_x,
+                            const int *job_side, double cutoff, int r_sketch, const int64_t *v_off,
+                            double *V_dev, double *e_dev, int *info_dev, double *edge_dev,
+                            void *work_dev, int64_t work_bytes, void *stream);
+
 /* K4 -- pairing of the left and right entangled modes of a bond whose two sides were both extracted.
  * replaces: utils.py:19-96 (block_svd) as called from slater.py:407, and the odd-index sign flips of
  * slater.py:410.  VL (x rows) / VR (L-x rows): stored mode matrices of the two jobs; their first k
@@ -169,6 +182,7 @@ typedef struct tmf_site_job {
   int mode, physical;
   int ka_bra, ka_ket;          /* always orbitals of each side                                */
   int sb, sk;                  /* sometimes orbitals of each side (sb includes the physical)  */
+  /* pad_[0] (internal): 1 = O and *det were prepared by the nested-projector kernel             */
   int emb;                     /* 1: Pfaffian path -- rows are re/im-interleaved Majorana components
                                   (4 per site); bra_cols -1..-4 = emb(w), J emb(w) of the physical
                                   site's lower mode (c^+ row, pfaffian.py:1667-1688) and the same
@@ -178,6 +192,25 @@ typedef struct tmf_site_job {
 int64_t tmf_site_desc_bytes(int nsites);   /* size of desc_dev for the call below */
 int tmf_site_overlap_schur_batched(const tmf_site_job *jobs_host, int nsites, void *desc_dev,
                                    void *stream);
+
+/* K8 + K9, nested-projector form (chain driver).  replaces: slater.py:1071-1090 for two neighbouring
+ * bonds of the *same* correlation matrix.  The filled spaces of the two blocks are nested up to the
+ * truncation threshold (F_ket = F_bra (+) edge vector, or F_ket = F_bra), so their elimination has the
+ * closed form  S = Y_b^T Y_k - (Z_b^T Z_k)(1 - Z_k^T Z_k)^-1  with Y = explicit orbitals (physical +
+ * entangled modes + edge vector) and Z = their leaks into the other side's filled space, all obtained
+ * from one pass over the n x k mode matrices (see siteprep.cu); the always-occupied *entangled* orbitals
+ * are then eliminated as in tmf_site_overlap_schur_batched.  Site jobs as above with V slots in the nested
+ * layout ([entangled | edge vector]; column codes of the plan: i < k entangled, k = edge vector). */
+typedef struct tmf_nested_job {
+  const double *e_bra, *e_ket; /* device: left eigenvalues of the bra / ket entangled modes           */
+  const double *a_col;         /* device: C[site, bra block] (n_bra contiguous doubles)               */
+  const double *c_edge;        /* device: &C[site, site]                                              */
+  int k_bra, k_ket;            /* entangled modes of the two bonds                                    */
+  int df;                      /* f_ket - f_bra: 1 if the ket's filled space has the edge vector      */
+  int pad_[5];
+} tmf_nested_job;
+int tmf_site_nested_batched(const tmf_site_job *jobs_host, const tmf_nested_job *njobs_host,
+                            int nsites, void *desc_dev, void *stream);
 
 /* K10 -- all minors of all charge blocks of all sites.  replaces: slater.py:828-869
  * (_tensor_block: gather + batched det) and the det_always scaling of :1137.
@@ -292,6 +325,15 @@ int tmf_chain_sites_sizes(tmf_chain *c, int64_t *q /* sites, sum n_blocks, sum n
 int tmf_chain_sites_export(tmf_chain *c, tmf_site_plan *plans, int64_t *blk_off, int *blocks,
                            int64_t *block_off, int64_t *row_off, int *row_p, int *row_alpha);
 int64_t tmf_chain_job_voff(tmf_chain *c, int job);
+/* Options (call right after tmf_chain_create):
+ *   TMF_OPT_SNAP   1 (default): mode weights equal within the eigenvalue accuracy are symmetrised
+ *                  before the enumeration (spin-pure degenerate modes); 0: the reference's literal
+ *                  behaviour (schmidt_utils.py:175-185 sees only degeneracies below degeneracy_tol).
+ *   TMF_OPT_NESTED 1 (default): nested-projector site stage (no filled bases); 0: explicit filled
+ *                  bases by pivoted Cholesky + overlap GEMM + blocked LU (also the automatic fallback). */
+#define TMF_OPT_SNAP 1
+#define TMF_OPT_NESTED 2
+int tmf_chain_set_option(tmf_chain *c, int option, int value);
 /* algorithmic flops of the reference's algorithm for this shard:
  * f[0] eigh, f[1] overlap GEMM, f[2] Schur, f[3] minors, f[4] number of minors */
 int tmf_chain_flops(tmf_chain *c, double *f);

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libtemfpy_b200.so")
 
 TMF_MAX_MODES = 64
 SIDE_L, SIDE_R = 0, 1
+OPT_SNAP, OPT_NESTED = 1, 2
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
@@ -47,6 +48,11 @@ class SiteJob(C.Structure):
                 ("sb", C.c_int), ("sk", C.c_int), ("emb", C.c_int), ("pad_", C.c_int * 3)]
 
 
+class NestedJob(C.Structure):
+    _fields_ = [("e_bra", C.c_void_p), ("e_ket", C.c_void_p), ("a_col", C.c_void_p), ("c_edge", C.c_void_p),
+                ("k_bra", C.c_int), ("k_ket", C.c_int), ("df", C.c_int), ("pad_", C.c_int * 5)]
+
+
 class MinorBlock(C.Structure):
     _fields_ = [("S", C.c_void_p), ("det", C.c_void_p), ("bra_masks", C.c_void_p),
                 ("ket_masks", C.c_void_p), ("out", C.c_void_p),
@@ -73,7 +79,7 @@ class GutzJob(C.Structure):
 
 
 assert C.sizeof(GemmJob) == 128 and C.sizeof(SiteJob) == 128 and C.sizeof(MinorBlock) == 64
-assert C.sizeof(PairJob) == 64 and C.sizeof(PfBlock) == 64
+assert C.sizeof(PairJob) == 64 and C.sizeof(PfBlock) == 64 and C.sizeof(NestedJob) == 64
 
 # name -> (restype, argtypes); this table is also what tests check against include/temfpy_b200.h
 SIGNATURES = {
@@ -88,6 +94,10 @@ SIGNATURES = {
     "tmf_slater_modes_batched": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p,
                                            C.c_double, C.c_int, c_i64_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "tmf_slater_modes_slot_cols": (C.c_int64, [C.c_int] * 5),
+    "tmf_slater_modes_nested": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p,
+                                          C.c_double, C.c_int, c_i64_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "tmf_slater_pair_bond_workspace": (C.c_int64, [C.c_int, C.c_int]),
     "tmf_slater_pair_bond": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, C.c_double,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -102,6 +112,8 @@ SIGNATURES = {
                               c_double_p, c_u64_p, c_u64_p, c_int_p, c_int_p, c_int_p]),
     "tmf_site_desc_bytes": (C.c_int64, [C.c_int]),
     "tmf_site_overlap_schur_batched": (C.c_int, [C.POINTER(SiteJob), C.c_int, C.c_void_p, C.c_void_p]),
+    "tmf_site_nested_batched": (C.c_int, [C.POINTER(SiteJob), C.POINTER(NestedJob), C.c_int, C.c_void_p,
+                                          C.c_void_p]),
     "tmf_minor_desc_bytes": (C.c_int64, [C.c_int]),
     "tmf_minors_blocks": (C.c_int, [C.POINTER(MinorBlock), C.c_int, C.c_void_p, C.c_void_p]),
     "tmf_chain_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
@@ -130,6 +142,7 @@ SIGNATURES = {
     "tmf_chain_sites_sizes": (C.c_int, [C.c_void_p, c_i64_p]),
     "tmf_chain_sites_export": (C.c_int, [C.c_void_p] * 8),
     "tmf_chain_job_voff": (C.c_int64, [C.c_void_p, C.c_int]),
+    "tmf_chain_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "tmf_chain_flops": (C.c_int, [C.c_void_p, c_double_p]),
     "tmf_launch_count": (C.c_longlong, [C.c_int]),
     "tmf_prof_enable": (C.c_int, [C.c_int]),

@@ -61,6 +61,7 @@ struct ChainBond {
 };
 struct ChainSite {
   int site = 0, mode = 0, bra_bond = 0, ket_bond = 0;
+  int f_common = 0, df = 0;   // nested mode: filled orbitals shared by the two bonds, f_ket - f_bra
   tmf::SitePlan plan;
   int64_t o_off = 0, s_off = 0;
   std::vector<int64_t> block_off;
@@ -79,6 +80,9 @@ struct tmf_chain {
   int64_t o_elems = 0, s_elems = 0, out_elems = 0, plan_bytes = 0;
   int nblocks = 0, max_chi = 0;
   bool enumerated = false;
+  bool nested = true;                // nested-projector site stage (no filled bases), see siteprep.cu
+  const double *e_dev_ptr = nullptr; // device spectra of the last tmf_chain_modes_enqueue (read by the nested site kernel)
+  std::vector<double> edge_host;     // nested: {|P_F e_edge|^2, rounding remainder of f} per job
   unsigned char *blob = nullptr;     // pinned staging of the per-site plan arrays (from the pool below)
   size_t blob_cap = 0;
   ~tmf_chain();
@@ -203,6 +207,21 @@ int fail_from(const std::exception &e) {
 
 }  // namespace
 
+// V slots of every job: n x n ([entangled | filled basis]) in the legacy layout, n x (Ritz columns + 1)
+// ([entangled | edge vector]) in the nested one
+static void chain_layout_slots(tmf_chain *c) {
+  c->v_elems = 0;
+  for (size_t j = 0; j < c->job_x.size(); ++j) {
+    const int bond = c->job_x[j], side = c->job_side[j];
+    ChainSide &s = c->bonds[bond].side[side];
+    const int64_t cols = tmf_slater_modes_slot_cols(c->L, bond, side, c->r_sketch, c->nested ? 1 : 0);
+    s.v_off = c->v_elems;
+    c->v_off[j] = s.v_off;
+    c->v_elems += (int64_t)s.n * cols + 32;  // + slack keeps every matrix 256-byte aligned
+    c->v_elems = (c->v_elems + 31) & ~int64_t(31);
+  }
+}
+
 extern "C" {
 
 tmf_chain *tmf_chain_create(int L, int ortho_center, int n_fermion, int chi_max, double svd_min,
@@ -221,6 +240,7 @@ tmf_chain *tmf_chain_create(int L, int ortho_center, int n_fermion, int chi_max,
     c->tp.sectors.assign(sectors, sectors + n_sectors);
   }
   c->bonds.resize(L + 1);
+  c->nested = std::getenv("TMF_LEGACY_FILLED") == nullptr;
   auto need = [&](int bond, int side) {
     ChainBond &b = c->bonds[bond];
     b.used = true;
@@ -228,12 +248,9 @@ tmf_chain *tmf_chain_create(int L, int ortho_center, int n_fermion, int chi_max,
     ChainSide &s = b.side[side];
     s.job = (int)c->job_x.size();
     s.n = (side == TMF_SIDE_L) ? bond : L - bond;
-    s.v_off = c->v_elems;
-    c->v_elems += (int64_t)s.n * s.n + 32;  // + slack keeps every matrix 256-byte aligned
-    c->v_elems = (c->v_elems + 31) & ~int64_t(31);
     c->job_x.push_back(bond);
     c->job_side.push_back(side);
-    c->v_off.push_back(s.v_off);
+    c->v_off.push_back(0);
   };
   for (int i = site_lo; i < site_hi; ++i) {
     const int side = (i >= ortho_center) ? TMF_SIDE_R : TMF_SIDE_L;
@@ -244,7 +261,19 @@ tmf_chain *tmf_chain_create(int L, int ortho_center, int n_fermion, int chi_max,
       need(ortho_center, TMF_SIDE_R);
     }
   }
+  chain_layout_slots(c);
   return c;
+}
+
+int tmf_chain_set_option(tmf_chain *c, int option, int value) {
+  if (option == TMF_OPT_SNAP) { c->tp.snap = value != 0; return TMF_OK; }
+  if (option == TMF_OPT_NESTED) {
+    c->nested = value != 0;
+    chain_layout_slots(c);
+    return TMF_OK;
+  }
+  tmf::set_error("tmf_chain_set_option: unknown option");
+  return TMF_ERR_VALUE;
 }
 
 void tmf_chain_destroy(tmf_chain *c) { delete c; }
@@ -254,6 +283,7 @@ int tmf_chain_modes_sizes(tmf_chain *c, int64_t *q) {
   q[1] = c->v_elems;
   q[2] = tmf_slater_modes_workspace(c->L, (int)c->job_x.size(), c->job_x.data(), c->job_side.data(),
                                     c->r_sketch);
+  q[3] = (int64_t)c->job_x.size() * (TMF_MAX_MODES + 2);   // doubles of e_dev (spectra + edge data)
   return TMF_OK;
 }
 
@@ -264,6 +294,11 @@ int tmf_chain_modes_enqueue(tmf_chain *c, const double *C_dev, int ldc, double *
                             int *info_dev, void *work_dev, int64_t work_bytes, void *stream) {
   const int nj = (int)c->job_x.size();
   const double cutoff = c->tp.svd_min * c->tp.svd_min;  // slater.py:318
+  c->e_dev_ptr = e_dev;
+  if (c->nested)
+    return tmf_slater_modes_nested(C_dev, c->L, ldc, nj, c->job_x.data(), c->job_side.data(), cutoff,
+                                   c->r_sketch, c->v_off.data(), V_dev, e_dev, info_dev,
+                                   e_dev + (size_t)nj * TMF_MAX_MODES, work_dev, work_bytes, stream);
   return tmf_slater_modes_batched(C_dev, c->L, ldc, nj, c->job_x.data(), c->job_side.data(), cutoff,
                                   c->r_sketch, c->v_off.data(), V_dev, e_dev, info_dev, work_dev,
                                   work_bytes, stream);
@@ -276,7 +311,8 @@ int tmf_chain_modes_finish(tmf_chain *c, const double *e_dev, const int *info_de
   // through pinned staging: a device -> pageable copy is executed synchronously inside the driver (it waits
   // there for the whole mode stage of this chunk), which stalled the kernel launches of the other pipeline
   // threads for milliseconds; cudaStreamSynchronize does not
-  const size_t e_bytes = sizeof(double) * TMF_MAX_MODES * (size_t)nj, i_bytes = sizeof(int) * 4 * (size_t)nj;
+  const size_t e_bytes = sizeof(double) * (TMF_MAX_MODES + (c->nested ? 2 : 0)) * (size_t)nj, i_bytes = sizeof(int) * 4 * (size_t)nj;
+  c->edge_host.assign(c->nested ? 2 * (size_t)nj : 0, 0.0);
   const size_t need = e_bytes + i_bytes + 512;
   if (c->blob_cap < need) {
     g_pinned.release(c->blob, c->blob_cap);
@@ -288,7 +324,8 @@ int tmf_chain_modes_finish(tmf_chain *c, const double *e_dev, const int *info_de
   if (rc) return rc;
   rc = tmf::copy_d2h_sync(st_e, e_dev, e_bytes, stream);
   if (rc) return rc;
-  std::memcpy(c->e_host.data(), st_e, e_bytes);
+  std::memcpy(c->e_host.data(), st_e, sizeof(double) * TMF_MAX_MODES * (size_t)nj);
+  if (c->nested) std::memcpy(c->edge_host.data(), st_e + sizeof(double) * TMF_MAX_MODES * (size_t)nj, sizeof(double) * 2 * (size_t)nj);
   std::memcpy(c->info_host.data(), st_i, i_bytes);
   for (int j = 0; j < nj; ++j) {
     const int st = c->info_host[4 * j + 2];
@@ -382,9 +419,27 @@ static int chain_enumerate_impl(tmf_chain *c, void *work_dev, int64_t work_bytes
       const int side = s.mode == 1 ? TMF_SIDE_R : TMF_SIDE_L;
       const ChainBond &bb = c->bonds[s.bra_bond], &kb = c->bonds[s.ket_bond];
       const ChainSide &bs = bb.side[side], &ks = kb.side[side];
-      tmf::site_plan(s.mode, bs.n, ks.n, bb.k, bs.f, c->nferm, (int)bb.bv.masks.size(),
-                     bb.bv.masks.data(), bb.bv.charge.data(), kb.k, ks.f, c->nferm,
+      if (!c->nested) {
+        tmf::site_plan(s.mode, bs.n, ks.n, bb.k, bs.f, c->nferm, (int)bb.bv.masks.size(),
+                       bb.bv.masks.data(), bb.bv.charge.data(), kb.k, ks.f, c->nferm,
+                       (int)kb.bv.masks.size(), kb.bv.masks.data(), kb.bv.charge.data(), s.plan);
+        return;
+      }
+      // nested: the filled orbitals the two bonds share are eliminated in closed form (siteprep.cu); what is
+      // left of them for the plan is the ket's edge vector (stored-V column k_ket) when its count grows
+      s.df = ks.f - bs.f;
+      s.f_common = bs.f;
+      if (s.df < 0 || s.df > 1)
+        throw std::invalid_argument("nested site stage: filled-orbital counts of neighbouring bonds differ by " +
+                                    std::to_string(s.df) + " (threshold noise); rerun with the legacy filled bases");
+      if (s.df == 1 && !(c->edge_host[2 * (size_t)ks.job] > 1e-24))
+        throw std::invalid_argument("nested site stage: edge vector of the filled space vanishes; rerun with the "
+                                    "legacy filled bases");
+      tmf::site_plan(s.mode, bs.n, ks.n, bb.k, 0, c->nferm, (int)bb.bv.masks.size(),
+                     bb.bv.masks.data(), bb.bv.charge.data(), kb.k, s.df, c->nferm,
                      (int)kb.bv.masks.size(), kb.bv.masks.data(), kb.bv.charge.data(), s.plan);
+      s.plan.h.f_bra = bs.f;
+      s.plan.h.f_ket = ks.f;
     });
     tm.lap("enumerate: site plans");
     // offsets
@@ -606,7 +661,26 @@ int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev,
   rc = tmf::copy_h2d(blob_dev, blob, bsz, stream);
   if (rc) return rc;
   tm.lap("tensors: upload blob");
-  rc = tmf_site_overlap_schur_batched(sj.data(), ns, site_desc, stream);
+  if (c->nested) {
+    std::vector<tmf_nested_job> nj(ns);
+    const double *e_dev = c->e_dev_ptr;
+    if (e_dev == nullptr) return fail(TMF_ERR_VALUE, "tmf_chain_modes has not run");
+    for (int u = 0; u < ns; ++u) {
+      const ChainSite &s = c->sites[u];
+      const int side = s.mode == 1 ? TMF_SIDE_R : TMF_SIDE_L;
+      const ChainBond &bb = c->bonds[s.bra_bond], &kb = c->bonds[s.ket_bond];
+      tmf_nested_job &q = nj[u];
+      std::memset(&q, 0, sizeof(q));
+      q.e_bra = e_dev + (size_t)bb.side[side].job * TMF_MAX_MODES;
+      q.e_ket = e_dev + (size_t)kb.side[side].job * TMF_MAX_MODES;
+      q.c_edge = C_dev + (int64_t)s.site * ldc + s.site;
+      q.a_col = (s.mode == 1) ? q.c_edge + 1 : C_dev + (int64_t)s.site * ldc;
+      q.k_bra = bb.k; q.k_ket = kb.k; q.df = s.df;
+    }
+    rc = tmf_site_nested_batched(sj.data(), nj.data(), ns, site_desc, stream);
+  } else {
+    rc = tmf_site_overlap_schur_batched(sj.data(), ns, site_desc, stream);
+  }
   if (rc) return rc;
   tm.lap("tensors: enqueue site kernels");
   rc = tmf_minors_blocks(mb.data(), (int)mb.size(), minor_desc, stream);
@@ -750,10 +824,12 @@ int tmf_chain_flops(tmf_chain *c, double *f) {
   }
   for (const ChainSite &s : c->sites) {
     const tmf_site_plan &h = s.plan.h;
-    const double cb = h.ka_bra + (h.s_bra - (h.ka_bra - h.k_always));
-    const double ck = h.ka_ket + (h.s_ket - (h.ka_ket - h.k_always));
+    // (the reference's O and always block contain the filled orbitals the nested form eliminates in closed form)
+    const double cb = h.ka_bra + (h.s_bra - (h.ka_bra - h.k_always)) + s.f_common;
+    const double ck = h.ka_ket + (h.s_ket - (h.ka_ket - h.k_always)) + s.f_common;
+    const double ka = (double)h.k_always + s.f_common;
     f[1] += 2.0 * (h.n_bra + 1.0) * cb * ck;
-    f[2] += 8.0 / 3.0 * (double)h.k_always * h.k_always * h.k_always;
+    f[2] += 8.0 / 3.0 * ka * ka * ka;
     for (int b = 0; b < h.n_blocks; ++b) {
       const int *bl = &s.plan.blocks[6 * b];
       f[3] += (double)bl[1] * bl[3] * (2.0 / 3.0) * bl[4] * bl[4] * bl[4];

@@ -369,7 +369,7 @@ int enumerate_device(int nb, const double *const *e_ptr, const int *k, const int
     const double *e = e_ptr[b];
     std::vector<double> a(kk), negs;
     for (int i = 0; i < kk; ++i) a[i] = std::log((1.0 - e[i]) / e[i]) / 2;   // slater.py:428, :663
-    snap_degenerate(a.data(), e, kk);
+    if (tp.snap) snap_degenerate(a.data(), e, kk);
     for (int i = 0; i < kk; ++i)
       if (a[i] < 0) { negs.push_back(a[i]); j.neg |= (1ull << i); }
     // NumPy's pairwise sum of the negative weights (schmidt_utils.py:274), as in bond_vectors()

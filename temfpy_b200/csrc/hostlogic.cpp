@@ -437,7 +437,7 @@ void bond_vectors(const double *e, int k, int filled_left, const TruncPar &tp, B
     a[i] = std::log((1.0 - e[i]) / e[i]) / 2;  // slater.py:428, :663
     if (a[i] < 0) negs.push_back(a[i]);
   }
-  snap_degenerate(a.data(), e, k);
+  if (tp.snap) snap_degenerate(a.data(), e, k);
   negs.clear();
   for (int i = 0; i < k; ++i)
     if (a[i] < 0) negs.push_back(a[i]);

@@ -19,6 +19,10 @@ struct TruncPar {
   double degeneracy_tol = 1e-12;
   std::vector<int> sectors;  // empty + !filter -> all sectors
   bool filter = false;
+  // symmetrise mode weights that are equal within the eigenvalue accuracy before the enumeration
+  // (hostlogic.cpp: snap_degenerate).  On by default for inputs with exactly degenerate (spin-pure)
+  // modes; off = the reference's literal behaviour (the cut inside such a multiplet is rounding noise).
+  bool snap = true;
   bool is_sector(int q) const;
 };
 

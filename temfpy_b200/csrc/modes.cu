@@ -252,14 +252,15 @@ extern "C" int64_t tmf_slater_modes_workspace(int L, int njobs, const int *job_x
   // descriptor blob: ~ (14 + 8 * panels) launches of nbig descriptors of 128 bytes
   const int panels = (r_sketch + PANEL_W - 1) / PANEL_W;
   bytes += align256((int64_t)(nbig + 1) * 128 * (16 + 10 * panels) + (int64_t)(nsmall + 1) * 64 + (int64_t)(L + 1) * 32 + 65536);
+  bytes += align256((int64_t)(njobs + 2) * 64);   // edge-vector descriptors (nested mode)
   return bytes;
 }
 
-extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int njobs,
-                                        const int *job_x, const int *job_side, double cutoff,
-                                        int r_sketch, const int64_t *v_off, double *V_dev,
-                                        double *e_dev, int *info_dev, void *work_dev,
-                                        int64_t work_bytes, void *stream) {
+static int modes_impl(const double *C_dev, int L, int ldc, int njobs,
+                      const int *job_x, const int *job_side, double cutoff,
+                      int r_sketch, const int64_t *v_off, double *V_dev,
+                      double *e_dev, int *info_dev, void *work_dev,
+                      int64_t work_bytes, void *stream, bool nested, double *edge_dev) {
   using namespace tmf;
   if (r_sketch <= 0 || r_sketch > R_SKETCH_MAX) {
     set_error("r_sketch must be in 1..160");
@@ -489,6 +490,22 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
   }
   const CholJob *cj_dev = blob.add(cj);
   const SmallJob *small_dev = blob.add(small);
+  // nested mode: edge vectors instead of the filled-space bases (no pivoted Cholesky)
+  std::vector<EdgeJob> edge_small, edge_big;
+  if (nested) {
+    auto mk_edge = [&](int j, const double *A, int n, int side) {
+      EdgeJob q;
+      q.A = A; q.V = V_dev + v_off[j]; q.e_left = e_dev + (int64_t)j * TMF_MAX_MODES; q.info = info_dev + 4 * j;
+      q.edge_out = edge_dev + 2 * (int64_t)j; q.n = n; q.lda = ldc; q.side = side; q.pad_ = 0;
+      return q;
+    };
+    for (auto &sj2 : small) {
+      const int j = (int)((sj2.info - info_dev) / 4);
+      edge_small.push_back(mk_edge(j, sj2.A, sj2.n, sj2.side));
+    }
+    for (auto &b : big) edge_big.push_back(mk_edge(b.job, b.A, b.n, b.side));
+  }
+  const EdgeJob *edge_small_dev = blob.add(edge_small), *edge_big_dev = blob.add(edge_big);
 
   if ((int64_t)(blob_dev - static_cast<unsigned char *>(work_dev)) + (int64_t)blob.host.size() > work_bytes) {
     set_error("modes: descriptor blob does not fit the workspace");
@@ -508,6 +525,10 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
     void *sstream = (nb > 0) ? fork.open(stream) : stream;
     rc = launch_t("small_modes", small_modes_kernel, (int)small.size(), small_threads, small_smem, sstream, small_dev, cutoff);
     if (rc) return rc;
+    if (nested) {
+      rc = launch_t("edge_vector", edge_vector_kernel, (int)edge_small.size(), 256, edge_smem_bytes(), sstream, edge_small_dev);
+      if (rc) return rc;
+    }
   }
   if (nb == 0) return TMF_OK;
   rc = launch_t("omega", omega_kernel, (int)(((int64_t)L * r_sketch + 1023) / 1024), 256, 0, stream, Om, L, r_sketch);
@@ -574,8 +595,44 @@ extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int
   int n_big = 1;
   for (auto &b : big) n_big = std::max(n_big, b.n);
   const double chol_tol = std::min(std::max(1e-8, 30.0 * cutoff), 0.25 / n_big);
-  rc = launch_t("pivchol", pivchol_kernel, nb, pivchol_threads, chol_smem, stream, cj_dev, chol_tol);
+  if (nested)
+    rc = launch_t("edge_vector", edge_vector_kernel, nb, 256, edge_smem_bytes(), stream, edge_big_dev);
+  else
+    rc = launch_t("pivchol", pivchol_kernel, nb, pivchol_threads, chol_smem, stream, cj_dev, chol_tol);
   if (rc) return rc;
   tm.lap("modes: launches", njobs);
   return fork.join(stream);
+}
+
+extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int njobs,
+                                        const int *job_x, const int *job_side, double cutoff,
+                                        int r_sketch, const int64_t *v_off, double *V_dev,
+                                        double *e_dev, int *info_dev, void *work_dev,
+                                        int64_t work_bytes, void *stream) {
+  return modes_impl(C_dev, L, ldc, njobs, job_x, job_side, cutoff, r_sketch, v_off, V_dev, e_dev, info_dev, work_dev,
+                    work_bytes, stream, false, nullptr);
+}
+
+// Columns a job's V slot must hold: the legacy form stores [entangled | filled basis] (n columns), the
+// nested form [entangled | edge vector] (at most min(n, m, r_sketch) Ritz columns + 1; small blocks are
+// diagonalised completely: n + 1).
+extern "C" int64_t tmf_slater_modes_slot_cols(int L, int x, int side, int r_sketch, int nested) {
+  int n, m;
+  tmf::job_geometry(L, x, side, n, m);
+  if (!nested) return n;
+  if (n <= tmf::SMALL_N) return n + 1;
+  return std::min(r_sketch, std::min(n, m)) + 1;
+}
+
+extern "C" int tmf_slater_modes_nested(const double *C_dev, int L, int ldc, int njobs,
+                                       const int *job_x, const int *job_side, double cutoff,
+                                       int r_sketch, const int64_t *v_off, double *V_dev,
+                                       double *e_dev, int *info_dev, double *edge_dev, void *work_dev,
+                                       int64_t work_bytes, void *stream) {
+  if (edge_dev == nullptr) {
+    tmf::set_error("tmf_slater_modes_nested: edge_dev is required");
+    return TMF_ERR_VALUE;
+  }
+  return modes_impl(C_dev, L, ldc, njobs, job_x, job_side, cutoff, r_sketch, v_off, V_dev, e_dev, info_dev, work_dev,
+                    work_bytes, stream, true, edge_dev);
 }

@@ -1009,6 +1009,95 @@ TMF_GLOBAL small_modes_kernel(const SmallJob *jobs, double cutoff) {
     if (k > TMF_MAX_MODES) jb.info[2] |= 2;
   }
 }
+// ---------------------------------------------------------------------------------------------
+// Edge vector of the filled space (nested-projector site stage, see siteprep.cu).
+// The filled space F of the block A gains at most one dimension when the block grows by one site, and
+// the new direction is the projection of that site's unit vector: g = P_F e_edge / |P_F e_edge| with
+// P_F = A - U diag(lam) U^T (never formed).  Written to column k of V (right after the k entangled
+// modes), orthogonalised against them.  Also derives the number of filled orbitals from the trace:
+// f = round(tr A - sum lam)  (the modes that are not selected contribute < cutoff each).
+// ---------------------------------------------------------------------------------------------
+struct EdgeJob {
+  const double *A;       // n x n diagonal block of C (symmetric), lda
+  double *V;             // column-major, ld = n: columns [0,k) entangled modes (in), column k = g (out)
+  const double *e_left;  // left eigenvalues of the k modes
+  int *info;             // reads info[0] = k, writes info[1] = f
+  double *edge_out;      // [0] = |P_F e_edge|^2, [1] = tr A - sum lam - f
+  int n, lda, side, pad_;
+};
+TMF_GLOBAL edge_vector_kernel(const EdgeJob *jobs) {
+  const EdgeJob jb = jobs[BLOCK_ID];
+  const int n = jb.n;
+  if (n <= 0) {
+    PAR_FOR(one, 1) { jb.info[1] = 0; jb.edge_out[0] = 0.0; jb.edge_out[1] = 0.0; }
+    return;
+  }
+  int k = jb.info[0];
+  if (k > TMF_MAX_MODES) k = TMF_MAX_MODES;   // flagged by the Ritz kernel (status 2)
+  const int edge = (jb.side == TMF_SIDE_R) ? 0 : n - 1;
+  DYN_SMEM(double, sm);
+  double *lam = sm, *wx = lam + TMF_MAX_MODES, *coef = wx + TMF_MAX_MODES;
+  double *part = coef + TMF_MAX_MODES;          // (TMF_MAX_MODES + 2) * 33
+  double *g = jb.V + (int64_t)k * n;
+  PAR_FOR(j, k) {
+    const double l = (jb.side == TMF_SIDE_L) ? jb.e_left[j] : 1.0 - jb.e_left[j];
+    lam[j] = l;
+    wx[j] = l * jb.V[(int64_t)j * n + edge];
+  }
+  PAR_FOR(lane, 32) {
+    double t = 0.0;
+    for (int r = lane; r < n; r += 32) t += jb.A[(int64_t)r * jb.lda + r];
+    part[TMF_MAX_MODES * 33 + lane] = t;
+  }
+  CTA_SYNC();
+  PAR_FOR(r, n) {
+    double v = jb.A[(int64_t)edge * jb.lda + r];
+    for (int j = 0; j < k; ++j) v -= jb.V[(int64_t)j * n + r] * wx[j];
+    g[r] = v;
+  }
+  CTA_SYNC();
+  PAR_FOR(item, k * 32) {
+    const int j = item >> 5, lane = item & 31;
+    const double *u = jb.V + (int64_t)j * n;
+    double t = 0.0;
+    for (int r = lane; r < n; r += 32) t += u[r] * g[r];
+    part[j * 33 + lane] = t;
+  }
+  CTA_SYNC();
+  PAR_FOR(j, k) {
+    double t = 0.0;
+    for (int l = 0; l < 32; ++l) t += part[j * 33 + l];
+    coef[j] = t;
+  }
+  CTA_SYNC();
+  PAR_FOR(r, n) {
+    double v = g[r];
+    for (int j = 0; j < k; ++j) v -= jb.V[(int64_t)j * n + r] * coef[j];
+    g[r] = v;
+  }
+  CTA_SYNC();
+  PAR_FOR(lane, 32) {
+    double t = 0.0;
+    for (int r = lane; r < n; r += 32) t += g[r] * g[r];
+    part[(TMF_MAX_MODES + 1) * 33 + lane] = t;
+  }
+  CTA_SYNC();
+  double gn2 = 0.0, tr = 0.0;
+  for (int l = 0; l < 32; ++l) { gn2 += part[(TMF_MAX_MODES + 1) * 33 + l]; tr += part[TMF_MAX_MODES * 33 + l]; }
+  const double inv = (gn2 > 0.0) ? 1.0 / sqrt(gn2) : 0.0;
+  CTA_SYNC();
+  PAR_FOR(r, n) g[r] *= inv;
+  PAR_FOR(one, 1) {
+    double s = tr;
+    for (int j = 0; j < k; ++j) s -= lam[j];
+    const double f = floor(s + 0.5);
+    jb.info[1] = (int)f;
+    jb.edge_out[0] = gn2;
+    jb.edge_out[1] = s - f;
+  }
+}
+inline size_t edge_smem_bytes() { return sizeof(double) * (3 * TMF_MAX_MODES + (TMF_MAX_MODES + 2) * 33); }
+
 inline size_t ritz_smem_bytes(int n) {
   int np = (n + 1) & ~1;
   size_t nj = (n > JAC_SMEM_J_MAX) ? 0 : (size_t)n * n;

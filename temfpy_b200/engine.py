@@ -285,6 +285,9 @@ class ChainResult:
     bonds: LazyMap = field(default_factory=LazyMap)    # x -> BondData   (wrapped on first access)
     sites: LazyMap = field(default_factory=LazyMap)    # i -> SiteTensor
     tables: list = field(default_factory=list)         # ShardTables of every chunk
+    timings: dict = field(default_factory=dict)
+    stats: dict = field(default_factory=dict)
+    options: dict = field(default_factory=dict)        # r_sketch / snap / nested the conversion ended up with
 
     def lam_charge(self, x):
         """(Schmidt values, charges) of bond x without wrapping a BondData."""
@@ -338,8 +341,6 @@ class LazySeq:
 
     def __iter__(self):
         return (self._m[i] for i in range(self._n))
-    timings: dict = field(default_factory=dict)
-    stats: dict = field(default_factory=dict)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -378,7 +379,7 @@ class SlaterChain:
     """One chain conversion on one device for the sites [site_lo, site_hi)."""
 
     def __init__(self, backend, L, trunc, n_fermion, ortho_center=None, site_lo=0, site_hi=None,
-                 r_sketch=48, n_threads=0):
+                 r_sketch=48, n_threads=0, snap=True, nested=None):
         self.be = backend
         self.lib = backend.lib
         self.L = int(L)
@@ -398,6 +399,10 @@ class SlaterChain:
                                                 self.site_hi, int(n_threads))
         if not self.handle:
             raise ValueError(self.lib.tmf_last_error().decode())
+        if not snap:
+            check(self.lib, self.lib.tmf_chain_set_option(self.handle, _lib.OPT_SNAP, 0))
+        if nested is not None:      # None: the library's default (nested unless TMF_LEGACY_FILLED is set)
+            check(self.lib, self.lib.tmf_chain_set_option(self.handle, _lib.OPT_NESTED, int(bool(nested))))
         self._buffers = {}
 
     def close(self):
@@ -420,10 +425,10 @@ class SlaterChain:
         be, lib = self.be, self.lib
         q = (C.c_int64 * 8)()
         check(lib, lib.tmf_chain_modes_sizes(self.handle, q))
-        njobs, v_elems, work_bytes = int(q[0]), int(q[1]), int(q[2])
+        njobs, v_elems, work_bytes, e_elems = int(q[0]), int(q[1]), int(q[2]), int(q[3])
         b = self._buffers
         b["V"] = be.empty(v_elems, np.float64)
-        b["e"] = be.empty(njobs * _lib.TMF_MAX_MODES, np.float64)
+        b["e"] = be.empty(max(e_elems, njobs * _lib.TMF_MAX_MODES), np.float64)
         b["info"] = be.empty(njobs * 4, np.int32)
         b["work"] = be.empty(work_bytes, np.uint8)
         check(lib, lib.tmf_chain_modes_enqueue(self.handle, be.ptr(C_dev), int(ldc), be.ptr(b["V"]),
@@ -509,6 +514,18 @@ class SlaterChain:
                           row_p=_ptr_array(row_p, plan.n_rows, np.int64),
                           row_alpha=_ptr_array(row_a, plan.n_rows, np.int64), qtotal=plan.qtotal)
 
+    def check_det(self):
+        """The nested site kernel reports filled spaces that are not nested (a vanishing principal-angle cosine)
+        through a NaN determinant; the driver then redoes the conversion with explicit filled bases.  Needs the
+        stream to be synchronised."""
+        det = self._buffers.get("det")
+        if det is None or not hasattr(self.be, "torch"):
+            if det is not None and not np.all(np.isfinite(np.asarray(det))):
+                raise ValueError("nested site stage: filled spaces of neighbouring bonds are not nested")
+            return
+        if not bool(self.be.torch.isfinite(det).all()):
+            raise ValueError("nested site stage: filled spaces of neighbouring bonds are not nested")
+
     def collect(self, fetch_tensors=True) -> ChainResult:
         """Brings the tensors to the host (one pinned copy) and exports the host-side tables in bulk;
         the per-bond / per-site objects are wrapped lazily from those."""
@@ -536,6 +553,7 @@ class SlaterChain:
         tab.normalized()
         t2 = time.perf_counter()
         self.be.sync()
+        self.check_det()
         t3 = time.perf_counter()
         res.tables = [tab]
         res.bonds.add([x for x in range(tab.first_bond, tab.first_bond + tab.n_bonds)
@@ -552,6 +570,20 @@ class SlaterChain:
         return res
 
 
+def snap_policy(C) -> bool:
+    """Whether mode weights that are equal within the eigenvalue accuracy are symmetrised before the
+    enumeration (``TMF_OPT_SNAP``).  Needed when the input has *spin-pure* exactly degenerate modes -- two
+    interleaved, decoupled species as built by ``spinful_correlation_matrix`` (slater.py:1183-1213): a cut
+    that splits such a multiplet differently on neighbouring bonds leaves tensors that vanish by the
+    conserved species numbers.  Everywhere else the reference's literal behaviour is kept (its ``truncate``,
+    schmidt_utils.py:175-185, only sees degeneracies below ``degeneracy_tol``), so that bond dimensions
+    match the reference's."""
+    C = np.asarray(C)
+    if C.ndim != 2 or len(C) < 2:
+        return False
+    return not np.any(np.abs(C[0::2, 1::2]) > 1e-14)
+
+
 class _NoGate:
     def before(self):
         pass
@@ -560,45 +592,58 @@ class _NoGate:
         pass
 
 
+class _Retry(Exception):
+    """A chunk asks for the whole conversion to be redone with other options (kept global so that every
+    chunk / rank builds a shared boundary bond with the same kernels and sketch width)."""
+
+    def __init__(self, kind, err):
+        super().__init__(str(err))
+        self.kind, self.err = kind, err
+
+
+SKETCH_WIDTHS = (48, 64, 128, 160)
+
+
 def _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch, n_threads,
-               fetch_tensors, lazy=False, gate=None):
-    last_err = None
+               fetch_tensors, lazy=False, gate=None, snap=True, nested=None):
+    import time
     gate = gate or _NoGate()
-    widths = [r for r in (64, 128, 160) if r > r_sketch]
-    for r in [r_sketch] + widths:
-        chain = SlaterChain(backend, L, trunc, n_fermion, ortho_center, lo, hi, r, n_threads)
-        ok = False
+    chain = SlaterChain(backend, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch, n_threads, snap=snap,
+                        nested=nested)
+    ok = False
+    try:
+        tt = [time.perf_counter()]
         try:
-            import time
-            tt = [time.perf_counter()]
-            try:
-                gate.before()
-                tt.append(time.perf_counter())
-                chain.enqueue_modes(C_dev, ldc)
-            finally:
-                gate.after()
+            gate.before()
             tt.append(time.perf_counter())
-            chain.finish_modes()
-            tt.append(time.perf_counter())
-            chain.run_enumerate()
-            tt.append(time.perf_counter())
-            chain.run_tensors(C_dev, ldc)
-            tt.append(time.perf_counter())
-            if lazy:
-                backend.sync()
-                tt.append(time.perf_counter())
-                chain.stage_times = tt      # gate wait, enqueue, modes, enumerate + plan, tensors enqueue, drain
-                ok = True
-                return chain
-            return chain.collect(fetch_tensors)
-        except ValueError as err:           # sketch too narrow -> widen (cylinders)
-            last_err = err
-            if "r_sketch" not in str(err) or r == 160:
-                raise
+            chain.enqueue_modes(C_dev, ldc)
         finally:
-            if not (lazy and ok):
-                chain.close()
-    raise last_err
+            gate.after()
+        tt.append(time.perf_counter())
+        chain.finish_modes()
+        tt.append(time.perf_counter())
+        chain.run_enumerate()
+        tt.append(time.perf_counter())
+        chain.run_tensors(C_dev, ldc)
+        tt.append(time.perf_counter())
+        if lazy:
+            backend.sync()
+            chain.check_det()
+            tt.append(time.perf_counter())
+            chain.stage_times = tt      # gate wait, enqueue, modes, enumerate + plan, tensors enqueue, drain
+            ok = True
+            return chain
+        return chain.collect(fetch_tensors)
+    except ValueError as err:
+        msg = str(err)
+        if "r_sketch" in msg:               # sketch too narrow -> widen (cylinders)
+            raise _Retry("sketch", err) from None
+        if "nested site stage" in msg:      # filled spaces not nested within the threshold noise -> explicit bases
+            raise _Retry("nested", err) from None
+        raise
+    finally:
+        if not (lazy and ok):
+            chain.close()
 
 
 class _StageGate:
@@ -679,14 +724,39 @@ class DeviceChainResult:
 
 
 def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_lo=0, site_hi=None,
-              r_sketch=48, n_threads=0, fetch_tensors=True, n_chunks=None, lazy=False):
+              r_sketch=48, n_threads=0, fetch_tensors=True, n_chunks=None, lazy=False, snap=True, nested=None):
     """C (device) -> Schmidt data of every bond and block-sparse tensor of every site.
 
     The site range is cut into cost-balanced chunks that run as a software pipeline: one worker
     thread and one CUDA stream per chunk, so that the host stages of a chunk (enumeration,
     planning; the native calls release the GIL) overlap with the kernels of the other chunks.
-    Chunks are independent (same decomposition as the multi-GPU shards, see ``dist.py``)."""
+    Chunks are independent (same decomposition as the multi-GPU shards, see ``dist.py``).
+
+    Two conditions make the *whole* conversion start over with other options, for all chunks alike (a
+    boundary bond is computed by both neighbouring chunks and must come out of identical kernels): a range
+    sketch that is too narrow for the entanglement spectrum (widened 48 -> 64 -> 128 -> 160; cylinders) and
+    filled spaces that are not nested within the threshold noise (explicit filled bases instead)."""
+    opts = dict(r_sketch=r_sketch, snap=snap, nested=nested)
+    while True:
+        try:
+            return _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi,
+                                   n_threads, fetch_tensors, n_chunks, lazy, opts)
+        except _Retry as rt:
+            if rt.kind == "sketch":
+                wider = [r for r in SKETCH_WIDTHS if r > opts["r_sketch"]]
+                if not wider:
+                    raise rt.err
+                opts["r_sketch"] = wider[0]
+            elif opts["nested"] is False:
+                raise rt.err
+            else:
+                opts["nested"] = False
+
+
+def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi, n_threads,
+                    fetch_tensors, n_chunks, lazy, opts):
     from .dist import partition
+    r_sketch, snap, nested = opts["r_sketch"], opts["snap"], opts["nested"]
     site_hi = L if site_hi is None else site_hi
     nsites = site_hi - site_lo
     if n_chunks is None:
@@ -694,8 +764,11 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
     n_chunks = max(1, min(n_chunks, nsites))
     if n_chunks == 1:
         r = _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi, r_sketch,
-                       n_threads, fetch_tensors, lazy)
-        return DeviceChainResult([r]) if lazy else r
+                       n_threads, fetch_tensors, lazy, snap=snap, nested=nested)
+        if lazy:
+            r = DeviceChainResult([r])
+        r.options = dict(opts)
+        return r
     import os
     # equal-cost chunks with a short last one: after the last mode stage only its host stage and tensor
     # kernels remain, and those scale with its number of sites
@@ -717,17 +790,30 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
     def work(pos):
         lo, hi = cuts[order[pos]]
         with backend.stream_context(backend.side_stream(pos)):
-            return _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch,
-                              n_threads, fetch_tensors, lazy, gate=stages.gate(pos) if stages else None)
+            try:
+                return _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch,
+                                  n_threads, fetch_tensors, lazy, gate=stages.gate(pos) if stages else None,
+                                  snap=snap, nested=nested)
+            except _Retry as rt:        # the other chunks finish; the driver then starts over
+                return rt
 
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=n_chunks) as pool:
         done = list(pool.map(work, range(n_chunks)))
+    retries = [r for r in done if isinstance(r, _Retry)]
+    if retries:
+        for r in done:
+            if lazy and not isinstance(r, _Retry):
+                r.close()
+        # a too narrow sketch takes precedence: the nested check is only meaningful on complete spectra
+        raise next((r for r in retries if r.kind == "sketch"), retries[0])
     parts = [None] * n_chunks
     for pos, r in enumerate(done):
         parts[order[pos]] = r
     if lazy:
-        return DeviceChainResult(parts)
+        out = DeviceChainResult(parts)
+        out.options = dict(opts)
+        return out
     res = ChainResult(L=L, ortho_center=parts[0].ortho_center, site_lo=site_lo, site_hi=site_hi)
     for p in parts:
         res.bonds.update(p.bonds)
@@ -738,4 +824,5 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
                      nblocks=sum(p.stats["nblocks"] for p in parts),
                      max_chi=max(p.stats["max_chi"] for p in parts),
                      njobs=sum(p.stats["njobs"] for p in parts), n_chunks=n_chunks)
+    res.options = dict(opts)
     return res

@@ -89,6 +89,11 @@ def run_native(backend, C, trunc, N=None, **kw) -> engine.ChainResult:
     return engine.run_chain(backend, Cd, L, L, to_stopping_condition(trunc), N, **kw)
 
 
+def default_policy(C):
+    """The options the public entry points choose for this input (slater.C_to_MPS)."""
+    return dict(snap=engine.snap_policy(C))
+
+
 def ambiguous_bonds(ref: so.DenseMPS, trunc, margin=1e-6):
     """Threshold-margin audit: bonds whose truncation decision lies inside the
     eigenvalue noise of the reference itself (a near-degenerate multiplet straddles the chi_max /
@@ -203,4 +208,70 @@ def compare_pf_mps(ref: so.DenseMPS, got: so.DenseMPS, half_bonds=(), ent_tol=1e
     o = abs(so.mps_overlap(ref, got)) / np.sqrt(abs(so.mps_overlap(ref, ref) * so.mps_overlap(got, got)))
     rep["overlap"] = float(o)
     assert o >= 1 - ov_tol, rep
+    return rep
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size per-bond fixtures written by oracle/make_golden_full.py from the live reference
+# ---------------------------------------------------------------------------------------------
+def fixture_bond(g, x):
+    """(k, filled_left, e, lam, masks, charge) of bond x as the reference computed them."""
+    a, b = int(g["chi_off"][x]), int(g["chi_off"][x + 1])
+    s0, s1 = int(g["sec_off"][x]), int(g["sec_off"][x + 1])
+    e0, e1 = int(g["e_off"][x]), int(g["e_off"][x + 1])
+    charge = np.repeat(g["sec_q"][s0:s1].astype(np.int64), g["sec_n"][s0:s1])
+    return int(g["k"][x]), int(g["filled_left"][x]), g["e"][e0:e1], g["lam"][a:b], g["masks"][a:b], charge
+
+
+def _lam_tol(a, noise, lam_abs=1e-8):
+    """Tolerance model of compare_mps: 1e-12 relative plus the mode-eigenvalue rounding noise."""
+    return 1e-12 * a + np.minimum(noise / (2 * a), lam_abs)
+
+
+def compare_bonds_fixture(g, get_bond, noise=None, max_multiplet=16):
+    """Integer + spectral parity of *every* bond against a reference-run fixture.
+
+    A bond is `exact` when k, the filled count, chi, the sector table and every occupation mask are
+    identical and the Schmidt values agree within the tolerance model.  Otherwise it must pass the
+    noise audit: the reference's `truncate` (schmidt_utils.py:140-185) cut inside / next to a multiplet whose
+    members are equal in exact arithmetic but differ by LAPACK rounding noise in the reference,
+    i.e. (1) per charge sector the spectra above the contested multiplet agree as multisets, (2) everything
+    below lies within 1 % of the cut, (3) at most `max_multiplet` values per side are contested.
+    Returns the counts; raises AssertionError for a bond that is neither."""
+    L = int(g["L"])
+    if noise is None:
+        noise = 4e-15 * np.sqrt(L)
+    rep = dict(bonds=L + 1, exact=0, ambiguous=0, max_dchi=0, lam_rel=0.0, entropy=0.0, k_noise=0,
+               ambiguous_list=[])
+    for x in range(L + 1):
+        k, fl, e, lam, masks, charge = fixture_bond(g, x)
+        b = get_bond(x)
+        bl = np.asarray(b.schmidt_values)
+        bq = np.asarray(b.charge, dtype=np.int64)
+        same = (len(bl) == len(lam) and b.k == k and b.filled_left == fl and np.array_equal(bq, charge)
+                and np.array_equal(np.asarray(b.masks, dtype=np.uint64), masks))
+        a_n, b_n = lam / np.linalg.norm(lam), bl / np.linalg.norm(bl)
+        if same and np.all(np.abs(a_n - b_n) <= _lam_tol(a_n, noise)):
+            rep["exact"] += 1
+            big = a_n > 0.05 * a_n.max()
+            rep["lam_rel"] = max(rep["lam_rel"], float(np.max(np.abs(a_n[big] - b_n[big]) / a_n[big])))
+            rep["entropy"] = max(rep["entropy"], float(abs(so.entropies([a_n])[0] - so.entropies([b_n])[0])))
+            continue
+        # ---- noise audit ---------------------------------------------------------------------
+        a_r, b_r = lam / lam.max(), bl / bl.max()
+        cutv = max(a_r.min(), b_r.min()) * (1 + 1e-3)
+        na, nb_ = int((a_r <= cutv).sum()), int((b_r <= cutv).sum())
+        assert na <= max_multiplet and nb_ <= max_multiplet, f"bond {x}: {na}/{nb_} contested values"
+        assert abs(len(lam) - len(bl)) <= max(na, nb_), f"bond {x}: chi {len(bl)} vs reference {len(lam)}"
+        lowest = min(a_r.min(), b_r.min())
+        assert lowest >= cutv * (1 - 1e-2), f"bond {x}: contested values spread below the cut ({lowest / cutv})"
+        for q in np.union1d(charge, bq):
+            sa = np.sort(a_r[(charge == q) & (a_r > cutv)])[::-1]
+            sb = np.sort(b_r[(bq == q) & (b_r > cutv)])[::-1]
+            assert len(sa) == len(sb), f"bond {x}, charge {q}: {len(sb)} vs {len(sa)} values above the cut"
+            assert np.all(np.abs(sa - sb) <= _lam_tol(sa, noise) * 4), f"bond {x}, charge {q}: spectrum differs"
+        rep["ambiguous"] += 1
+        rep["ambiguous_list"].append(x)
+        rep["max_dchi"] = max(rep["max_dchi"], abs(len(lam) - len(bl)))
+        rep["k_noise"] += int(b.k != k)
     return rep
