@@ -182,7 +182,8 @@ typedef struct tmf_site_job {
   int mode, physical;
   int ka_bra, ka_ket;          /* always orbitals of each side                                */
   int sb, sk;                  /* sometimes orbitals of each side (sb includes the physical)  */
-  /* pad_[0] (internal): 1 = O and *det were prepared by the nested-projector kernel             */
+  /* pad_[0] (internal): 1 = O and *det were prepared by the nested-projector kernel;
+   * pad_[1]: 1 = report a vanishing pivot of the always block (|pivot| < 1e-9) as *det = NaN     */
   int emb;                     /* 1: Pfaffian path -- rows are re/im-interleaved Majorana components
                                   (4 per site); bra_cols -1..-4 = emb(w), J emb(w) of the physical
                                   site's lower mode (c^+ row, pfaffian.py:1667-1688) and the same

@@ -641,6 +641,7 @@ int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev,
     j.O = O_dev + s.o_off; j.S = S_dev + s.s_off; j.det = det_dev + u;
     j.n_bra = h.n_bra; j.n_ket = h.n_ket; j.mode = h.mode; j.physical = h.physical;
     j.ka_bra = h.ka_bra; j.ka_ket = h.ka_ket; j.sb = sb0; j.sk = sk0;
+    j.pad_[1] = 1;   // report a singular always block (incompatible neighbouring bonds) as NaN
     const uint64_t *bm = reinterpret_cast<const uint64_t *>(put(so[u].bm, s.plan.bra_masks.data(), 8 * (size_t)h.n_rows));
     const uint64_t *km = reinterpret_cast<const uint64_t *>(put(so[u].km, s.plan.ket_masks.data(), 8 * (size_t)h.chi_ket));
     for (int b = 0; b < h.n_blocks; ++b) {

@@ -18,6 +18,7 @@ int gemm_launch_uploaded(const tmf_gemm_job *jobs_dev, const int *prefix_dev, in
                          void *stream, const char *tag);
 
 constexpr int NB = 16;
+constexpr double SCHUR_MIN_PIVOT = 1e-9;
 static_assert(sizeof(tmf_site_job) == 128, "site descriptor must be 128 bytes");
 
 // Frame of the elimination: the side with more always-occupied orbitals provides the rows, so that
@@ -90,7 +91,10 @@ TMF_GLOBAL schur_kernel(const tmf_site_job *jobs) {
       }
     }
   }
-  PAR_FOR(one, 1) red[36] = nested ? *jb.det : 1.0;  // running determinant
+  PAR_FOR(one, 1) {
+    red[36] = nested ? *jb.det : 1.0;  // running determinant
+    red[38] = 1.0;                     // smallest |pivot|
+  }
   CTA_SYNC();
 
   for (int t0 = 0; t0 < k; t0 += NB) {
@@ -123,6 +127,7 @@ TMF_GLOBAL schur_kernel(const tmf_site_job *jobs) {
         double pv = Lp[j * nr + bi];
         red[36] *= (bi != j) ? -pv : pv;
         red[37] = (pv != 0.0) ? 1.0 / pv : 0.0;
+        red[38] = fmin(red[38], fabs(pv));
       }
       CTA_SYNC();
       const int p = piv[j];
@@ -201,7 +206,11 @@ TMF_GLOBAL schur_kernel(const tmf_site_job *jobs) {
     if (fr.tr) jb.S[(int64_t)ref_r * s_bra + c] = v;   // row side = ket -> column of S
     else jb.S[(int64_t)c * s_bra + ref_r] = v;
   }
-  PAR_FOR(one, 1) *jb.det = red[36];
+  // A vanishing pivot = an always-occupied orbital of one bond that is orthogonal to every always-occupied
+  // orbital of the other: the kept Schmidt vectors of the two bonds are incompatible (a numerically degenerate
+  // multiplet of spin-pure modes was cut differently on the two bonds).  Reported as NaN; the driver redoes the
+  // conversion with symmetrised weights (TMF_OPT_SNAP).  Only for jobs that ask for it (pad_[1], chain driver).
+  PAR_FOR(one, 1) *jb.det = (jb.pad_[1] != 0 && red[38] < SCHUR_MIN_PIVOT) ? nan("") : red[36];
 }
 
 

@@ -379,7 +379,7 @@ class SlaterChain:
     """One chain conversion on one device for the sites [site_lo, site_hi)."""
 
     def __init__(self, backend, L, trunc, n_fermion, ortho_center=None, site_lo=0, site_hi=None,
-                 r_sketch=48, n_threads=0, snap=True, nested=None):
+                 r_sketch=48, n_threads=0, snap=False, nested=None):
         self.be = backend
         self.lib = backend.lib
         self.L = int(L)
@@ -515,16 +515,19 @@ class SlaterChain:
                           row_alpha=_ptr_array(row_a, plan.n_rows, np.int64), qtotal=plan.qtotal)
 
     def check_det(self):
-        """The nested site kernel reports filled spaces that are not nested (a vanishing principal-angle cosine)
-        through a NaN determinant; the driver then redoes the conversion with explicit filled bases.  Needs the
-        stream to be synchronised."""
+        """The site kernels report an elimination that broke down through a NaN determinant: filled spaces that
+        are not nested (nested kernel) or always-occupied orbitals of the two bonds that are orthogonal (Schur
+        kernel: incompatible truncations of a degenerate multiplet).  The driver then redoes the conversion with
+        other options.  Needs the stream to be synchronised."""
         det = self._buffers.get("det")
-        if det is None or not hasattr(self.be, "torch"):
-            if det is not None and not np.all(np.isfinite(np.asarray(det))):
-                raise ValueError("nested site stage: filled spaces of neighbouring bonds are not nested")
+        if det is None:
             return
-        if not bool(self.be.torch.isfinite(det).all()):
-            raise ValueError("nested site stage: filled spaces of neighbouring bonds are not nested")
+        if hasattr(self.be, "torch"):
+            ok = bool(self.be.torch.isfinite(det).all())
+        else:
+            ok = bool(np.all(np.isfinite(np.asarray(det))))
+        if not ok:
+            raise ValueError("site stage: singular elimination (incompatible neighbouring bonds)")
 
     def collect(self, fetch_tensors=True) -> ChainResult:
         """Brings the tensors to the host (one pinned copy) and exports the host-side tables in bulk;
@@ -570,20 +573,6 @@ class SlaterChain:
         return res
 
 
-def snap_policy(C) -> bool:
-    """Whether mode weights that are equal within the eigenvalue accuracy are symmetrised before the
-    enumeration (``TMF_OPT_SNAP``).  Needed when the input has *spin-pure* exactly degenerate modes -- two
-    interleaved, decoupled species as built by ``spinful_correlation_matrix`` (slater.py:1183-1213): a cut
-    that splits such a multiplet differently on neighbouring bonds leaves tensors that vanish by the
-    conserved species numbers.  Everywhere else the reference's literal behaviour is kept (its ``truncate``,
-    schmidt_utils.py:175-185, only sees degeneracies below ``degeneracy_tol``), so that bond dimensions
-    match the reference's."""
-    C = np.asarray(C)
-    if C.ndim != 2 or len(C) < 2:
-        return False
-    return not np.any(np.abs(C[0::2, 1::2]) > 1e-14)
-
-
 class _NoGate:
     def before(self):
         pass
@@ -605,7 +594,7 @@ SKETCH_WIDTHS = (48, 64, 128, 160)
 
 
 def _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch, n_threads,
-               fetch_tensors, lazy=False, gate=None, snap=True, nested=None):
+               fetch_tensors, lazy=False, gate=None, snap=False, nested=None):
     import time
     gate = gate or _NoGate()
     chain = SlaterChain(backend, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch, n_threads, snap=snap,
@@ -640,6 +629,8 @@ def _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r
             raise _Retry("sketch", err) from None
         if "nested site stage" in msg:      # filled spaces not nested within the threshold noise -> explicit bases
             raise _Retry("nested", err) from None
+        if "singular elimination" in msg:
+            raise _Retry("singular", err) from None
         raise
     finally:
         if not (lazy and ok):
@@ -724,7 +715,7 @@ class DeviceChainResult:
 
 
 def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_lo=0, site_hi=None,
-              r_sketch=48, n_threads=0, fetch_tensors=True, n_chunks=None, lazy=False, snap=True, nested=None):
+              r_sketch=48, n_threads=0, fetch_tensors=True, n_chunks=None, lazy=False, snap=False, nested=None):
     """C (device) -> Schmidt data of every bond and block-sparse tensor of every site.
 
     The site range is cut into cost-balanced chunks that run as a software pipeline: one worker
@@ -732,10 +723,16 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
     planning; the native calls release the GIL) overlap with the kernels of the other chunks.
     Chunks are independent (same decomposition as the multi-GPU shards, see ``dist.py``).
 
-    Two conditions make the *whole* conversion start over with other options, for all chunks alike (a
+    Three conditions make the *whole* conversion start over with other options, for all chunks alike (a
     boundary bond is computed by both neighbouring chunks and must come out of identical kernels): a range
-    sketch that is too narrow for the entanglement spectrum (widened 48 -> 64 -> 128 -> 160; cylinders) and
-    filled spaces that are not nested within the threshold noise (explicit filled bases instead)."""
+    sketch that is too narrow for the entanglement spectrum (widened 48 -> 64 -> 128 -> 160; cylinders),
+    neighbouring bonds whose kept Schmidt vectors are incompatible (``snap``: the truncation then never cuts
+    inside a numerically degenerate multiplet) and filled spaces that are not nested within the threshold
+    noise (explicit filled bases instead).
+
+    ``snap=False`` (default) is the reference's literal truncation (schmidt_utils.py:140-185 only sees
+    degeneracies below ``degeneracy_tol``; where a multiplet that is degenerate in exact arithmetic straddles
+    ``chi_max`` the kept part is decided by the rounding noise of the mode eigenvalues, in the reference as here)."""
     opts = dict(r_sketch=r_sketch, snap=snap, nested=nested)
     while True:
         try:
@@ -747,6 +744,8 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
                 if not wider:
                     raise rt.err
                 opts["r_sketch"] = wider[0]
+            elif rt.kind == "singular" and not opts["snap"]:
+                opts["snap"] = True             # never cut inside a numerically degenerate multiplet
             elif opts["nested"] is False:
                 raise rt.err
             else:

@@ -158,8 +158,7 @@ def C_to_MPS(C: np.ndarray, trunc_par: dict | StoppingCondition, *, diag_tol: fl
     logger.info("Central bond %d", ortho_center or L // 2)
     Cd = be.from_host(C.ravel())
     _check_projector(C, be=be, Cd=Cd)
-    res = engine.run_chain(be, Cd, L, L, trunc_par, n_fermion, ortho_center=ortho_center,
-                           snap=spinful is not None or engine.snap_policy(C))
+    res = engine.run_chain(be, Cd, L, L, trunc_par, n_fermion, ortho_center=ortho_center)
     mps = _chain_to_mps(res, unit_cell_width)
     return mps.to_tenpy() if _want_tenpy(as_tenpy) else mps
 
@@ -213,7 +212,7 @@ class SchmidtVectors:
             lo = L - 1
         Cd = be.from_host(C.ravel())
         res = engine.run_chain(be, Cd, L, L, trunc_par, nf, ortho_center=oc or None, site_lo=lo, site_hi=lo + 1,
-                               fetch_tensors=False, snap=engine.snap_policy(C))
+                               fetch_tensors=False)
         b = res.bonds[x]
         return cls(e=b.e, sets=b.sets, schmidt_values=b.schmidt_values, idx_L=b.idx_L,
                    n_filled_left=b.filled_left, nL=x, nR=L - x, n_fermion=nf)

@@ -25,18 +25,24 @@ def _C_for(name):
     raise KeyError(name)
 
 
-@pytest.mark.parametrize("name,min_exact", [("bonds_cfg1_chain_L64", 0.5), ("bonds_cfg3_spinful_ph_L512", 0.5),
-                                            ("bonds_cfg4_cylinder_6x64", 0.5), ("bonds_cfg5_chain_L1024", 0.9)])
-def test_every_bond_against_reference_fixture(gpu_backend, name, min_exact):
+# (fixture, minimal fraction of exact bonds, bound on the number of contested Schmidt vectors at the cut: the
+# width-6 cylinder has 96-fold exactly degenerate multiplets from its momentum / particle-hole symmetries; on the
+# svd_min-limited bonds of cfg5 every vector that flips the mode at the cutoff e ~ svd_min^2 = 1e-14 carries that
+# eigenvalue's relative rounding noise (up to 50 %), 100-200 of them sit within it of the threshold)
+@pytest.mark.parametrize("name,min_exact,max_contested", [("bonds_cfg1_chain_L64", 0.5, 16),
+                                                          ("bonds_cfg3_spinful_ph_L512", 0.5, 32),
+                                                          ("bonds_cfg4_cylinder_6x64", 0.5, 128),
+                                                          ("bonds_cfg5_chain_L1024", 0.8, 256)])
+def test_every_bond_against_reference_fixture(gpu_backend, name, min_exact, max_contested):
     g = helpers.golden(name)
     C, N = _C_for(name)
     assert N == int(g["N"]) and abs(float(np.sum(C)) - float(g["C_sum"])) < 1e-9     # same input as the reference run
     tp = helpers.golden_trunc(g)
-    res = helpers.run_native(gpu_backend, C, tp, N, fetch_tensors=False, **helpers.default_policy(C))
-    rep = helpers.compare_bonds_fixture(g, lambda x: res.bonds[x])
-    print(f"\n{name}: bonds {rep['bonds']} exact {rep['exact']} ambiguous {rep['ambiguous']} "
-          f"max|dchi| {rep['max_dchi']} k_noise {rep['k_noise']} lam_rel {rep['lam_rel']:.2e} "
-          f"entropy {rep['entropy']:.2e} options {res.options}")
-    assert rep["exact"] + rep["ambiguous"] == rep["bonds"]
+    res = helpers.run_native(gpu_backend, C, tp, N, fetch_tensors=False)
+    rep = helpers.compare_bonds_fixture(g, lambda x: res.bonds[x], max_contested=max_contested, rerun_limit=48)
+    print(f"\n{name}: bonds {rep['bonds']} exact {rep['exact']} noise-decided {rep['noise_decided']} "
+          f"chi equal {rep['chi_equal']} max|dchi| {rep['max_dchi']} k differs {rep['k_differs']} "
+          f"|de| {rep['e_abs']:.1e} lam_rel {rep['lam_rel']:.2e} entropy {rep['entropy']:.2e} options {res.options}")
+    assert rep["exact"] + rep["noise_decided"] == rep["bonds"]
     assert rep["lam_rel"] < 1e-12 and rep["entropy"] < 1e-10
     assert rep["exact"] >= min_exact * rep["bonds"], rep
