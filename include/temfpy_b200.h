@@ -325,6 +325,8 @@ int tmf_chain_bonds_export(tmf_chain *c, int64_t *chi_off, int *head /* k, fille
 int tmf_chain_sites_sizes(tmf_chain *c, int64_t *q /* sites, sum n_blocks, sum n_rows */);
 int tmf_chain_sites_export(tmf_chain *c, tmf_site_plan *plans, int64_t *blk_off, int *blocks,
                            int64_t *block_off, int64_t *row_off, int *row_p, int *row_alpha);
+/* (row_p / row_alpha may be NULL: the row order is a function of the bra bond's charges -- [p = 0 | p = 1]
+ * stably sorted by charge +- p, slater.py:1053-1058 -- and callers can derive it lazily) */
 int64_t tmf_chain_job_voff(tmf_chain *c, int job);
 /* Options (call right after tmf_chain_create):
  *   TMF_OPT_SNAP   1 (default): mode weights equal within the eigenvalue accuracy are symmetrised
@@ -334,6 +336,8 @@ int64_t tmf_chain_job_voff(tmf_chain *c, int job);
  *                  bases by pivoted Cholesky + overlap GEMM + blocked LU (also the automatic fallback). */
 #define TMF_OPT_SNAP 1
 #define TMF_OPT_NESTED 2
+#define TMF_OPT_DEVICE_PLAN 3  /* 1 (default): site planning (slater.py:760-825, :1027-1058, :1106-1141) on the
+                                * device from the resident enumeration tables (nested mode); 0: host threads */
 int tmf_chain_set_option(tmf_chain *c, int option, int value);
 /* algorithmic flops of the reference's algorithm for this shard:
  * f[0] eigh, f[1] overlap GEMM, f[2] Schur, f[3] minors, f[4] number of minors */

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libtemfpy_b200.so")
 
 TMF_MAX_MODES = 64
 SIDE_L, SIDE_R = 0, 1
-OPT_SNAP, OPT_NESTED = 1, 2
+OPT_SNAP, OPT_NESTED, OPT_DEVICE_PLAN = 1, 2, 3
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)

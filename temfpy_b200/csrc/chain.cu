@@ -19,6 +19,7 @@
 
 #include "cta.hpp"
 #include "hostlogic.hpp"
+#include "plan.hpp"
 
 namespace {
 struct StageTimer {   // TMF_DEBUG_TIMING=1 prints host-side stage times to stderr
@@ -43,7 +44,11 @@ namespace tmf {
 int64_t enum_workspace_bytes(int nb, int chi_max);
 int enumerate_device(int nb, const double *const *e_ptr, const int *k, const int *filled_left, const TruncPar &tp,
                      std::vector<BondVectors *> &out, void *work_dev, int64_t work_bytes, void *stream,
-                     unsigned char *stage, size_t stage_bytes, int n_threads);
+                     unsigned char *stage, size_t stage_bytes, int n_threads, EnumResident *keep);
+size_t enumerate_tables_stage_bytes(const EnumResident &r);
+int enumerate_fetch_tables(const EnumResident &r, unsigned char *stage, void *stream);
+void enumerate_unpack_tables(const EnumResident &r, const unsigned char *stage, const int *k, const int *filled_left,
+                             std::vector<BondVectors *> &out, int n_threads);
 }  // namespace tmf
 
 extern "C" int64_t tmf_site_desc_bytes(int nsites);
@@ -62,6 +67,11 @@ struct ChainBond {
 struct ChainSite {
   int site = 0, mode = 0, bra_bond = 0, ket_bond = 0;
   int f_common = 0, df = 0;   // nested mode: filled orbitals shared by the two bonds, f_ket - f_bra
+  // device-planned sites: the per-site arrays live in the caller's enumeration workspace
+  const uint64_t *bra_masks_dev = nullptr, *ket_masks_dev = nullptr;
+  const int *cols_dev = nullptr;
+  const double *signs_dev = nullptr;
+  bool rows_ready = false;    // row_p / row_alpha derived on the host (lazily) from the bra bond's charges
   tmf::SitePlan plan;
   int64_t o_off = 0, s_off = 0;
   std::vector<int64_t> block_off;
@@ -81,6 +91,15 @@ struct tmf_chain {
   int nblocks = 0, max_chi = 0;
   bool enumerated = false;
   bool nested = true;                // nested-projector site stage (no filled bases), see siteprep.cu
+  bool want_device_plan = true;      // plan the sites on the device when the enumeration ran there (nested mode)
+  bool device_plan = false;          // ... and it did: bond tables + site plans are resident in the workspace
+  bool tables_pending = false;       // bond tables still have to be unpacked from `tab_stage`
+  tmf::EnumResident enum_res;
+  std::vector<int> used_bonds;       // bond of every enumeration slot
+  unsigned char *tab_stage = nullptr;  // pinned staging of the bond tables (asynchronous download)
+  size_t tab_cap = 0;
+  void *tab_event = nullptr;         // cudaEvent_t recorded after that download
+  std::mutex tab_mu;
   const double *e_dev_ptr = nullptr; // device spectra of the last tmf_chain_modes_enqueue (read by the nested site kernel)
   std::vector<double> edge_host;     // nested: {|P_F e_edge|^2, rounding remainder of f} per job
   unsigned char *blob = nullptr;     // pinned staging of the per-site plan arrays (from the pool below)
@@ -129,7 +148,13 @@ struct PinnedPool {
 PinnedPool g_pinned;
 }  // namespace
 
-tmf_chain::~tmf_chain() { g_pinned.release(blob, blob_cap); }
+tmf_chain::~tmf_chain() {
+  g_pinned.release(blob, blob_cap);
+  g_pinned.release(tab_stage, tab_cap);
+#if !defined(TMF_HOSTSIM)
+  if (tab_event) cudaEventDestroy((cudaEvent_t)tab_event);
+#endif
+}
 
 
 namespace {
@@ -272,6 +297,7 @@ int tmf_chain_set_option(tmf_chain *c, int option, int value) {
     chain_layout_slots(c);
     return TMF_OK;
   }
+  if (option == TMF_OPT_DEVICE_PLAN) { c->want_device_plan = value != 0; return TMF_OK; }
   tmf::set_error("tmf_chain_set_option: unknown option");
   return TMF_ERR_VALUE;
 }
@@ -344,6 +370,33 @@ int tmf_chain_modes(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, d
   return tmf_chain_modes_finish(c, e_dev, info_dev, stream);
 }
 
+// device buffers of the site planner (plan.cu), carved from the enumeration workspace after the bond tables
+static int64_t plan_site_bytes(int64_t cap) {
+  return tmf::align256(16 * cap) + tmf::align256(8 * cap) + tmf::align256(4 * 2 * tmf::PLAN_MAX_ORB) +
+         tmf::align256(8 * 2 * tmf::PLAN_MAX_ORB);
+}
+static int64_t plan_workspace_bytes(int ns, int64_t cap) {
+  return (int64_t)ns * plan_site_bytes(cap) + tmf::align256((int64_t)ns * sizeof(tmf::PlanJob)) +
+         tmf::align256((int64_t)ns * 4 * (tmf::PLAN_HDR_INTS + 6 * tmf::PLAN_MAX_BLOCKS)) + 4096;
+}
+
+// bra rows of a site in the reference order: [p = 0 | p = 1], stably sorted by the pipe charge (slater.py:1053-1058)
+static void rows_from_charges(int mode, int chi_b, const int *charge_b, std::vector<int> &row_p, std::vector<int> &row_alpha) {
+  const int n_rows = 2 * chi_b;
+  row_p.resize(n_rows); row_alpha.resize(n_rows);
+  if (chi_b == 0) return;
+  int qmin = 1 << 30, qmax = -(1 << 30);
+  for (int a = 0; a < chi_b; ++a) { qmin = std::min(qmin, charge_b[a] - 1); qmax = std::max(qmax, charge_b[a] + 1); }
+  std::vector<int> start((size_t)(qmax - qmin + 2), 0);
+  auto rq = [&](int r) { const int p = r / chi_b, a = r % chi_b; return charge_b[a] + (mode == 0 ? p : -p); };
+  for (int r = 0; r < n_rows; ++r) ++start[rq(r) - qmin + 1];
+  for (size_t q = 1; q < start.size(); ++q) start[q] += start[q - 1];
+  for (int r = 0; r < n_rows; ++r) {
+    const int pos = start[rq(r) - qmin]++;
+    row_p[pos] = r / chi_b; row_alpha[pos] = r % chi_b;
+  }
+}
+
 // enumeration (device kernel when a workspace is given, host otherwise) + planning (host).  Requires
 // tmf_chain_modes to have completed.
 static int chain_enumerate_impl(tmf_chain *c, void *work_dev, int64_t work_bytes, void *stream);
@@ -352,11 +405,128 @@ int64_t tmf_chain_enum_workspace(tmf_chain *c) {
   int nb = 0;
   for (int b = 0; b <= c->L; ++b)
     if (c->bonds[b].used) ++nb;
-  return tmf::enum_workspace_bytes(nb, c->tp.chi_max);
+  int64_t bytes = tmf::enum_workspace_bytes(nb, c->tp.chi_max);
+  if (c->tp.chi_max >= 0) bytes += plan_workspace_bytes(c->site_hi - c->site_lo, c->tp.chi_max + 2);
+  return bytes;
 }
 int tmf_chain_enumerate_dev(tmf_chain *c, void *work_dev, int64_t work_bytes, void *stream) {
   return chain_enumerate_impl(c, work_dev, work_bytes, stream);
 }
+// Site plans on the device (plan.cu) from the resident bond tables; only the headers and block tables
+// (~1.7 KB per site) come back to the host, which needs them for the output offsets and the descriptors.
+static int chain_plan_device(tmf_chain *c, void *work_dev, int64_t work_bytes, void *stream) {
+  const tmf::EnumResident &er = c->enum_res;
+  const int ns = (int)c->sites.size();
+  const int64_t cap = er.cap;
+  std::vector<int> slot(c->L + 1, -1);
+  for (size_t u = 0; u < c->used_bonds.size(); ++u) slot[c->used_bonds[u]] = (int)u;
+  tmf::Arena ar(work_dev, work_bytes);
+  ar.take<unsigned char>(tmf::enum_workspace_bytes(er.nb, c->tp.chi_max));
+  tmf::PlanJob *jobs_dev = ar.take<tmf::PlanJob>(ns);
+  const int HB = tmf::PLAN_HDR_INTS + 6 * tmf::PLAN_MAX_BLOCKS;
+  int *hb_dev = ar.take<int>((int64_t)ns * HB);
+  std::vector<tmf::PlanJob> jobs(ns);
+  for (int u = 0; u < ns; ++u) {
+    ChainSite &s = c->sites[u];
+    const int side = s.mode == 1 ? TMF_SIDE_R : TMF_SIDE_L;
+    const ChainBond &bb = c->bonds[s.bra_bond], &kb = c->bonds[s.ket_bond];
+    const ChainSide &bs = bb.side[side], &ks = kb.side[side];
+    s.df = ks.f - bs.f;
+    s.f_common = bs.f;
+    if (s.df < 0 || s.df > 1)
+      throw std::invalid_argument("nested site stage: filled-orbital counts of neighbouring bonds differ by " +
+                                  std::to_string(s.df) + " (threshold noise); rerun with the legacy filled bases");
+    if (s.df == 1 && !(c->edge_host[2 * (size_t)ks.job] > 1e-24))
+      throw std::invalid_argument("nested site stage: edge vector of the filled space vanishes; rerun with the "
+                                  "legacy filled bases");
+    uint64_t *bm = ar.take<uint64_t>(2 * cap), *km = ar.take<uint64_t>(cap);
+    int *cols = ar.take<int>(2 * tmf::PLAN_MAX_ORB);
+    double *signs = ar.take<double>(2 * tmf::PLAN_MAX_ORB);
+    s.bra_masks_dev = bm; s.ket_masks_dev = km; s.cols_dev = cols; s.signs_dev = signs;
+    s.rows_ready = false;
+    const int sb = slot[s.bra_bond], sk = slot[s.ket_bond];
+    tmf::PlanJob &j = jobs[u];
+    std::memset(&j, 0, sizeof(j));
+    j.masks_b = er.masks_dev + (int64_t)sb * cap; j.masks_k = er.masks_dev + (int64_t)sk * cap;
+    j.charge_b = er.charge_dev + (int64_t)sb * cap; j.charge_k = er.charge_dev + (int64_t)sk * cap;
+    j.head_b = er.head_dev + (int64_t)sb * er.hw; j.head_k = er.head_dev + (int64_t)sk * er.hw;
+    j.bra_masks = bm; j.ket_masks = km; j.cols = cols; j.signs = signs;
+    j.hdr = hb_dev + (int64_t)u * HB; j.blocks = j.hdr + tmf::PLAN_HDR_INTS;
+    j.mode = s.mode; j.k_bra = bb.k; j.k_ket = kb.k; j.df = s.df;
+    j.n_bra = bs.n; j.n_ket = ks.n; j.f_bra = bs.f; j.f_ket = ks.f;
+  }
+  if (!ar.ok()) return fail(TMF_ERR_VALUE, "enumeration workspace too small for the device site plans");
+  int rc = tmf::copy_h2d(jobs_dev, jobs.data(), sizeof(tmf::PlanJob) * (size_t)ns, stream);
+  if (rc) return rc;
+  rc = tmf::plan_sites_device(jobs_dev, ns, stream);
+  if (rc) return rc;
+  // headers + block tables through the pinned staging (the enumeration's job staging is dead by now)
+  const size_t hb_bytes = sizeof(int) * (size_t)ns * HB;
+  if (c->blob_cap < hb_bytes + 256) {
+    g_pinned.release(c->blob, c->blob_cap);
+    c->blob = g_pinned.acquire(hb_bytes + 256, c->blob_cap);
+    if (!c->blob) { c->blob_cap = 0; return fail(TMF_ERR_RUNTIME, "cannot allocate pinned staging memory"); }
+  }
+  rc = tmf::copy_d2h_sync(c->blob, hb_dev, hb_bytes, stream);
+  if (rc) return rc;
+  const int *hb = reinterpret_cast<const int *>(c->blob);
+  for (int u = 0; u < ns; ++u) {
+    ChainSite &s = c->sites[u];
+    const int *h = hb + (size_t)u * HB;
+    if (h[18] == 2) throw std::invalid_argument("sometimes matrix larger than 64 rows/cols is not supported");
+    if (h[18] != 0) throw std::runtime_error("particle numbers of bra and ket block differ (slater.py:855)");
+    std::memcpy(&s.plan.h, h, sizeof(tmf_site_plan));
+    s.plan.blocks.assign(h + tmf::PLAN_HDR_INTS, h + tmf::PLAN_HDR_INTS + 6 * s.plan.h.n_blocks);
+    s.plan.bra_cols.clear(); s.plan.ket_cols.clear(); s.plan.bra_masks.clear(); s.plan.ket_masks.clear();
+    s.plan.row_p.clear(); s.plan.row_alpha.clear();
+  }
+  c->tables_pending = true;
+  return TMF_OK;
+}
+
+// Brings the bond tables of a device-planned chain to the host (once): waits for the asynchronous download
+// enqueued by tmf_chain_tensors (or performs it now) and unpacks it into the per-bond vectors.
+static int chain_ensure_tables(tmf_chain *c) {
+  if (!c->device_plan || !c->tables_pending) return TMF_OK;
+  std::lock_guard<std::mutex> lk(c->tab_mu);
+  if (!c->tables_pending) return TMF_OK;
+  const tmf::EnumResident &er = c->enum_res;
+#if !defined(TMF_HOSTSIM)
+  if (c->tab_event) {
+    int rc = tmf::check_cuda(cudaEventSynchronize((cudaEvent_t)c->tab_event), "cudaEventSynchronize");
+    if (rc) return rc;
+  } else
+#endif
+  {
+    const size_t need = tmf::enumerate_tables_stage_bytes(er);
+    if (c->tab_cap < need) {
+      g_pinned.release(c->tab_stage, c->tab_cap);
+      c->tab_stage = g_pinned.acquire(need, c->tab_cap);
+      if (!c->tab_stage) { c->tab_cap = 0; return fail(TMF_ERR_RUNTIME, "cannot allocate pinned staging memory"); }
+    }
+    int rc = tmf::enumerate_fetch_tables(er, c->tab_stage, nullptr);
+    if (rc) return rc;
+    rc = tmf::stream_sync(nullptr);
+    if (rc) return rc;
+  }
+  const int nbu = (int)c->used_bonds.size();
+  std::vector<int> kk(nbu), fl(nbu);
+  std::vector<tmf::BondVectors *> outp(nbu);
+  for (int u = 0; u < nbu; ++u) {
+    ChainBond &B = c->bonds[c->used_bonds[u]];
+    kk[u] = B.k; fl[u] = B.filled_left; outp[u] = &B.bv;
+  }
+  tmf::enumerate_unpack_tables(er, c->tab_stage, kk.data(), fl.data(), outp, c->n_threads > 0 ? c->n_threads : 4);
+  c->tables_pending = false;
+  return TMF_OK;
+}
+static void chain_site_rows(tmf_chain *c, ChainSite &s) {
+  if (!c->device_plan || s.rows_ready) return;
+  const ChainBond &bb = c->bonds[s.bra_bond];
+  rows_from_charges(s.mode, (int)bb.bv.charge.size(), bb.bv.charge.data(), s.plan.row_p, s.plan.row_alpha);
+  s.rows_ready = true;
+}
+
 static int chain_enumerate_impl(tmf_chain *c, void *work_dev, int64_t work_bytes, void *stream) {
   try {
     StageTimer tm;
@@ -395,10 +565,16 @@ static int chain_enumerate_impl(tmf_chain *c, void *work_dev, int64_t work_bytes
         c->blob = g_pinned.acquire(need, c->blob_cap);
         if (!c->blob) c->blob_cap = 0;
       }
+      c->device_plan = false;
+      c->used_bonds = used;
+      const bool try_resident = c->nested && c->want_device_plan && c->tp.chi_max >= 0;
       int rc = tmf::enumerate_device(nbu, ep.data(), kk.data(), fl.data(), c->tp, outp, work_dev, work_bytes, stream,
-                                     c->blob, c->blob_cap, c->n_threads > 0 ? c->n_threads : 8);
+                                     c->blob, c->blob_cap, c->n_threads > 0 ? c->n_threads : 8,
+                                     try_resident ? &c->enum_res : nullptr);
       if (rc) return rc;
+      c->device_plan = try_resident && c->enum_res.resident;
     } else {
+    c->device_plan = false;
     parallel_for((int)used.size(), c->n_threads, [&](int u) {
       ChainBond &B = c->bonds[used[u]];
       const int job = (B.side[TMF_SIDE_L].job >= 0) ? B.side[TMF_SIDE_L].job : B.side[TMF_SIDE_R].job;
@@ -414,6 +590,11 @@ static int chain_enumerate_impl(tmf_chain *c, void *work_dev, int64_t work_bytes
       else { s.mode = 0; s.bra_bond = i; s.ket_bond = i + 1; }               // slater.py:1326-1335
       c->sites.push_back(std::move(s));
     }
+    if (c->device_plan) {
+      int rc = chain_plan_device(c, work_dev, work_bytes, stream);
+      if (rc) return rc;
+      tm.lap("enumerate: site plans (device)");
+    } else
     parallel_for((int)c->sites.size(), c->n_threads, [&](int u) {
       ChainSite &s = c->sites[u];
       const int side = s.mode == 1 ? TMF_SIDE_R : TMF_SIDE_L;
@@ -461,9 +642,10 @@ static int chain_enumerate_impl(tmf_chain *c, void *work_dev, int64_t work_bytes
       }
       c->nblocks += h.n_blocks;
       c->max_chi = std::max(c->max_chi, std::max(h.chi_bra, h.chi_ket));
-      plan += tmf::align256(4 * (int64_t)rows) + tmf::align256(4 * (int64_t)cols) +
-              tmf::align256(8 * (int64_t)rows) + tmf::align256(8 * (int64_t)cols) +
-              tmf::align256(8 * (int64_t)h.n_rows) + tmf::align256(8 * (int64_t)h.chi_ket);
+      if (!c->device_plan)
+        plan += tmf::align256(4 * (int64_t)rows) + tmf::align256(4 * (int64_t)cols) +
+                tmf::align256(8 * (int64_t)rows) + tmf::align256(8 * (int64_t)cols) +
+                tmf::align256(8 * (int64_t)h.n_rows) + tmf::align256(8 * (int64_t)h.chi_ket);
     }
     const int kc = c->bonds[c->oc].used ? c->bonds[c->oc].k : 0;
     const int64_t pair = tmf_slater_pair_bond_workspace(c->L, kc) + 512;
@@ -481,6 +663,7 @@ int tmf_chain_tensor_sizes(tmf_chain *c, int64_t *q) {
   if (!c->enumerated) return fail(TMF_ERR_VALUE, "tmf_chain_enumerate has not run");
   q[0] = c->plan_bytes; q[1] = c->o_elems; q[2] = c->s_elems; q[3] = (int64_t)c->sites.size();
   q[4] = c->nblocks; q[5] = c->out_elems; q[6] = c->max_chi;
+  q[7] = (c->nested ? 1 : 0) | (c->device_plan ? 2 : 0);   // which site stage / planner this chain uses
   return TMF_OK;
 }
 
@@ -578,6 +761,85 @@ static int centre_pairing(tmf_chain *c, const double *C_dev, int ldc, double *V_
                               V_dev + B.side[TMF_SIDE_R].v_off, work, wb, stream);
 }
 
+// Tensor stage of a device-planned chain: the per-site arrays are already in device memory; the host only
+// writes the kernel descriptors (pointers + sizes) and, after the last kernel, enqueues the download of the
+// bond tables for the result accessors.
+static int chain_tensors_device_plan(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, tmf::Arena &ar,
+                                     double *O_dev, double *S_dev, double *det_dev, double *out_dev, void *stream) {
+  const int ns = (int)c->sites.size();
+  std::vector<tmf_site_job> sj(ns);
+  std::vector<tmf_nested_job> nj(ns);
+  std::vector<tmf_minor_block> mb((size_t)c->nblocks);
+  const double *e_dev = c->e_dev_ptr;
+  if (e_dev == nullptr) return fail(TMF_ERR_VALUE, "tmf_chain_modes has not run");
+  int mb0 = 0;
+  for (int u = 0; u < ns; ++u) {
+    ChainSite &s = c->sites[u];
+    const tmf_site_plan &h = s.plan.h;
+    const int side = s.mode == 1 ? TMF_SIDE_R : TMF_SIDE_L;
+    const ChainBond &bb = c->bonds[s.bra_bond], &kb = c->bonds[s.ket_bond];
+    const ChainSide &bs = bb.side[side], &ks = kb.side[side];
+    const int sb0 = h.s_bra - (h.ka_bra - h.k_always), sk0 = h.s_ket - (h.ka_ket - h.k_always);
+    tmf_site_job &j = sj[u];
+    std::memset(&j, 0, sizeof(j));
+    j.Vb = V_dev + bs.v_off; j.Vk = V_dev + ks.v_off;
+    j.ldb = std::max(bs.n, 1); j.ldk = std::max(ks.n, 1);
+    j.bra_cols = s.cols_dev; j.ket_cols = s.cols_dev + tmf::PLAN_MAX_ORB;
+    j.bra_sign = s.signs_dev; j.ket_sign = s.signs_dev + tmf::PLAN_MAX_ORB;
+    j.O = O_dev + s.o_off; j.S = S_dev + s.s_off; j.det = det_dev + u;
+    j.n_bra = h.n_bra; j.n_ket = h.n_ket; j.mode = h.mode; j.physical = h.physical;
+    j.ka_bra = h.ka_bra; j.ka_ket = h.ka_ket; j.sb = sb0; j.sk = sk0;
+    j.pad_[1] = 1;
+    tmf_nested_job &q = nj[u];
+    std::memset(&q, 0, sizeof(q));
+    q.e_bra = e_dev + (size_t)bs.job * TMF_MAX_MODES;
+    q.e_ket = e_dev + (size_t)ks.job * TMF_MAX_MODES;
+    q.c_edge = C_dev + (int64_t)s.site * ldc + s.site;
+    q.a_col = (s.mode == 1) ? q.c_edge + 1 : C_dev + (int64_t)s.site * ldc;
+    q.k_bra = bb.k; q.k_ket = kb.k; q.df = s.df;
+    for (int b = 0; b < h.n_blocks; ++b) {
+      const int *bl = &s.plan.blocks[6 * b];
+      tmf_minor_block &k = mb[mb0 + b];
+      std::memset(&k, 0, sizeof(k));
+      k.S = j.S; k.det = j.det;
+      k.bra_masks = s.bra_masks_dev + bl[0]; k.ket_masks = s.ket_masks_dev + bl[2];
+      k.out = out_dev + s.block_off[b];
+      k.s_bra = h.s_bra; k.s_ket = h.s_ket; k.n_bra = bl[1]; k.n_ket = bl[3]; k.minor = bl[4];
+    }
+    mb0 += h.n_blocks;
+  }
+  void *site_desc = ar.take<unsigned char>(tmf_site_desc_bytes(ns));
+  void *minor_desc = ar.take<unsigned char>(tmf_minor_desc_bytes((int)mb.size()));
+  if (!ar.ok()) return fail(TMF_ERR_VALUE, "plan workspace too small");
+  int rc = tmf_site_nested_batched(sj.data(), nj.data(), ns, site_desc, stream);
+  if (rc) return rc;
+  rc = tmf_minors_blocks(mb.data(), (int)mb.size(), minor_desc, stream);
+  if (rc) return rc;
+  // bond tables -> pinned host staging, behind the kernels (read by the accessors / bulk exports)
+  {
+    std::lock_guard<std::mutex> lk(c->tab_mu);
+    const size_t need = tmf::enumerate_tables_stage_bytes(c->enum_res);
+    if (c->tab_cap < need) {
+      g_pinned.release(c->tab_stage, c->tab_cap);
+      c->tab_stage = g_pinned.acquire(need, c->tab_cap);
+      if (!c->tab_stage) { c->tab_cap = 0; return fail(TMF_ERR_RUNTIME, "cannot allocate pinned staging memory"); }
+    }
+    rc = tmf::enumerate_fetch_tables(c->enum_res, c->tab_stage, stream);
+    if (rc) return rc;
+#if !defined(TMF_HOSTSIM)
+    if (!c->tab_event) {
+      cudaEvent_t ev;
+      rc = tmf::check_cuda(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate");
+      if (rc) return rc;
+      c->tab_event = ev;
+    }
+    rc = tmf::check_cuda(cudaEventRecord((cudaEvent_t)c->tab_event, (cudaStream_t)stream), "cudaEventRecord");
+    if (rc) return rc;
+#endif
+  }
+  return TMF_OK;
+}
+
 int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev, void *plan_dev,
                       int64_t plan_bytes, double *O_dev, double *S_dev, double *det_dev, double *out_dev,
                       void *stream) {
@@ -588,6 +850,7 @@ int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev,
   int rc = centre_pairing(c, C_dev, ldc, V_dev, ar, stream);
   if (rc) return rc;
   tm.lap("tensors: centre pairing");
+  if (c->device_plan) return chain_tensors_device_plan(c, C_dev, ldc, V_dev, ar, O_dev, S_dev, det_dev, out_dev, stream);
   // ---- one blob with every per-site index / sign / mask array ------------------------------
   // pass 1 (serial, cheap): offsets of every array; pass 2 (threads over sites): copy + descriptors
   const int ns = (int)c->sites.size();
@@ -695,6 +958,7 @@ int tmf_chain_bond(tmf_chain *c, int bond, int *q, const double **lam, const int
                    const double **e) {
   if (bond < 0 || bond > c->L || !c->bonds[bond].used || !c->enumerated)
     return fail(TMF_ERR_VALUE, "bond not available on this shard");
+  if (int rc = chain_ensure_tables(c)) return rc;
   const ChainBond &B = c->bonds[bond];
   q[0] = (int)B.bv.masks.size(); q[1] = B.k; q[2] = B.filled_left; q[3] = (int)B.bv.sec_q.size();
   q[4] = B.side[0].job; q[5] = B.side[1].job; q[6] = B.side[0].f; q[7] = B.side[1].f;
@@ -710,6 +974,8 @@ int tmf_chain_site(tmf_chain *c, int site, tmf_site_plan *plan, const int **bloc
                    int64_t *offs) {
   if (site < c->site_lo || site >= c->site_hi || !c->enumerated)
     return fail(TMF_ERR_VALUE, "site not available on this shard");
+  if (int rc = chain_ensure_tables(c)) return rc;
+  chain_site_rows(c, c->sites[site - c->site_lo]);
   const ChainSite &s = c->sites[site - c->site_lo];
   *plan = s.plan.h;
   *blocks = s.plan.blocks.data(); *block_off = s.block_off.data();
@@ -723,6 +989,7 @@ int tmf_chain_site(tmf_chain *c, int site, tmf_site_plan *plan, const int **bloc
 // q = {first bond, number of bonds, sum of chi, sum of sector counts}
 int tmf_chain_bonds_sizes(tmf_chain *c, int64_t *q) {
   if (!c->enumerated) return fail(TMF_ERR_VALUE, "tmf_chain_enumerate has not run");
+  if (int rc = chain_ensure_tables(c)) return rc;
   int first = -1, last = -1;
   int64_t chi = 0, nsec = 0;
   for (int b = 0; b <= c->L; ++b)
@@ -790,12 +1057,15 @@ int tmf_chain_sites_sizes(tmf_chain *c, int64_t *q) {
 int tmf_chain_sites_export(tmf_chain *c, tmf_site_plan *plans, int64_t *blk_off, int *blocks,
                            int64_t *block_off, int64_t *row_off, int *row_p, int *row_alpha) {
   if (!c->enumerated) return fail(TMF_ERR_VALUE, "tmf_chain_enumerate has not run");
+  if (row_p != nullptr && row_alpha != nullptr)
+    if (int rc = chain_ensure_tables(c)) return rc;
   const int ns = (int)c->sites.size();
   int64_t bo = 0, ro = 0;
   for (int u = 0; u < ns; ++u) { blk_off[u] = bo; row_off[u] = ro; bo += c->sites[u].plan.h.n_blocks; ro += c->sites[u].plan.h.n_rows; }
   blk_off[ns] = bo;
   row_off[ns] = ro;
   parallel_for(ns, c->n_threads > 0 ? c->n_threads : 4, [&](int u) {
+    if (row_p != nullptr && row_alpha != nullptr) chain_site_rows(c, c->sites[u]);
     const ChainSite &s = c->sites[u];
     const tmf_site_plan &h = s.plan.h;
     plans[u] = h;
@@ -803,7 +1073,7 @@ int tmf_chain_sites_export(tmf_chain *c, tmf_site_plan *plans, int64_t *blk_off,
       std::memcpy(blocks + 6 * blk_off[u], s.plan.blocks.data(), sizeof(int) * 6 * (size_t)h.n_blocks);
       std::memcpy(block_off + blk_off[u], s.block_off.data(), sizeof(int64_t) * (size_t)h.n_blocks);
     }
-    if (h.n_rows) {
+    if (h.n_rows && row_p != nullptr && row_alpha != nullptr) {
       std::memcpy(row_p + row_off[u], s.plan.row_p.data(), sizeof(int) * (size_t)h.n_rows);
       std::memcpy(row_alpha + row_off[u], s.plan.row_alpha.data(), sizeof(int) * (size_t)h.n_rows);
     }

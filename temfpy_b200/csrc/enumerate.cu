@@ -327,7 +327,8 @@ int64_t enum_workspace_bytes(int nb, int chi_max) {
 
 int enumerate_device(int nb, const double *const *e_ptr, const int *k, const int *filled_left, const TruncPar &tp,
                      std::vector<BondVectors *> &out, void *work_dev, int64_t work_bytes, void *stream,
-                     unsigned char *stage, size_t stage_bytes, int n_threads) {
+                     unsigned char *stage, size_t stage_bytes, int n_threads, EnumResident *keep) {
+  if (keep) keep->resident = false;
   const double max_logval = -std::log(tp.svd_min) + tp.degeneracy_tol;
   const int pool = (std::min(60000, std::max(tp.chi_max, 0) + 96) + 7) & ~7;   // multiple of 8: keeps the shared arrays aligned
   const bool device_ok = tp.chi_max >= 0 && max_logval > 0.0 && max_logval < 64.0 && pool < 65000 &&
@@ -428,6 +429,40 @@ int enumerate_device(int nb, const double *const *e_ptr, const int *k, const int
   rc = launch_t("enumerate", enumerate_kernel, nb, 32, enum_smem_bytes(pool), stream, (const EnumJob *)jobs_dev, par);
   if (rc) return rc;
   int *head = reinterpret_cast<int *>(stage + o_head);
+  if (keep != nullptr) {
+    // Resident form: only the heads (chi, sector tables, status) come to the host now; the tables stay in
+    // device memory for the planning / tensor kernels and are downloaded later, off the critical path
+    // (enumerate_fetch_tables).  A bond the device could not finish is recomputed on the host and uploaded.
+    rc = copy_d2h_sync(head, head_dev, (size_t)nb * HW * 4, stream);
+    if (rc) return rc;
+    keep->resident = true;
+    keep->nb = nb; keep->cap = cap; keep->hw = HW;
+    keep->masks_dev = masks_dev; keep->lam_dev = lam_dev; keep->charge_dev = charge_dev; keep->head_dev = head_dev;
+    keep->head_host.assign(head, head + (size_t)nb * HW);
+    for (int b = 0; b < nb; ++b) {
+      int *h = keep->head_host.data() + (size_t)b * HW;
+      if (h[2] == ENUM_EMPTY) throw std::runtime_error("-1|No Schmidt vectors left after filtering by `trunc_par.sectors`!");
+      if (h[2] == ENUM_NOCUT) throw std::runtime_error("-2|truncate: no admissible cut");
+      if (h[2] != ENUM_FALLBACK) continue;
+      BondVectors bv;
+      bond_vectors(e_ptr[b], k[b], filled_left[b], tp, bv);
+      const int chi = (int)bv.masks.size(), ns = (int)bv.sec_q.size();
+      if (chi > cap || ns > ENUM_MAX_SECTORS) { keep->resident = false; break; }   // does not fit: host path for everything
+      h[0] = chi; h[1] = ns; h[2] = ENUM_OK;
+      std::copy(bv.sec_q.begin(), bv.sec_q.end(), h + 4);
+      std::copy(bv.sec_start.begin(), bv.sec_start.end(), h + 4 + ENUM_MAX_SECTORS);
+      if ((rc = copy_h2d(head_dev + (size_t)b * HW, h, sizeof(int) * HW, stream))) return rc;
+      if ((rc = copy_h2d(masks_dev + (size_t)b * cap, bv.masks.data(), sizeof(uint64_t) * chi, stream))) return rc;
+      if ((rc = copy_h2d(lam_dev + (size_t)b * cap, bv.lam.data(), sizeof(double) * chi, stream))) return rc;
+      if ((rc = copy_h2d(charge_dev + (size_t)b * cap, bv.charge.data(), sizeof(int) * chi, stream))) return rc;
+    }
+    if (keep->resident) return TMF_OK;
+    // (fall through: classic path below re-reads everything)
+    for (int b = 0; b < nb; ++b) {          // restore the device statuses for the classic unpacking
+      int *h = head + (size_t)b * HW;
+      (void)h;
+    }
+  }
   rc = copy_d2h_async(head, head_dev, (size_t)nb * HW * 4, stream);
   if (rc) return rc;
   rc = copy_d2h_async(stage + o_masks, masks_dev, (size_t)nb * cap * 8, stream);
@@ -461,6 +496,39 @@ int enumerate_device(int nb, const double *const *e_ptr, const int *k, const int
     if (err[b] == 2) throw std::runtime_error("-2|truncate: no admissible cut");
   }
   return TMF_OK;
+}
+
+// Downloads the tables of a resident enumeration (asynchronously, into pinned `stage`) -- the caller
+// synchronises (event / stream) and then unpacks with enumerate_unpack_tables.
+size_t enumerate_tables_stage_bytes(const EnumResident &r) {
+  return (size_t)r.nb * r.cap * (8 + 8 + 4) + 1024;
+}
+int enumerate_fetch_tables(const EnumResident &r, unsigned char *stage, void *stream) {
+  const size_t o_lam = (size_t)r.nb * r.cap * 8, o_charge = 2 * o_lam;
+  int rc = copy_d2h_async(stage, r.masks_dev, (size_t)r.nb * r.cap * 8, stream);
+  if (rc) return rc;
+  rc = copy_d2h_async(stage + o_lam, r.lam_dev, (size_t)r.nb * r.cap * 8, stream);
+  if (rc) return rc;
+  return copy_d2h_async(stage + o_charge, r.charge_dev, (size_t)r.nb * r.cap * 4, stream);
+}
+void enumerate_unpack_tables(const EnumResident &r, const unsigned char *stage, const int *k, const int *filled_left,
+                             std::vector<BondVectors *> &out, int n_threads) {
+  const size_t o_lam = (size_t)r.nb * r.cap * 8, o_charge = 2 * o_lam;
+  const uint64_t *masks_h = reinterpret_cast<const uint64_t *>(stage);
+  const double *lam_h = reinterpret_cast<const double *>(stage + o_lam);
+  const int *charge_h = reinterpret_cast<const int *>(stage + o_charge);
+  pool_for(r.nb, std::max(1, n_threads), [&](int b) {
+    const int *h = r.head_host.data() + (size_t)b * r.hw;
+    BondVectors &o = *out[b];
+    const int chi = h[0], ns = h[1];
+    o.k = k[b];
+    o.filled_left = filled_left[b];
+    o.masks.assign(masks_h + (size_t)b * r.cap, masks_h + (size_t)b * r.cap + chi);
+    o.lam.assign(lam_h + (size_t)b * r.cap, lam_h + (size_t)b * r.cap + chi);
+    o.charge.assign(charge_h + (size_t)b * r.cap, charge_h + (size_t)b * r.cap + chi);
+    o.sec_q.assign(h + 4, h + 4 + ns);
+    o.sec_start.assign(h + 4 + ENUM_MAX_SECTORS, h + 4 + ENUM_MAX_SECTORS + ns + 1);
+  });
 }
 
 }  // namespace tmf

@@ -60,6 +60,18 @@ void site_plan(int mode, int n_bra, int n_ket, int k_bra, int f_bra, int nferm_b
                int nferm_ket, int chi_ket, const uint64_t *masks_ket, const int *charge_ket,
                SitePlan &out);
 
+// Device-resident result of the enumeration kernel (enumerate.cu): tables stay in the caller's workspace.
+struct EnumResident {
+  bool resident = false;
+  int nb = 0, hw = 0;
+  int64_t cap = 0;
+  uint64_t *masks_dev = nullptr;     // nb x cap
+  double *lam_dev = nullptr;         // nb x cap
+  int *charge_dev = nullptr;         // nb x cap
+  int *head_dev = nullptr;           // nb x hw: chi, sectors, status, pops, sec_q[66], sec_start[67]
+  std::vector<int> head_host;        // host copy of the heads
+};
+
 void set_error(const std::string &msg);
 
 // Runs f(0) .. f(n-1) on a persistent pool of host threads (at most max_threads of them plus the caller,

@@ -620,7 +620,7 @@ extern "C" int64_t tmf_slater_modes_slot_cols(int L, int x, int side, int r_sket
   int n, m;
   tmf::job_geometry(L, x, side, n, m);
   if (!nested) return n;
-  if (n <= tmf::SMALL_N) return n + 1;
+  if (n <= tmf::small_n()) return n + 1;
   return std::min(r_sketch, std::min(n, m)) + 1;
 }
 

@@ -231,11 +231,9 @@ class ShardTables:
             self.blocks = np.empty((nblk, 6), np.int32)
             self.block_off = np.empty(nblk, np.int64)
             self.row_off = np.empty(ns + 1, np.int64)
-            self.row_p = np.empty(nrows, np.int32)
-            self.row_alpha = np.empty(nrows, np.int32)
+            # the bra-row order is derived lazily per site (see site_rows) instead of exporting 2 chi ints per site
             check(lib, lib.tmf_chain_sites_export(h, C.addressof(self.plans), p(self.blk_off), p(self.blocks),
-                                                  p(self.block_off), p(self.row_off), p(self.row_p),
-                                                  p(self.row_alpha)))
+                                                  p(self.block_off), p(self.row_off), None, None))
 
     def normalized(self):
         """(norms, normalised Schmidt values) of all bonds of the shard in one vectorised pass; computed once
@@ -262,18 +260,31 @@ class ShardTables:
         return BondData(x=int(x), k=k, filled_left=fl, e=self.e[i, :k], masks=self.masks[a:b],
                         schmidt_values=self.lam[a:b], charge=self.charge[a:b], idx_L=idx_L)
 
+    def site_rows(self, i, plan):
+        """(row_p, row_alpha) of site i: bra rows in the reference order -- [p = 0 | p = 1], stably sorted by the
+        pipe charge q(alpha) + p (left tensors) / q(alpha) - p (right tensors), slater.py:1053-1058."""
+        x = i if plan.mode == 0 else i + 1                    # bra bond
+        k = x - self.first_bond
+        a, b = int(self.chi_off[k]), int(self.chi_off[k + 1])
+        q = self.charge[a:b]
+        chi = b - a
+        p = np.repeat(np.arange(2, dtype=np.int64), chi)
+        al = np.tile(np.arange(chi, dtype=np.int64), 2)
+        order = np.argsort(q[al] + (p if plan.mode == 0 else -p), kind="stable")
+        return p[order], al[order]
+
     def site(self, i) -> "SiteTensor":
         u = i - self.site_lo
         plan = self.plans[u]
         b0, b1 = int(self.blk_off[u]), int(self.blk_off[u + 1])
-        r0_, r1_ = int(self.row_off[u]), int(self.row_off[u + 1])
         out = []
         for b in range(b0, b1):
             r0, nr, c0, nc, _, qk = (int(v) for v in self.blocks[b])
             o = int(self.block_off[b])
             out.append((qk, r0, nr, c0, nc, self.out_host[o: o + nr * nc].reshape(nr, nc)))
+        row_p, row_alpha = self.site_rows(i, plan)
         return SiteTensor(site=int(i), mode="left" if plan.mode == 0 else "right", plan=plan, blocks=out,
-                          row_p=self.row_p[r0_:r1_], row_alpha=self.row_alpha[r0_:r1_], qtotal=plan.qtotal)
+                          row_p=row_p, row_alpha=row_alpha, qtotal=plan.qtotal)
 
 
 @dataclass
@@ -379,7 +390,7 @@ class SlaterChain:
     """One chain conversion on one device for the sites [site_lo, site_hi)."""
 
     def __init__(self, backend, L, trunc, n_fermion, ortho_center=None, site_lo=0, site_hi=None,
-                 r_sketch=48, n_threads=0, snap=False, nested=None):
+                 r_sketch=48, n_threads=0, snap=False, nested=None, device_plan=None):
         self.be = backend
         self.lib = backend.lib
         self.L = int(L)
@@ -403,6 +414,8 @@ class SlaterChain:
             check(self.lib, self.lib.tmf_chain_set_option(self.handle, _lib.OPT_SNAP, 0))
         if nested is not None:      # None: the library's default (nested unless TMF_LEGACY_FILLED is set)
             check(self.lib, self.lib.tmf_chain_set_option(self.handle, _lib.OPT_NESTED, int(bool(nested))))
+        if device_plan is not None:
+            check(self.lib, self.lib.tmf_chain_set_option(self.handle, _lib.OPT_DEVICE_PLAN, int(bool(device_plan))))
         self._buffers = {}
 
     def close(self):
@@ -465,8 +478,8 @@ class SlaterChain:
         q = (C.c_int64 * 8)()
         check(lib, lib.tmf_chain_tensor_sizes(self.handle, q))
         plan_bytes, o_elems, s_elems, nsites, nblocks, out_elems, max_chi = (int(x) for x in q[:7])
-        b = self._buffers
-        b.pop("work", None)      # the mode workspace is dead by now
+        self.path = dict(nested=bool(int(q[7]) & 1), device_plan=bool(int(q[7]) & 2))
+        b = self._buffers           # ("work" stays: it holds the resident enumeration tables / site plans)
         b["plan"] = be.empty(plan_bytes, np.uint8)
         b["O"] = be.empty(o_elems, np.float64)
         b["S"] = be.empty(s_elems, np.float64)
@@ -569,7 +582,7 @@ class SlaterChain:
             res.timings["d2h_GBps"] = 8e-6 * self.out_elems / max(res.timings["d2h_ms"], 1e-9)
             res.timings["t_done"] = time.perf_counter()
         res.stats = dict(out_elems=self.out_elems, nblocks=self.nblocks, max_chi=self.max_chi,
-                         njobs=self.njobs)
+                         njobs=self.njobs, path=self.path)
         return res
 
 
@@ -594,11 +607,11 @@ SKETCH_WIDTHS = (48, 64, 128, 160)
 
 
 def _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch, n_threads,
-               fetch_tensors, lazy=False, gate=None, snap=False, nested=None):
+               fetch_tensors, lazy=False, gate=None, snap=False, nested=None, device_plan=None):
     import time
     gate = gate or _NoGate()
     chain = SlaterChain(backend, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch, n_threads, snap=snap,
-                        nested=nested)
+                        nested=nested, device_plan=device_plan)
     ok = False
     try:
         tt = [time.perf_counter()]
@@ -715,7 +728,8 @@ class DeviceChainResult:
 
 
 def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_lo=0, site_hi=None,
-              r_sketch=48, n_threads=0, fetch_tensors=True, n_chunks=None, lazy=False, snap=False, nested=None):
+              r_sketch=48, n_threads=0, fetch_tensors=True, n_chunks=None, lazy=False, snap=False, nested=None,
+              device_plan=None):
     """C (device) -> Schmidt data of every bond and block-sparse tensor of every site.
 
     The site range is cut into cost-balanced chunks that run as a software pipeline: one worker
@@ -733,7 +747,7 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
     ``snap=False`` (default) is the reference's literal truncation (schmidt_utils.py:140-185 only sees
     degeneracies below ``degeneracy_tol``; where a multiplet that is degenerate in exact arithmetic straddles
     ``chi_max`` the kept part is decided by the rounding noise of the mode eigenvalues, in the reference as here)."""
-    opts = dict(r_sketch=r_sketch, snap=snap, nested=nested)
+    opts = dict(r_sketch=r_sketch, snap=snap, nested=nested, device_plan=device_plan)
     while True:
         try:
             return _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi,
@@ -755,7 +769,7 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
 def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi, n_threads,
                     fetch_tensors, n_chunks, lazy, opts):
     from .dist import partition
-    r_sketch, snap, nested = opts["r_sketch"], opts["snap"], opts["nested"]
+    r_sketch, snap, nested, device_plan = opts["r_sketch"], opts["snap"], opts["nested"], opts["device_plan"]
     site_hi = L if site_hi is None else site_hi
     nsites = site_hi - site_lo
     if n_chunks is None:
@@ -763,7 +777,7 @@ def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site
     n_chunks = max(1, min(n_chunks, nsites))
     if n_chunks == 1:
         r = _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi, r_sketch,
-                       n_threads, fetch_tensors, lazy, snap=snap, nested=nested)
+                       n_threads, fetch_tensors, lazy, snap=snap, nested=nested, device_plan=device_plan)
         if lazy:
             r = DeviceChainResult([r])
         r.options = dict(opts)
@@ -792,7 +806,7 @@ def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site
             try:
                 return _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch,
                                   n_threads, fetch_tensors, lazy, gate=stages.gate(pos) if stages else None,
-                                  snap=snap, nested=nested)
+                                  snap=snap, nested=nested, device_plan=device_plan)
             except _Retry as rt:        # the other chunks finish; the driver then starts over
                 return rt
 

@@ -161,3 +161,35 @@ def test_structured_inputs_vs_oracle(sim_backend, case):
     rep = helpers.compare_mps(so.C_to_MPS(Cm, tp), helpers.chain_to_dense(res), tp)
     # (with an svd_min-limited cut a near-degenerate multiplet may straddle the cut: compare_mps audits it)
     assert rep["ambiguous"] == [] or "svd_min" in case
+
+
+@pytest.mark.parametrize("case", ["random", "chain", "oc"])
+def test_device_site_plans_match_host(sim_backend, case):
+    """The device planner (plan.cu) against the host planner (hostlogic.cpp site_plan, the restatement of
+    slater.py:760-825, :1027-1058, :1106-1141): identical headers, block tables and tensors."""
+    kw = {}
+    if case == "random":
+        Cm, n = so.correlation_matrix(helpers.random_hamiltonian(60, 4))
+        tp = {"chi_max": 48}
+    elif case == "chain":
+        Cm, n = so.correlation_matrix(so.hopping_chain(40))
+        tp = {"chi_max": 32, "svd_min": 1e-7}
+    else:
+        Cm, n = so.correlation_matrix(helpers.random_hamiltonian(50, 9, 3.0))
+        tp, kw = {"chi_max": 40}, dict(ortho_center=13)
+    dev = helpers.run_native(sim_backend, Cm, tp, n, device_plan=True, **kw)
+    host = helpers.run_native(sim_backend, Cm, tp, n, device_plan=False, **kw)
+    assert dev.stats["path"] == dict(nested=True, device_plan=True)
+    assert host.stats["path"] == dict(nested=True, device_plan=False)
+    for i in range(len(Cm)):
+        a, b = dev.sites[i], host.sites[i]
+        for f, _ in a.plan._fields_:
+            assert getattr(a.plan, f) == getattr(b.plan, f), (i, f)
+        assert np.array_equal(a.row_p, b.row_p) and np.array_equal(a.row_alpha, b.row_alpha)
+        assert len(a.blocks) == len(b.blocks)
+        for ba, bb in zip(a.blocks, b.blocks):
+            assert ba[:5] == bb[:5] and np.array_equal(ba[5], bb[5])
+    for x in range(len(Cm) + 1):
+        assert np.array_equal(dev.bonds[x].masks, host.bonds[x].masks)
+        assert np.array_equal(dev.bonds[x].schmidt_values, host.bonds[x].schmidt_values)
+        assert dev.bonds[x].idx_L == host.bonds[x].idx_L
