@@ -179,8 +179,16 @@ TMF_GLOBAL enumerate_kernel(const EnumJob *jobs, EnumPar par) {
           pnext[best] = free_head;
           free_head = best;
         } else if (have_over) {
-          if (n_over > 1) { status = ENUM_FALLBACK; break; }   // would need the order of the other overflow items
+          // The best item beyond the window.  Popping it normally ends the search (its sum exceeds the admissible
+          // range); if the search had to go on (sector filters), the order of the other overflow items would be
+          // needed -- they were not kept: fall back to the host.
           s = o_sum; set = o_set; ii = o_i;
+          if (n_over > 1) {
+            const bool accepted = enum_is_sector(par, jb.filled_left + enum_popc(set));
+            const double fr = (n == 0) ? s : front;
+            const bool ends = accepted && (n + 1 > par.chi_max || s - fr > par.max_logval);
+            if (!ends) { status = ENUM_FALLBACK; break; }
+          }
           have_over = false;
           n_over = 0;
         } else {
@@ -439,29 +447,33 @@ int enumerate_device(int nb, const double *const *e_ptr, const int *k, const int
     keep->nb = nb; keep->cap = cap; keep->hw = HW;
     keep->masks_dev = masks_dev; keep->lam_dev = lam_dev; keep->charge_dev = charge_dev; keep->head_dev = head_dev;
     keep->head_host.assign(head, head + (size_t)nb * HW);
+    std::vector<int> fb;
     for (int b = 0; b < nb; ++b) {
-      int *h = keep->head_host.data() + (size_t)b * HW;
+      const int *h = keep->head_host.data() + (size_t)b * HW;
       if (h[2] == ENUM_EMPTY) throw std::runtime_error("-1|No Schmidt vectors left after filtering by `trunc_par.sectors`!");
       if (h[2] == ENUM_NOCUT) throw std::runtime_error("-2|truncate: no admissible cut");
-      if (h[2] != ENUM_FALLBACK) continue;
-      BondVectors bv;
-      bond_vectors(e_ptr[b], k[b], filled_left[b], tp, bv);
-      const int chi = (int)bv.masks.size(), ns = (int)bv.sec_q.size();
-      if (chi > cap || ns > ENUM_MAX_SECTORS) { keep->resident = false; break; }   // does not fit: host path for everything
-      h[0] = chi; h[1] = ns; h[2] = ENUM_OK;
-      std::copy(bv.sec_q.begin(), bv.sec_q.end(), h + 4);
-      std::copy(bv.sec_start.begin(), bv.sec_start.end(), h + 4 + ENUM_MAX_SECTORS);
-      if ((rc = copy_h2d(head_dev + (size_t)b * HW, h, sizeof(int) * HW, stream))) return rc;
-      if ((rc = copy_h2d(masks_dev + (size_t)b * cap, bv.masks.data(), sizeof(uint64_t) * chi, stream))) return rc;
-      if ((rc = copy_h2d(lam_dev + (size_t)b * cap, bv.lam.data(), sizeof(double) * chi, stream))) return rc;
-      if ((rc = copy_h2d(charge_dev + (size_t)b * cap, bv.charge.data(), sizeof(int) * chi, stream))) return rc;
+      if (h[2] == ENUM_FALLBACK) fb.push_back(b);
+    }
+    if (!fb.empty()) {
+      std::vector<BondVectors> bvs(fb.size());
+      pool_for((int)fb.size(), n_threads, [&](int t) { bond_vectors(e_ptr[fb[t]], k[fb[t]], filled_left[fb[t]], tp, bvs[t]); });
+      for (size_t t = 0; t < fb.size() && keep->resident; ++t) {
+        const int b = fb[t];
+        const BondVectors &bv = bvs[t];
+        int *h = keep->head_host.data() + (size_t)b * HW;
+        const int chi = (int)bv.masks.size(), ns = (int)bv.sec_q.size();
+        if (chi > cap || ns > ENUM_MAX_SECTORS) { keep->resident = false; break; }   // does not fit: host path for everything
+        h[0] = chi; h[1] = ns; h[2] = ENUM_OK;
+        std::copy(bv.sec_q.begin(), bv.sec_q.end(), h + 4);
+        std::copy(bv.sec_start.begin(), bv.sec_start.end(), h + 4 + ENUM_MAX_SECTORS);
+        if ((rc = copy_h2d(head_dev + (size_t)b * HW, h, sizeof(int) * HW, stream))) return rc;
+        if ((rc = copy_h2d(masks_dev + (size_t)b * cap, bv.masks.data(), sizeof(uint64_t) * chi, stream))) return rc;
+        if ((rc = copy_h2d(lam_dev + (size_t)b * cap, bv.lam.data(), sizeof(double) * chi, stream))) return rc;
+        if ((rc = copy_h2d(charge_dev + (size_t)b * cap, bv.charge.data(), sizeof(int) * chi, stream))) return rc;
+      }
     }
     if (keep->resident) return TMF_OK;
-    // (fall through: classic path below re-reads everything)
-    for (int b = 0; b < nb; ++b) {          // restore the device statuses for the classic unpacking
-      int *h = head + (size_t)b * HW;
-      (void)h;
-    }
+    // (a table did not fit its slot: the classic path below re-reads everything and unpacks on the host)
   }
   rc = copy_d2h_async(head, head_dev, (size_t)nb * HW * 4, stream);
   if (rc) return rc;
