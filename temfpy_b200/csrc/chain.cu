@@ -117,13 +117,15 @@ struct PinnedPool {
   unsigned char *acquire(size_t bytes, size_t &cap) {
     {
       std::lock_guard<std::mutex> lk(mu);
+      int best = -1;                       // best fit: big buffers stay available for big requests
       for (size_t i = 0; i < free_list.size(); ++i)
-        if (free_list[i].second >= bytes) {
-          auto r = free_list[i];
-          free_list.erase(free_list.begin() + i);
-          cap = r.second;
-          return r.first;
-        }
+        if (free_list[i].second >= bytes && (best < 0 || free_list[i].second < free_list[best].second)) best = (int)i;
+      if (best >= 0) {
+        auto r = free_list[best];
+        free_list.erase(free_list.begin() + best);
+        cap = r.second;
+        return r.first;
+      }
     }
     cap = std::max<size_t>(bytes + bytes / 4, 1 << 20);
     unsigned char *p = nullptr;
@@ -137,7 +139,9 @@ struct PinnedPool {
   void release(unsigned char *p, size_t cap) {
     if (!p) return;
     std::lock_guard<std::mutex> lk(mu);
-    if (free_list.size() < 32) { free_list.emplace_back(p, cap); return; }
+    // (cudaFreeHost synchronises the device: keep enough buffers for several conversions in flight -- chains are
+    //  destroyed by a background thread, a step can start before the previous one has returned its buffers)
+    if (free_list.size() < 256) { free_list.emplace_back(p, cap); return; }
 #if defined(TMF_HOSTSIM)
     std::free(p);
 #else

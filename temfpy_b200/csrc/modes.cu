@@ -241,7 +241,7 @@ extern "C" int64_t tmf_slater_modes_workspace(int L, int njobs, const int *job_x
   for (int j = 0; j < njobs; ++j) {
     int n, m;
     job_geometry(L, job_x[j], job_side[j], n, m);
-    if (n > SMALL_N) {
+    if (n > std::min(small_n(true), small_n(false))) {   // (upper bound of both forms)
       int rr = std::min(r_sketch, std::min(n, m));
       bytes += align256(big_job_doubles(n, m, rr) * 8);
       ++nbig;
@@ -286,7 +286,7 @@ static int modes_impl(const double *C_dev, int L, int ldc, int njobs,
     if (x < 0 || x > L) { set_error("bond position out of range"); return TMF_ERR_VALUE; }
     job_geometry(L, x, side, n, m);
     const double *A = (side == TMF_SIDE_L) ? C_dev : C_dev + (int64_t)x * ldc + x;
-    if (n <= SMALL_N) {
+    if (n <= small_n(nested)) {
       SmallJob s;
       s.A = A; s.V = V_dev + v_off[j]; s.e_out = e_dev + (int64_t)j * TMF_MAX_MODES;
       s.info = info_dev + 4 * j; s.n = n; s.lda = ldc; s.side = side; s.pad_ = 0;
@@ -620,7 +620,7 @@ extern "C" int64_t tmf_slater_modes_slot_cols(int L, int x, int side, int r_sket
   int n, m;
   tmf::job_geometry(L, x, side, n, m);
   if (!nested) return n;
-  if (n <= tmf::small_n()) return n + 1;
+  if (n <= tmf::small_n(true)) return n + 1;
   return std::min(r_sketch, std::min(n, m)) + 1;
 }
 

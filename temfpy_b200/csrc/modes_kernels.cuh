@@ -12,16 +12,17 @@ namespace tmf {
 constexpr int PANEL_W = 16;        // panel width of the block Gram-Schmidt
 constexpr int JAC_MAX_SWEEPS = 40;
 constexpr int SMALL_N_MAX = 64;    // largest block the direct solver's shared-memory layout is sized for
-// blocks up to this size are diagonalised directly (TMF_SMALL_N overrides, for experiments)
-inline int small_n() {
-  static const int v = [] {
+// Blocks up to this size are diagonalised directly (one CTA, Jacobi: ~2 ms for n = 64, 0.5 ms for n = 32), larger
+// ones go through the sketch path.  The nested chain driver only needs the entangled modes and uses 32; the
+// legacy form (explicit filled bases; iMPS / Pfaffian drivers) keeps 64.  TMF_SMALL_N overrides both.
+inline int small_n(bool nested) {
+  static const int env = [] {
     const char *e = std::getenv("TMF_SMALL_N");
-    int x = e ? std::atoi(e) : 64;
-    return x < 1 ? 1 : (x > SMALL_N_MAX ? SMALL_N_MAX : x);
+    const int x = e ? std::atoi(e) : 0;
+    return x < 0 ? 0 : (x > SMALL_N_MAX ? SMALL_N_MAX : x);
   }();
-  return v;
+  return env > 0 ? env : (nested ? 32 : 64);
 }
-#define SMALL_N (small_n())
 constexpr int JAC_SMEM_J_MAX = 96; // above this the Jacobi rotation matrix lives in global memory
 constexpr int PIVCHOL_MAX_PARTS = 8;
 constexpr int R_SKETCH_MAX = 160;  // G (r x r) must fit in shared memory
