@@ -96,22 +96,70 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the reference's algorithm (oracle port) on a bounded sample of the same workload
+# CPU arm: the reference's algorithm on a bounded sample of the same workload, all host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_sample(L, tp, n_sites=16):
-    """Times the reference algorithm for `n_sites` evenly spaced sites of the L-site chain: for each
-    sampled site the marginal work of one iteration of the loops slater.py:1301-1346 (one new bond:
-    eigh + enumeration; tensor data: overlap + Schur; all charge blocks: batched det)."""
-    import slater_oracle as so
+def workload_name(L, chi, svd_min):
+    return (f"1D tight-binding chain L={L}, half filling, chi_max={chi}, svd_min={svd_min:g} "
+            "(BASELINE configs[4]); finite MPS: all site tensors + Schmidt data")
+
+
+_CPU = {}
+
+
+def _cpu_init(L, tp, use_ref):
+    """Worker start-up: one BLAS thread per process (the parallelism is over sites), the correlation matrix,
+    and the implementation: the live reference through oracle/ref_shim.py where /root/reference exists
+    (kind "reference"), else the oracle restatement of the same functions (kind "port")."""
+    try:
+        from threadpoolctl import threadpool_limits
+        _CPU["limit"] = threadpool_limits(1)
+    except Exception:
+        pass
     C, _ = ground_state_C(L)
-    trunc = so.Trunc.make(tp)
+    _CPU.update(C=C, L=L, tp=tp, ref=None)
+    if use_ref:
+        import ref_shim
+        _CPU["ref"] = ref_shim.load("pass")
+    else:
+        import slater_oracle as so
+        _CPU["so"] = so
+        _CPU["trunc"] = so.Trunc.make(tp)
+
+
+def _cpu_site(i):
+    """One iteration of the reference's site loops (slater.py:1301-1310 / :1326-1335): the new bond
+    (eigh + enumeration), the tensor data (overlap + Schur) and every charge block (batched det)."""
+    C, L, tp = _CPU["C"], _CPU["L"], _CPU["tp"]
     oc = L // 2
-    stride = max(1, L // n_sites)
-    sites = list(range(stride // 2, L, stride))[:n_sites]
-    t_total = 0.0
-    for i in sites:
-        if i >= oc:
-            prev = so.bond_vectors_from_C(C, i, trunc, "LR" if i == oc else "R")      # not timed (carried over)
+    right = i >= oc
+    t0 = time.perf_counter()
+    if _CPU["ref"] is not None:
+        sl = _CPU["ref"].slater
+        SV = sl.SchmidtVectors.from_correlation_matrix
+        if right:
+            prev = SV(C, i, tp, which="LR" if i == oc else "R")
+            t0 = time.perf_counter()
+            new = SV(C, i + 1, tp, which="R")
+            td = sl.MPSTensorData.from_schmidt_vectors(new, prev, "right")
+        else:
+            prev = SV(C, i + 1, tp, which="LR" if i + 1 == oc else "L")
+            t0 = time.perf_counter()
+            new = SV(C, i, tp, which="L")
+            td = sl.MPSTensorData.from_schmidt_vectors(new, prev, "left")
+        # the block loop of to_npc_array (slater.py:1132-1141); TeNPy's packing itself is not installed
+        chi_b = len(td.new_sets_bra) // 2
+        q_alpha = np.zeros(chi_b, dtype=np.int64)
+        for q, slc in td.idx_bra.items():
+            q_alpha[slc] = q
+        q_rows = np.sort(np.concatenate([q_alpha, q_alpha + (1 if td.mode == "left" else -1)]), kind="stable")
+        for q_ket, slc in td.idx_ket.items():
+            rows = np.flatnonzero(q_rows == q_ket)
+            if rows.size:
+                td.det_always * sl._tensor_block(td.sometimes_matrix, td.new_sets_bra[rows], td.new_sets_ket[slc])
+    else:
+        so, trunc = _CPU["so"], _CPU["trunc"]
+        if right:
+            prev = so.bond_vectors_from_C(C, i, trunc, "LR" if i == oc else "R")
             t0 = time.perf_counter()
             new = so.bond_vectors_from_C(C, i + 1, trunc, "R")
             so.dense_tensor(so.tensor_data(new, prev, "right"))
@@ -120,8 +168,46 @@ def cpu_sample(L, tp, n_sites=16):
             t0 = time.perf_counter()
             new = so.bond_vectors_from_C(C, i, trunc, "L")
             so.dense_tensor(so.tensor_data(new, prev, "left"))
-        t_total += time.perf_counter() - t0
-    return len(sites) / t_total, len(sites), t_total
+    return time.perf_counter() - t0
+
+
+class CpuArm:
+    """Pool of worker processes (one per host core) converting sampled sites of the chain with the
+    reference's algorithm.  The previous bond of a sampled site is carried over in the reference's loop, so it
+    is computed but not timed; everything else of the iteration is."""
+
+    def __init__(self, L, tp, procs=None):
+        import multiprocessing as mp
+        import ref_shim
+        self.use_ref = ref_shim.available()
+        self.kind = "reference" if self.use_ref else "port"
+        self.L = L
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except AttributeError:
+            ncpu = os.cpu_count() or 1
+        self.procs = procs or ncpu
+        self.pool = mp.get_context("fork").Pool(self.procs, initializer=_cpu_init, initargs=(L, tp, self.use_ref))
+
+    def sample(self, n_sites):
+        """Converts n_sites evenly spaced sites; returns (sites / s by wall clock, n, wall s, summed core s)."""
+        stride = max(1, self.L // n_sites)
+        sites = list(range(stride // 2, self.L, stride))[:n_sites]
+        t0 = time.perf_counter()
+        core = sum(self.pool.map(_cpu_site, sites, chunksize=1))
+        wall = time.perf_counter() - t0
+        return len(sites) / wall, len(sites), wall, core
+
+    def describe(self, ns, wall, core):
+        impl = ("the reference's own functions (slater.SchmidtVectors / MPSTensorData / _tensor_block, imported "
+                "through oracle/ref_shim.py)" if self.use_ref else
+                "oracle restatement of slater.SchmidtVectors / MPSTensorData / _tensor_block (oracle/slater_oracle.py)")
+        return (f"{ns} evenly spaced sites of the L={self.L} chain per step, one loop iteration of slater.py:1301-1346 "
+                f"each (eigh + enumeration + overlap/Schur + batched det); {impl}; {self.procs} worker processes "
+                f"(one BLAS thread each), {wall:.1f} s wall / {core:.1f} core-s; TeNPy packing excluded")
+
+    def close(self):
+        self.pool.terminate()
 
 
 def run_reference(args):
@@ -129,25 +215,23 @@ def run_reference(args):
     if rank != 0:
         return
     tp = {"chi_max": args.chi, "svd_min": args.svd_min}
-    cores = os.cpu_count()
+    arm = CpuArm(args.L, tp)
     for _ in range(max(args.warmup, 0)):
-        cpu_sample(args.L, tp, n_sites=2)
-    vals = []
+        arm.sample(min(arm.procs, args.cpu_sites))
+    vals, walls, cores = [], [], []
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        v, ns, tt = cpu_sample(args.L, tp, n_sites=args.cpu_sites)
-        vals.append(v)
-    wall = time.perf_counter() - t0
+        v, ns, wall, core = arm.sample(args.cpu_sites)
+        vals.append(v); walls.append(wall); cores.append(core)
+    total = time.perf_counter() - t0
+    arm.close()
     value = float(np.mean(vals))
-    sample = (f"{args.cpu_sites} evenly spaced sites of the L={args.L} chain per step (one loop iteration of "
-              "slater.py:1301-1346 each), oracle port of the reference (TeNPy packing excluded), NumPy/OpenBLAS")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"1D tight-binding chain L={args.L}, half filling, chi_max={args.chi}, "
-                                   f"svd_min={args.svd_min:g} (BASELINE configs[4]); finite MPS; host arrays in, "
-                                   "host arrays out (reference's NumPy path)"},
-            "cpu_baseline": {"value": value, "unit": "sites/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": workload_name(args.L, args.chi, args.svd_min)},
+            "cpu_baseline": {"value": value, "unit": "sites/s", "cores": arm.procs, "kind": arm.kind,
+                             "sample": arm.describe(args.cpu_sites, float(np.mean(walls)), float(np.mean(cores)))},
             "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -217,6 +301,7 @@ def run_native(args):
             state["flops"] = [float(x) for x in res.flops()]
             state["out_elems"] = res.out_elems
             state["max_chi"] = max(c.max_chi for c in res.chains)
+            state["path"] = dict(res.chains[0].path, **res.options)
         be.sync()
         res.close()
 
@@ -315,94 +400,123 @@ def run_native(args):
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / n_e2e
         e2e = {"value": L / dt, "unit": "sites/s", "h2d_bytes_per_step": be.h2d_bytes // n_e2e,
-               "d2h_bytes_per_step": be.d2h_bytes // n_e2e, "ms_per_step": dt * 1e3}
+               "d2h_bytes_per_step": be.d2h_bytes // n_e2e, "ms_per_step": dt * 1e3,
+               "api": "temfpy_b200.slater.C_to_MPS"}
     else:
-        # every rank converts its shard from host C and brings its tensors back to its host
+        # the same quantity as at N = 1: host C on rank 0 -> dist.C_to_MPS (broadcast, sharded conversion, gather over
+        # NVLink onto rank 0, pinned device -> host copy there) -> complete BlockMPS in rank 0's host memory
         import torch.distributed as dist
-        res = engine.run_chain(be, be.from_host(C_host.ravel()), L, L, tp, N, site_lo=lo, site_hi=hi,
-                               r_sketch=args.r_sketch, n_threads=args.threads)      # warm-up (pinned allocations)
-        del res
+        C_arg = C_host if rank == 0 else None
+        mps = tdist.C_to_MPS(C_arg, tp_dict, backend=be, n_threads=args.threads)      # warm-up (pinned allocations)
+        del mps
         be.h2d_bytes = be.d2h_bytes = 0
         n_e2e = max(1, min(args.steps, 3))
         barrier()
         t0 = time.perf_counter()
         for _ in range(n_e2e):
-            Cd = be.from_host(C_host.ravel())
-            res = engine.run_chain(be, Cd, L, L, tp, N, site_lo=lo, site_hi=hi, r_sketch=args.r_sketch,
-                                   n_threads=args.threads)
-            del res
+            mps = tdist.C_to_MPS(C_arg, tp_dict, backend=be, n_threads=args.threads)
+            del mps
         barrier()
         dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=be.device)
-        be.h2d_bytes //= n_e2e
-        be.d2h_bytes //= n_e2e
-        by = torch.tensor([be.h2d_bytes, be.d2h_bytes], dtype=torch.float64, device=be.device)
+        by = torch.tensor([be.h2d_bytes // n_e2e, be.d2h_bytes // n_e2e], dtype=torch.float64, device=be.device)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dist.all_reduce(by)
         e2e = {"value": L / float(dt.item()), "unit": "sites/s", "h2d_bytes_per_step": int(by[0].item()),
-               "d2h_bytes_per_step": int(by[1].item()), "ms_per_step": float(dt.item()) * 1e3}
+               "d2h_bytes_per_step": int(by[1].item()), "ms_per_step": float(dt.item()) * 1e3,
+               "api": "temfpy_b200.dist.C_to_MPS (result assembled on rank 0's host)"}
 
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    # ---- roofline of the dominant kernel, stage by stage ---------------------------------------------
+    # `achieved` counts the flops of the *reference's* algorithm for the stage a kernel implements (SURVEY 8d:
+    # eigh (10/3) n^3 per block, overlap 2 (n+1) c_b c_k, Schur (8/3) k^3, minors sum nsb nsk (2/3) q^3); each
+    # kernel group is charged only its own stage.  Bound: the FP64 pipe for every stage (DFMA and DMMA peak
+    # coincide on B200; HBM traffic of the step is ~3 GB = 0.5 ms at the measured 6.5 TB/s).
     fl = [float(x) for x in flops.tolist()]
     alg = {"eigh": fl[0], "overlap": fl[1], "schur": fl[2], "minors": fl[3]}
-    # algorithmic flops attributed to each kernel family (reference's algorithm)
-    family_flops = {"minors": alg["minors"], "schur": alg["schur"],
-                    "gemm": alg["overlap"], "modes": alg["eigh"]}
-    modes_tags = ("small_modes", "omega", "colnorm", "panel_mgs2", "svd_select", "ritz", "pivchol")
+    groups = {"modes": ("eigh", ("omega", "sketch_scan", "colnorm", "panel_cholqr", "panel_mgs2", "gemm_modes",
+                                 "svd_select", "ritz", "pivchol", "edge_vector", "small_modes")),
+              "site": ("overlap+schur", ("gemm_site", "schur", "nested_site", "gemm")),
+              "enumerate+plan": (None, ("enumerate", "site_plan")),
+              "minors": ("minors", ("minors",))}
+    stages = {}
+    for name, (what, tags) in groups.items():
+        tms = sum(prof[t][0] for t in tags if t in prof)
+        a_fl = 0.0 if what is None else sum(alg[w] for w in what.split("+"))
+        stages[name] = {"kernel_ms": round(tms, 4), "reference_flops": a_fl,
+                        "frac_of_fp64_peak": (a_fl / world / (tms * 1e-3) / 1e12 / peak) if tms > 0 and a_fl > 0 else None}
     dom = max(prof, key=lambda k: prof[k][0]) if prof else None
+    ncu = {}
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except (OSError, ValueError):
+        pass
     roof = None
     if dom:
         dms, dcnt = prof[dom]
-        if dom == "minors":
-            a_fl = alg["minors"]
-        elif dom == "schur":
-            a_fl = alg["schur"]
-        elif dom == "gemm_site":
-            a_fl = alg["overlap"]
-        else:                     # any kernel of the mode extraction: the reference's eigh flops
-            a_fl = alg["eigh"]
+        stage = next((n for n, (_, tags) in groups.items() if dom in tags), None)
+        # the dominant kernel's share of its stage's reference flops = its share of the stage's kernel time
+        a_fl = stages[stage]["reference_flops"] * (dms / stages[stage]["kernel_ms"]) if stage and stages[stage]["kernel_ms"] else 0.0
         achieved = a_fl / world / (dms * 1e-3) / 1e12
-        traffic = None          # DRAM bytes per launch of this kernel from the committed ncu full-set capture
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
-            if tj and tj["launches_per_step"] == dcnt and tj["n_gpus"] == world and L == 1024 and args.chi == 1024:
-                traffic = tj["dram_bytes_per_launch"]
-        except (OSError, ValueError, KeyError):
-            pass
-        roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": traffic, "launches_per_step": dcnt, "ms_per_step": dms,
-                "algorithmic_flops_per_step": a_fl,
-                "note": "FP64 pipe roofline (vector DFMA and tensor DMMA peak coincide on B200); achieved counts the "
-                        "reference algorithm's flops for this stage (SURVEY 8d), the kernel itself needs far fewer",
+        tj = ncu.get(dom) or {}
+        same = (tj.get("launches_per_step") == dcnt and tj.get("n_gpus") == world and L == 1024 and args.chi == 1024)
+        roof = {"bound": "fp64", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": tj.get("dram_bytes_per_launch") if same else None,
+                "launches_per_step": dcnt, "ms_per_step": dms, "algorithmic_flops_per_step": a_fl,
+                "fp64_pipe_pct_ncu": tj.get("fp64_pipe_pct"), "issue_slot_pct_ncu": tj.get("issue_slot_pct"),
+                "note": "FP64 pipe roofline (no tensor instructions in this kernel; vector DFMA and tensor DMMA peak "
+                        "coincide on B200).  `achieved` counts the reference algorithm's flops for the stage (SURVEY 8d); "
+                        "the kernel itself executes far fewer (shared row reduction: ~67x fewer for the minors), so the "
+                        "ncu pipe utilisation (fp64_pipe_pct_ncu) is the measure of how busy the pipe really is",
                 "peak_source": f"measured in this run: FP64 DFMA probe {dfma_tflops:.1f} TF/s, cuBLAS DGEMM 4096^3 "
                                f"{dgemm_tflops:.1f} TF/s (MEASURED_PEAKS.json has no FP64 figure)"}
     total_alg = sum(alg.values())
     whole = {"algorithmic_flops_per_step": total_alg, "achieved_tflops": total_alg / (ms_total / args.steps * 1e-3) / 1e12,
              "frac_of_fp64_peak": total_alg / (ms_total / args.steps * 1e-3) / 1e12 / (peak * world),
+             "stages": stages,
              "kernel_ms_per_step": {k: round(v[0], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
-             "host_ms_per_step": host_ms, "minors_per_step": fl[4], "out_bytes_per_step": 8 * state["out_elems"], "max_chi": state["max_chi"]}
+             "host_ms_per_step": host_ms, "minors_per_step": fl[4], "out_bytes_per_step": 8 * state["out_elems"],
+             "max_chi": state["max_chi"], "path": state.get("path")}
+
+    # ---- parity of this very configuration against the reference-run fixture (tests/golden) ----------
+    parity = None
+    if world == 1 and L == 1024 and args.chi == 1024 and abs(args.svd_min - 1e-7) < 1e-20:
+        try:
+            from tests import helpers
+            g = helpers.golden("bonds_cfg5_chain_L1024")
+            res = engine.run_chain(be, C_dev, L, L, tp, N, fetch_tensors=False)
+            rep = helpers.compare_bonds_fixture(g, lambda x: res.bonds[x], max_contested=256, rerun_limit=0)
+            parity = {"fixture": "tests/golden/bonds_cfg5_chain_L1024.npz (reference run, oracle/make_golden_full.py)",
+                      "bonds": rep["bonds"], "bonds_exact": rep["exact"], "bonds_noise_decided": rep["noise_decided"],
+                      "bonds_chi_equal": rep["chi_equal"], "max_abs_dchi": rep["max_dchi"],
+                      "schmidt_rel_max_wellcond": rep["lam_rel"], "entropy_abs_max": rep["entropy"],
+                      "eigenvalue_abs_max": rep["e_abs"],
+                      "schmidt_tolerance": "|dlam| <= 1e-12 lam + min(noise / (2 lam), 1e-8), noise = 4e-15 sqrt(L) "
+                                           "(mode eigenvalues carry ~1e-15 absolute rounding noise in LAPACK as here; "
+                                           "1e-12 relative holds for lam > 0.05 lam_max, SURVEY 7.3)"}
+        except Exception as err:       # the fixture is test infrastructure; the bench line does not depend on it
+            parity = {"error": repr(err)}
 
     cpu = None
     if world == 1 and not args.no_cpu:
-        v, ns, tt = cpu_sample(L, tp_dict, n_sites=args.cpu_sites)
-        cpu = {"value": v, "unit": "sites/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"{ns} evenly spaced sites of the L={L} chain ({tt:.1f} s): one loop iteration of "
-                         "slater.py:1301-1346 each (eigh + enumeration + overlap/Schur + batched det), oracle port, "
-                         "NumPy/OpenBLAS threads = all cores"}
+        arm = CpuArm(L, tp_dict)
+        arm.sample(arm.procs)
+        v, ns, wall, core = arm.sample(args.cpu_sites)
+        arm.close()
+        cpu = {"value": v, "unit": "sites/s", "cores": arm.procs, "kind": arm.kind, "sample": arm.describe(ns, wall, core)}
     line = {"metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"1D tight-binding chain L={L}, half filling, chi_max={args.chi}, "
-                                   f"svd_min={args.svd_min:g} (BASELINE configs[4]); finite MPS; C resident in HBM -> "
-                                   "all site tensors + Schmidt data resident in HBM",
+            "config": {"workload": workload_name(L, args.chi, args.svd_min),
+                       "residency": "value: C resident in HBM -> all site tensors + Schmidt data resident in HBM; "
+                                    "e2e: host C -> complete MPS in host memory",
                        "l2": f"working set {(8 * state['out_elems'] + 6e8) / 1e9:.1f} GB per step >> 126 MB L2",
                        "parallelism": (f"sites sharded over {world} GPU(s), broadcast(C) + gather(tensors) over NCCL"
                                        if world > 1 else "1 GPU") + f"; {args.chunks or 'auto (6 at >= 512 sites per GPU)'} pipeline chunks per GPU"},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roof,
-            "whole_step": whole, "cpu_baseline": cpu}
+            "whole_step": whole, "parity": parity, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -420,7 +534,7 @@ def main():
     ap.add_argument("--r-sketch", type=int, default=48)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--chunks", type=int, default=0, help="pipeline chunks per GPU (streams + host threads)")
-    ap.add_argument("--cpu-sites", type=int, default=16)
+    ap.add_argument("--cpu-sites", type=int, default=128, help="sampled sites per step of the CPU arm")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

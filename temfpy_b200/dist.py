@@ -190,3 +190,128 @@ class StreamingGather:
         out = dict(self.result)
         out[self.dst] = own
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+# public multi-GPU entry point
+# ---------------------------------------------------------------------------------------------
+def _t(buf):
+    """torch view of a backend buffer (CUDA tensor of the PyTorch backend, NumPy array of the simulator)."""
+    import torch
+    return buf if torch.is_tensor(buf) else torch.from_numpy(buf)
+
+
+def C_to_MPS(C, trunc_par, *, ortho_center=None, spinful=None, unit_cell_width=None, dst=0, backend=None,
+             n_threads=0):
+    """``slater.C_to_MPS`` over all GPUs of the process group (reference slater.py:1216-1353, one process per
+    GPU, ``torch.distributed`` initialised by the caller).  Every rank calls it; ``C`` is read on rank ``dst``
+    only (the others may pass ``None``).  The correlation matrix is broadcast, every rank converts a contiguous,
+    cost-balanced range of sites (no data-path exchange: a bond is a function of C alone), the block-sparse
+    tensors are gathered on ``dst`` over NCCL / NVLink and the Schmidt tables with them.  Returns the complete
+    ``BlockMPS`` on ``dst`` and ``None`` elsewhere.
+
+    Sketch-width / fallback decisions (``engine.run_chain``) are taken for all ranks together, so that the
+    boundary bond two ranks share comes out of identical kernels on both."""
+    import torch
+    import torch.distributed as dist
+    from . import engine, slater
+    from .schmidt_utils import to_stopping_condition
+    world, rank = dist.get_world_size(), dist.get_rank()
+    be = backend or slater._be()
+    tp = to_stopping_condition(trunc_par)
+    meta = [None]
+    if rank == dst:
+        Cp = slater._prepare_C(np.asarray(C), spinful)
+        L = len(Cp)
+        if unit_cell_width is None:
+            unit_cell_width = L
+        elif L % unit_cell_width != 0:
+            raise ValueError(f"{unit_cell_width = } does not divide system size {L}")
+        meta = [(L, int(np.round(np.trace(Cp))), unit_cell_width)]
+    dist.broadcast_object_list(meta, src=dst)
+    L, n_fermion, unit_cell_width = meta[0]
+    C_dev = be.from_host(Cp.ravel()) if rank == dst else be.empty(L * L, np.float64)
+    broadcast_C(_t(C_dev), src=dst)
+    if rank == dst:
+        slater._check_projector(Cp, be=be, Cd=C_dev)
+    lo, hi = partition(L, world, tp.chi_max, ortho_center)[rank]
+    opts = dict(r_sketch=48, snap=False, nested=None, device_plan=None)
+    codes = {"sketch": 1, "singular": 2, "nested": 3}
+    dev = _t(C_dev).device
+    while True:
+        res, code, err = None, 0, None
+        try:
+            res = engine._run_chain_once(be, C_dev, L, L, tp, n_fermion, ortho_center, lo, hi, n_threads, True, None,
+                                         True, opts)
+        except engine._Retry as rt:
+            code, err = codes[rt.kind], rt.err
+        flag = torch.tensor([code], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        worst = int(flag.item())
+        if worst == 0:
+            break
+        if res is not None:
+            res.close()
+        if worst == 1:
+            wider = [r for r in engine.SKETCH_WIDTHS if r > opts["r_sketch"]]
+            if not wider:
+                raise err or ValueError("range sketch too narrow on another rank")
+            opts["r_sketch"] = wider[0]
+        elif worst == 2 and not opts["snap"]:
+            opts["snap"] = True
+        elif opts["nested"] is False:
+            raise err or ValueError("site stage failed on another rank")
+        else:
+            opts["nested"] = False
+    # ---- tensors -> dst (device, NVLink), Schmidt / plan tables with them ---------------------------
+    parts = [(_t(b), n) for b, n in res.out_buffers()]
+    full, offs = gather_tensors(parts, dst=dst)
+    states = [ShardState(engine.ShardTables(c, None, want_sites=True).state(), c.out_elems, c.site_lo, c.site_hi,
+                         (c.nblocks, c.max_chi, c.njobs)) for c in res.chains]
+    gathered = [None] * world if rank == dst else None
+    dist.gather_object(states, gathered, dst=dst)
+    res.close()
+    if rank != dst:
+        return None
+    if hasattr(be, "to_host_async") and full.is_cuda:
+        pinned = be.to_host_async(full)
+        be.sync()
+        host = pinned.numpy()
+    else:
+        pinned, host = None, full.numpy()
+    out = engine.ChainResult(L=L, ortho_center=ortho_center or L // 2, site_lo=0, site_hi=L)
+    out._pinned = pinned
+    o = 0
+    nblocks = max_chi = njobs = 0
+    for r in range(world):
+        assert o == int(offs[r])
+        for st in gathered[r]:
+            tab = engine.ShardTables.from_state(st.state, host[o: o + st.out_elems])
+            tab.normalized()
+            o += st.out_elems
+            out.tables.append(tab)
+            out.bonds.add([x for x in range(tab.first_bond, tab.first_bond + tab.n_bonds)
+                           if st.site_lo <= x <= st.site_hi or x == out.ortho_center], tab.bond)
+            out.sites.add(range(st.site_lo, st.site_hi), tab.site)
+            nblocks += st.stats[0]; max_chi = max(max_chi, st.stats[1]); njobs += st.stats[2]
+    out.stats = dict(out_elems=o, nblocks=nblocks, max_chi=max_chi, njobs=njobs, n_ranks=world)
+    out.options = dict(opts)
+    return slater._chain_to_mps(out, unit_cell_width)
+
+
+class ShardState:
+    """What a rank sends to ``dst`` for each of its pipeline chunks (picklable)."""
+
+    def __init__(self, state, out_elems, site_lo, site_hi, stats):
+        self.state, self.out_elems, self.site_lo, self.site_hi, self.stats = state, out_elems, site_lo, site_hi, stats
+
+
+def H_to_MPS(H, trunc_par, **kw):
+    """``slater.H_to_MPS`` over all GPUs of the process group (reference slater.py:1568-1627): the one-off
+    ``eigh(H)`` + ``C = Phi Phi^T`` run on rank ``dst``, the conversion on all ranks (see ``C_to_MPS``)."""
+    import torch.distributed as dist
+    from . import slater
+    C = None
+    if dist.get_rank() == kw.get("dst", 0):
+        C, _ = slater.correlation_matrix(H, _backend=kw.get("backend"))
+    return C_to_MPS(C, trunc_par, **kw)

@@ -201,7 +201,29 @@ class ShardTables:
     """Host-side results of one shard in bulk arrays (``tmf_chain_bonds_export`` / ``_sites_export``);
     the per-bond and per-site objects are views into them."""
 
-    def __init__(self, chain, out_host):
+    _STATE = ("first_bond", "n_bonds", "chi_off", "head", "lam", "charge", "masks", "sec_off", "sec_q", "sec_start",
+              "e", "site_lo", "blk_off", "blocks", "block_off", "row_off")
+
+    def state(self) -> dict:
+        """Picklable form (NumPy arrays + the plan headers as bytes) for the gather of a multi-GPU conversion."""
+        st = {k: getattr(self, k) for k in self._STATE if hasattr(self, k)}
+        if hasattr(self, "plans"):
+            st["plans"] = bytes(self.plans)
+        return st
+
+    @classmethod
+    def from_state(cls, st: dict, out_host):
+        self = cls.__new__(cls)
+        for k, v in st.items():
+            if k != "plans":
+                setattr(self, k, v)
+        if "plans" in st:
+            n = len(st["plans"]) // C.sizeof(SitePlan)
+            self.plans = (SitePlan * max(n, 1)).from_buffer_copy(st["plans"])
+        self.out_host = out_host
+        return self
+
+    def __init__(self, chain, out_host, want_sites=None):
         lib, h = chain.lib, chain.handle
         q = (C.c_int64 * 4)()
         check(lib, lib.tmf_chain_bonds_sizes(h, q))
@@ -223,7 +245,7 @@ class ShardTables:
         self.charge = self.charge.astype(np.int64)
         self.out_host = out_host
         self.site_lo = chain.site_lo
-        if out_host is not None:
+        if out_host is not None or want_sites:
             check(lib, lib.tmf_chain_sites_sizes(h, q))
             ns, nblk, nrows = int(q[0]), int(q[1]), int(q[2])
             self.plans = (SitePlan * max(ns, 1))()

@@ -64,3 +64,42 @@ def test_two_rank_gloo_sharding(tmp_path, L, chi):
     mp.spawn(_worker, args=(2, _free_port(), L, chi, out), nprocs=2, join=True)
     ok, gathered, ref = np.load(out)
     assert ok == 1 and gathered == ref > 0
+
+
+def _worker_public(rank, world, port, L, chi, out_path):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import slater_oracle as so
+        from temfpy_b200 import dist as tdist, slater
+        from tests import helpers
+        from tests.hostsim import NumpyBackend
+        be = NumpyBackend()
+        Cm = None
+        if rank == 0:
+            Cm, _ = so.correlation_matrix(helpers.random_hamiltonian(L, 5))
+        mps = tdist.C_to_MPS(Cm, {"chi_max": chi}, backend=be)          # public multi-rank entry point
+        if rank == 0:
+            ref = slater.C_to_MPS(Cm, {"chi_max": chi}, as_tenpy=False, _backend=be)
+            ok = mps is not None and mps.L == ref.L and mps.form == ref.form
+            for x in range(L + 1):
+                ok = ok and np.array_equal(mps.lams[x], ref.lams[x]) and np.array_equal(mps.charges[x], ref.charges[x])
+            for i in range(L):
+                ok = ok and np.array_equal(mps.tensors[i].dense(), ref.tensors[i].dense())
+            np.save(out_path, np.array([int(ok)]))
+        else:
+            assert mps is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_public_C_to_MPS(tmp_path):
+    """dist.C_to_MPS (broadcast of C, sharded conversion, gather of tensors + tables, assembly on rank 0)
+    returns the same BlockMPS, bit for bit, as the single-process slater.C_to_MPS."""
+    out = str(tmp_path / "ok.npy")
+    mp.spawn(_worker_public, args=(2, _free_port(), 26, 16, out), nprocs=2, join=True)
+    assert np.load(out)[0] == 1
