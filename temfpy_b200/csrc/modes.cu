@@ -519,7 +519,8 @@ static int modes_impl(const double *C_dev, int L, int ldc, int njobs,
   // ---- launches ----------------------------------------------------------------------------
   // The direct solver of the small blocks (<= 65 latency-bound CTAs) runs on a forked stream next to
   // the sketch path of the large blocks and is joined at the end.
-  static const int small_threads = std::getenv("TMF_SMALL_THREADS") ? std::atoi(std::getenv("TMF_SMALL_THREADS")) : 1024;
+  // (8 lanes per Jacobi column pair for n <= 64: 32 pairs = 256 threads)
+  static const int small_threads = std::getenv("TMF_SMALL_THREADS") ? std::atoi(std::getenv("TMF_SMALL_THREADS")) : 256;
   ForkedStream fork;
   if (!small.empty()) {
     void *sstream = (nb > 0) ? fork.open(stream) : stream;
@@ -579,7 +580,9 @@ static int modes_impl(const double *C_dev, int L, int ldc, int njobs,
   static const double sketch_floor = std::getenv("TMF_SKETCH_FLOOR") ? std::atof(std::getenv("TMF_SKETCH_FLOOR")) : 1e-26;
   // one warp per column pair of a Jacobi round (latency-bound: more warps per CTA, not more CTAs)
   static const int jac_env = std::getenv("TMF_JAC_THREADS") ? std::atoi(std::getenv("TMF_JAC_THREADS")) : 0;
-  const int jac_threads = jac_env > 0 ? jac_env : std::min(1024, 32 * std::max(4, (r_sketch + 1) / 2));
+  // one group of GW lanes per column pair of a Jacobi round (jacobi_onesided: GW = 8 / 16 / 32 by matrix size)
+  const int jac_gw = (r_sketch <= 64) ? 8 : (r_sketch <= 128 ? 16 : 32);
+  const int jac_threads = jac_env > 0 ? jac_env : std::min(1024, std::max(128, (jac_gw * ((r_sketch + 1) / 2) + 31) & ~31));
   rc = launch_t("svd_select", svd_select_kernel, nb, jac_threads, svd_smem, stream, sj_dev, thr, sketch_floor);
   if (rc) return rc;
   if ((rc = run(L_u0[0]))) return rc;

@@ -437,27 +437,34 @@ TMF_DEVICE int jacobi_onesided(double *G, int ldg, double *J, int ldj, int n, do
     CTA_SYNC();
     for (int round = 0; round < np - 1; ++round) {
 #if !defined(TMF_HOSTSIM)
-      // CUDA path: one warp per column pair.  Pairs of a round touch disjoint columns, so the dot
-      // products (shuffle reductions), the rotation and the column updates of a pair need no CTA
-      // barrier; one __syncthreads per round separates the pairings.
+      // CUDA path: one group of GW lanes per column pair (GW = 8 for n <= 64: four pairs share a warp).  The
+      // rotation scalars are computed redundantly by every lane, ~45 FP64 instructions per warp and round
+      // whatever the number of pairs in the warp, and with 6 warps per scheduler the Jacobi kernels are bound
+      // by the FP64 issue rate of the SM -- four pairs per warp cost a quarter of it per pair.  Pairs of a
+      // round touch disjoint columns, so the dot products (shuffle reductions inside the group), the rotation
+      // and the column updates of a pair need no CTA barrier; one __syncthreads per round separates the pairings.
       {
+        const int GW = (n <= 64) ? 8 : (n <= 128 ? 16 : 32);
+        const int gpw = 32 / GW;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-        for (int pr = warp; pr < half; pr += nwarp) {
+        const int sub = lane / GW, gl = lane - sub * GW;
+        for (int base = warp * gpw; base < half; base += nwarp * gpw) {
+          const int pr = base + sub;
           int p = round + pr, q = round + np - 1 - pr;      // circle method without integer division
           if (p >= np - 1) p -= np - 1;
           if (q >= np - 1) q -= np - 1;
           if (pr == 0) p = np - 1;
-          if (p >= n || q >= n) continue;
-          double *gp = G + (int64_t)p * ldg, *gq = G + (int64_t)q * ldg;
+          const bool active = pr < half && p < n && q < n;   // (bye of an odd n, tail of the last warp)
+          double *gp = G + (int64_t)(active ? p : 0) * ldg, *gq = G + (int64_t)(active ? q : 0) * ldg;
           double a = 0.0, b = 0.0, c = 0.0;
-          for (int r = lane; r < n; r += 32) {
-            const double x = gp[r], y = gq[r];
-            a += x * x;
-            b += y * y;
-            c += x * y;
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
+          if (active)
+            for (int r = gl; r < n; r += GW) {
+              const double x = gp[r], y = gq[r];
+              a += x * x;
+              b += y * y;
+              c += x * y;
+            }
+          for (int o = GW >> 1; o > 0; o >>= 1) {             // uniform for the whole warp
             a += __shfl_xor_sync(0xffffffffu, a, o);
             b += __shfl_xor_sync(0xffffffffu, b, o);
             c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -465,12 +472,11 @@ TMF_DEVICE int jacobi_onesided(double *G, int ldg, double *J, int ldj, int n, do
           // a column with norm < 1e-15 (all our matrices have norm O(1)) is numerically null: rounding
           // noise of the rotations with the other columns keeps changing it by O(1) of its own size, so
           // pairs involving it would never meet the relative criterion -- skip them (as LAPACK's dgesvj)
-          if (c * c > 1e-30 * a * b && a > 1e-30 && b > 1e-30) {
+          if (active && c * c > 1e-30 * a * b && a > 1e-30 && b > 1e-30) {
             // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b - a) / (2 c), written without the
-            // two IEEE divisions and the IEEE square root: every lane of the warp computes the same scalars
-            // and those three emulated operations (~25 FP64 instructions each) were the bulk of the FP64-pipe
-            // time of a Jacobi round.  rsqrt and a Newton-refined reciprocal are accurate to a few ulp, ample
-            // for a rotation angle (cs^2 + sn^2 = 1 holds to the same few ulp; J is renormalised at the end).
+            // two IEEE divisions and the IEEE square root (~25 FP64 instructions each when emulated).  rsqrt and a
+            // Newton-refined reciprocal are accurate to a few ulp, ample for a rotation angle (cs^2 + sn^2 = 1
+            // holds to the same few ulp; J is renormalised at the end).
             const double d = b - a, h = 2.0 * c;
             const double q2 = d * d + h * h;
             const double rs = rsqrt(q2);
@@ -486,15 +492,15 @@ TMF_DEVICE int jacobi_onesided(double *G, int ldg, double *J, int ldj, int n, do
             }
             const double t = ((d >= 0.0) == (h >= 0.0) ? fabs(h) : -fabs(h)) * rc;
             const double cs = rsqrt(1.0 + t * t), sn = cs * t;
-            if (lane == 0) *flag = 1;
-            for (int r = lane; r < n; r += 32) {
+            if (gl == 0) *flag = 1;
+            for (int r = gl; r < n; r += GW) {
               const double x = gp[r], y = gq[r];
               gp[r] = cs * x - sn * y;
               gq[r] = sn * x + cs * y;
             }
             if (J != nullptr) {
               double *jp = J + (int64_t)p * ldj, *jq = J + (int64_t)q * ldj;
-              for (int r = lane; r < n; r += 32) {
+              for (int r = gl; r < n; r += GW) {
                 const double x = jp[r], y = jq[r];
                 jp[r] = cs * x - sn * y;
                 jq[r] = sn * x + cs * y;
