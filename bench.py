@@ -514,7 +514,7 @@ def run_native(args):
                                     "e2e: host C -> complete MPS in host memory",
                        "l2": f"working set {(8 * state['out_elems'] + 6e8) / 1e9:.1f} GB per step >> 126 MB L2",
                        "parallelism": (f"sites sharded over {world} GPU(s), broadcast(C) + gather(tensors) over NCCL"
-                                       if world > 1 else "1 GPU") + f"; {args.chunks or 'auto (6 at >= 512 sites per GPU)'} pipeline chunks per GPU"},
+                                       if world > 1 else "1 GPU") + f"; {args.chunks or 'auto (3 at >= 384 sites per GPU, 2 at >= 192, else 1)'} pipeline chunks per GPU"},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roof,
             "whole_step": whole, "parity": parity, "cpu_baseline": cpu}
     print(json.dumps(line))

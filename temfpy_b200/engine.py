@@ -795,7 +795,9 @@ def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site
     site_hi = L if site_hi is None else site_hi
     nsites = site_hi - site_lo
     if n_chunks is None:
-        n_chunks = (6 if nsites >= 768 else 4 if nsites >= 384 else 2 if nsites >= 192 else 1) if hasattr(backend, "side_stream") else 1
+        # (measured on B200 at L = 1024: 3 chunks 14.8 ms, 6 chunks 15.6 ms, 1 chunk 18 ms per conversion -- the host
+        #  stages are short since the site planning moved to the device, more chunks only add contention)
+        n_chunks = (3 if nsites >= 384 else 2 if nsites >= 192 else 1) if hasattr(backend, "side_stream") else 1
     n_chunks = max(1, min(n_chunks, nsites))
     if n_chunks == 1:
         r = _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi, r_sketch,
