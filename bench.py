@@ -271,6 +271,10 @@ def run_native(args):
             args.threads = max(2, ncpu // world)
     be = engine.TorchBackend(f"cuda:{local}")
     slater._backend = be
+    # both arms run with the reference's self-checks off (oracle/ref_shim.py loads the reference with
+    # TEST_ACTION = "pass" as well; under the default "warn" both would verify the central bond, testing.py:131-177)
+    from temfpy_b200 import testing as _testing
+    _testing.TEST_ACTION = "pass"
     lib = be.lib
     L = args.L
     tp_dict = {"chi_max": args.chi, "svd_min": args.svd_min}
@@ -512,6 +516,7 @@ def run_native(args):
             "config": {"workload": workload_name(L, args.chi, args.svd_min),
                        "residency": "value: C resident in HBM -> all site tensors + Schmidt data resident in HBM; "
                                     "e2e: host C -> complete MPS in host memory",
+                       "test_action": "pass (self-checks of testing.py off in both arms)",
                        "l2": f"working set {(8 * state['out_elems'] + 6e8) / 1e9:.1f} GB per step >> 126 MB L2",
                        "parallelism": (f"sites sharded over {world} GPU(s), broadcast(C) + gather(tensors) over NCCL"
                                        if world > 1 else "1 GPU") + f"; {args.chunks or 'auto (3 at >= 384 sites per GPU, 2 at >= 192, else 1)'} pipeline chunks per GPU"},

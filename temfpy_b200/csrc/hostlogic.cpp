@@ -18,13 +18,28 @@
 
 namespace tmf {
 
+// Last error message.  Every thread keeps its own (the pipeline drives the library from several threads at
+// once); the process-wide copy serves callers that read the message from another thread than the failing one
+// and is guarded by a mutex (concurrent failures of several chunks -- e.g. the sketch-width retry -- would
+// otherwise race on the string).  The pointer handed out always refers to a thread-local buffer.
 static thread_local std::string g_error;
+static thread_local std::string g_error_out;
+static std::mutex g_error_mu;
 static std::string g_error_shared;
 void set_error(const std::string &msg) {
   g_error = msg;
+  std::lock_guard<std::mutex> lk(g_error_mu);
   g_error_shared = msg;
 }
-const char *last_error_cstr() { return g_error.empty() ? g_error_shared.c_str() : g_error.c_str(); }
+const char *last_error_cstr() {
+  if (!g_error.empty()) {
+    g_error_out = g_error;
+  } else {
+    std::lock_guard<std::mutex> lk(g_error_mu);
+    g_error_out = g_error_shared;
+  }
+  return g_error_out.c_str();
+}
 
 // -------------------------------------------------------------------------------------------
 // persistent host thread pool

@@ -511,6 +511,10 @@ class SlaterChain:
         check(lib, lib.tmf_chain_tensors(self.handle, be.ptr(C_dev), int(ldc), be.ptr(b["V"]),
                                          be.ptr(b["plan"]), plan_bytes, be.ptr(b["O"]), be.ptr(b["S"]),
                                          be.ptr(b["det"]), be.ptr(b["out"]), be.stream))
+        # the per-site determinants (8 bytes each) come back with a plain copy: a NaN among them reports a broken
+        # elimination (check_det) -- no library reduction kernels on the stream
+        if hasattr(be, "to_host_async"):
+            b["det_host"] = be.to_host_async(b["det"], nsites)
 
     # -- results ----------------------------------------------------------------------------------
     def bond(self, x) -> BondData:
@@ -554,13 +558,15 @@ class SlaterChain:
         are not nested (nested kernel) or always-occupied orbitals of the two bonds that are orthogonal (Schur
         kernel: incompatible truncations of a degenerate multiplet).  The driver then redoes the conversion with
         other options.  Needs the stream to be synchronised."""
-        det = self._buffers.get("det")
+        det = self._buffers.get("det_host")
         if det is None:
-            return
-        if hasattr(self.be, "torch"):
-            ok = bool(self.be.torch.isfinite(det).all())
+            d = self._buffers.get("det")
+            if d is None:
+                return
+            det = self.be.to_host(d) if hasattr(self.be, "torch") else np.asarray(d)
         else:
-            ok = bool(np.all(np.isfinite(np.asarray(det))))
+            det = det.numpy() if hasattr(det, "numpy") else np.asarray(det)
+        ok = bool(np.all(np.isfinite(det)))
         if not ok:
             raise ValueError("site stage: singular elimination (incompatible neighbouring bonds)")
 

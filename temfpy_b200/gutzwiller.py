@@ -70,6 +70,18 @@ def _check_unit_cell_width(mps: BlockMPS, unit_cell_width, group=2):
     return unit_cell_width
 
 
+def _unwrap(mps):
+    """The BlockMPS behind a TeNPy MPS produced by ``BlockMPS.to_tenpy`` (the drivers return TeNPy objects
+    automatically where TeNPy is installed; the projection works on the block storage)."""
+    inner = getattr(mps, "_temfpy_b200", None)
+    if inner is not None:
+        return inner
+    if not isinstance(mps, BlockMPS):
+        raise TypeError("gutzwiller: expected the result of temfpy_b200.slater.C_to_MPS / H_to_MPS "
+                        f"(a BlockMPS, or the TeNPy MPS made from it by to_tenpy()), got {type(mps).__name__}")
+    return mps
+
+
 def _validate(mps):
     assert mps.L % 2 == 0, "Odd-length MPS cannot represent an Abrikosov fermion Hilbert space"
     assert mps.site_type == "FermionSite", f"All sites must be fermionic, found: {mps.site_type}"
@@ -275,6 +287,7 @@ def abrikosov(mps: BlockMPS, *, inplace: bool = False, return_canonical: bool = 
     r"""Projection from Abrikosov fermions to a spin-1/2 Hilbert space (gutzwiller.py:95-281):
     single occupation of :math:`f_{i\uparrow}` -> up, of :math:`f_{i\downarrow}` -> down."""
     from . import slater as _sl
+    mps = _unwrap(mps)
     _validate(mps)
     if inplace:
         raise NotImplementedError("`inplace=True` is not supported: BlockMPS results are immutable")
@@ -299,6 +312,7 @@ def abrikosov_ph(mps: BlockMPS, *, inplace: bool = False, return_canonical: bool
     r"""Projection from particle-hole rotated Abrikosov fermions (gutzwiller.py:284-486):
     zero occupation -> down, double occupation -> up; :math:`2S^z` = number - bond index is conserved."""
     from . import slater as _sl
+    mps = _unwrap(mps)
     _validate(mps)
     if inplace:
         raise NotImplementedError("`inplace=True` is not supported: BlockMPS results are immutable")

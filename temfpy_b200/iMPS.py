@@ -59,13 +59,18 @@ class iMPSError(NamedTuple):
         return "iMPSError()" if not fields else "iMPSError(\n" + (",\n".join(fields)) + "\n)"
 
 
-def basis_rotation(overlap: np.ndarray, q_bra, q_ket, Schmidt_bra, Schmidt_ket, mode: str = "left", *,
+def basis_rotation(overlap: np.ndarray, Schmidt_bra, Schmidt_ket, mode: str = "left", *,
                    form: str = "B", numerical_tol=_NUMERICAL_TOL, unitary_tol=_UNITARY_TOL,
-                   schmidt_tol=_SCHMIDT_TOL):
-    """Unitary closest to the overlap of two Schmidt bases (reference iMPS.py:65-192) for a dense,
-    charge-block-diagonal ``overlap[bra, ket]`` (charges ``q_bra``, ``q_ket``): unitarity test,
-    orthogonal Procrustes per charge sector (``npc.svd`` is block-wise), Schmidt-mixing test.
+                   schmidt_tol=_SCHMIDT_TOL, q_bra=None, q_ket=None):
+    """Unitary closest to the overlap of two Schmidt bases (reference iMPS.py:65-192; same positional
+    signature) for a dense ``overlap[bra, ket]``: unitarity test, orthogonal Procrustes per charge sector
+    (``npc.svd`` is block-wise), Schmidt-mixing test.  The charges of the two legs, which the reference reads
+    off the ``npc.Array``, are passed as the keyword-only ``q_bra`` / ``q_ket`` (default: one sector).
     Returns ``(rotation, unitary_error, schmidt_error)``."""
+    if q_bra is None:
+        q_bra = np.zeros(np.shape(overlap)[0], dtype=np.int64)
+    if q_ket is None:
+        q_ket = np.zeros(np.shape(overlap)[1], dtype=np.int64)
     mode = mode.lower()
     assert mode in ["left", "right"], f"`mode` must be either 'left' or 'right', got {mode!r}"
     form = form.upper()
@@ -390,8 +395,8 @@ def slater_C_to_iMPS(C_short, C_long, trunc_par, sites_per_cell, cut, *, diag_to
     for b, blk in zip(gplan.blocks, blocks[-1]):
         r0, nr, c0, nc = int(b[0]), int(b[1]), int(b[2]), int(b[3])
         Cov[gplan.row_alpha[r0: r0 + nr][:, None], np.arange(c0, c0 + nc)[None, :]] = blk
-    R, left_unitary, left_schmidt = basis_rotation(Cov, b_short.charge, b_long.charge, b_short.lam, b_long.lam,
-                                                   "left", unitary_tol=unitary_tol, schmidt_tol=schmidt_tol)
+    R, left_unitary, left_schmidt = basis_rotation(Cov, b_short.lam, b_long.lam, "left", unitary_tol=unitary_tol,
+                                                   schmidt_tol=schmidt_tol, q_bra=b_short.charge, q_ket=b_long.charge)
     # ---- assemble; first tensor <- R . B_0 on the device (slater.py:1554) -------------------------
     tensors = []
     for i in range(cell):

@@ -63,9 +63,44 @@ class BlockMPS:
         return T
 
     # ------------------------------------------------------------------------------------------
+    def _site_to_npc(self, i, npc, site, chinfo):
+        """One fermion site tensor as ``npc.Array``, block by block -- a mirror of the reference's
+        ``MPSTensorData.to_npc_array`` (slater.py:1106-1143): bra leg = ``LegPipe([fermion_leg, leg_bra])``
+        (physical index more major, sorted + bunched by TeNPy exactly like our bra rows: stable sort by pipe
+        charge), ket leg from the sector table, blocks assigned by charge, ``split_legs()`` at the end.  No dense
+        ``chi x 2 x chi`` intermediate."""
+        t = self.tensors[i]
+        left = t.mode == "left"
+        qconj = (+1, -1) if left else (-1, +1)
+        name_bra, name_ket = ("vL", "vR") if left else ("vR", "vL")
+        q_bra = np.asarray(self.charges[i] if left else self.charges[i + 1])
+        q_ket = np.asarray(self.charges[i + 1] if left else self.charges[i])
+
+        def qdict(q):
+            cuts = np.flatnonzero(np.diff(q)) + 1
+            starts = np.concatenate(([0], cuts, [len(q)]))
+            return {(int(q[a]),): slice(int(a), int(b)) for a, b in zip(starts[:-1], starts[1:])}
+
+        leg_bra = npc.LegCharge.from_qdict(chinfo, qdict(q_bra), qconj=qconj[0])
+        leg_ket = npc.LegCharge.from_qdict(chinfo, qdict(q_ket), qconj=qconj[1])
+        pipe = npc.LegPipe([site.leg, leg_bra], qconj=leg_bra.qconj)
+        blocks = t.blocks
+        dtype = blocks[0][5].dtype if blocks else np.float64
+        B = npc.zeros([pipe, leg_ket], labels=[f"(p.{name_bra})", name_ket], dtype=dtype, qtotal=(t.qtotal,))
+        qd = pipe.to_qdict()
+        for (q_k, r0, nr, c0, nc, arr) in blocks:
+            sl_bra = qd[(q_k + t.qtotal * qconj[0],)]
+            assert sl_bra.stop - sl_bra.start == nr, "bra pipe sector does not match the block"
+            B[sl_bra, slice(c0, c0 + nc)] = np.asarray(arr)
+        return B.split_legs()
+
     def to_tenpy(self):
         """The wave function as ``tenpy.networks.mps.MPS`` (labels ``vL, p, vR``; virtual charges =
-        conserved charge to the left of the bond, as in slater.py:1111-1128)."""
+        conserved charge to the left of the bond, as in slater.py:1111-1128).  Number-conserving fermion
+        tensors are packed block by block (``_site_to_npc``); other site types through ``from_ndarray``.
+        The ``BlockMPS`` stays attached to the result (``._temfpy_b200``) so that ``gutzwiller.abrikosov*``
+        accept either object.  (TeNPy is not part of the build image: this adapter is exercised only where
+        ``physics-tenpy >= 1.1`` is installed.)"""
         try:
             import tenpy.linalg.np_conserved as npc
             from tenpy import networks
@@ -78,6 +113,11 @@ class BlockMPS:
         chinfo = site.leg.chinfo
         tensors = []
         for i in range(self.L):
+            t = self.tensors[i]
+            if self.site_type == "FermionSite" and self.conserve == "N" and hasattr(t, "blocks") and hasattr(t, "mode") \
+                    and self.bc == "finite":
+                tensors.append(self._site_to_npc(i, npc, site, chinfo))
+                continue
             T = self.get_B_dense(i)
             if chinfo.qnumber:
                 qL = np.asarray(self.charges[i]).reshape(-1, 1)
@@ -90,6 +130,7 @@ class BlockMPS:
             else:
                 B = npc.Array.from_ndarray_trivial(T, labels=["vL", "p", "vR"])
             tensors.append(B)
-        lams = self.lams if self.bc == "finite" else self.lams
-        return networks.mps.MPS([site] * self.L, tensors, lams, bc=self.bc, form=self.form,
-                                unit_cell_width=self.unit_cell_width)
+        out = networks.mps.MPS([site] * self.L, tensors, self.lams, bc=self.bc, form=self.form,
+                               unit_cell_width=self.unit_cell_width)
+        out._temfpy_b200 = self
+        return out

@@ -158,6 +158,11 @@ def C_to_MPS(C: np.ndarray, trunc_par: dict | StoppingCondition, *, diag_tol: fl
     logger.info("Central bond %d", ortho_center or L // 2)
     Cd = be.from_host(C.ravel())
     _check_projector(C, be=be, Cd=Cd)
+    from . import testing
+    if testing.TEST_ACTION != "pass" and 0 < (ortho_center or L // 2) < L:
+        # the reference's consistency check of the central bond (slater.py:420-421 -> testing.py:131-177)
+        SchmidtModes.from_correlation_matrix(C, ortho_center or L // 2, trunc_par, which="LR", diag_tol=diag_tol,
+                                             _backend=be)
     res = engine.run_chain(be, Cd, L, L, trunc_par, n_fermion, ortho_center=ortho_center)
     mps = _chain_to_mps(res, unit_cell_width)
     return mps.to_tenpy() if _want_tenpy(as_tenpy) else mps
@@ -171,6 +176,130 @@ def H_to_MPS(H: np.ndarray, trunc_par: dict | StoppingCondition, *, diag_tol: fl
     C, _ = correlation_matrix(H, _backend=_backend)
     return C_to_MPS(C, trunc_par, diag_tol=diag_tol, ortho_center=ortho_center, spinful=spinful,
                     unit_cell_width=unit_cell_width, as_tenpy=as_tenpy, _backend=_backend)
+
+
+#### Schmidt modes of a single bond ####
+@dataclass(frozen=True)
+class SchmidtModes:
+    r"""Schmidt modes of a Slater determinant on one bond (reference slater.py:41-490).
+
+    Same fields as the reference's dataclass.  ``vL`` / ``vR`` hold the orbitals the conversion uses -- the
+    filled and the entangled eigenvectors of ``C[:x,:x]`` / ``C[x:,x:]``; the never-occupied ("empty")
+    eigenvectors, which the reference computes and then drops (slater.py:792-797), are omitted, so
+    ``ixL["empty"]`` / ``ixR["empty"]`` are empty slices and the matrices are ``n x (filled + entangled)``.
+    Column order as in the reference: L = filled, entangled (decreasing eigenvalue); R = entangled, filled."""
+    e: np.ndarray
+    vL: np.ndarray | None
+    vR: np.ndarray | None
+    ixL: dict | None
+    ixR: dict | None
+    nL: int
+    nR: int
+    n_fermion: int
+
+    @property
+    def n_entangled(self) -> int:
+        return self.e.size
+
+    def size(self, which: str = "T") -> int:
+        w = which[0].upper()
+        if w not in "LRT":
+            raise ValueError("`which` must start with L, R, or T, got " + repr(which))
+        return self.nL if w == "L" else self.nR if w == "R" else self.nL + self.nR
+
+    def n_filled(self, which: str) -> int:
+        """slater.py:145-174."""
+        w = which[0].upper()
+        n = lambda sl: sl.stop - sl.start
+        if w == "L":
+            return n(self.ixL["filled"]) if self.ixL is not None else self.n_fermion - self.n_entangled - n(self.ixR["filled"])
+        if w == "R":
+            return n(self.ixR["filled"]) if self.ixR is not None else self.n_fermion - self.n_entangled - n(self.ixL["filled"])
+        raise ValueError("`which` must start with L or R, got " + repr(which))
+
+    @property
+    def vL_entangled(self):
+        return None if self.vL is None else self.vL[:, self.ixL["entangled"]]
+
+    @property
+    def vR_entangled(self):
+        return None if self.vR is None else self.vR[:, self.ixR["entangled"]]
+
+    def mode_vectors(self, which: str, entangled: bool = False):
+        w = which[0].upper()
+        if w == "L":
+            return self.vL_entangled if entangled else self.vL
+        if w == "R":
+            return self.vR_entangled if entangled else self.vR
+        raise ValueError("`which` must start with L or R, got " + which)
+
+    def eigenvalues(self, which: str, entangled: bool = False):
+        """slater.py:212-250."""
+        w = which[0].upper()
+        if w == "L":
+            v, ix, e = self.vL, self.ixL, self.e
+        elif w == "R":
+            v, ix, e = self.vR, self.ixR, 1 - self.e[::-1]
+        else:
+            raise ValueError("`which` must start with L or R, got " + repr(which))
+        if v is None:
+            return None
+        if entangled:
+            return e
+        E = np.zeros(v.shape[1])
+        E[ix["filled"]] = 1
+        E[ix["entangled"]] = e
+        return E
+
+    @property
+    def singular_values(self):
+        """slater.py:252-268."""
+        if self.vL is None or self.vR is None:
+            return None
+        SV = (self.e * (1 - self.e)) ** 0.5
+        return SV * (-1) ** (np.arange(SV.size)[::-1])
+
+    @property
+    def e_ratio(self):
+        """slater.py:425-428."""
+        return np.log((1 - self.e) / self.e)
+
+    @classmethod
+    def from_correlation_matrix(cls, C, x, trunc_par, *, which="LR", diag_tol=_DIAG_TOL, _backend=None):
+        r"""Schmidt modes for a cut between sites ``x-1`` and ``x`` (slater.py:270-423): mode extraction on the
+        device (``tmf_slater_modes_batched``), pairing of the two sides of an ``"LR"`` bond
+        (``tmf_slater_pair_bond``: ``utils.block_svd`` + the sign flips of :410) and, for ``"LR"``,
+        ``testing.check_schmidt_decomposition`` under the global ``TEST_ACTION``."""
+        from . import _lib, testing
+        which = which.upper()
+        assert ("L" in which) or ("R" in which), "`which` must specify at least one of (L)eft or (R)ight"
+        trunc_par = to_stopping_condition(trunc_par)
+        be = _backend or _be()
+        C = _real_or_raise(C, "correlation matrix")
+        L = len(C)
+        Cd = be.from_host(C.ravel())
+        jobs = [(x, s) for s, w in ((_lib.SIDE_L, "L"), (_lib.SIDE_R, "R")) if w in which]
+        m = _iMPS._Modes(be, Cd, L, jobs, trunc_par.svd_min ** 2)                                   # :318, :347
+        if len(jobs) == 2:
+            m.pair(0, 1, x, trunc_par.degeneracy_tol)                                               # :394-410
+        out = {}
+        for j, (_, side) in enumerate(jobs):
+            n, k, f = int(m.n[j]), int(m.k[j]), int(m.f[j])
+            V = be.to_host(m.V[int(m.v_off[j]): int(m.v_off[j]) + n * n], n * n).reshape(n, n).T if n else np.zeros((0, 0))
+            ent, fil = V[:, :k], V[:, k: k + f]
+            if side == _lib.SIDE_L:      # filled, entangled
+                out["L"] = (np.hstack([fil, ent]),
+                            dict(filled=slice(0, f), entangled=slice(f, f + k), empty=slice(f + k, f + k)))
+            else:                         # entangled (the reference's column j is our mode k-1-j), filled
+                out["R"] = (np.hstack([ent[:, ::-1], fil]),
+                            dict(empty=slice(0, 0), entangled=slice(0, k), filled=slice(k, k + f)))
+        k0 = int(m.k[0])
+        modes = cls(e=np.array(m.e[0][:k0]), vL=out.get("L", (None, None))[0], vR=out.get("R", (None, None))[0],
+                    ixL=out.get("L", (None, None))[1], ixR=out.get("R", (None, None))[1], nL=int(x), nR=int(L - x),
+                    n_fermion=int(np.round(np.trace(C))))                                           # :414
+        if which == "LR":
+            testing.check_schmidt_decomposition(modes, C, diag_tol)                                  # :420-421
+        return modes
 
 
 #### Schmidt vectors of a single bond ####
@@ -228,3 +357,23 @@ def H_to_iMPS(H_short, H_long, trunc_par, sites_per_cell, cut, **kwargs):
     C_short, _ = correlation_matrix(H_short, _backend=kwargs.get("_backend"))
     C_long, _ = correlation_matrix(H_long, _backend=kwargs.get("_backend"))
     return C_to_iMPS(C_short, C_long, trunc_par, sites_per_cell, cut, **kwargs)
+
+
+#### MPS tensor data ####
+MPSTensorData = engine.SiteTensor
+"""Counterpart of the reference's ``MPSTensorData`` (slater.py:872-1143): the site tensor as charge blocks in the
+layout ``to_npc_array`` writes (``blocks``, ``row_p``, ``row_alpha``, ``qtotal``, ``plan`` with the orbital counts)."""
+
+
+#### TeNPy bindings (slater.py:30-36), created on first use: TeNPy is optional here ####
+def __getattr__(name):
+    if name in ("fermion_site", "fermion_leg", "chinfo"):
+        try:
+            from tenpy import networks
+        except ImportError as err:
+            raise AttributeError(f"temfpy_b200.slater.{name} needs physics-tenpy (not installed)") from err
+        site = networks.site.FermionSite()
+        vals = dict(fermion_site=site, fermion_leg=site.leg, chinfo=site.leg.chinfo)
+        globals().update(vals)
+        return vals[name]
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

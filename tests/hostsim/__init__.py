@@ -14,7 +14,7 @@ import numpy as np
 from temfpy_b200 import _lib
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SIM_PATH = os.path.join(HERE, "libtemfpy_b200_hostsim.so")
+SIM_PATH = os.environ.get("TMF_SIM_PATH") or os.path.join(HERE, "libtemfpy_b200_hostsim.so")   # (override: ASan build)
 CSRC = os.path.join(os.path.dirname(HERE), "..", "temfpy_b200", "csrc")
 
 _sim = None
@@ -23,7 +23,8 @@ _sim = None
 def load_sim():
     global _sim
     if _sim is None:
-        subprocess.run(["make", "-s", "-C", CSRC, "hostsim"], check=True, capture_output=True)
+        if not os.environ.get("TMF_SIM_PATH"):
+            subprocess.run(["make", "-s", "-C", CSRC, "hostsim"], check=True, capture_output=True)
         _sim = _lib.bind(SIM_PATH)
         assert _sim.tmf_is_cuda() == 0
     return _sim

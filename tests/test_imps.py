@@ -98,7 +98,7 @@ def test_basis_rotation_matches_oracle():
     S = np.sort(rng.uniform(size=6))[::-1]
     S /= np.linalg.norm(S)
     R1, u1, s1 = so.basis_rotation(Cm * 0.3, q, q, S, S)
-    R2, u2, s2 = iMPS.basis_rotation(Cm * 0.3, q, q, S, S, "left", unitary_tol=10, schmidt_tol=10)
+    R2, u2, s2 = iMPS.basis_rotation(Cm * 0.3, S, S, "left", unitary_tol=10, schmidt_tol=10, q_bra=q, q_ket=q)
     assert np.allclose(R1, R2) and abs(u1 - u2) < 1e-14 and abs(s1 - s2) < 1e-14
     assert np.allclose(R2 @ R2.T, np.eye(6))
 
