@@ -12,6 +12,12 @@
 // double-buffered with register prefetch of the next k-tile.  Tiles of all jobs are enumerated by
 // a prefix table so that one grid covers the whole group (grid >> 148 for the chain workloads).
 #include "cta.hpp"
+#if !defined(TMF_HOSTSIM)
+#include <cuda.h>
+#include <map>
+#include <mutex>
+#include <tuple>
+#endif
 
 namespace tmf {
 
@@ -119,6 +125,15 @@ struct OperandLoader {
 #pragma unroll
     for (int i = 0; i < 4; ++i) r[i] = (p[i] != nullptr && k0 + kk[i] < K) ? p[i][(int64_t)(k0 / TK) * kstep] : 0.0;
   }
+  // the same with the k axis shifted by `sh` (0 / 1): tile position k' holds element k' - sh (zero at k' < sh)
+  __device__ __forceinline__ void load_shifted(double (&r)[4], int k0, int K, int sh) const {
+    const int64_t unit = kstep / TK;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + kk[i] - sh;
+      r[i] = (p[i] != nullptr && k >= 0 && k < K) ? p[i][(int64_t)(k0 / TK) * kstep - sh * unit] : 0.0;
+    }
+  }
   __device__ __forceinline__ void store(double *tile, const double (&r)[4]) const {
 #pragma unroll
     for (int i = 0; i < 4; ++i) tile[so[i]] = r[i];
@@ -190,6 +205,162 @@ __device__ __forceinline__ void gemm_tile(const tmf_gemm_job &j, int m0, int n0,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-staged variant for jobs whose A operand is a k-contiguous sub-block of the correlation matrix
+// (W^T = B^T Q and A U0 of the mode extraction: ~85 % of the GEMM flops of a conversion).  One tensor map
+// describes the whole L x L matrix; a job addresses its block by the coordinates of its origin (pad_[1] =
+// first row, pad_[2] = first column), so no alignment condition falls on the block itself.  The A tiles
+// (64 rows x 16 k = 8 KB) are fetched by cp.async.bulk.tensor into a 3-stage ring with the 128-byte swizzle
+// (conflict-free fragment loads without padding) and signalled through mbarriers; one thread issues the
+// copies two k-tiles ahead.  The (gathered / small) B operand keeps the register-prefetch path.  The
+// per-iteration __syncthreads of the B double buffer also orders the reuse of an A stage, so no "empty"
+// barriers are needed.  Rows / k beyond the block read neighbouring entries of C (finite) that meet zeros
+// of the B tile or unused accumulator rows.
+// ---------------------------------------------------------------------------------------------
+constexpr int TMA_STAGES = 3;
+constexpr int TMA_TILE_BYTES = 64 * TK * 8;   // 8192
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TMF_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TMF_MBAR_DONE;\n"
+      "bra TMF_MBAR_WAIT;\n"
+      "TMF_MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <bool BKC>
+__device__ __forceinline__ void gemm_tile_tma(const tmf_gemm_job &j, int m0, int n0, unsigned char *At, double *Bs,
+                                              uint64_t *bars, const CUtensorMap *map) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
+  OperandLoader<BKC> lb;
+  lb.init(j.B, j.ldb, j.b_idx, n0, j.N, j.b_row_off, tid);
+  double acc[2][4][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  // The box of a bulk tensor copy must start on a 16-byte boundary, i.e. at an even column of C: a block that
+  // starts at an odd column is read from the column before it (ksh = 1) and the k axis of the B tile is shifted
+  // by one, with a zero in front (the extra column of C meets that zero).
+  const int ksh = (j.pad_[2] + j.a_row_off) & 1;
+  const int nk = (j.K + ksh + TK - 1) / TK;
+  const int row0 = j.pad_[1] + m0, col0 = j.pad_[2] + j.a_row_off - ksh;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TMA_STAGES; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < TMA_STAGES - 1 && s < nk; ++s) {
+      mbar_expect_tx(bars + s, TMA_TILE_BYTES);
+      tma_load_2d(At + s * TMA_TILE_BYTES, map, col0 + s * TK, row0, bars + s);
+    }
+  }
+  double rb[4];
+  int buf = 0;
+  if (nk > 0) {
+    lb.load_shifted(rb, 0, j.K, ksh);
+    lb.store(Bs, rb);
+  }
+  __syncthreads();
+  const int fr = lane >> 2, fk = lane & 3;
+  for (int kt = 0; kt < nk; ++kt) {
+    // stage (kt + 2) % 3 was read last in iteration kt - 1, which every warp left through the barrier below
+    if (tid == 0 && kt + TMA_STAGES - 1 < nk) {
+      const int s = (kt + TMA_STAGES - 1) % TMA_STAGES;
+      mbar_expect_tx(bars + s, TMA_TILE_BYTES);
+      tma_load_2d(At + s * TMA_TILE_BYTES, map, col0 + (kt + TMA_STAGES - 1) * TK, row0, bars + s);
+    }
+    if (kt + 1 < nk) lb.load_shifted(rb, (kt + 1) * TK, j.K, ksh);
+    const int st = kt % TMA_STAGES;
+    mbar_wait(bars + st, (uint32_t)((kt / TMA_STAGES) & 1));
+    const unsigned char *as = At + st * TMA_TILE_BYTES;
+    const double *bs = Bs + buf * TILE_DOUBLES;
+#pragma unroll
+    for (int ks = 0; ks < TK; ks += 4) {
+      double fa[2], fb[4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        // 128-byte swizzle: the 16-byte chunk index of an element is XORed with (row & 7)
+        const int r = wm + a * 8 + fr, k = ks + fk;
+        fa[a] = *reinterpret_cast<const double *>(as + r * 128 + ((((k >> 1) ^ (r & 7))) << 4) + ((k & 1) << 3));
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) fb[b] = OperandLoader<BKC>::frag(bs, wn + b * 8 + fr, ks + fk);
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dmma(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
+    }
+    if (kt + 1 < nk) lb.store(Bs + (buf ^ 1) * TILE_DOUBLES, rb);
+    __syncthreads();
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      int m = m0 + wm + a * 8 + fr, n = n0 + wn + b * 8 + 2 * fk;
+      store_c(j, m, n, acc[a][b][0]);
+      store_c(j, m, n + 1, acc[a][b][1]);
+    }
+}
+
+__global__ void __launch_bounds__(256, 2)
+gemm_grouped_tma_kernel(const tmf_gemm_job *__restrict__ jobs, const int *__restrict__ prefix, int njobs,
+                        const __grid_constant__ CUtensorMap tmapC) {
+  __shared__ __align__(1024) unsigned char At[TMA_STAGES * TMA_TILE_BYTES];   // 24 KB; doubles as As of the plain path
+  static_assert(TMA_STAGES * TMA_TILE_BYTES >= 2 * TILE_DOUBLES * 8, "A staging must cover the plain double buffer");
+  double *As = reinterpret_cast<double *>(At);
+  __shared__ double Bs[2 * TILE_DOUBLES];
+  __shared__ __align__(8) uint64_t bars[TMA_STAGES];
+  __shared__ tmf_gemm_job js;
+  const int tile = blockIdx.x;
+  const int jid = find_job(prefix, njobs, tile);
+  if (threadIdx.x < sizeof(tmf_gemm_job) / 8)
+    reinterpret_cast<uint64_t *>(&js)[threadIdx.x] =
+        reinterpret_cast<const uint64_t *>(&jobs[jid])[threadIdx.x];
+  __syncthreads();
+  const tmf_gemm_job &j = js;
+  const int t = tile - prefix[jid];
+  const int tiles_m = (j.M + TM - 1) / TM;
+  const int m0 = (t % tiles_m) * TM, n0 = (t / tiles_m) * TN;
+  const bool akc = j.transA != 0, bkc = j.transB == 0;
+  if (j.pad_[0] == 1 && akc && j.a_idx == nullptr) {
+    if (bkc) gemm_tile_tma<true>(j, m0, n0, At, Bs, bars, &tmapC);
+    else gemm_tile_tma<false>(j, m0, n0, At, Bs, bars, &tmapC);
+    return;
+  }
+  if (akc) {
+    if (bkc) gemm_tile<true, true>(j, m0, n0, As, Bs);
+    else gemm_tile<true, false>(j, m0, n0, As, Bs);
+  } else {
+    if (bkc) gemm_tile<false, true>(j, m0, n0, As, Bs);
+    else gemm_tile<false, false>(j, m0, n0, As, Bs);
+  }
+}
+
 __global__ void __launch_bounds__(256, 2)
 gemm_grouped_kernel(const tmf_gemm_job *__restrict__ jobs, const int *__restrict__ prefix,
                     int njobs) {
@@ -242,6 +413,58 @@ int gemm_launch_uploaded(const tmf_gemm_job *jobs_dev, const int *prefix_dev, in
                          void *stream, const char *tag) {
   if (ntiles <= 0) return TMF_OK;
   return launch_t(tag, gemm_grouped_kernel, ntiles, 256, 0, stream, jobs_dev, prefix_dev, njobs);
+}
+
+// Launch with the A operands flagged pad_[0] = 1 staged by TMA from the matrix `Cmat` (L x L doubles, row pitch
+// ldc).  Falls back to the plain kernel when the matrix does not meet the tensor-map conditions (16-byte
+// aligned base and pitch) or the driver entry point is missing.
+int gemm_launch_uploaded_tma(const tmf_gemm_job *jobs_dev, const int *prefix_dev, int njobs, int ntiles,
+                             void *stream, const char *tag, const double *Cmat, int L, int ldc) {
+  if (ntiles <= 0) return TMF_OK;
+#if !defined(TMF_HOSTSIM)
+  static const bool off = std::getenv("TMF_NO_TMA") != nullptr;
+  if (!off && Cmat != nullptr && (reinterpret_cast<uintptr_t>(Cmat) & 15) == 0 && (ldc & 1) == 0 && L >= TK) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+      void *fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+          qres != cudaDriverEntryPointSuccess)
+        fn = nullptr;
+      return reinterpret_cast<EncodeFn>(fn);
+    }();
+    if (encode != nullptr) {
+      static std::mutex mu;
+      static std::map<std::tuple<const void *, int, int>, CUtensorMap> cache;
+      CUtensorMap map;
+      bool ok = true;
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        auto key = std::make_tuple((const void *)Cmat, L, ldc);
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+          if (cache.size() > 64) cache.clear();
+          const cuuint64_t dims[2] = {(cuuint64_t)L, (cuuint64_t)L};
+          const cuuint64_t strides[1] = {(cuuint64_t)ldc * 8};
+          const cuuint32_t box[2] = {(cuuint32_t)TK, 64};
+          const cuuint32_t estr[2] = {1, 1};
+          ok = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(Cmat), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+          if (ok) cache[key] = map;
+        } else {
+          map = it->second;
+        }
+      }
+      if (ok) return launch_t(tag, gemm_grouped_tma_kernel, ntiles, 256, 0, stream, jobs_dev, prefix_dev, njobs, map);
+    }
+  }
+#else
+  (void)Cmat; (void)L; (void)ldc;
+#endif
+  return gemm_launch_uploaded(jobs_dev, prefix_dev, njobs, ntiles, stream, tag);
 }
 
 int64_t gemm_desc_bytes(int njobs) {

@@ -179,6 +179,8 @@ tmf_gemm_job mk_gemm(const double *A, int lda, int transA, const double *B, int 
 // defined in gemm.cu (kernel symbol shared through this launcher)
 int gemm_launch_uploaded(const tmf_gemm_job *jobs_dev, const int *prefix_dev, int njobs, int ntiles,
                          void *stream, const char *tag);
+int gemm_launch_uploaded_tma(const tmf_gemm_job *jobs_dev, const int *prefix_dev, int njobs, int ntiles,
+                             void *stream, const char *tag, const double *Cmat, int L, int ldc);
 
 static int64_t big_job_doubles(int n, int m, int rr) {
   // Y, Wt, Wt0, coef, Rw, Jsel, U0, AU, TE, Zsel, norm0y, norm0w, eside (+ ints)
@@ -437,7 +439,16 @@ static int modes_impl(const double *C_dev, int L, int ldc, int njobs,
   build_orth(orthY, false);
   // 4. Wt = B^T Q
   g.clear();
-  for (auto &b : big) g.push_back(mk_gemm(b.B, ldc, 1, b.Y, b.n, 0, b.Wt, b.m, b.m, b.rr, b.n));
+  // (A operands that are k-contiguous sub-blocks of C are flagged for the TMA-staged kernel: pad_[1] / pad_[2] =
+  //  row / column of the block's origin inside C)
+  auto flag_tma = [&](tmf_gemm_job &j) {
+    const int64_t off = j.A - C_dev;
+    j.pad_[0] = 1; j.pad_[1] = (int)(off / ldc); j.pad_[2] = (int)(off % ldc);
+  };
+  for (auto &b : big) {
+    g.push_back(mk_gemm(b.B, ldc, 1, b.Y, b.n, 0, b.Wt, b.m, b.m, b.rr, b.n));
+    flag_tma(g.back());
+  }
   L_wt[0] = add_gemm(blob, g);
   build_orth(orthW, true);
   // 7. Rw = Qw^T Wt0
@@ -459,7 +470,11 @@ static int modes_impl(const double *C_dev, int L, int ldc, int njobs,
   for (auto &b : big) g.push_back(mk_gemm(b.Y, b.n, 0, b.Jsel, b.rr, 0, b.U0, b.n, b.n, b.rr, b.rr));
   L_u0[0] = add_gemm(blob, g);
   g.clear();
-  for (auto &b : big) g.push_back(mk_gemm(b.A, ldc, 0, b.U0, b.n, 0, b.AU, b.n, b.n, b.rr, b.n));
+  // A U0 with A read as A^T (the diagonal block of C is symmetric): k-contiguous, TMA-staged
+  for (auto &b : big) {
+    g.push_back(mk_gemm(b.A, ldc, 1, b.U0, b.n, 0, b.AU, b.n, b.n, b.rr, b.n));
+    flag_tma(g.back());
+  }
   L_au[0] = add_gemm(blob, g);
   g.clear();
   for (auto &b : big) g.push_back(mk_gemm(b.U0, b.n, 1, b.AU, b.n, 0, b.TE, b.rr, b.rr, b.rr, b.n));
@@ -538,6 +553,10 @@ static int modes_impl(const double *C_dev, int L, int ldc, int njobs,
     if (gl.ntiles == 0) return (int)TMF_OK;
     return gemm_launch_uploaded(gl.jobs, gl.prefix, gl.njobs, gl.ntiles, stream, "gemm_modes");
   };
+  auto run_tma = [&](const GemmLaunch &gl) {
+    if (gl.ntiles == 0) return (int)TMF_OK;
+    return gemm_launch_uploaded_tma(gl.jobs, gl.prefix, gl.njobs, gl.ntiles, stream, "gemm_modes", C_dev, L, ldc);
+  };
   auto run_orth = [&](OrthPlan &op) -> int {
     int r2 = launch_t("colnorm", colnorm_kernel, nb, 256, op.norm_smem, stream, op.norm);
     if (r2) return r2;
@@ -571,7 +590,7 @@ static int modes_impl(const double *C_dev, int L, int ldc, int njobs,
     if (rc) return rc;
   }
   if ((rc = run_orth(orthY))) return rc;
-  if ((rc = run(L_wt[0]))) return rc;
+  if ((rc = run_tma(L_wt[0]))) return rc;
   rc = copy_d2d(wt_begin + wt_bytes, wt_begin, wt_bytes, stream);
   if (rc) return rc;
   if ((rc = run_orth(orthW))) return rc;
@@ -586,7 +605,7 @@ static int modes_impl(const double *C_dev, int L, int ldc, int njobs,
   rc = launch_t("svd_select", svd_select_kernel, nb, jac_threads, svd_smem, stream, sj_dev, thr, sketch_floor);
   if (rc) return rc;
   if ((rc = run(L_u0[0]))) return rc;
-  if ((rc = run(L_au[0]))) return rc;
+  if ((rc = run_tma(L_au[0]))) return rc;
   if ((rc = run(L_te[0]))) return rc;
   rc = launch_t("ritz", ritz_kernel, nb, jac_threads, ritz_smem, stream, rj_dev, cutoff);
   if (rc) return rc;
