@@ -96,6 +96,22 @@ int tmf_slater_modes_nested(const double *C_dev, int L, int ldc, int njobs, cons
                             double *V_dev, double *e_dev, int *info_dev, double *edge_dev,
                             void *work_dev, int64_t work_bytes, void *stream);
 
+/* Complex Slater determinants (slater.py:1150-1180 keeps a complex C; :347 then diagonalises complex Hermitian
+ * blocks).  The library takes the re/im-interleaved real embedding Cemb (2L x 2L real symmetric projector,
+ * Cemb[2i+a, 2j+b] = [[Re, -Im], [Im, Re]] of C_ij) with the cuts at 2x: the real kernels extract the modes (every
+ * complex eigenvector is a doubly degenerate real pair), a pairing kernel picks the k complex modes -- stored
+ * as interleaved complex columns in the same slots -- and the embedded edge vector is the complex one.
+ * On return info[4j] = k complex modes, info[4j+1] = f, e[0..k) the left eigenvalues. */
+int tmf_slater_modes_nested_emb(const double *Cemb_dev, int L2, int ldc, int njobs, const int *job_x2,
+                                const int *job_side, double cutoff, int r_sketch, const int64_t *v_off,
+                                double *V_dev, double *e_dev, int *info_dev, double *edge_dev,
+                                void *work_dev, int64_t work_bytes, void *stream);
+/* complex form of tmf_slater_pair_bond (utils.py:19-96 + slater.py:410 with complex mode matrices) */
+int64_t tmf_slater_pair_bond_c_workspace(int L, int k);
+int tmf_slater_pair_bond_c(const double *Cemb_dev, int ldc, int L, int x, int k, const double *e_host,
+                           double degeneracy_tol, double *VL_dev, double *VR_dev, void *work_dev,
+                           int64_t work_bytes, void *stream);
+
 /* K4 -- pairing of the left and right entangled modes of a bond whose two sides were both extracted.
  * replaces: utils.py:19-96 (block_svd) as called from slater.py:407, and the odd-index sign flips of
  * slater.py:410.  VL (x rows) / VR (L-x rows): stored mode matrices of the two jobs; their first k
@@ -213,6 +229,12 @@ typedef struct tmf_nested_job {
 int tmf_site_nested_batched(const tmf_site_job *jobs_host, const tmf_nested_job *njobs_host,
                             int nsites, void *desc_dev, void *stream);
 
+/* complex128 form (complex Slater determinants): V slots hold interleaved complex columns (ldb / ldk in complex
+ * elements), a_col / c_edge point into the embedded matrix (row 2e holds conj(C[e, :]) = C[:, e]^T), O / S / det
+ * are complex; the always-occupied entangled orbitals are eliminated in the same kernel (<= 32 modes per bond). */
+int tmf_site_nested_c_batched(const tmf_site_job *jobs_host, const tmf_nested_job *njobs_host,
+                              int nsites, void *desc_dev, void *stream);
+
 /* K10 -- all minors of all charge blocks of all sites.  replaces: slater.py:828-869
  * (_tensor_block: gather + batched det) and the det_always scaling of :1137.
  * Block descriptors (host) are copied to desc_dev.  For block b:
@@ -230,6 +252,8 @@ typedef struct tmf_minor_block {
 int64_t tmf_minor_desc_bytes(int nblocks); /* size of desc_dev for the call below */
 int tmf_minors_blocks(const tmf_minor_block *blocks_host, int nblocks, void *desc_dev,
                       void *stream);
+/* c128 variant (slater.py:857-869 with a complex sometimes matrix): S, det and out are complex, re/im interleaved */
+int tmf_minors_blocks_c(const tmf_minor_block *blocks_host, int nblocks, void *desc_dev, void *stream);
 
 
 /* ---- Pfaffian (Bogoliubov) path --------------------------------------------------------------
@@ -336,6 +360,9 @@ int64_t tmf_chain_job_voff(tmf_chain *c, int job);
  *                  bases by pivoted Cholesky + overlap GEMM + blocked LU (also the automatic fallback). */
 #define TMF_OPT_SNAP 1
 #define TMF_OPT_NESTED 2
+#define TMF_OPT_COMPLEX 4      /* 1: complex Slater determinant -- C_dev of modes / tensors is the 2L x 2L real embedding
+                                * (pitch ldc doubles), r_sketch counts real columns (twice the complex modes), V /
+                                * O / S / det / out buffers hold complex numbers (2 doubles per element) */
 #define TMF_OPT_DEVICE_PLAN 3  /* 1 (default): site planning (slater.py:760-825, :1027-1058, :1106-1141) on the
                                 * device from the resident enumeration tables (nested mode); 0: host threads */
 int tmf_chain_set_option(tmf_chain *c, int option, int value);

@@ -205,4 +205,7 @@ if __name__ == "__main__":
     dump_case(ref, "slater_random_L11_N4", random_hamiltonian(11, 3), {"chi_max": 64}, N=4)
     dump_case(ref, "slater_chain_L16", hopping_chain(16), {"chi_max": 64})
     dump_case(ref, "slater_random_L40", random_hamiltonian(40, 1), {"chi_max": 64})
+    # complex Hamiltonians (the reference's own acceptance example, examples/slater.py:15-27, is complex)
+    dump_case(ref, "slater_complex_L12", random_hamiltonian(12, 5, cplx=True), {"chi_max": 1000, "svd_min": 1e-7})
+    dump_case(ref, "slater_complex_L24_chi32", random_hamiltonian(24, 6, cplx=True), {"chi_max": 32})
     dump_lowest_sums(ref)

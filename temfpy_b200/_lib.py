@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libtemfpy_b200.so")
 
 TMF_MAX_MODES = 64
 SIDE_L, SIDE_R = 0, 1
-OPT_SNAP, OPT_NESTED, OPT_DEVICE_PLAN = 1, 2, 3
+OPT_SNAP, OPT_NESTED, OPT_DEVICE_PLAN, OPT_COMPLEX = 1, 2, 3, 4
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
@@ -98,6 +98,12 @@ SIGNATURES = {
     "tmf_slater_modes_nested": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p,
                                           C.c_double, C.c_int, c_i64_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "tmf_slater_modes_nested_emb": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p,
+                                              C.c_double, C.c_int, c_i64_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "tmf_slater_pair_bond_c_workspace": (C.c_int64, [C.c_int, C.c_int]),
+    "tmf_slater_pair_bond_c": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, C.c_double,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "tmf_slater_pair_bond_workspace": (C.c_int64, [C.c_int, C.c_int]),
     "tmf_slater_pair_bond": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, C.c_double,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -114,6 +120,9 @@ SIGNATURES = {
     "tmf_site_overlap_schur_batched": (C.c_int, [C.POINTER(SiteJob), C.c_int, C.c_void_p, C.c_void_p]),
     "tmf_site_nested_batched": (C.c_int, [C.POINTER(SiteJob), C.POINTER(NestedJob), C.c_int, C.c_void_p,
                                           C.c_void_p]),
+    "tmf_site_nested_c_batched": (C.c_int, [C.POINTER(SiteJob), C.POINTER(NestedJob), C.c_int, C.c_void_p,
+                                            C.c_void_p]),
+    "tmf_minors_blocks_c": (C.c_int, [C.POINTER(MinorBlock), C.c_int, C.c_void_p, C.c_void_p]),
     "tmf_minor_desc_bytes": (C.c_int64, [C.c_int]),
     "tmf_minors_blocks": (C.c_int, [C.POINTER(MinorBlock), C.c_int, C.c_void_p, C.c_void_p]),
     "tmf_chain_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,

@@ -91,6 +91,8 @@ struct tmf_chain {
   int nblocks = 0, max_chi = 0;
   bool enumerated = false;
   bool nested = true;                // nested-projector site stage (no filled bases), see siteprep.cu
+  bool cplx = false;                 // complex Slater determinant: C_dev is the 2L x 2L real embedding (TMF_OPT_COMPLEX)
+  std::vector<int> job_x2;           // cplx: cut positions in the embedded matrix (2 x)
   bool want_device_plan = true;      // plan the sites on the device when the enumeration ran there (nested mode)
   bool device_plan = false;          // ... and it did: bond tables + site plans are resident in the workspace
   bool tables_pending = false;       // bond tables still have to be unpacked from `tab_stage`
@@ -240,13 +242,18 @@ int fail_from(const std::exception &e) {
 // ([entangled | edge vector]) in the nested one
 static void chain_layout_slots(tmf_chain *c) {
   c->v_elems = 0;
+  c->job_x2.resize(c->job_x.size());
+  for (size_t j = 0; j < c->job_x.size(); ++j) c->job_x2[j] = 2 * c->job_x[j];
   for (size_t j = 0; j < c->job_x.size(); ++j) {
     const int bond = c->job_x[j], side = c->job_side[j];
     ChainSide &s = c->bonds[bond].side[side];
-    const int64_t cols = tmf_slater_modes_slot_cols(c->L, bond, side, c->r_sketch, c->nested ? 1 : 0);
+    // (complex: the slot holds the real columns of the embedded 2n-row block; afterwards the same memory read as
+    //  interleaved complex columns of n rows)
+    const int es = c->cplx ? 2 : 1;
+    const int64_t cols = tmf_slater_modes_slot_cols(es * c->L, es * bond, side, c->r_sketch, c->nested ? 1 : 0);
     s.v_off = c->v_elems;
     c->v_off[j] = s.v_off;
-    c->v_elems += (int64_t)s.n * cols + 32;  // + slack keeps every matrix 256-byte aligned
+    c->v_elems += (int64_t)es * s.n * cols + 32;  // + slack keeps every matrix 256-byte aligned
     c->v_elems = (c->v_elems + 31) & ~int64_t(31);
   }
 }
@@ -302,6 +309,12 @@ int tmf_chain_set_option(tmf_chain *c, int option, int value) {
     return TMF_OK;
   }
   if (option == TMF_OPT_DEVICE_PLAN) { c->want_device_plan = value != 0; return TMF_OK; }
+  if (option == TMF_OPT_COMPLEX) {
+    c->cplx = value != 0;
+    if (c->cplx) c->nested = true;      // the complex kernels exist in the nested form only
+    chain_layout_slots(c);
+    return TMF_OK;
+  }
   tmf::set_error("tmf_chain_set_option: unknown option");
   return TMF_ERR_VALUE;
 }
@@ -311,8 +324,8 @@ void tmf_chain_destroy(tmf_chain *c) { delete c; }
 int tmf_chain_modes_sizes(tmf_chain *c, int64_t *q) {
   q[0] = (int64_t)c->job_x.size();
   q[1] = c->v_elems;
-  q[2] = tmf_slater_modes_workspace(c->L, (int)c->job_x.size(), c->job_x.data(), c->job_side.data(),
-                                    c->r_sketch);
+  q[2] = c->cplx ? tmf_slater_modes_workspace(2 * c->L, (int)c->job_x.size(), c->job_x2.data(), c->job_side.data(), c->r_sketch)
+                 : tmf_slater_modes_workspace(c->L, (int)c->job_x.size(), c->job_x.data(), c->job_side.data(), c->r_sketch);
   q[3] = (int64_t)c->job_x.size() * (TMF_MAX_MODES + 2);   // doubles of e_dev (spectra + edge data)
   return TMF_OK;
 }
@@ -325,6 +338,10 @@ int tmf_chain_modes_enqueue(tmf_chain *c, const double *C_dev, int ldc, double *
   const int nj = (int)c->job_x.size();
   const double cutoff = c->tp.svd_min * c->tp.svd_min;  // slater.py:318
   c->e_dev_ptr = e_dev;
+  if (c->cplx)
+    return tmf_slater_modes_nested_emb(C_dev, 2 * c->L, ldc, nj, c->job_x2.data(), c->job_side.data(), cutoff,
+                                       c->r_sketch, c->v_off.data(), V_dev, e_dev, info_dev,
+                                       e_dev + (size_t)nj * TMF_MAX_MODES, work_dev, work_bytes, stream);
   if (c->nested)
     return tmf_slater_modes_nested(C_dev, c->L, ldc, nj, c->job_x.data(), c->job_side.data(), cutoff,
                                    c->r_sketch, c->v_off.data(), V_dev, e_dev, info_dev,
@@ -360,6 +377,7 @@ int tmf_chain_modes_finish(tmf_chain *c, const double *e_dev, const int *info_de
   for (int j = 0; j < nj; ++j) {
     const int st = c->info_host[4 * j + 2];
     if (st & 2) return fail(TMF_ERR_VALUE, "more than 64 entangled modes on one bond");
+    if (st & 4) return fail(TMF_ERR_RUNTIME, "complex modes: the real eigenvector pairs of the embedded matrix could not be paired");
     if (st & 1)
       return fail(TMF_ERR_VALUE,
                   "range sketch too narrow for this entanglement spectrum: rerun with a larger r_sketch");
@@ -652,7 +670,7 @@ static int chain_enumerate_impl(tmf_chain *c, void *work_dev, int64_t work_bytes
                 tmf::align256(8 * (int64_t)h.n_rows) + tmf::align256(8 * (int64_t)h.chi_ket);
     }
     const int kc = c->bonds[c->oc].used ? c->bonds[c->oc].k : 0;
-    const int64_t pair = tmf_slater_pair_bond_workspace(c->L, kc) + 512;
+    const int64_t pair = (c->cplx ? tmf_slater_pair_bond_c_workspace(c->L, kc) : tmf_slater_pair_bond_workspace(c->L, kc)) + 512;
     c->plan_bytes = plan + tmf_site_desc_bytes((int)c->sites.size()) + tmf_minor_desc_bytes(c->nblocks) +
                     pair + 4096;
     c->enumerated = true;
@@ -756,6 +774,15 @@ static int centre_pairing(tmf_chain *c, const double *C_dev, int ldc, double *V_
                           void *stream) {
   ChainBond &B = c->bonds[c->oc];
   if (!B.used || B.side[0].job < 0 || B.side[1].job < 0 || B.k == 0) return TMF_OK;
+  if (c->cplx) {
+    const int64_t wbc = tmf_slater_pair_bond_c_workspace(c->L, B.k);
+    void *workc = ar.take<unsigned char>(wbc);
+    if (!ar.ok()) return fail(TMF_ERR_VALUE, "plan workspace too small (pairing)");
+    return tmf_slater_pair_bond_c(C_dev, ldc, c->L, c->oc, B.k,
+                                  c->e_host.data() + (size_t)B.side[TMF_SIDE_L].job * TMF_MAX_MODES,
+                                  c->tp.degeneracy_tol, V_dev + B.side[TMF_SIDE_L].v_off,
+                                  V_dev + B.side[TMF_SIDE_R].v_off, workc, wbc, stream);
+  }
   const int64_t wb = tmf_slater_pair_bond_workspace(c->L, B.k);
   void *work = ar.take<unsigned char>(wb);
   if (!ar.ok()) return fail(TMF_ERR_VALUE, "plan workspace too small (pairing)");
@@ -776,6 +803,7 @@ static int chain_tensors_device_plan(tmf_chain *c, const double *C_dev, int ldc,
   std::vector<tmf_minor_block> mb((size_t)c->nblocks);
   const double *e_dev = c->e_dev_ptr;
   if (e_dev == nullptr) return fail(TMF_ERR_VALUE, "tmf_chain_modes has not run");
+  const int es = c->cplx ? 2 : 1;      // doubles per element of O / S / det / out (and per row of C_dev)
   int mb0 = 0;
   for (int u = 0; u < ns; ++u) {
     ChainSite &s = c->sites[u];
@@ -790,7 +818,7 @@ static int chain_tensors_device_plan(tmf_chain *c, const double *C_dev, int ldc,
     j.ldb = std::max(bs.n, 1); j.ldk = std::max(ks.n, 1);
     j.bra_cols = s.cols_dev; j.ket_cols = s.cols_dev + tmf::PLAN_MAX_ORB;
     j.bra_sign = s.signs_dev; j.ket_sign = s.signs_dev + tmf::PLAN_MAX_ORB;
-    j.O = O_dev + s.o_off; j.S = S_dev + s.s_off; j.det = det_dev + u;
+    j.O = O_dev + es * s.o_off; j.S = S_dev + es * s.s_off; j.det = det_dev + es * u;
     j.n_bra = h.n_bra; j.n_ket = h.n_ket; j.mode = h.mode; j.physical = h.physical;
     j.ka_bra = h.ka_bra; j.ka_ket = h.ka_ket; j.sb = sb0; j.sk = sk0;
     j.pad_[1] = 1;
@@ -798,8 +826,9 @@ static int chain_tensors_device_plan(tmf_chain *c, const double *C_dev, int ldc,
     std::memset(&q, 0, sizeof(q));
     q.e_bra = e_dev + (size_t)bs.job * TMF_MAX_MODES;
     q.e_ket = e_dev + (size_t)ks.job * TMF_MAX_MODES;
-    q.c_edge = C_dev + (int64_t)s.site * ldc + s.site;
-    q.a_col = (s.mode == 1) ? q.c_edge + 1 : C_dev + (int64_t)s.site * ldc;
+    // (embedded complex matrix: row 2e holds conj(C[e, :]) = C[:, e]^T interleaved, entry [2e][2e] = C[e, e])
+    q.c_edge = C_dev + (int64_t)es * s.site * ldc + es * s.site;
+    q.a_col = (s.mode == 1) ? q.c_edge + es : C_dev + (int64_t)es * s.site * ldc;
     q.k_bra = bb.k; q.k_ket = kb.k; q.df = s.df;
     for (int b = 0; b < h.n_blocks; ++b) {
       const int *bl = &s.plan.blocks[6 * b];
@@ -807,7 +836,7 @@ static int chain_tensors_device_plan(tmf_chain *c, const double *C_dev, int ldc,
       std::memset(&k, 0, sizeof(k));
       k.S = j.S; k.det = j.det;
       k.bra_masks = s.bra_masks_dev + bl[0]; k.ket_masks = s.ket_masks_dev + bl[2];
-      k.out = out_dev + s.block_off[b];
+      k.out = out_dev + es * s.block_off[b];
       k.s_bra = h.s_bra; k.s_ket = h.s_ket; k.n_bra = bl[1]; k.n_ket = bl[3]; k.minor = bl[4];
     }
     mb0 += h.n_blocks;
@@ -815,9 +844,11 @@ static int chain_tensors_device_plan(tmf_chain *c, const double *C_dev, int ldc,
   void *site_desc = ar.take<unsigned char>(tmf_site_desc_bytes(ns));
   void *minor_desc = ar.take<unsigned char>(tmf_minor_desc_bytes((int)mb.size()));
   if (!ar.ok()) return fail(TMF_ERR_VALUE, "plan workspace too small");
-  int rc = tmf_site_nested_batched(sj.data(), nj.data(), ns, site_desc, stream);
+  int rc = c->cplx ? tmf_site_nested_c_batched(sj.data(), nj.data(), ns, site_desc, stream)
+                   : tmf_site_nested_batched(sj.data(), nj.data(), ns, site_desc, stream);
   if (rc) return rc;
-  rc = tmf_minors_blocks(mb.data(), (int)mb.size(), minor_desc, stream);
+  rc = c->cplx ? tmf_minors_blocks_c(mb.data(), (int)mb.size(), minor_desc, stream)
+               : tmf_minors_blocks(mb.data(), (int)mb.size(), minor_desc, stream);
   if (rc) return rc;
   // bond tables -> pinned host staging, behind the kernels (read by the accessors / bulk exports)
   {
@@ -855,6 +886,7 @@ int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev,
   if (rc) return rc;
   tm.lap("tensors: centre pairing");
   if (c->device_plan) return chain_tensors_device_plan(c, C_dev, ldc, V_dev, ar, O_dev, S_dev, det_dev, out_dev, stream);
+  const int es = c->cplx ? 2 : 1;      // doubles per element of O / S / det / out
   // ---- one blob with every per-site index / sign / mask array ------------------------------
   // pass 1 (serial, cheap): offsets of every array; pass 2 (threads over sites): copy + descriptors
   const int ns = (int)c->sites.size();
@@ -905,7 +937,7 @@ int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev,
     j.ket_cols = reinterpret_cast<const int *>(put(so[u].kc, s.plan.ket_cols.data(), 4 * (size_t)cols));
     j.bra_sign = reinterpret_cast<const double *>(put(so[u].bs, s.plan.bra_sign.data(), 8 * (size_t)rows));
     j.ket_sign = reinterpret_cast<const double *>(put(so[u].ks, s.plan.ket_sign.data(), 8 * (size_t)cols));
-    j.O = O_dev + s.o_off; j.S = S_dev + s.s_off; j.det = det_dev + u;
+    j.O = O_dev + es * s.o_off; j.S = S_dev + es * s.s_off; j.det = det_dev + es * u;
     j.n_bra = h.n_bra; j.n_ket = h.n_ket; j.mode = h.mode; j.physical = h.physical;
     j.ka_bra = h.ka_bra; j.ka_ket = h.ka_ket; j.sb = sb0; j.sk = sk0;
     j.pad_[1] = 1;   // report a singular always block (incompatible neighbouring bonds) as NaN
@@ -917,7 +949,7 @@ int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev,
       std::memset(&k, 0, sizeof(k));
       k.S = j.S; k.det = j.det;
       k.bra_masks = bm + bl[0]; k.ket_masks = km + bl[2];
-      k.out = out_dev + s.block_off[b];
+      k.out = out_dev + es * s.block_off[b];
       k.s_bra = h.s_bra; k.s_ket = h.s_ket; k.n_bra = bl[1]; k.n_ket = bl[3]; k.minor = bl[4];
     }
   });
@@ -941,17 +973,19 @@ int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev,
       std::memset(&q, 0, sizeof(q));
       q.e_bra = e_dev + (size_t)bb.side[side].job * TMF_MAX_MODES;
       q.e_ket = e_dev + (size_t)kb.side[side].job * TMF_MAX_MODES;
-      q.c_edge = C_dev + (int64_t)s.site * ldc + s.site;
-      q.a_col = (s.mode == 1) ? q.c_edge + 1 : C_dev + (int64_t)s.site * ldc;
+      q.c_edge = C_dev + (int64_t)es * s.site * ldc + es * s.site;
+      q.a_col = (s.mode == 1) ? q.c_edge + es : C_dev + (int64_t)es * s.site * ldc;
       q.k_bra = bb.k; q.k_ket = kb.k; q.df = s.df;
     }
-    rc = tmf_site_nested_batched(sj.data(), nj.data(), ns, site_desc, stream);
+    rc = c->cplx ? tmf_site_nested_c_batched(sj.data(), nj.data(), ns, site_desc, stream)
+                 : tmf_site_nested_batched(sj.data(), nj.data(), ns, site_desc, stream);
   } else {
     rc = tmf_site_overlap_schur_batched(sj.data(), ns, site_desc, stream);
   }
   if (rc) return rc;
   tm.lap("tensors: enqueue site kernels");
-  rc = tmf_minors_blocks(mb.data(), (int)mb.size(), minor_desc, stream);
+  rc = c->cplx ? tmf_minors_blocks_c(mb.data(), (int)mb.size(), minor_desc, stream)
+               : tmf_minors_blocks(mb.data(), (int)mb.size(), minor_desc, stream);
   tm.lap("tensors: enqueue minors");
   return rc;
 }

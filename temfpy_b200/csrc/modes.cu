@@ -255,6 +255,7 @@ extern "C" int64_t tmf_slater_modes_workspace(int L, int njobs, const int *job_x
   const int panels = (r_sketch + PANEL_W - 1) / PANEL_W;
   bytes += align256((int64_t)(nbig + 1) * 128 * (16 + 10 * panels) + (int64_t)(nsmall + 1) * 64 + (int64_t)(L + 1) * 32 + 65536);
   bytes += align256((int64_t)(njobs + 2) * 64);   // edge-vector descriptors (nested mode)
+  bytes += align256((int64_t)(njobs + 2) * 32);   // complex pairing descriptors (embedded complex matrices)
   return bytes;
 }
 
@@ -262,7 +263,7 @@ static int modes_impl(const double *C_dev, int L, int ldc, int njobs,
                       const int *job_x, const int *job_side, double cutoff,
                       int r_sketch, const int64_t *v_off, double *V_dev,
                       double *e_dev, int *info_dev, void *work_dev,
-                      int64_t work_bytes, void *stream, bool nested, double *edge_dev) {
+                      int64_t work_bytes, void *stream, bool nested, double *edge_dev, bool emb = false) {
   using namespace tmf;
   if (r_sketch <= 0 || r_sketch > R_SKETCH_MAX) {
     set_error("r_sketch must be in 1..160");
@@ -511,7 +512,7 @@ static int modes_impl(const double *C_dev, int L, int ldc, int njobs,
     auto mk_edge = [&](int j, const double *A, int n, int side) {
       EdgeJob q;
       q.A = A; q.V = V_dev + v_off[j]; q.e_left = e_dev + (int64_t)j * TMF_MAX_MODES; q.info = info_dev + 4 * j;
-      q.edge_out = edge_dev + 2 * (int64_t)j; q.n = n; q.lda = ldc; q.side = side; q.pad_ = 0;
+      q.edge_out = edge_dev + 2 * (int64_t)j; q.n = n; q.lda = ldc; q.side = side; q.emb = emb ? 1 : 0;
       return q;
     };
     for (auto &sj2 : small) {
@@ -521,6 +522,17 @@ static int modes_impl(const double *C_dev, int L, int ldc, int njobs,
     for (auto &b : big) edge_big.push_back(mk_edge(b.job, b.A, b.n, b.side));
   }
   const EdgeJob *edge_small_dev = blob.add(edge_small), *edge_big_dev = blob.add(edge_big);
+  // embedded complex matrix: complex modes out of the real eigenvector pairs, after everything else
+  std::vector<PairCJob> pairc;
+  if (emb)
+    for (int j = 0; j < njobs; ++j) {
+      int n, m;
+      job_geometry(L, job_x[j], job_side[j], n, m);
+      PairCJob q;
+      q.V = V_dev + v_off[j]; q.e_left = e_dev + (int64_t)j * TMF_MAX_MODES; q.info = info_dev + 4 * j; q.n_emb = n; q.side = job_side[j];
+      pairc.push_back(q);
+    }
+  const PairCJob *pairc_dev = blob.add(pairc);
 
   if ((int64_t)(blob_dev - static_cast<unsigned char *>(work_dev)) + (int64_t)blob.host.size() > work_bytes) {
     set_error("modes: descriptor blob does not fit the workspace");
@@ -546,7 +558,10 @@ static int modes_impl(const double *C_dev, int L, int ldc, int njobs,
       if (rc) return rc;
     }
   }
-  if (nb == 0) return TMF_OK;
+  if (nb == 0) {
+    if (emb) return launch_t("pair_complex", pair_complex_kernel, njobs, 256, pairc_smem_bytes(), stream, pairc_dev);
+    return TMF_OK;
+  }
   rc = launch_t("omega", omega_kernel, (int)(((int64_t)L * r_sketch + 1023) / 1024), 256, 0, stream, Om, L, r_sketch);
   if (rc) return rc;
   auto run = [&](const GemmLaunch &gl) {
@@ -623,7 +638,10 @@ static int modes_impl(const double *C_dev, int L, int ldc, int njobs,
     rc = launch_t("pivchol", pivchol_kernel, nb, pivchol_threads, chol_smem, stream, cj_dev, chol_tol);
   if (rc) return rc;
   tm.lap("modes: launches", njobs);
-  return fork.join(stream);
+  rc = fork.join(stream);
+  if (rc) return rc;
+  if (emb) rc = launch_t("pair_complex", pair_complex_kernel, njobs, 256, pairc_smem_bytes(), stream, pairc_dev);
+  return rc;
 }
 
 extern "C" int tmf_slater_modes_batched(const double *C_dev, int L, int ldc, int njobs,
@@ -657,4 +675,23 @@ extern "C" int tmf_slater_modes_nested(const double *C_dev, int L, int ldc, int 
   }
   return modes_impl(C_dev, L, ldc, njobs, job_x, job_side, cutoff, r_sketch, v_off, V_dev, e_dev, info_dev, work_dev,
                     work_bytes, stream, true, edge_dev);
+}
+
+// The same for the re/im-interleaved real embedding (2L x 2L, cuts at 2x) of a complex Hermitian projector
+// (complex Slater determinants, slater.py:1150-1180 keeps complex C): the per-bond eigenproblems of the complex
+// blocks (slater.py:347, zheevd in the reference) run through the real kernels, every complex eigenvector showing
+// up as a doubly degenerate real pair; pair_complex_kernel then picks the k complex modes (interleaved complex
+// = the same memory as the real columns) and the edge vector is the embedding of the complex one.
+// On return: info[0] = k complex modes, info[1] = f complex filled orbitals, e[0..k) their left eigenvalues.
+extern "C" int tmf_slater_modes_nested_emb(const double *Cemb_dev, int L2, int ldc, int njobs,
+                                           const int *job_x2, const int *job_side, double cutoff,
+                                           int r_sketch, const int64_t *v_off, double *V_dev,
+                                           double *e_dev, int *info_dev, double *edge_dev, void *work_dev,
+                                           int64_t work_bytes, void *stream) {
+  if (edge_dev == nullptr || (L2 & 1)) {
+    tmf::set_error("tmf_slater_modes_nested_emb: edge_dev is required and the embedded size must be even");
+    return TMF_ERR_VALUE;
+  }
+  return modes_impl(Cemb_dev, L2, ldc, njobs, job_x2, job_side, cutoff, r_sketch, v_off, V_dev, e_dev, info_dev,
+                    work_dev, work_bytes, stream, true, edge_dev, true);
 }

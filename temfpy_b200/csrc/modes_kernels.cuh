@@ -1040,7 +1040,7 @@ struct EdgeJob {
   const double *e_left;  // left eigenvalues of the k modes
   int *info;             // reads info[0] = k, writes info[1] = f
   double *edge_out;      // [0] = |P_F e_edge|^2, [1] = tr A - sum lam - f
-  int n, lda, side, pad_;
+  int n, lda, side, emb;   // emb = 1: re/im-interleaved embedding of a complex matrix (the edge site has two rows)
 };
 TMF_GLOBAL edge_vector_kernel(const EdgeJob *jobs) {
   const EdgeJob jb = jobs[BLOCK_ID];
@@ -1051,7 +1051,7 @@ TMF_GLOBAL edge_vector_kernel(const EdgeJob *jobs) {
   }
   int k = jb.info[0];
   if (k > TMF_MAX_MODES) k = TMF_MAX_MODES;   // flagged by the Ritz kernel (status 2)
-  const int edge = (jb.side == TMF_SIDE_R) ? 0 : n - 1;
+  const int edge = (jb.side == TMF_SIDE_R) ? 0 : n - (jb.emb ? 2 : 1);   // (embedded: the row of the real part)
   DYN_SMEM(double, sm);
   double *lam = sm, *wx = lam + TMF_MAX_MODES, *coef = wx + TMF_MAX_MODES;
   double *part = coef + TMF_MAX_MODES;          // (TMF_MAX_MODES + 2) * 33
@@ -1114,6 +1114,149 @@ TMF_GLOBAL edge_vector_kernel(const EdgeJob *jobs) {
   }
 }
 inline size_t edge_smem_bytes() { return sizeof(double) * (3 * TMF_MAX_MODES + (TMF_MAX_MODES + 2) * 33); }
+
+// ---------------------------------------------------------------------------------------------
+// Complex modes out of the real eigenvectors of an embedded Hermitian matrix (complex Slater path).
+// The re/im-interleaved embedding of a complex vector w is the real vector emb(w); every complex eigenvector
+// of the Hermitian block appears in the embedded real block as the plane span{emb(w), J emb(w)} (J = times i)
+// with a doubly degenerate eigenvalue, and the real solver returns an arbitrary orthonormal basis of it (or of
+// the union of several planes when eigenvalues coincide numerically).  Any unit vector of the plane is emb of
+// a phase times w -- a valid eigenvector -- so the k complex modes are picked by a complex Gram-Schmidt sweep
+// over the 2k real columns in eigenvalue order: a column whose remainder after removing the *complex* span of
+// the modes chosen so far keeps more than a quarter of its norm opens a new mode.  In place: chosen mode j
+// (as interleaved complex = the same memory as a real column) goes to column j, its eigenvalue to e[j], the
+// edge vector moves from column 2k to column k.
+// ---------------------------------------------------------------------------------------------
+struct PairCJob {
+  double *V;        // n_emb x (k_emb + 1), ld = n_emb
+  double *e_left;   // in: k_emb eigenvalues (pairs), out: k
+  int *info;        // in: [0] = k_emb, [1] = f_emb; out: k, f; [2] |= 4 on failure
+  int n_emb, side;
+};
+TMF_GLOBAL pair_complex_kernel(const PairCJob *jobs) {
+  const PairCJob jb = jobs[BLOCK_ID];
+  const int n = jb.n_emb, ke = jb.info[0] > TMF_MAX_MODES ? TMF_MAX_MODES : jb.info[0];
+  DYN_SMEM(double, sm);
+  double *part = sm;                     // 3 * 33
+  double *eo = part + 3 * 33 + 1;        // TMF_MAX_MODES: eigenvalues of the chosen modes
+  double *absw = eo + TMF_MAX_MODES;     // weight of the skipped columns inside every chosen mode's plane
+  double *tmpw = absw + TMF_MAX_MODES;
+  int *misc = reinterpret_cast<int *>(tmpw + TMF_MAX_MODES);
+  if (n <= 0) return;
+  PAR_FOR(j, TMF_MAX_MODES) absw[j] = 0.0;
+  PAR_FOR(one, 1) misc[0] = 0;
+  CTA_SYNC();
+  for (int c = 0; c < ke; ++c) {
+    double *a = jb.V + (int64_t)c * n;
+    const int m = misc[0];
+    for (int j = 0; j < m; ++j) {
+      const double *w = jb.V + (int64_t)j * n;
+      // coef = w^dagger a  (complex inner product of the interleaved vectors)
+      PAR_FOR(lane, 32) {
+        double re = 0.0, im = 0.0;
+        for (int r = 2 * lane; r < n; r += 64) {
+          re += w[r] * a[r] + w[r + 1] * a[r + 1];
+          im += w[r] * a[r + 1] - w[r + 1] * a[r];
+        }
+        part[lane] = re; part[33 + lane] = im;
+      }
+      CTA_SYNC();
+      double re = 0.0, im = 0.0;
+      for (int l = 0; l < 32; ++l) { re += part[l]; im += part[33 + l]; }
+      CTA_SYNC();
+      PAR_FOR(one, 1) tmpw[j] = re * re + im * im;
+      PAR_FOR(h, n / 2) {
+        const double wr = w[2 * h], wi = w[2 * h + 1];
+        a[2 * h] -= wr * re - wi * im;
+        a[2 * h + 1] -= wr * im + wi * re;
+      }
+      CTA_SYNC();
+    }
+    PAR_FOR(lane, 32) {
+      double t = 0.0;
+      for (int r = lane; r < n; r += 32) t += a[r] * a[r];
+      part[66 + lane] = t;
+    }
+    CTA_SYNC();
+    double nrm2 = 0.0;
+    for (int l = 0; l < 32; ++l) nrm2 += part[66 + l];
+    CTA_SYNC();
+    if (nrm2 > 0.25 && m < TMF_MAX_MODES / 2) {
+      const double inv = 1.0 / sqrt(nrm2);
+      double *dst = jb.V + (int64_t)m * n;
+      PAR_FOR(r, n) dst[r] = a[r] * inv;
+      PAR_FOR(one, 1) { eo[m] = jb.e_left[c]; misc[0] = m + 1; }
+    } else {
+      PAR_FOR(j, m) absw[j] += tmpw[j];
+    }
+    CTA_SYNC();
+  }
+  const int k = misc[0];
+  // edge vector: column k_emb -> column k (k <= k_emb; equal only for k_emb <= 1, when nothing has to move),
+  // orthogonalised against the *complex* span of the chosen modes (a no-op unless a pair was split by the
+  // entanglement cutoff: then its lone member stands for the complex mode and the partner J v leaves the filled space)
+  double *g = jb.V + (int64_t)k * n;
+  if (k != ke) {
+    const double *src = jb.V + (int64_t)ke * n;
+    PAR_FOR(r, n) g[r] = src[r];
+    CTA_SYNC();
+  }
+  for (int j = 0; j < k; ++j) {
+    const double *w = jb.V + (int64_t)j * n;
+    PAR_FOR(lane, 32) {
+      double re = 0.0, im = 0.0;
+      for (int r = 2 * lane; r < n; r += 64) {
+        re += w[r] * g[r] + w[r + 1] * g[r + 1];
+        im += w[r] * g[r + 1] - w[r + 1] * g[r];
+      }
+      part[lane] = re; part[33 + lane] = im;
+    }
+    CTA_SYNC();
+    double re = 0.0, im = 0.0;
+    for (int l = 0; l < 32; ++l) { re += part[l]; im += part[33 + l]; }
+    CTA_SYNC();
+    PAR_FOR(h, n / 2) {
+      const double wr = w[2 * h], wi = w[2 * h + 1];
+      g[2 * h] -= wr * re - wi * im;
+      g[2 * h + 1] -= wr * im + wi * re;
+    }
+    CTA_SYNC();
+  }
+  PAR_FOR(lane, 32) {
+    double t = 0.0;
+    for (int r = lane; r < n; r += 32) t += g[r] * g[r];
+    part[66 + lane] = t;
+  }
+  CTA_SYNC();
+  double gn2 = 0.0;
+  for (int l = 0; l < 32; ++l) gn2 += part[66 + l];
+  CTA_SYNC();
+  if (gn2 > 0.0) {
+    const double inv = 1.0 / sqrt(gn2);
+    PAR_FOR(r, n) g[r] *= inv;
+  }
+  PAR_FOR(one, 1) {
+    // lone members (no skipped partner inside their plane): the partner was classified filled (side eigenvalue
+    // ~ 1) or empty (~ 0) by the cutoff; the complex mode counts as entangled, the filled count loses the partner
+    int f_emb = jb.info[1], lone = 0;
+    for (int j = 0; j < k; ++j)
+      if (absw[j] < 0.5) {
+        ++lone;
+        const double lam = (jb.side == TMF_SIDE_L) ? eo[j] : 1.0 - eo[j];
+        if (lam > 0.5) --f_emb;
+      }
+#if defined(TMF_HOSTSIM)
+    if ((2 * k - lone != ke || (f_emb & 1) || f_emb < 0) && std::getenv("TMF_DEBUG_PAIR"))
+      fprintf(stderr, "pair_complex: n_emb %d k_emb %d chosen %d lone %d f_emb %d -> %d\n", n, ke, k, lone, jb.info[1], f_emb);
+#endif
+    if (2 * k - lone != ke || (f_emb & 1) || f_emb < 0) jb.info[2] |= 4;
+    jb.info[0] = k;
+    jb.info[1] = f_emb / 2;
+  }
+  CTA_SYNC();
+  PAR_FOR(j, TMF_MAX_MODES) jb.e_left[j] = (j < k) ? eo[j] : 0.0;
+}
+inline size_t pairc_smem_bytes() { return sizeof(double) * (3 * 33 + 1 + 3 * TMF_MAX_MODES) + 64; }
 
 inline size_t ritz_smem_bytes(int n) {
   int np = (n + 1) & ~1;

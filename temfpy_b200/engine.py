@@ -129,7 +129,8 @@ class SiteTensor:
 
     def dense_pab(self) -> np.ndarray:
         """T[p, alpha(bra), beta(ket)] exactly like the oracle's dense_tensor."""
-        T = np.zeros((2, self.plan.chi_bra, self.plan.chi_ket))
+        dtype = self.blocks[0][5].dtype if self.blocks else np.float64
+        T = np.zeros((2, self.plan.chi_bra, self.plan.chi_ket), dtype=dtype)
         for (_, r0, nr, c0, nc, blk) in self.blocks:
             rows = slice(r0, r0 + nr)
             T[self.row_p[rows][:, None], self.row_alpha[rows][:, None], np.arange(c0, c0 + nc)[None, :]] = blk
@@ -412,8 +413,10 @@ class SlaterChain:
     """One chain conversion on one device for the sites [site_lo, site_hi)."""
 
     def __init__(self, backend, L, trunc, n_fermion, ortho_center=None, site_lo=0, site_hi=None,
-                 r_sketch=48, n_threads=0, snap=False, nested=None, device_plan=None):
+                 r_sketch=48, n_threads=0, snap=False, nested=None, device_plan=None, cplx=False):
         self.be = backend
+        self.cplx = bool(cplx)
+        self.es = 2 if cplx else 1       # doubles per tensor element
         self.lib = backend.lib
         self.L = int(L)
         self.oc = ortho_center or self.L // 2                      # slater.py:1291
@@ -438,6 +441,8 @@ class SlaterChain:
             check(self.lib, self.lib.tmf_chain_set_option(self.handle, _lib.OPT_NESTED, int(bool(nested))))
         if device_plan is not None:
             check(self.lib, self.lib.tmf_chain_set_option(self.handle, _lib.OPT_DEVICE_PLAN, int(bool(device_plan))))
+        if cplx:      # C_dev of the stages below is the 2L x 2L real embedding, r_sketch counts real columns
+            check(self.lib, self.lib.tmf_chain_set_option(self.handle, _lib.OPT_COMPLEX, 1))
         self._buffers = {}
 
     def close(self):
@@ -502,11 +507,12 @@ class SlaterChain:
         plan_bytes, o_elems, s_elems, nsites, nblocks, out_elems, max_chi = (int(x) for x in q[:7])
         self.path = dict(nested=bool(int(q[7]) & 1), device_plan=bool(int(q[7]) & 2))
         b = self._buffers           # ("work" stays: it holds the resident enumeration tables / site plans)
+        es = self.es
         b["plan"] = be.empty(plan_bytes, np.uint8)
-        b["O"] = be.empty(o_elems, np.float64)
-        b["S"] = be.empty(s_elems, np.float64)
-        b["det"] = be.empty(nsites, np.float64)
-        b["out"] = out if out is not None else be.empty(out_elems, np.float64)
+        b["O"] = be.empty(es * o_elems, np.float64)
+        b["S"] = be.empty(es * s_elems, np.float64)
+        b["det"] = be.empty(es * nsites, np.float64)
+        b["out"] = out if out is not None else be.empty(es * out_elems, np.float64)
         self.out_elems, self.nblocks, self.max_chi = out_elems, nblocks, max_chi
         check(lib, lib.tmf_chain_tensors(self.handle, be.ptr(C_dev), int(ldc), be.ptr(b["V"]),
                                          be.ptr(b["plan"]), plan_bytes, be.ptr(b["O"]), be.ptr(b["S"]),
@@ -514,7 +520,7 @@ class SlaterChain:
         # the per-site determinants (8 bytes each) come back with a plain copy: a NaN among them reports a broken
         # elimination (check_det) -- no library reduction kernels on the stream
         if hasattr(be, "to_host_async"):
-            b["det_host"] = be.to_host_async(b["det"], nsites)
+            b["det_host"] = be.to_host_async(b["det"], es * nsites)
 
     # -- results ----------------------------------------------------------------------------------
     def bond(self, x) -> BondData:
@@ -584,14 +590,16 @@ class SlaterChain:
                 tc = self.be.torch.cuda
                 evs = (tc.Event(enable_timing=True), tc.Event(enable_timing=True))
                 evs[0].record(tc.current_stream(self.be.device))
-            host = self.be.to_host_async(self._buffers["out"], self.out_elems)   # overlaps the table export
+            host = self.be.to_host_async(self._buffers["out"], self.es * self.out_elems)   # overlaps the table export
             if evs:
                 evs[1].record(self.be.torch.cuda.current_stream(self.be.device))
         t1 = time.perf_counter()
         if fetch_tensors and host is None:
-            out_host = self.be.to_host(self._buffers["out"], self.out_elems)
+            out_host = self.be.to_host(self._buffers["out"], self.es * self.out_elems)
         else:
             out_host = host.numpy() if host is not None else None
+        if out_host is not None and self.cplx:
+            out_host = out_host.view(np.complex128)
         tab = ShardTables(self, out_host)
         tab._pinned = host
         tab.normalized()
@@ -635,11 +643,11 @@ SKETCH_WIDTHS = (48, 64, 128, 160)
 
 
 def _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch, n_threads,
-               fetch_tensors, lazy=False, gate=None, snap=False, nested=None, device_plan=None):
+               fetch_tensors, lazy=False, gate=None, snap=False, nested=None, device_plan=None, cplx=False):
     import time
     gate = gate or _NoGate()
     chain = SlaterChain(backend, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch, n_threads, snap=snap,
-                        nested=nested, device_plan=device_plan)
+                        nested=nested, device_plan=device_plan, cplx=cplx)
     ok = False
     try:
         tt = [time.perf_counter()]
@@ -733,7 +741,7 @@ class DeviceChainResult:
         return sum(c.out_elems for c in self.chains)
 
     def out_buffers(self):
-        return [(c._buffers["out"], c.out_elems) for c in self.chains]
+        return [(c._buffers["out"], c.es * c.out_elems) for c in self.chains]
 
     def bond(self, x):
         for c in self.chains:
@@ -757,7 +765,7 @@ class DeviceChainResult:
 
 def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_lo=0, site_hi=None,
               r_sketch=48, n_threads=0, fetch_tensors=True, n_chunks=None, lazy=False, snap=False, nested=None,
-              device_plan=None):
+              device_plan=None, cplx=False):
     """C (device) -> Schmidt data of every bond and block-sparse tensor of every site.
 
     The site range is cut into cost-balanced chunks that run as a software pipeline: one worker
@@ -775,7 +783,7 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
     ``snap=False`` (default) is the reference's literal truncation (schmidt_utils.py:140-185 only sees
     degeneracies below ``degeneracy_tol``; where a multiplet that is degenerate in exact arithmetic straddles
     ``chi_max`` the kept part is decided by the rounding noise of the mode eigenvalues, in the reference as here)."""
-    opts = dict(r_sketch=r_sketch, snap=snap, nested=nested, device_plan=device_plan)
+    opts = dict(r_sketch=r_sketch, snap=snap, nested=nested, device_plan=device_plan, cplx=cplx)
     while True:
         try:
             return _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi,
@@ -788,7 +796,7 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
                 opts["r_sketch"] = wider[0]
             elif rt.kind == "singular" and not opts["snap"]:
                 opts["snap"] = True             # never cut inside a numerically degenerate multiplet
-            elif opts["nested"] is False:
+            elif opts["nested"] is False or opts.get("cplx"):
                 raise rt.err
             else:
                 opts["nested"] = False
@@ -798,6 +806,7 @@ def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site
                     fetch_tensors, n_chunks, lazy, opts):
     from .dist import partition
     r_sketch, snap, nested, device_plan = opts["r_sketch"], opts["snap"], opts["nested"], opts["device_plan"]
+    cplx = opts.get("cplx", False)
     site_hi = L if site_hi is None else site_hi
     nsites = site_hi - site_lo
     if n_chunks is None:
@@ -807,7 +816,7 @@ def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site
     n_chunks = max(1, min(n_chunks, nsites))
     if n_chunks == 1:
         r = _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi, r_sketch,
-                       n_threads, fetch_tensors, lazy, snap=snap, nested=nested, device_plan=device_plan)
+                       n_threads, fetch_tensors, lazy, snap=snap, nested=nested, device_plan=device_plan, cplx=cplx)
         if lazy:
             r = DeviceChainResult([r])
         r.options = dict(opts)
@@ -836,7 +845,7 @@ def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site
             try:
                 return _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch,
                                   n_threads, fetch_tensors, lazy, gate=stages.gate(pos) if stages else None,
-                                  snap=snap, nested=nested, device_plan=device_plan)
+                                  snap=snap, nested=nested, device_plan=device_plan, cplx=cplx)
             except _Retry as rt:        # the other chunks finish; the driver then starts over
                 return rt
 

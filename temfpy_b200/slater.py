@@ -43,14 +43,35 @@ def _want_tenpy(as_tenpy):
     return bool(as_tenpy)
 
 
-def _real_or_raise(M, what):
+def _real_or_complex(M):
+    """float64 array, or complex128 if the imaginary part does not vanish (slater.py:1178-1179 drops a ~0 one)."""
     M = np.asarray(M)
     if np.iscomplexobj(M):
         if np.allclose(M.imag, 0.0, rtol=0, atol=1e-14):
             return np.ascontiguousarray(M.real, dtype=np.float64)
-        raise NotImplementedError(f"complex {what}: the sm_100a kernels of this release are FP64 real "
-                                  "(complex128 variant: see DESIGN.md 'out of scope')")
+        return np.ascontiguousarray(M, dtype=np.complex128)
     return np.ascontiguousarray(M, dtype=np.float64)
+
+
+def _real_or_raise(M, what):
+    M = _real_or_complex(M)
+    if np.iscomplexobj(M):
+        raise NotImplementedError(f"complex {what}: this entry point is real-only (complex Slater determinants are "
+                                  "supported by correlation_matrix / C_to_MPS / H_to_MPS)")
+    return M
+
+
+def embed_complex(C: np.ndarray) -> np.ndarray:
+    """Re/im-interleaved real embedding of a complex matrix: ``E[2i+a, 2j+b]`` = ``[[Re, -Im], [Im, Re]]`` of
+    ``C[i, j]``.  A Hermitian projector becomes a real symmetric projector of twice the rank; the embedding of a
+    vector, ``(Re v_0, Im v_0, Re v_1, ...)``, is the same memory as the interleaved complex vector."""
+    L, M = C.shape
+    E = np.empty((2 * L, 2 * M))
+    E[0::2, 0::2] = C.real
+    E[1::2, 1::2] = C.real
+    E[1::2, 0::2] = C.imag
+    E[0::2, 1::2] = -C.imag
+    return E
 
 
 #### High-level functions ####
@@ -60,7 +81,7 @@ def correlation_matrix(H: np.ndarray, N: int | None = None, *, _backend=None) ->
     The one-off ``eigh(H)`` (K1) stays on LAPACK like in the reference; the rank-N update
     ``C = Phi Phi^T`` (K2) runs on the DMMA GEMM (``tmf_corr_build``)."""
     be = _backend or _be()
-    H = _real_or_raise(H, "Hamiltonian")
+    H = _real_or_complex(H)
     e, v = np.linalg.eigh(H)
     if N is None:
         occupied = e < 0
@@ -71,6 +92,15 @@ def correlation_matrix(H: np.ndarray, N: int | None = None, *, _backend=None) ->
     L = len(H)
     if N == 0:
         return np.zeros((L, L)), 0
+    if np.iscomplexobj(v):
+        # complex orbitals: C = Phi Phi^H through the real embedding (emb(Phi) emb(Phi)^T = emb(Phi Phi^H)) on the
+        # same DMMA GEMM; C is read back from the even columns of the embedded product
+        phi = be.from_host(embed_complex(v).ravel())
+        Cd = be.empty(4 * L * L, np.float64)
+        engine.check(be.lib, be.lib.tmf_corr_build(be.ptr(phi), 2 * L, 2 * N, 2 * N, be.ptr(Cd), 2 * L, be.stream))
+        be.sync()
+        E = be.to_host(Cd, 4 * L * L).reshape(2 * L, 2 * L)
+        return E[0::2, 0::2] + 1j * E[1::2, 0::2], N
     phi = be.from_host(np.ascontiguousarray(v).ravel())
     Cd = be.empty(L * L, np.float64)
     engine.check(be.lib, be.lib.tmf_corr_build(be.ptr(phi), L, N, N, be.ptr(Cd), L, be.stream))
@@ -97,7 +127,7 @@ def _prepare_C(C, spinful):
         raise ValueError(f"`spinful` must be 'simple', 'PH', or `None`, got {spinful!r}")
     L = len(C)
     assert C.shape == (L, L), f"Got non-square {C.shape} correlation matrix"
-    return _real_or_raise(C, "correlation matrix")
+    return _real_or_complex(C)
 
 
 def _check_projector(C, tol=1e-8, be=None, Cd=None):
@@ -154,8 +184,17 @@ def C_to_MPS(C: np.ndarray, trunc_par: dict | StoppingCondition, *, diag_tol: fl
     be = _backend or _be()
     C = _prepare_C(C, spinful)
     L = len(C)
-    n_fermion = int(np.round(np.trace(C)))                                   # slater.py:414
+    n_fermion = int(np.round(np.trace(C).real))                              # slater.py:414
     logger.info("Central bond %d", ortho_center or L // 2)
+    if np.iscomplexobj(C):
+        # complex Slater determinant: the library works on the real embedding (cuts at 2x) and returns complex tensors
+        E = embed_complex(C)
+        Ed = be.from_host(E.ravel())
+        _check_projector(E, be=be, Cd=Ed)
+        res = engine.run_chain(be, Ed, 2 * L, L, trunc_par, n_fermion, ortho_center=ortho_center, r_sketch=96,
+                               cplx=True)
+        mps = _chain_to_mps(res, unit_cell_width)
+        return mps.to_tenpy() if _want_tenpy(as_tenpy) else mps
     Cd = be.from_host(C.ravel())
     _check_projector(C, be=be, Cd=Cd)
     from . import testing

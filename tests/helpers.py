@@ -10,11 +10,13 @@ from temfpy_b200.schmidt_utils import to_stopping_condition
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def random_hamiltonian(L, seed, decay=2.0):
-    """Pattern of the reference's examples/slater.py:15-20."""
+def random_hamiltonian(L, seed, decay=2.0, cplx=False):
+    """Pattern of the reference's examples/slater.py:15-20 (complex Hermitian with cplx=True, as there)."""
     rng = np.random.default_rng(seed)
     H = rng.normal(size=(L, L))
-    H = H + H.T
+    if cplx:
+        H = H + 1j * rng.normal(size=(L, L))
+    H = H + H.conj().T
     d = np.abs(np.subtract.outer(np.arange(L), np.arange(L)))
     return H * np.exp(-d / decay)
 
@@ -84,7 +86,12 @@ def chain_to_dense(res: engine.ChainResult) -> so.DenseMPS:
 def run_native(backend, C, trunc, N=None, **kw) -> engine.ChainResult:
     L = len(C)
     if N is None:
-        N = int(round(np.trace(C)))
+        N = int(round(np.trace(C).real))
+    if np.iscomplexobj(C):      # complex Slater determinant: the library works on the real embedding (slater.C_to_MPS)
+        from temfpy_b200.slater import embed_complex
+        Ed = backend.from_host(embed_complex(np.asarray(C)).ravel())
+        kw.setdefault("r_sketch", 96)
+        return engine.run_chain(backend, Ed, 2 * L, L, to_stopping_condition(trunc), N, cplx=True, **kw)
     Cd = backend.from_host(np.ascontiguousarray(C, dtype=np.float64).ravel())
     return engine.run_chain(backend, Cd, L, L, to_stopping_condition(trunc), N, **kw)
 

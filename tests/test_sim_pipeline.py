@@ -193,3 +193,41 @@ def test_device_site_plans_match_host(sim_backend, case):
         assert np.array_equal(dev.bonds[x].masks, host.bonds[x].masks)
         assert np.array_equal(dev.bonds[x].schmidt_values, host.bonds[x].schmidt_values)
         assert dev.bonds[x].idx_L == host.bonds[x].idx_L
+
+
+@pytest.mark.parametrize("name", ["slater_complex_L12", "slater_complex_L24_chi32"])
+def test_complex_reference_fixtures(sim_backend, name):
+    """Complex Hamiltonians (the reference's own example, examples/slater.py:15-27): embedded mode extraction,
+    complex pairing, complex nested site stage and complex minors against fixtures of the live reference."""
+    g = helpers.golden(name)
+    tp = helpers.golden_trunc(g)
+    res = helpers.run_native(sim_backend, g["C"], tp, int(g["N"]))
+    assert res.sites[0].blocks[0][5].dtype == np.complex128
+    helpers.compare_mps(helpers.golden_dense_mps(g), helpers.chain_to_dense(res), tp)
+
+
+@pytest.mark.parametrize("L,N,seed", [(8, 5, 8), (11, None, 11)])
+def test_complex_exact_amplitudes(sim_backend, L, N, seed):
+    """Known answer for complex orbitals: psi(occ) = det Phi[occ, :] (SURVEY 8c pin (i): L = 8 complex N = 5, L = 11 complex)."""
+    H = helpers.random_hamiltonian(L, seed, cplx=True)
+    Cm, n = so.correlation_matrix(H, N)
+    Phi = np.linalg.eigh(H)[1][:, :n]
+    res = helpers.run_native(sim_backend, Cm, {"chi_max": 4096, "svd_min": 1e-7}, n)
+    psi = so.mps_to_state(helpers.chain_to_dense(res))
+    assert abs(abs(np.vdot(so.exact_slater_state(Phi), psi)) - 1) < 1e-13
+
+
+def test_complex_public_api_vs_oracle(sim_backend):
+    from temfpy_b200 import slater, testing
+    old, testing.TEST_ACTION = testing.TEST_ACTION, "pass"
+    try:
+        H = helpers.random_hamiltonian(36, 2, cplx=True)
+        C, N = slater.correlation_matrix(H, _backend=sim_backend)
+        Co, No = so.correlation_matrix(H)
+        assert N == No and np.abs(C - Co).max() < 1e-14 and np.iscomplexobj(C)
+        tp = {"chi_max": 40}
+        mps = slater.H_to_MPS(H, tp, as_tenpy=False, _backend=sim_backend, ortho_center=13)
+        rep = helpers.compare_mps(so.C_to_MPS(Co, tp, ortho_center=13), helpers.block_mps_to_dense(mps), tp)
+        assert rep["overlap"] >= 1 - 1e-10
+    finally:
+        testing.TEST_ACTION = old
