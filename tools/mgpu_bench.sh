@@ -2,7 +2,7 @@
 # runs bench.py at the given GPU counts (torchrun, one rank per GPU) and prints the headline numbers
 for n in "$@"; do
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) \
-    bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err
+    bench.py --gpus $n --steps 20 --warmup 5 $BENCH_EXTRA > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err
   python - $n <<'PY'
 import json, sys
 n = sys.argv[1]
