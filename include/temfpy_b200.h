@@ -370,16 +370,25 @@ int tmf_chain_set_option(tmf_chain *c, int option, int value);
  * f[0] eigh, f[1] overlap GEMM, f[2] Schur, f[3] minors, f[4] number of minors */
 int tmf_chain_flops(tmf_chain *c, double *f);
 
-/* K14 -- Gutzwiller projection of one pair of fermion sites onto a spin-1/2 site.
- * replaces: the TeNPy arithmetic behind gutzwiller.py:227 (group_sites(2)) and :242 (iproject)
- * (abrikosov) resp. :409, :424 (abrikosov_ph).  Jobs: out (m x n) = A (m x k) * B (k x n), all
- * row-major dense charge blocks; this is a thin wrapper over the grouped GEMM. */
+/* K14 -- Gutzwiller projection, one fused launch for all spin sites of an MPS.
+ * replaces: the TeNPy arithmetic behind gutzwiller.py:227 (group_sites(2)) + :242 (iproject) + :244 (drop_charge)
+ * (abrikosov) resp. :409, :424, :437-441 (abrikosov_ph).  A job is one surviving charge chain of one pair of
+ * fermion sites:
+ *     out[i * so_i + n] = row_scale[i] * sum_k A[i * sa_i + k * sa_k] * k_scale[k] * B[k * sb_k + n * sb_n] * col_scale[n]
+ * (strides in elements; elements are f64, or interleaved c128 when `cplx_flag` is set; the three real scalings are
+ * optional: the Schmidt values of the orthogonality centre).  A / B point into the block-sparse fermion tensors
+ * where tmf_chain_tensors left them in HBM, `out` into the dense spin-site tensor T[vL, s, vR].  The call zero-fills
+ * [out_dev, out_dev + out_bytes), uploads the descriptors to `desc_dev` (tmf_gutz_desc_bytes) and launches. */
 typedef struct tmf_gutz_job {
-  const double *A, *B;
-  double *out;
-  int m, k, n, pad_;
+  const void *A, *B;
+  void *out;
+  const double *k_scale, *row_scale, *col_scale;
+  int64_t sa_i, sa_k, sb_k, sb_n, so_i;
+  int m, k, n, pad_[7];
 } tmf_gutz_job;
-int tmf_gutzwiller_site(const tmf_gutz_job *jobs_host, int njobs, void *desc_dev, void *stream);
+int64_t tmf_gutz_desc_bytes(const tmf_gutz_job *jobs_host, int njobs);
+int tmf_gutzwiller_project(const tmf_gutz_job *jobs_host, int njobs, int cplx_flag, void *out_dev,
+                           int64_t out_bytes, void *desc_dev, void *stream);
 
 /* measurement hooks used by bench.py: kernel launch counter (always on) and per-kernel CUDA-event
  * timing (off by default; enabled only in the profiling pass). */

@@ -75,11 +75,14 @@ class PfBlock(C.Structure):
 
 class GutzJob(C.Structure):
     _fields_ = [("A", C.c_void_p), ("B", C.c_void_p), ("out", C.c_void_p),
-                ("m", C.c_int), ("k", C.c_int), ("n", C.c_int), ("pad_", C.c_int)]
+                ("k_scale", C.c_void_p), ("row_scale", C.c_void_p), ("col_scale", C.c_void_p),
+                ("sa_i", C.c_int64), ("sa_k", C.c_int64), ("sb_k", C.c_int64), ("sb_n", C.c_int64),
+                ("so_i", C.c_int64), ("m", C.c_int), ("k", C.c_int), ("n", C.c_int), ("pad_", C.c_int * 7)]
 
 
 assert C.sizeof(GemmJob) == 128 and C.sizeof(SiteJob) == 128 and C.sizeof(MinorBlock) == 64
 assert C.sizeof(PairJob) == 64 and C.sizeof(PfBlock) == 64 and C.sizeof(NestedJob) == 64
+assert C.sizeof(GutzJob) == 128
 
 # name -> (restype, argtypes); this table is also what tests check against include/temfpy_b200.h
 SIGNATURES = {
@@ -161,7 +164,9 @@ SIGNATURES = {
     "tmf_pfaffian_pair_modes": (C.c_int, [C.POINTER(PairJob), C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "tmf_pf_desc_bytes": (C.c_int64, [C.c_int]),
     "tmf_pfaffians_blocks": (C.c_int, [C.POINTER(PfBlock), C.c_int, C.c_void_p, C.c_void_p]),
-    "tmf_gutzwiller_site": (C.c_int, [C.POINTER(GutzJob), C.c_int, C.c_void_p, C.c_void_p]),
+    "tmf_gutz_desc_bytes": (C.c_int64, [C.POINTER(GutzJob), C.c_int]),
+    "tmf_gutzwiller_project": (C.c_int, [C.POINTER(GutzJob), C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                                         C.c_void_p]),
     "tmf_fp64_peak_probe": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_float), c_double_p, C.c_void_p]),
 }
 

@@ -126,6 +126,7 @@ class SiteTensor:
     row_p: np.ndarray
     row_alpha: np.ndarray
     qtotal: int
+    dev: tuple | None = None    # (device buffer, element offset of every block) while the shard stays resident in HBM
 
     def dense_pab(self) -> np.ndarray:
         """T[p, alpha(bra), beta(ket)] exactly like the oracle's dense_tensor."""
@@ -306,8 +307,11 @@ class ShardTables:
             o = int(self.block_off[b])
             out.append((qk, r0, nr, c0, nc, self.out_host[o: o + nr * nc].reshape(nr, nc)))
         row_p, row_alpha = self.site_rows(i, plan)
+        dev = None
+        if getattr(self, "out_dev", None) is not None:
+            dev = (self.out_dev, [int(v) for v in self.block_off[b0:b1]])
         return SiteTensor(site=int(i), mode="left" if plan.mode == 0 else "right", plan=plan, blocks=out,
-                          row_p=row_p, row_alpha=row_alpha, qtotal=plan.qtotal)
+                          row_p=row_p, row_alpha=row_alpha, qtotal=plan.qtotal, dev=dev)
 
 
 @dataclass
@@ -602,6 +606,8 @@ class SlaterChain:
             out_host = out_host.view(np.complex128)
         tab = ShardTables(self, out_host)
         tab._pinned = host
+        if getattr(self, "keep_device", False) and fetch_tensors:
+            tab.out_dev = self._buffers["out"]        # the shard's tensors stay addressable in HBM (Gutzwiller)
         tab.normalized()
         t2 = time.perf_counter()
         self.be.sync()
@@ -643,11 +649,13 @@ SKETCH_WIDTHS = (48, 64, 128, 160)
 
 
 def _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch, n_threads,
-               fetch_tensors, lazy=False, gate=None, snap=False, nested=None, device_plan=None, cplx=False):
+               fetch_tensors, lazy=False, gate=None, snap=False, nested=None, device_plan=None, cplx=False,
+               keep_device=False):
     import time
     gate = gate or _NoGate()
     chain = SlaterChain(backend, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch, n_threads, snap=snap,
                         nested=nested, device_plan=device_plan, cplx=cplx)
+    chain.keep_device = keep_device
     ok = False
     try:
         tt = [time.perf_counter()]
@@ -765,7 +773,7 @@ class DeviceChainResult:
 
 def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_lo=0, site_hi=None,
               r_sketch=48, n_threads=0, fetch_tensors=True, n_chunks=None, lazy=False, snap=False, nested=None,
-              device_plan=None, cplx=False):
+              device_plan=None, cplx=False, keep_device=False):
     """C (device) -> Schmidt data of every bond and block-sparse tensor of every site.
 
     The site range is cut into cost-balanced chunks that run as a software pipeline: one worker
@@ -783,7 +791,8 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
     ``snap=False`` (default) is the reference's literal truncation (schmidt_utils.py:140-185 only sees
     degeneracies below ``degeneracy_tol``; where a multiplet that is degenerate in exact arithmetic straddles
     ``chi_max`` the kept part is decided by the rounding noise of the mode eigenvalues, in the reference as here)."""
-    opts = dict(r_sketch=r_sketch, snap=snap, nested=nested, device_plan=device_plan, cplx=cplx)
+    opts = dict(r_sketch=r_sketch, snap=snap, nested=nested, device_plan=device_plan, cplx=cplx,
+                keep_device=keep_device)
     while True:
         try:
             return _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi,
@@ -807,6 +816,7 @@ def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site
     from .dist import partition
     r_sketch, snap, nested, device_plan = opts["r_sketch"], opts["snap"], opts["nested"], opts["device_plan"]
     cplx = opts.get("cplx", False)
+    keep = opts.get("keep_device", False)
     site_hi = L if site_hi is None else site_hi
     nsites = site_hi - site_lo
     if n_chunks is None:
@@ -816,7 +826,8 @@ def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site
     n_chunks = max(1, min(n_chunks, nsites))
     if n_chunks == 1:
         r = _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi, r_sketch,
-                       n_threads, fetch_tensors, lazy, snap=snap, nested=nested, device_plan=device_plan, cplx=cplx)
+                       n_threads, fetch_tensors, lazy, snap=snap, nested=nested, device_plan=device_plan, cplx=cplx,
+                       keep_device=keep)
         if lazy:
             r = DeviceChainResult([r])
         r.options = dict(opts)
@@ -845,7 +856,7 @@ def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site
             try:
                 return _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch,
                                   n_threads, fetch_tensors, lazy, gate=stages.gate(pos) if stages else None,
-                                  snap=snap, nested=nested, device_plan=device_plan, cplx=cplx)
+                                  snap=snap, nested=nested, device_plan=device_plan, cplx=cplx, keep_device=keep)
             except _Retry as rt:        # the other chunks finish; the driver then starts over
                 return rt
 

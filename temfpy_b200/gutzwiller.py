@@ -85,104 +85,170 @@ def _unwrap(mps):
 def _validate(mps):
     assert mps.L % 2 == 0, "Odd-length MPS cannot represent an Abrikosov fermion Hilbert space"
     assert mps.site_type == "FermionSite", f"All sites must be fermionic, found: {mps.site_type}"
-    if mps.conserve != "N":
-        raise NotImplementedError("only number-conserving fermion MPS (slater.C_to_MPS) are supported in this "
-                                  f"release, got conserve={mps.conserve!r}")
+    if mps.conserve not in ("N", "parity"):
+        raise ValueError(f"FermionSite must conserve either 'N' or 'parity', found {mps.conserve!r}")
     if mps.bc != "finite":
         raise NotImplementedError(f"Boundary condition {mps.bc!r} not supported in this release")
 
 
-def _sub_block(t, q_left, p, q_right):
-    """Dense view of ``T[vL in sector q_left, p, vR in sector q_right]`` inside the block storage of a
-    fermion site tensor, as ``(array, vL indices, vR indices, transposed)``; ``transposed`` means the
-    array is stored as ``[vR, vL]`` (right-canonical tensors keep the bra = right bond as rows)."""
-    want = q_right if t.mode == "left" else q_left
-    for (qk, r0, nr, c0, nc, arr) in t.blocks:
-        if qk != want:
-            continue
-        sel = np.flatnonzero(t.row_p[r0: r0 + nr] == p)
-        if sel.size == 0:
-            return None
-        assert sel[-1] - sel[0] + 1 == sel.size          # contiguous: stable sort by pipe charge
-        sub = arr[sel[0]: sel[-1] + 1]
-        alpha = t.row_alpha[r0 + sel[0]: r0 + sel[-1] + 1]
-        cols = np.arange(c0, c0 + nc)
-        if t.mode == "left":
-            return sub, alpha, cols, False
-        return sub, cols, alpha, True
-    return None
+@dataclass
+class _Blk:
+    """One charge block ``T[vL in sector qL, p, vR in sector qR]`` of a fermion site tensor: index ranges on the two
+    bonds, where its elements live (``("dev", buffer, element offset)`` inside the HBM-resident result of the
+    conversion, or ``("host", array)`` to be staged) and the element strides along vL / vR."""
+    qL: int
+    p: int
+    qR: int
+    vL0: int
+    nL: int
+    vR0: int
+    nR: int
+    src: tuple
+    sL: int
+    sR: int
+    cplx: bool = False
 
 
-def _project(mps: BlockMPS, rules, keep, be):
-    """Contracts the pairs (2j, 2j+1) restricted to the surviving charge chains.
+def _contiguous(idx):
+    return idx.size > 0 and int(idx[-1]) - int(idx[0]) + 1 == idx.size
 
-    rules(j) -> list of (spin index, p_a, p_b, q_left, q_mid, q_right);  keep(j, charges) -> bool mask of
-    the virtual indices of bond 2j that survive.  Returns the dense projected tensors and kept indices."""
+
+def _blocks_of(mps, i, mod):
+    """Charge blocks of fermion site ``i`` keyed by ``(qL, p)``.  Results of the Slater conversion are addressed in
+    place (left-canonical tensors store [vL, vR] rows, right-canonical ones [vR, vL]; the rows of one physical value
+    are a contiguous range of a block, slater.py:1053-1058); any other tensor type is cut out of its dense form."""
+    from .engine import SiteTensor
+    t = mps.tensors[i]
+    out = {}
+    if isinstance(t, SiteTensor):
+        for bi, (qk, r0, nr, c0, nc, arr) in enumerate(t.blocks):
+            rp = t.row_p[r0: r0 + nr]
+            for p in (0, 1):
+                sel = np.flatnonzero(rp == p)
+                if sel.size == 0:
+                    continue
+                s0, n = int(sel[0]), int(sel.size)
+                a0 = int(t.row_alpha[r0 + s0])
+                assert _contiguous(sel) and int(t.row_alpha[r0 + s0 + n - 1]) == a0 + n - 1
+                src = ("dev", t.dev[0], t.dev[1][bi] + s0 * nc) if t.dev is not None else ("host", arr[s0: s0 + n])
+                if t.mode == "left":
+                    blk = _Blk(qk - p, p, qk, a0, n, c0, nc, src, nc, 1, np.iscomplexobj(arr))
+                else:
+                    blk = _Blk(qk, p, qk + p, c0, nc, a0, n, src, 1, nc, np.iscomplexobj(arr))
+                out[(blk.qL, p)] = blk
+        return out
+    T = t.dense()
+    cL, cR = np.asarray(mps.charges[i]).ravel(), np.asarray(mps.charges[i + 1]).ravel()
+    qt = int(getattr(t, "qtotal", 0) or 0)
+    for qL in np.unique(cL):
+        iL = np.flatnonzero(cL == qL)
+        for p in (0, 1):
+            qR = int(qL) + p - qt
+            if mod:
+                qR %= mod
+            iR = np.flatnonzero(cR == qR)
+            if iR.size == 0:
+                continue
+            if not (_contiguous(iL) and _contiguous(iR)):
+                raise NotImplementedError("gutzwiller: charge sectors of the input MPS must be contiguous index ranges")
+            sub = np.ascontiguousarray(T[iL[0]: iL[-1] + 1, p, iR[0]: iR[-1] + 1])
+            if not sub.any():
+                continue
+            out[(int(qL), p)] = _Blk(int(qL), p, qR, int(iL[0]), iL.size, int(iR[0]), iR.size, ("host", sub),
+                                     iR.size, 1, np.iscomplexobj(sub))
+    return out
+
+
+def _project(mps: BlockMPS, keep, spin_rules, be, mod=0):
+    """All pairs (2j, 2j+1) contracted and projected in one launch of ``tmf_gutzwiller_project``.
+
+    keep(j, charges) -> bool mask of the virtual indices of bond 2j that survive; spin_rules = ((s, p_a, p_b), ...)
+    the pair occupations that become spin index s.  Only the charge chains (qL, p_a) -> q_m -> (p_b, qR) with
+    surviving ends are multiplied; the operands are read in place in HBM when the fermion MPS is resident there
+    (otherwise the needed blocks are staged once), the results land at their place in the dense spin-site tensors
+    ``T[vL, s, vR]``.  Returns (tensors on the host, kept indices per spin bond, number of chains, device copy)."""
     lib = be.lib
     Ls = mps.L // 2
-    oc = mps.ortho_center
-    keepers = [np.flatnonzero(keep(j, mps.charges[2 * j])) for j in range(Ls + 1)]
+    finite = mps.bc == "finite"
+    oc = mps.ortho_center if finite else None
+    nb = Ls + 1 if finite else Ls
+    bond = lambda j: 2 * j if finite else (2 * j) % mps.L
+    keepers = [np.flatnonzero(keep(j, np.asarray(mps.charges[bond(j)]).ravel())) for j in range(nb)]
     pos = []
-    for j in range(Ls + 1):
-        m = -np.ones(len(mps.charges[2 * j]), dtype=np.int64)
+    for j in range(nb):
+        m = -np.ones(len(np.asarray(mps.charges[bond(j)]).ravel()), dtype=np.int64)
         m[keepers[j]] = np.arange(len(keepers[j]))
         pos.append(m)
-    chunks, jobs, off = [], [], 0
-
-    def stage(arr):
-        nonlocal off
-        a = np.ascontiguousarray(arr, dtype=np.float64)
-        chunks.append(a.ravel())
-        o = off
-        off += a.size
-        return o
-
-    out_off = 0
+    # chains
+    chains, staged, stage_off = [], [], 0
+    out_off, offs = 0, []
     for j in range(Ls):
-        ta, tb = mps.tensors[2 * j], mps.tensors[2 * j + 1]
-        for (s, pa, pb, qL, qm, qR) in rules(j):
-            A = _sub_block(ta, qL, pa, qm)
-            B = _sub_block(tb, qm, pb, qR)
-            if A is None or B is None:
-                continue
-            Xa, vL, ma, ta_t = A
-            Xb, mb, vR, tb_t = B
-            assert np.array_equal(ma, mb), "bond sectors of neighbouring tensors do not match"
-            if oc == 2 * j + 1:            # Schmidt values of the centre bond sit inside this pair
-                lam = mps.lams[oc][ma]
-                Xa = Xa * (lam[:, None] if ta_t else lam[None, :])
-            jobs.append(dict(j=j, s=s, vL=vL, vR=vR, a=stage(Xa), b=stage(Xb), ta=ta_t, tb=tb_t,
-                             nL=len(vL), nm=len(ma), nR=len(vR), out=out_off))
-            out_off += len(vL) * len(vR)
-    outs = np.zeros(0)
-    if jobs:
-        buf = be.from_host(np.concatenate(chunks))
-        outd = be.empty(out_off, np.float64)
-        g = (_lib.GemmJob * len(jobs))()
-        for u, jb in enumerate(jobs):
-            # row-major out[vL, vR] == column-major out^T (nR x nL) = Xb^T (nR x nm) . Xa^T (nm x nL)
-            g[u].A = be.ptr(buf) + 8 * jb["b"]
-            g[u].transA, g[u].lda = (1, jb["nm"]) if jb["tb"] else (0, jb["nR"])
-            g[u].B = be.ptr(buf) + 8 * jb["a"]
-            g[u].transB, g[u].ldb = (1, jb["nL"]) if jb["ta"] else (0, jb["nm"])
-            g[u].C, g[u].ldc = be.ptr(outd) + 8 * jb["out"], jb["nR"]
-            g[u].M, g[u].N, g[u].K = jb["nR"], jb["nL"], jb["nm"]
-            g[u].alpha, g[u].beta = 1.0, 0.0
-        desc = be.empty(int(lib.tmf_gemm_desc_bytes(len(jobs))), np.uint8)
-        check(lib, lib.tmf_gemm_grouped(g, len(jobs), be.ptr(desc), be.stream))
-        be.sync()
-        outs = be.to_host(outd, out_off)
-    tensors = [np.zeros((len(keepers[j]), 2, len(keepers[j + 1]))) for j in range(Ls)]
-    for jb in jobs:
-        blk = outs[jb["out"]: jb["out"] + jb["nL"] * jb["nR"]].reshape(jb["nL"], jb["nR"])
-        j = jb["j"]
-        tensors[j][pos[j][jb["vL"]][:, None], jb["s"], pos[j + 1][jb["vR"]][None, :]] = blk
-    if oc % 2 == 0 and oc // 2 < Ls:       # centre bond between two pairs: A..A lam B..B
-        j0 = oc // 2
-        tensors[j0] = tensors[j0] * mps.lams[oc][keepers[j0]][:, None, None]
-    elif oc == mps.L:
-        tensors[-1] = tensors[-1] * mps.lams[oc][keepers[Ls]][None, None, :]
-    return tensors, keepers, len(jobs)
+        jr = j + 1 if finite else (j + 1) % Ls
+        nLk, nRk = len(keepers[j]), len(keepers[jr])
+        offs.append(out_off)
+        out_off += nLk * 2 * nRk
+        if nLk == 0 or nRk == 0:
+            continue
+        ba, bb = _blocks_of(mps, 2 * j, mod), _blocks_of(mps, 2 * j + 1, mod)
+        for (s, pa, pb) in spin_rules:
+            for (qL, p), A in ba.items():
+                if p != pa or pos[j][A.vL0] < 0:
+                    continue
+                B = bb.get((A.qR, pb))
+                if B is None or pos[jr][B.vR0] < 0:
+                    continue
+                assert (A.vR0, A.nR) == (B.vL0, B.nL), "bond sectors of neighbouring tensors do not match"
+                chains.append((j, s, A, B, int(pos[j][A.vL0]), int(pos[jr][B.vR0]), nRk))
+    cplx = any(X.cplx for c in chains for X in (c[2], c[3]))
+    es = 2 if cplx else 1
+    dt = np.complex128 if cplx else np.float64
+    for (_, _, A, B, *_r) in chains:
+        for X in (A, B):
+            if X.src[0] == "host" and len(X.src) == 2:
+                arr = np.ascontiguousarray(X.src[1], dtype=dt).ravel()
+                staged.append(arr)
+                X.src = ("host", X.src[1], stage_off)
+                stage_off += arr.size
+    stage_d = be.from_host(np.concatenate(staged).view(np.float64)) if staged else None
+    lam_d = None
+    if oc is not None:
+        lam_d = be.from_host(np.ascontiguousarray(mps.lams[oc], dtype=np.float64))
+    outd = be.empty(max(es * out_off, 1), np.float64)
+
+    def addr(X):
+        if X.src[0] == "dev":
+            return be.ptr(X.src[1]) + 8 * es * int(X.src[2])
+        return be.ptr(stage_d) + 8 * es * int(X.src[2])
+    jobs = (_lib.GutzJob * max(len(chains), 1))()
+    for u, (j, s, A, B, pL, pR, nRk) in enumerate(chains):
+        g = jobs[u]
+        g.A, g.sa_i, g.sa_k = addr(A), A.sL, A.sR
+        g.B, g.sb_k, g.sb_n = addr(B), B.sL, B.sR
+        g.m, g.k, g.n = A.nL, A.nR, B.nR
+        g.out = be.ptr(outd) + 8 * es * (offs[j] + (pL * 2 + s) * nRk + pR)
+        g.so_i = 2 * nRk
+        if oc is not None:
+            if oc == 2 * j + 1:                 # Schmidt values of the centre bond sit inside this pair
+                g.k_scale = be.ptr(lam_d) + 8 * A.vR0
+            elif oc == 2 * j:                   # ... on its left bond: A..A lam B..B
+                g.row_scale = be.ptr(lam_d) + 8 * A.vL0
+            elif oc == mps.L and j == Ls - 1:
+                g.col_scale = be.ptr(lam_d) + 8 * B.vR0
+    desc = be.empty(int(lib.tmf_gutz_desc_bytes(jobs, len(chains))), np.uint8)
+    check(lib, lib.tmf_gutzwiller_project(jobs, len(chains), int(cplx), be.ptr(outd), 8 * es * out_off,
+                                          be.ptr(desc), be.stream))
+    be.sync()
+    outs = be.to_host(outd, es * out_off)
+    if cplx:
+        outs = outs.view(np.complex128)
+    tensors = []
+    for j in range(Ls):
+        jr = j + 1 if finite else (j + 1) % Ls
+        nLk, nRk = len(keepers[j]), len(keepers[jr])
+        tensors.append(outs[offs[j]: offs[j] + nLk * 2 * nRk].reshape(nLk, 2, nRk))
+    resident = sum(1 for c in chains for X in (c[2], c[3]) if X.src[0] == "dev")
+    return tensors, keepers, dict(chains=len(chains), resident_operands=resident, staged_elems=stage_off,
+                                  device=(outd, offs))
 
 
 def _svd(M):
@@ -217,7 +283,7 @@ def _canonical_form_finite(tensors, qs, qp, cutoff):
             newR.append((c, R))
             newq += [q] * Q.shape[1]
         k = len(newq)
-        Qf, Rf = np.zeros((a * d, k)), np.zeros((k, b))
+        Qf, Rf = np.zeros((a * d, k), dtype=M.dtype), np.zeros((k, b), dtype=M.dtype)
         o = 0
         for (r, Q), (c, R) in zip(newQ, newR):
             w = Q.shape[1]
@@ -246,7 +312,7 @@ def _canonical_form_finite(tensors, qs, qp, cutoff):
             parts.append((r, c, U[:, keep], S[keep], Vh[keep]))
             newq += [q] * int(keep.sum())
         k = len(newq)
-        Uf, Sf, Vf = np.zeros((a, k)), np.zeros(k), np.zeros((k, d * b))
+        Uf, Sf, Vf = np.zeros((a, k), dtype=M.dtype), np.zeros(k), np.zeros((k, d * b), dtype=M.dtype)
         o = 0
         for r, c, U, S, Vh in parts:
             w = len(S)
@@ -265,8 +331,10 @@ def _canonical_form_finite(tensors, qs, qp, cutoff):
     return T, lams, qs
 
 
-def _finish(mps, tensors, keepers, qvirt, qp, conserve, return_canonical, cutoff, unit_cell_width, n_jobs):
+def _finish(mps, tensors, keepers, qvirt, qp, conserve, return_canonical, cutoff, unit_cell_width, info):
     Ls = len(tensors)
+    meta = dict(gemm_jobs=info["chains"], kept=[len(k) for k in keepers], resident_operands=info["resident_operands"],
+                staged_elems=info["staged_elems"])
     if return_canonical:
         T, lams, qs = _canonical_form_finite(tensors, qvirt, qp, cutoff)
         form = ["B"] * Ls
@@ -277,65 +345,69 @@ def _finish(mps, tensors, keepers, qvirt, qp, conserve, return_canonical, cutoff
              "Consider setting 'return_canonical=True'")
         T, qs, form, oc = tensors, qvirt, [None] * Ls, None
         lams = [np.ones(len(q)) / np.sqrt(max(len(q), 1)) for q in qs]                       # gutzwiller.py:258
+        meta["device"] = info["device"]             # the projected tensors also stay in HBM: (buffer, offsets)
     return BlockMPS(L=Ls, tensors=[DenseSite(t) for t in T], lams=lams, charges=qs, form=form,
                     unit_cell_width=unit_cell_width, ortho_center=oc, bc="finite", site_type="SpinHalfSite",
-                    conserve=conserve, meta=dict(gemm_jobs=n_jobs, kept=[len(k) for k in keepers]))
+                    conserve=conserve, meta=meta)
 
 
 def abrikosov(mps: BlockMPS, *, inplace: bool = False, return_canonical: bool = True, cutoff: float = 1e-12,
               q_left: None | int = None, unit_cell_width: int | None = None, _backend=None):
     r"""Projection from Abrikosov fermions to a spin-1/2 Hilbert space (gutzwiller.py:95-281):
-    single occupation of :math:`f_{i\uparrow}` -> up, of :math:`f_{i\downarrow}` -> down."""
+    single occupation of :math:`f_{i\uparrow}` -> up, of :math:`f_{i\downarrow}` -> down.  The input may conserve
+    the fermion number (``slater.C_to_MPS``) or only the parity (``pfaffian.C_to_MPS``)."""
     from . import slater as _sl
     mps = _unwrap(mps)
     _validate(mps)
     if inplace:
         raise NotImplementedError("`inplace=True` is not supported: BlockMPS results are immutable")
-    total = int(np.asarray(mps.charges[mps.L])[0])
+    total = int(np.asarray(mps.charges[mps.L]).ravel()[0])
     target = mps.L // 2
-    assert total == target, f"Total charge must match number of spin sites. Got {total}, expected {target}"
+    err = f"Total charge must match number of spin sites. Got {total}, expected {target}"
+    if mps.conserve == "N":
+        assert total == target, err                                                    # gutzwiller.py:177-186
+        mod = 0
+        keep = lambda j, q: number_mask(q, j)        # exactly one fermion per pair: bond 2j carries charge j (:236-238)
+    else:
+        assert total % 2 == target % 2, err + " (mod 2)"
+        mod = 2
+        keep = lambda j, q: parity_mask(q, j)
     if q_left not in (None, 0):
         warn(f"`q_left` must be 0 for finite MPS, got {q_left = }, setting it to 0.")
     ucw = _check_unit_cell_width(mps, unit_cell_width)
     be = _backend or _sl._be()
-    # exactly one fermion per pair: bond 2j carries charge j (gutzwiller.py:236-238)
-    rules = lambda j: [(0, 1, 0, j, j + 1, j + 1), (1, 0, 1, j, j, j + 1)]
-    keep = lambda j, q: number_mask(q, j)
-    tensors, keepers, nj = _project(mps, rules, keep, be)
+    tensors, keepers, info = _project(mps, keep, ((0, 1, 0), (1, 0, 1)), be, mod)
     qvirt = [np.zeros(len(k), dtype=np.int64) for k in keepers]      # all charges dropped (:244)
     logger.info("Completed projection to spin-1/2 space. No conserved charges left.")
-    return _finish(mps, tensors, keepers, qvirt, np.zeros(2, dtype=np.int64), None, return_canonical, cutoff, ucw, nj)
+    return _finish(mps, tensors, keepers, qvirt, np.zeros(2, dtype=np.int64), None, return_canonical, cutoff, ucw, info)
 
 
 def abrikosov_ph(mps: BlockMPS, *, inplace: bool = False, return_canonical: bool = True, cutoff: float = 1e-12,
                  offset: int = 0, parity: int = 0, unit_cell_width: int | None = None, _backend=None):
     r"""Projection from particle-hole rotated Abrikosov fermions (gutzwiller.py:284-486):
-    zero occupation -> down, double occupation -> up; :math:`2S^z` = number - bond index is conserved."""
+    zero occupation -> down, double occupation -> up.  For number-conserving input :math:`2S^z` = number - bond
+    index is conserved; parity-conserving input (``pfaffian.C_to_MPS``) leaves no charge (:364-367, :444)."""
     from . import slater as _sl
     mps = _unwrap(mps)
     _validate(mps)
     if inplace:
         raise NotImplementedError("`inplace=True` is not supported: BlockMPS results are immutable")
-    total = int(np.asarray(mps.charges[mps.L])[0])
+    total = int(np.asarray(mps.charges[mps.L]).ravel()[0])
     assert total % 2 == 0, f"Total fermion parity of MPS must be even, got {total}"
     if parity != 0:
         warn(f"Must use even parity sector in finite MPS, ignoring {parity = }")
-    if offset != 0:
+    if offset != 0 and mps.conserve == "N":
         warn(f"Cannot offset charge of finite MPS, ignoring {offset = }")
     ucw = _check_unit_cell_width(mps, unit_cell_width)
     be = _backend or _sl._be()
-    sectors = [np.unique(np.asarray(q)[parity_mask(q, 0)]) for q in mps.charges[::2]]
-
-    def rules(j):
-        out = []
-        for q in sectors[j]:
-            q = int(q)
-            out.append((0, 0, 0, q, q, q))              # (0,0) -> down  (index 0, 2Sz = -1)
-            out.append((1, 1, 1, q, q + 1, q + 2))      # (1,1) -> up    (index 1, 2Sz = +1)
-        return out
     keep = lambda j, q: parity_mask(q, 0)
-    tensors, keepers, nj = _project(mps, rules, keep, be)
-    qvirt = [np.asarray(mps.charges[2 * j])[keepers[j]].astype(np.int64) - j for j in range(len(keepers))]  # :437-441
-    logger.info("Completed projection to spin-1/2 space. Conserved charge is now Sz")
-    return _finish(mps, tensors, keepers, qvirt, np.array([-1, 1], dtype=np.int64), "Sz", return_canonical, cutoff,
-                   ucw, nj)
+    # (0,0) -> down (index 0, 2Sz = -1), (1,1) -> up (index 1, 2Sz = +1)
+    tensors, keepers, info = _project(mps, keep, ((0, 0, 0), (1, 1, 1)), be, 0 if mps.conserve == "N" else 2)
+    if mps.conserve == "N":
+        qvirt = [np.asarray(mps.charges[2 * j])[keepers[j]].astype(np.int64) - j for j in range(len(keepers))]  # :437-441
+        qp, conserve = np.array([-1, 1], dtype=np.int64), "Sz"
+    else:
+        qvirt = [np.zeros(len(k), dtype=np.int64) for k in keepers]
+        qp, conserve = np.zeros(2, dtype=np.int64), None
+    logger.info("Completed projection to spin-1/2 space. Conserved charge is now %s", conserve)
+    return _finish(mps, tensors, keepers, qvirt, qp, conserve, return_canonical, cutoff, ucw, info)

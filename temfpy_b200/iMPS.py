@@ -428,14 +428,17 @@ def slater_C_to_iMPS(C_short, C_long, trunc_par, sites_per_cell, cut, *, diag_to
     if gj:
         rt_d = be.from_host(np.concatenate(rt_chunks))
         o2_d = be.empty(o2_off, np.float64)
-        jobs = (_lib.GutzJob * len(gj))()
+        jobs = (_lib.GemmJob * len(gj))()
         for u, (ao, bo, oo, m, k, n) in enumerate(gj):
-            jobs[u].A = be.ptr(outd) + 8 * ao          # B_0 block: (bra rows) x (long index)
-            jobs[u].B = be.ptr(rt_d) + 8 * bo          # R^T block: (long index) x (short index)
-            jobs[u].out = be.ptr(o2_d) + 8 * oo
-            jobs[u].m, jobs[u].k, jobs[u].n = m, k, n
+            # row-major out (m x n) = B_0 block (m x k: bra rows x long index) . R^T block (k x n: long x short index)
+            # == column-major out^T (n x m) = (R^T)^T . (B_0 block)^T
+            jobs[u].A, jobs[u].lda, jobs[u].transA = be.ptr(rt_d) + 8 * bo, n, 0
+            jobs[u].B, jobs[u].ldb, jobs[u].transB = be.ptr(outd) + 8 * ao, k, 0
+            jobs[u].C, jobs[u].ldc = be.ptr(o2_d) + 8 * oo, n
+            jobs[u].M, jobs[u].N, jobs[u].K = n, m, k
+            jobs[u].alpha, jobs[u].beta = 1.0, 0.0
         desc = be.empty(int(lib.tmf_gemm_desc_bytes(len(gj))), np.uint8)
-        check(lib, lib.tmf_gutzwiller_site(jobs, len(gj), be.ptr(desc), be.stream))
+        check(lib, lib.tmf_gemm_grouped(jobs, len(gj), be.ptr(desc), be.stream))
         be.sync()
         o2 = be.to_host(o2_d, o2_off)
         for (ao, bo, oo, m, k, n), (r0, nr, arows) in zip(gj, keep):

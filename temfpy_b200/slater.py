@@ -173,9 +173,15 @@ def _chain_to_mps(res: engine.ChainResult, unit_cell_width) -> BlockMPS:
 
 def C_to_MPS(C: np.ndarray, trunc_par: dict | StoppingCondition, *, diag_tol: float = _DIAG_TOL,
              ortho_center: int = None, spinful: Literal["simple", "PH", None] = None,
-             unit_cell_width: int | None = None, as_tenpy: bool | None = None, _backend=None):
+             unit_cell_width: int | None = None, as_tenpy: bool | None = None, _backend=None,
+             _keep_device: bool | None = None):
     r"""MPS representation of a Slater determinant from its correlation matrix
-    (slater.py:1216-1353; same parameters)."""
+    (slater.py:1216-1353; same parameters).
+
+    With ``spinful`` set (Abrikosov-fermion states, whose next stop is ``gutzwiller.abrikosov(_ph)``) the site
+    tensors also stay resident in HBM behind the returned object, so that the projection reads them where the
+    conversion left them; the device memory is released with the MPS."""
+    keep = (spinful is not None) if _keep_device is None else bool(_keep_device)
     trunc_par = to_stopping_condition(trunc_par)
     if unit_cell_width is None:
         unit_cell_width = len(C)
@@ -192,7 +198,7 @@ def C_to_MPS(C: np.ndarray, trunc_par: dict | StoppingCondition, *, diag_tol: fl
         Ed = be.from_host(E.ravel())
         _check_projector(E, be=be, Cd=Ed)
         res = engine.run_chain(be, Ed, 2 * L, L, trunc_par, n_fermion, ortho_center=ortho_center, r_sketch=96,
-                               cplx=True)
+                               cplx=True, keep_device=keep)
         mps = _chain_to_mps(res, unit_cell_width)
         return mps.to_tenpy() if _want_tenpy(as_tenpy) else mps
     Cd = be.from_host(C.ravel())
@@ -202,7 +208,7 @@ def C_to_MPS(C: np.ndarray, trunc_par: dict | StoppingCondition, *, diag_tol: fl
         # the reference's consistency check of the central bond (slater.py:420-421 -> testing.py:131-177)
         SchmidtModes.from_correlation_matrix(C, ortho_center or L // 2, trunc_par, which="LR", diag_tol=diag_tol,
                                              _backend=be)
-    res = engine.run_chain(be, Cd, L, L, trunc_par, n_fermion, ortho_center=ortho_center)
+    res = engine.run_chain(be, Cd, L, L, trunc_par, n_fermion, ortho_center=ortho_center, keep_device=keep)
     mps = _chain_to_mps(res, unit_cell_width)
     return mps.to_tenpy() if _want_tenpy(as_tenpy) else mps
 

@@ -121,6 +121,68 @@ def test_sim_ortho_center_inside_pair(sim_backend):
         assert abs(np.vdot(phi, got)) / np.linalg.norm(phi) > 1 - 1e-10
 
 
+def _resident_vs_staged(be, L, kind, tp):
+    """The projection reads the fermion blocks where the conversion left them (no staging) and gives the same
+    numbers, bit for bit, as the path that stages host-resident blocks."""
+    C_, _ = so.correlation_matrix(so.hopping_chain(L))
+    fn = gw.abrikosov if kind == "simple" else gw.abrikosov_ph
+    fm = slater.C_to_MPS(C_, tp, spinful=kind, _backend=be, as_tenpy=False)
+    a = fn(fm, return_canonical=False, _backend=be)
+    assert a.meta["resident_operands"] == 2 * a.meta["gemm_jobs"] > 0 and a.meta["staged_elems"] == 0
+    fm2 = slater.C_to_MPS(C_, tp, spinful=kind, _backend=be, as_tenpy=False, _keep_device=False)
+    b = fn(fm2, return_canonical=False, _backend=be)
+    assert b.meta["resident_operands"] == 0 and b.meta["staged_elems"] > 0
+    for i in range(a.L):
+        assert np.array_equal(a.get_B_dense(i), b.get_B_dense(i))
+    return a
+
+
+@pytest.mark.parametrize("kind", ["simple", "PH"])
+def test_sim_resident_blocks(sim_backend, kind):
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _resident_vs_staged(sim_backend, 8, kind, {"chi_max": 4096, "svd_min": 1e-7})
+
+
+def _pf_projection(be, kind, canonical):
+    """Parity-conserving input (pfaffian.C_to_MPS, complex tensors): the projection of the MPS equals the
+    brute-force projection of its own dense state (gutzwiller.py:171-172 / :364-367)."""
+    import pfaffian_oracle as po
+    from temfpy_b200 import pfaffian as pf
+    fn = gw.abrikosov if kind == "simple" else gw.abrikosov_ph
+    done = 0
+    for seed in range(12):
+        Cm = po.correlation_matrix(po.random_bdg(6, 100 + seed), "C->C")
+        fm = pf.C_to_MPS(Cm, {"chi_max": 4096, "svd_min": 1e-7}, basis="C", _backend=be, as_tenpy=False)
+        total = int(np.asarray(fm.charges[fm.L]).ravel()[0])
+        if total % 2 != ((fm.L // 2) % 2 if kind == "simple" else 0):
+            with pytest.raises(AssertionError):
+                fn(fm, _backend=be)
+            continue
+        psi = so.mps_to_state(helpers.block_mps_to_dense(fm))
+        phi = brute_force(psi, kind)
+        sm = fn(fm, return_canonical=canonical, _backend=be)
+        assert sm.conserve is None and all(np.all(q == 0) for q in sm.charges)
+        got = spin_state(sm)
+        ov = abs(np.vdot(phi, got)) / (np.linalg.norm(phi) * np.linalg.norm(got))
+        assert ov > 1 - 1e-10, (seed, ov)
+        if not canonical:
+            assert abs(np.linalg.norm(got) - np.linalg.norm(phi)) < 1e-10 * np.linalg.norm(phi) + 1e-13
+        done += 1
+        if done == 2:
+            break
+    assert done > 0
+
+
+@pytest.mark.parametrize("kind,canonical", [("simple", False), ("PH", False), ("PH", True)])
+def test_sim_parity_conserving_input(sim_backend, kind, canonical):
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _pf_projection(sim_backend, kind, canonical)
+
+
 def test_sim_validation(sim_backend):
     C_, _ = so.correlation_matrix(so.hopping_chain(5))
     fm = slater.C_to_MPS(C_, {"chi_max": 64}, _backend=sim_backend, as_tenpy=False)
@@ -141,10 +203,12 @@ def test_gpu_projection_vs_brute_force(gpu_backend, L, kind):
 
 
 @pytest.mark.gpu
-def test_gpu_cfg3_heisenberg_L64(gpu_backend):
-    """BASELINE configs[2] at reduced length (the dense brute force is impossible at L=256): Gutzwiller-projected
-    half-filled Fermi sea, both conventions must give the same spin state, a singlet."""
-    L, tp = 64, {"chi_max": 256}
+@pytest.mark.parametrize("L", [64, 256])
+def test_gpu_cfg3_heisenberg(gpu_backend, L):
+    """BASELINE configs[2] (L = 256 spin sites from 512 fermion sites, chi = 256) and a shorter chain: the
+    Gutzwiller-projected half-filled Fermi sea; both conventions must give the same spin state,
+    a reference-independent check at the size where the dense brute force is impossible."""
+    tp = {"chi_max": 256}
     H = so.hopping_chain(L)
     C_, _ = so.correlation_matrix(H)
     a = gw.abrikosov(slater.C_to_MPS(C_, tp, spinful="simple", _backend=gpu_backend, as_tenpy=False), _backend=gpu_backend)
@@ -156,3 +220,14 @@ def test_gpu_cfg3_heisenberg_L64(gpu_backend):
     assert abs(abs(E[0, 0]) - 1) < 1e-6, E
     assert max(a.chi) <= 256 and max(b.chi) <= 256
     print("cfg3-like chi_proj:", max(a.chi), max(b.chi), "overlap", abs(E[0, 0]))
+
+
+@pytest.mark.gpu
+def test_gpu_resident_blocks_and_parity_input(gpu_backend):
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for kind in ("simple", "PH"):
+            _resident_vs_staged(gpu_backend, 48, kind, {"chi_max": 128})
+        _pf_projection(gpu_backend, "PH", True)
+        _pf_projection(gpu_backend, "simple", False)
