@@ -285,7 +285,12 @@ def run_native(args):
 
     state = {}
 
-    gather = tdist.StreamingGather(be.device) if world > 1 and not os.environ.get("TMF_SIMPLE_GATHER") else None
+    # N > 1: the tensors of all ranks end up in one buffer in rank 0's HBM.  Default: the gather is fused into the
+    # tensor kernels (P2P stores into a peer window on rank 0, dist.FusedGather); TMF_GATHER=nccl selects the
+    # NCCL send/recv gather after the conversion (streaming, or TMF_SIMPLE_GATHER for the plain one).
+    mode = os.environ.get("TMF_GATHER", "fused") if world > 1 else None
+    fused = tdist.FusedGather(be) if mode == "fused" else None
+    gather = tdist.StreamingGather(be.device) if mode == "nccl" and not os.environ.get("TMF_SIMPLE_GATHER") else None
 
     def step(collect_stats=False, n_chunks=None):
         if world > 1:
@@ -293,8 +298,13 @@ def run_native(args):
                 gather.begin()
             tdist.broadcast_C(C_dev)
         res = engine.run_chain(be, C_dev, L, L, tp, N, site_lo=lo, site_hi=hi, r_sketch=args.r_sketch,
-                               n_threads=args.threads, n_chunks=n_chunks if n_chunks else (args.chunks or None), lazy=True)
-        if world > 1:
+                               n_threads=args.threads, n_chunks=n_chunks if n_chunks else (args.chunks or None), lazy=True,
+                               out_provider=fused)
+        if fused is not None:
+            be.sync()
+            full, offs = fused.complete()       # every rank's kernels are done: the window on rank 0 is complete
+            state["gathered"] = None if full is None else int(offs[-1])
+        elif world > 1:
             if gather is not None:
                 got = gather.finish(res.out_buffers())
                 state["gathered"] = None if got is None else int(sum(b.numel() for b in got.values()))
@@ -518,7 +528,9 @@ def run_native(args):
                                     "e2e: host C -> complete MPS in host memory",
                        "test_action": "pass (self-checks of testing.py off in both arms)",
                        "l2": f"working set {(8 * state['out_elems'] + 6e8) / 1e9:.1f} GB per step >> 126 MB L2",
-                       "parallelism": (f"sites sharded over {world} GPU(s), broadcast(C) + gather(tensors) over NCCL"
+                       "parallelism": (f"sites sharded over {world} GPU(s), broadcast(C) over NCCL, gather(tensors) "
+                                       + ("fused into the tensor kernels (P2P stores into a peer window on rank 0 "
+                                          "over NVLink)" if fused is not None else "over NCCL send/recv")
                                        if world > 1 else "1 GPU") + f"; {args.chunks or 'auto (3 at >= 384 sites per GPU, 2 at >= 192, else 1)'} pipeline chunks per GPU"},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roof,
             "whole_step": whole, "parity": parity, "cpu_baseline": cpu}

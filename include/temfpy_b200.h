@@ -365,6 +365,9 @@ int64_t tmf_chain_job_voff(tmf_chain *c, int job);
                                 * O / S / det / out buffers hold complex numbers (2 doubles per element) */
 #define TMF_OPT_DEVICE_PLAN 3  /* 1 (default): site planning (slater.py:760-825, :1027-1058, :1106-1141) on the
                                 * device from the resident enumeration tables (nested mode); 0: host threads */
+#define TMF_OPT_PEER_OUT 5     /* 1: out_dev of tmf_chain_tensors is memory of another GPU (peer window, tmf_ipc_open):
+                                * the minors kernel collects every tensor row in shared memory and writes it with
+                                * whole 256-byte warp stores (NVLink carries each store as one packet) */
 int tmf_chain_set_option(tmf_chain *c, int option, int value);
 /* algorithmic flops of the reference's algorithm for this shard:
  * f[0] eigh, f[1] overlap GEMM, f[2] Schur, f[3] minors, f[4] number of minors */
@@ -389,6 +392,20 @@ typedef struct tmf_gutz_job {
 int64_t tmf_gutz_desc_bytes(const tmf_gutz_job *jobs_host, int njobs);
 int tmf_gutzwiller_project(const tmf_gutz_job *jobs_host, int njobs, int cplx_flag, void *out_dev,
                            int64_t out_bytes, void *desc_dev, void *stream);
+
+/* Multi-GPU plumbing of the sharded conversion (temfpy_b200/dist.py; SURVEY 8(e): "gather of per-site tensors").
+ * Peer window: a buffer in the destination rank's HBM, exported with tmf_ipc_export (64-byte CUDA IPC handle +
+ * offset of dev_ptr inside its allocation) and mapped by the other ranks of the node with tmf_ipc_open (returns the
+ * base of the allocation; add the offset).  Passed as `out_dev` of tmf_chain_tensors, the minors kernels store the
+ * site tensors straight into the destination GPU over NVLink -- the gather is fused into the producing kernel.
+ * Host segments: tmf_host_register pins a (shared-memory) mapping so that tmf_copy_d2h_async moves a shard to the
+ * destination process's address space over the GPU's own PCIe link. */
+int tmf_ipc_export(const void *dev_ptr, unsigned char *handle64, int64_t *offset_out);
+int tmf_ipc_open(const unsigned char *handle64, void **base_out);
+int tmf_ipc_close(void *base);
+int tmf_host_register(void *ptr, int64_t bytes);
+int tmf_host_unregister(void *ptr);
+int tmf_copy_d2h_async(void *dst_host, const void *src_dev, int64_t bytes, void *stream);
 
 /* measurement hooks used by bench.py: kernel launch counter (always on) and per-kernel CUDA-event
  * timing (off by default; enabled only in the profiling pass). */

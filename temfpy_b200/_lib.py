@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libtemfpy_b200.so")
 
 TMF_MAX_MODES = 64
 SIDE_L, SIDE_R = 0, 1
-OPT_SNAP, OPT_NESTED, OPT_DEVICE_PLAN, OPT_COMPLEX = 1, 2, 3, 4
+OPT_SNAP, OPT_NESTED, OPT_DEVICE_PLAN, OPT_COMPLEX, OPT_PEER_OUT = 1, 2, 3, 4, 5
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
@@ -167,6 +167,12 @@ SIGNATURES = {
     "tmf_gutz_desc_bytes": (C.c_int64, [C.POINTER(GutzJob), C.c_int]),
     "tmf_gutzwiller_project": (C.c_int, [C.POINTER(GutzJob), C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
                                          C.c_void_p]),
+    "tmf_ipc_export": (C.c_int, [C.c_void_p, C.c_char_p, c_i64_p]),
+    "tmf_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "tmf_ipc_close": (C.c_int, [C.c_void_p]),
+    "tmf_host_register": (C.c_int, [C.c_void_p, C.c_int64]),
+    "tmf_host_unregister": (C.c_int, [C.c_void_p]),
+    "tmf_copy_d2h_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "tmf_fp64_peak_probe": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_float), c_double_p, C.c_void_p]),
 }
 

@@ -91,6 +91,7 @@ struct tmf_chain {
   int nblocks = 0, max_chi = 0;
   bool enumerated = false;
   bool nested = true;                // nested-projector site stage (no filled bases), see siteprep.cu
+  bool peer_out = false;             // out_dev of the tensor stage is a peer window of another GPU (TMF_OPT_PEER_OUT)
   bool cplx = false;                 // complex Slater determinant: C_dev is the 2L x 2L real embedding (TMF_OPT_COMPLEX)
   std::vector<int> job_x2;           // cplx: cut positions in the embedded matrix (2 x)
   bool want_device_plan = true;      // plan the sites on the device when the enumeration ran there (nested mode)
@@ -309,6 +310,7 @@ int tmf_chain_set_option(tmf_chain *c, int option, int value) {
     return TMF_OK;
   }
   if (option == TMF_OPT_DEVICE_PLAN) { c->want_device_plan = value != 0; return TMF_OK; }
+  if (option == TMF_OPT_PEER_OUT) { c->peer_out = value != 0; return TMF_OK; }
   if (option == TMF_OPT_COMPLEX) {
     c->cplx = value != 0;
     if (c->cplx) c->nested = true;      // the complex kernels exist in the nested form only
@@ -847,6 +849,7 @@ static int chain_tensors_device_plan(tmf_chain *c, const double *C_dev, int ldc,
   int rc = c->cplx ? tmf_site_nested_c_batched(sj.data(), nj.data(), ns, site_desc, stream)
                    : tmf_site_nested_batched(sj.data(), nj.data(), ns, site_desc, stream);
   if (rc) return rc;
+  if (c->peer_out && !mb.empty()) mb[0].pad_ |= 1;       // row-staged stores (NVLink-friendly)
   rc = c->cplx ? tmf_minors_blocks_c(mb.data(), (int)mb.size(), minor_desc, stream)
                : tmf_minors_blocks(mb.data(), (int)mb.size(), minor_desc, stream);
   if (rc) return rc;
@@ -984,6 +987,7 @@ int tmf_chain_tensors(tmf_chain *c, const double *C_dev, int ldc, double *V_dev,
   }
   if (rc) return rc;
   tm.lap("tensors: enqueue site kernels");
+  if (c->peer_out && !mb.empty()) mb[0].pad_ |= 1;
   rc = c->cplx ? tmf_minors_blocks_c(mb.data(), (int)mb.size(), minor_desc, stream)
                : tmf_minors_blocks(mb.data(), (int)mb.size(), minor_desc, stream);
   tm.lap("tensors: enqueue minors");

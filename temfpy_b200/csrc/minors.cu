@@ -323,8 +323,12 @@ __device__ __forceinline__ void reduce_row_regs(const double *Ssm, int ldS, int 
 }
 #endif
 
-template <typename MT>
-TMF_GLOBAL minors_kernel(const tmf_minor_block *blocks, const int *cta_prefix, int nblocks,
+// STAGE: the entries of a bra row are collected in a shared-memory row buffer of the warp and written out as
+// whole 256-byte warp stores.  Used when `out` is a peer window of another GPU (multi-GPU gather fused into this
+// kernel, dist.FusedGather): the bins below produce the entries of a row in scattered order, which the local L2
+// merges but NVLink would carry as 8-byte packets.
+template <typename MT, bool STAGE>
+TMF_GLOBAL_LB(256, 3) minors_kernel(const tmf_minor_block *blocks, const int *cta_prefix, int nblocks,
                          int nmax, int smax, int nkmax) {
   int lo = 0, hi = nblocks;
   const int cta = BLOCK_ID;
@@ -346,6 +350,8 @@ TMF_GLOBAL minors_kernel(const tmf_minor_block *blocks, const int *cta_prefix, i
   MT *kmask = reinterpret_cast<MT *>(metas + MB_WARPS);          // nkmax
   MT *kpp = kmask + nkmax;                                       // nkmax
   unsigned short *queues = reinterpret_cast<unsigned short *>(kpp + nkmax);   // MB_WARPS * NCLS * QCAP
+  double *rows_all = reinterpret_cast<double *>(
+      (reinterpret_cast<uintptr_t>(queues + (size_t)MB_WARPS * NCLS * QCAP) + 7) & ~uintptr_t(7));   // STAGE: MB_WARPS * nkmax
 
   const double det_always = blk.det ? *blk.det : 1.0;
   PAR_FOR(idx, sb * sk) {
@@ -489,8 +495,10 @@ TMF_GLOBAL minors_kernel(const tmf_minor_block *blocks, const int *cta_prefix, i
       }
 #endif
       // ---- the entries of the row -------------------------------------------------------------
-      double *orow = blk.out + (int64_t)(row0 + a) * blk.n_ket;
+      double *grow = blk.out + (int64_t)(row0 + a) * blk.n_ket;
+      double *orow = STAGE ? rows_all + (size_t)w * nkmax : grow;
 #if defined(TMF_HOSTSIM)
+      orow = grow;
       LANE_FOR(l) {
         const MT c0 = (MT)mt->c0, pp0 = (MT)mt->pp0;
         for (int c = l; c < blk.n_ket; c += 32)
@@ -534,6 +542,10 @@ TMF_GLOBAL minors_kernel(const tmf_minor_block *blocks, const int *cta_prefix, i
         if (cnt[2]) flush_bin<3, MT>(q + 2 * QCAP, 0, cnt[2], lane, x, smax, colrow, c0, pp0, kmask, kpp, scale, orow);
         if (cnt[3]) flush_bin<4, MT>(q + 3 * QCAP, 0, cnt[3], lane, x, smax, colrow, c0, pp0, kmask, kpp, scale, orow);
         if (cnt[4]) flush_bin<5, MT>(q + 4 * QCAP, 0, cnt[4], lane, x, smax, colrow, c0, pp0, kmask, kpp, scale, orow);
+        if (STAGE) {
+          __syncwarp();
+          for (int c = lane; c < blk.n_ket; c += 32) grow[c] = orow[c];
+        }
       }
 #endif
       WSYNC();
@@ -541,10 +553,11 @@ TMF_GLOBAL minors_kernel(const tmf_minor_block *blocks, const int *cta_prefix, i
   }
 }
 
-static size_t minors_smem_bytes(int nmax, int smax, int nkmax, size_t mask_bytes) {
+static size_t minors_smem_bytes(int nmax, int smax, int nkmax, size_t mask_bytes, bool stage) {
   return sizeof(double) * ((size_t)smax * (smax | 1) + (size_t)MB_WARPS * nmax * smax + MB_WARPS * 16 + 2) +
          sizeof(WarpMeta) * MB_WARPS +
-         2 * mask_bytes * (size_t)nkmax + sizeof(unsigned short) * MB_WARPS * NCLS * QCAP + 64;
+         2 * mask_bytes * (size_t)nkmax + sizeof(unsigned short) * MB_WARPS * NCLS * QCAP + 64 +
+         (stage ? sizeof(double) * (size_t)MB_WARPS * nkmax + 8 : 0);
 }
 
 }  // namespace tmf
@@ -584,11 +597,16 @@ extern "C" int tmf_minors_blocks(const tmf_minor_block *blocks_host, int nblocks
   rc = copy_h2d(d + o_pref, prefix.data(), sizeof(int) * (size_t)(nblocks + 1), stream);
   if (rc) return rc;
   // occupation masks fit 32 bits for the usual sometimes matrices (<= 32 columns): half the integer work
-  if (smax <= 32)
-    return launch_t("minors", minors_kernel<uint32_t>, prefix[nblocks], 32 * tmf::MB_WARPS,
-                    minors_smem_bytes(nmax, smax, nkmax, 4), stream, reinterpret_cast<const tmf_minor_block *>(d),
-                    reinterpret_cast<const int *>(d + o_pref), nblocks, nmax, smax, nkmax);
-  return launch_t("minors", minors_kernel<uint64_t>, prefix[nblocks], 32 * tmf::MB_WARPS,
-                  minors_smem_bytes(nmax, smax, nkmax, 8), stream, reinterpret_cast<const tmf_minor_block *>(d),
-                  reinterpret_cast<const int *>(d + o_pref), nblocks, nmax, smax, nkmax);
+  const bool stage = (blocks_host[0].pad_ & 1) != 0;      // out is a peer window: row-staged 256-byte stores
+  const tmf_minor_block *bd = reinterpret_cast<const tmf_minor_block *>(d);
+  const int *pd = reinterpret_cast<const int *>(d + o_pref);
+  const int grid = prefix[nblocks], thr = 32 * tmf::MB_WARPS;
+  if (smax <= 32) {
+    const size_t sm = minors_smem_bytes(nmax, smax, nkmax, 4, stage);
+    return stage ? launch_t("minors", minors_kernel<uint32_t, true>, grid, thr, sm, stream, bd, pd, nblocks, nmax, smax, nkmax)
+                 : launch_t("minors", minors_kernel<uint32_t, false>, grid, thr, sm, stream, bd, pd, nblocks, nmax, smax, nkmax);
+  }
+  const size_t sm = minors_smem_bytes(nmax, smax, nkmax, 8, stage);
+  return stage ? launch_t("minors", minors_kernel<uint64_t, true>, grid, thr, sm, stream, bd, pd, nblocks, nmax, smax, nkmax)
+               : launch_t("minors", minors_kernel<uint64_t, false>, grid, thr, sm, stream, bd, pd, nblocks, nmax, smax, nkmax);
 }

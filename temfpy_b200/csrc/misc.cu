@@ -248,3 +248,88 @@ extern "C" int tmf_prof_timeline(char *buf, int cap) {
   std::memcpy(buf, out.c_str(), out.size() + 1);
   return TMF_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Peer windows (multi-GPU gather fused into the tensor kernels) and shared pinned host segments.
+//
+// A *peer window* is a buffer in the HBM of the destination rank that the other ranks of the node map through
+// CUDA IPC; their minors kernels then store the site tensors straight into it over NVLink (P2P stores), so the
+// "gather" of a sharded conversion is the kernels' own output traffic.  The host segments are POSIX shared memory
+// mapped by every rank and registered with the driver, so that each GPU copies its shard to the destination
+// process's address space over its own PCIe link.
+// ---------------------------------------------------------------------------------------------
+extern "C" int tmf_ipc_export(const void *dev_ptr, unsigned char *handle64, int64_t *offset_out) {
+#if defined(TMF_HOSTSIM)
+  (void)dev_ptr; (void)handle64; (void)offset_out;
+  tmf::set_error("peer windows need the CUDA build");
+  return TMF_ERR_RUNTIME;
+#else
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  typedef int (*RangeFn)(unsigned long long *, size_t *, unsigned long long);
+  static RangeFn range = [] {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<RangeFn>(fn);
+  }();
+  if (!range) { tmf::set_error("cuMemGetAddressRange unavailable"); return TMF_ERR_RUNTIME; }
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (range(&base, &size, (unsigned long long)(uintptr_t)dev_ptr) != 0) {
+    tmf::set_error("cuMemGetAddressRange failed");
+    return TMF_ERR_RUNTIME;
+  }
+  cudaIpcMemHandle_t h;
+  int rc = tmf::check_cuda(cudaIpcGetMemHandle(&h, reinterpret_cast<void *>((uintptr_t)base)), "cudaIpcGetMemHandle");
+  if (rc) return rc;
+  std::memcpy(handle64, &h, 64);
+  *offset_out = (int64_t)((unsigned long long)(uintptr_t)dev_ptr - base);
+  return TMF_OK;
+#endif
+}
+
+extern "C" int tmf_ipc_open(const unsigned char *handle64, void **base_out) {
+#if defined(TMF_HOSTSIM)
+  (void)handle64; (void)base_out;
+  tmf::set_error("peer windows need the CUDA build");
+  return TMF_ERR_RUNTIME;
+#else
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  // (the flag enables peer access from the current device to the owner of the allocation)
+  return tmf::check_cuda(cudaIpcOpenMemHandle(base_out, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+#endif
+}
+
+extern "C" int tmf_ipc_close(void *base) {
+#if defined(TMF_HOSTSIM)
+  (void)base;
+  return TMF_OK;
+#else
+  return tmf::check_cuda(cudaIpcCloseMemHandle(base), "cudaIpcCloseMemHandle");
+#endif
+}
+
+extern "C" int tmf_host_register(void *ptr, int64_t bytes) {
+#if defined(TMF_HOSTSIM)
+  (void)ptr; (void)bytes;
+  return TMF_OK;
+#else
+  return tmf::check_cuda(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable), "cudaHostRegister");
+#endif
+}
+
+extern "C" int tmf_host_unregister(void *ptr) {
+#if defined(TMF_HOSTSIM)
+  (void)ptr;
+  return TMF_OK;
+#else
+  return tmf::check_cuda(cudaHostUnregister(ptr), "cudaHostUnregister");
+#endif
+}
+
+extern "C" int tmf_copy_d2h_async(void *dst_host, const void *src_dev, int64_t bytes, void *stream) {
+  return tmf::copy_d2h_async(dst_host, src_dev, (size_t)bytes, stream);
+}

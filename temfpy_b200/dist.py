@@ -193,6 +193,349 @@ class StreamingGather:
 
 
 # ---------------------------------------------------------------------------------------------
+# gather fused into the tensor kernels: peer window in the destination rank's HBM
+# ---------------------------------------------------------------------------------------------
+def _shm_dir():
+    import os
+    import tempfile
+    return "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+
+
+class HostBoard:
+    """All-gather of a few integers between the ranks of one node through POSIX shared memory: every rank owns a
+    row (sequence number + two payload banks), publishes its values and spins until all rows carry the sequence
+    number.  A few microseconds, no GPU work, no NCCL launch -- used where the ranks must agree on sizes in the
+    middle of a conversion (offsets inside the peer window) and as the completion point of a fused gather."""
+    WIDTH = 6
+
+    def __init__(self, dst=0, timeout=120.0):
+        import os
+        import torch.distributed as dist
+        self.world, self.rank, self.timeout = dist.get_world_size(), dist.get_rank(), timeout
+        name = [None]
+        if self.rank == dst:
+            name = [os.path.join(_shm_dir(), f"tmfpy_board_{os.getpid()}_{id(self):x}")]
+            np.zeros((self.world, 16), dtype=np.int64).tofile(name[0])
+        dist.broadcast_object_list(name, src=dst)
+        self.path, self.owner = name[0], self.rank == dst
+        self.arr = np.memmap(self.path, dtype=np.int64, mode="r+", shape=(self.world, 16))
+        self.seq = 0
+        dist.barrier()                      # everybody has mapped the file: the name can go
+        if self.owner:
+            os.unlink(self.path)
+
+    def all_gather(self, vals):
+        import time
+        vals = [int(v) for v in vals]
+        assert len(vals) <= self.WIDTH
+        self.seq += 1
+        bank = 2 + 7 * (self.seq & 1)
+        row = self.arr[self.rank]
+        row[bank: bank + len(vals)] = vals
+        row[0] = self.seq                   # published after the payload (x86 keeps the store order)
+        t0 = time.perf_counter()
+        spins = 0
+        while int(self.arr[:, 0].min()) < self.seq:
+            spins += 1
+            if spins & 1023 == 0:
+                if time.perf_counter() - t0 > self.timeout:
+                    raise RuntimeError("HostBoard.all_gather: a rank did not arrive (timeout)")
+                time.sleep(0)
+        return np.array(self.arr[:, bank: bank + self.WIDTH])
+
+
+class _RawBuffer:
+    """Device memory that PyTorch did not allocate in this process (a slice of a peer window)."""
+
+    def __init__(self, ptr, nbytes):
+        self._ptr, self.nbytes = int(ptr), int(nbytes)
+
+    def data_ptr(self):
+        return self._ptr
+
+
+class PeerWindow:
+    """``nbytes`` of HBM on rank ``dst`` that every rank of the node can address: allocated by ``dst``, exported
+    as a CUDA IPC handle, mapped by the others (``tmf_ipc_export`` / ``tmf_ipc_open``).  With the simulator
+    backend (CPU tests) the window is a shared-memory file instead."""
+
+    def __init__(self, be, nbytes, dst=0):
+        import ctypes as C
+        import os
+        import torch.distributed as dist
+        from ._lib import check
+        self.be, self.dst, self.nbytes = be, dst, int(nbytes)
+        self.rank = dist.get_rank()
+        self.cuda = hasattr(be, "torch")
+        self.base = None
+        info = [None]
+        if self.cuda:
+            if self.rank == dst:
+                self.buf = be.empty(self.nbytes, np.uint8)
+                h, off = C.create_string_buffer(64), C.c_int64()
+                check(be.lib, be.lib.tmf_ipc_export(be.ptr(self.buf), h, C.byref(off)))
+                info = [(h.raw, int(off.value))]
+            dist.broadcast_object_list(info, src=dst)
+            if self.rank == dst:
+                self.ptr = be.ptr(self.buf)
+            else:
+                base = C.c_void_p()
+                check(be.lib, be.lib.tmf_ipc_open(info[0][0], C.byref(base)))
+                self.base = base.value
+                self.ptr = self.base + info[0][1]
+        else:
+            if self.rank == dst:
+                info = [os.path.join(_shm_dir(), f"tmfpy_win_{os.getpid()}_{id(self):x}")]
+                with open(info[0], "wb") as f:
+                    f.truncate(max(self.nbytes, 8))
+            dist.broadcast_object_list(info, src=dst)
+            self.buf = np.memmap(info[0], dtype=np.float64, mode="r+", shape=(max(self.nbytes // 8, 1),))
+            dist.barrier()
+            if self.rank == dst:
+                os.unlink(info[0])
+
+    def slice(self, off_bytes, nbytes):
+        """Backend buffer for [off_bytes, off_bytes + nbytes) of the window."""
+        assert 0 <= off_bytes and off_bytes + nbytes <= self.nbytes
+        if not self.cuda:
+            return self.buf[off_bytes // 8: (off_bytes + nbytes) // 8]
+        if self.rank == self.dst:
+            return self.buf[off_bytes: off_bytes + nbytes].view(self.be.torch.float64)
+        return _RawBuffer(self.ptr + off_bytes, nbytes)
+
+    def close(self):
+        if self.cuda and self.base is not None:
+            self.be.lib.tmf_ipc_close(self.base)
+            self.base = None
+        self.buf = None
+
+
+class FusedGather:
+    """Gather of a sharded conversion without a gather step: ``engine.run_chain(..., out_provider=FusedGather)``
+    makes every rank's tensor kernels store their output directly into the rank's slice of a peer window on
+    ``dst`` (P2P stores over NVLink, overlapped with the minors arithmetic tile by tile).  The slices follow each
+    other in rank = site order, so ``dst`` ends up with the same contiguous buffer ``gather_tensors`` returns.
+
+    The slice offsets need every rank's tensor size, which is known after its enumeration stage: the sizes are
+    exchanged through a :class:`HostBoard` (no device work).  A rank that leaves the conversion early (retry with
+    other options, ``engine._Retry``) publishes -1 and the others follow it out."""
+
+    def __init__(self, be, dst=0):
+        import torch.distributed as dist
+        self.be, self.dst = be, dst
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.board = HostBoard(dst)
+        self.win = None
+        self.sizes = None
+
+    def _ensure(self, nbytes):
+        if self.win is not None and self.win.nbytes >= nbytes:
+            return
+        if self.win is not None:
+            if hasattr(self.be, "sync"):
+                self.be.sync()
+            self.board.all_gather([0])              # nobody still writes into the old window
+            self.win.close()
+        cap = max(int(nbytes * 1.25), 1 << 20)
+        self.win = PeerWindow(self.be, (cap + 255) & ~255, self.dst)
+
+    def __call__(self, chain):
+        from . import engine
+        n = int(chain.tensor_doubles())
+        sizes = self.board.all_gather([n])[:, 0]
+        if (sizes < 0).any():
+            raise engine._Retry("peer", ValueError("another rank restarts the conversion with other options"))
+        self._ensure(8 * int(sizes.sum()))          # collective: every rank sees the same sizes
+        self.sizes = sizes
+        return self.win.slice(8 * int(sizes[: self.rank].sum()), 8 * n)
+
+    def abort(self):
+        self.board.all_gather([-1])
+
+    def complete(self):
+        """Completion point: call after the local stream is synchronised; returns (buffer, offsets) on ``dst`` once
+        every rank's kernels have finished, (None, None) elsewhere."""
+        self.board.all_gather([1])
+        if self.rank != self.dst:
+            return None, None
+        offs = np.concatenate(([0], np.cumsum(self.sizes))).astype(np.int64)
+        return self.win.slice(0, 8 * int(offs[-1])), offs
+
+    def close(self):
+        if self.win is not None:
+            self.win.close()
+            self.win = None
+
+
+# ---------------------------------------------------------------------------------------------
+# results to the destination *process*: shared pinned host segments, one PCIe link per GPU
+# ---------------------------------------------------------------------------------------------
+class _Segment:
+    """A file in shared memory mapped into this process.  Layout: int64[0] lease flag (1 while the destination
+    process holds views of the contents), int64[1] length of the pickled directory that starts at byte 64, data
+    from byte ``DATA`` on.  The owner (the rank that fills it) registers the mapping with the CUDA driver so that
+    its device -> host copies run at PCIe speed and asynchronously."""
+    DATA = 1 << 16
+
+    def __init__(self, path, nbytes, lib=None, create=False):
+        import mmap
+        import os
+        self.path, self.nbytes, self.lib, self.owner = path, int(nbytes), lib, create
+        fd = os.open(path, os.O_RDWR | (os.O_CREAT if create else 0), 0o600)
+        try:
+            if create:
+                os.ftruncate(fd, self.nbytes)
+            self.mm = mmap.mmap(fd, self.nbytes)
+        finally:
+            os.close(fd)
+        self.arr = np.frombuffer(self.mm, dtype=np.uint8)
+        self.head = self.arr[:16].view(np.int64)
+        self.registered = False
+        if create:
+            self.head[:] = 0
+            if lib is not None and lib.tmf_is_cuda():
+                from ._lib import check
+                check(lib, lib.tmf_host_register(self.arr.ctypes.data, self.nbytes))
+                self.registered = True
+
+    def close(self):
+        import os
+        if self.registered:
+            self.lib.tmf_host_unregister(self.arr.ctypes.data)
+            self.registered = False
+        if self.owner:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+            self.owner = False
+
+
+class HostExchange:
+    """Moves every rank's shard (tensors + Schmidt / plan tables) into the destination process without passing
+    through the destination GPU: each rank copies device -> its own shared pinned segment over its own PCIe link
+    (all links in parallel), publishes the segment through the :class:`HostBoard`, and the destination process maps
+    the segments and wraps the arrays in place (zero copy).  A segment is leased to the destination until the last
+    NumPy view of it is garbage-collected there; the filling rank then reuses it (registration is paid once)."""
+
+    def __init__(self, be, dst=0):
+        import atexit
+        import os
+        import torch.distributed as dist
+        self.be, self.dst = be, dst
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.board = HostBoard(dst)
+        tok = [f"tmfpy_seg_{os.getpid()}_{id(self):x}" if self.rank == dst else None]
+        dist.broadcast_object_list(tok, src=dst)
+        self.prefix = os.path.join(_shm_dir(), tok[0])
+        self.mine = []          # segments this rank fills
+        self.peers = {}         # dst: (rank, index) -> _Segment
+        atexit.register(self.close)
+
+    def _acquire(self, need):
+        for i, seg in enumerate(self.mine):
+            if seg.nbytes >= need and int(seg.head[0]) == 0:
+                return i, seg
+        for i, seg in enumerate(self.mine):           # too small and free: replace
+            if int(seg.head[0]) == 0:
+                seg.close()
+                self.mine[i] = None
+        self.mine = [m for m in self.mine if m is not None]
+        i = getattr(self, "_next", 0)
+        self._next = i + 1
+        cap = (int(need * 1.25) + (1 << 21)) & ~((1 << 21) - 1)
+        seg = _Segment(f"{self.prefix}_r{self.rank}_{i}", cap, self.be.lib, create=True)
+        seg.index = i
+        self.mine.append(seg)
+        return i, seg
+
+    def send(self, res, extra=None):
+        """Every rank: shard ``res`` (``engine.DeviceChainResult``) -> its segment; returns on ``dst`` the list,
+        in rank order, of ``(directory, root array)`` per rank, ``None`` elsewhere."""
+        import pickle
+        from . import engine
+        be, lib = self.be, self.be.lib
+        chains = res.chains
+        tabs = [engine.ShardTables(c, None, want_sites=True) for c in chains]
+        states = [t.state() for t in tabs]
+        need = _Segment.DATA
+        for c, st in zip(chains, states):
+            need += 8 * c.es * c.out_elems + 256
+            for v in st.values():
+                need += (len(v) if isinstance(v, (bytes, bytearray)) else getattr(v, "nbytes", 64)) + 64
+        idx, seg = self._acquire(need)
+        seg.head[0] = 1                                   # leased from now on
+        o = _Segment.DATA
+        directory = []
+        cuda = hasattr(be, "torch")
+        for c, st in zip(chains, states):
+            nb = 8 * c.es * c.out_elems
+            if cuda:
+                from ._lib import check
+                check(lib, lib.tmf_copy_d2h_async(seg.arr.ctypes.data + o, be.ptr(c._buffers["out"]), nb, be.stream))
+                be.d2h_bytes += nb
+            else:
+                seg.arr[o: o + nb] = np.asarray(c._buffers["out"]).view(np.uint8)[:nb]
+            ent = dict(out=(o, c.out_elems, c.es), site_lo=c.site_lo, site_hi=c.site_hi,
+                       stats=(c.nblocks, c.max_chi, c.njobs), arrays={}, scalars={})
+            o = (o + nb + 63) & ~63
+            for k, v in st.items():                       # tables: written while the tensor copy is in flight
+                if isinstance(v, (bytes, bytearray)):
+                    v = np.frombuffer(v, dtype=np.uint8)
+                if isinstance(v, np.ndarray):
+                    v = np.ascontiguousarray(v)
+                    seg.arr[o: o + v.nbytes] = v.reshape(-1).view(np.uint8)
+                    ent["arrays"][k] = (o, v.dtype.str, v.shape)
+                    o = (o + v.nbytes + 63) & ~63
+                else:
+                    ent["scalars"][k] = v
+            directory.append(ent)
+        blob = pickle.dumps(dict(chunks=directory, extra=extra), protocol=pickle.HIGHEST_PROTOCOL)
+        assert 64 + len(blob) <= _Segment.DATA and o <= seg.nbytes
+        seg.arr[64: 64 + len(blob)] = np.frombuffer(blob, dtype=np.uint8)
+        seg.head[1] = len(blob)
+        be.sync()                                          # the tensor copy has landed
+        got = self.board.all_gather([seg.index, seg.nbytes])
+        if self.rank != self.dst:
+            return None
+        out = []
+        for r in range(self.world):
+            key, nbytes = (r, int(got[r, 0])), int(got[r, 1])
+            ps = self.peers.get(key)
+            if ps is None or ps.nbytes != nbytes:
+                ps = seg if r == self.rank else _Segment(f"{self.prefix}_r{r}_{key[1]}", nbytes)
+                self.peers[key] = ps
+            root = np.frombuffer(ps.mm, dtype=np.uint8)    # fresh root: every view of this result hangs off it
+            import weakref
+            weakref.finalize(root, _release, ps.head)
+            d = pickle.loads(root[64: 64 + int(ps.head[1])].tobytes())
+            out.append((d, root))
+        return out
+
+    def close(self):
+        for seg in self.mine:
+            seg.close()
+        self.mine = []
+
+
+def _release(head):
+    head[0] = 0
+
+
+def _tables_from_segment(ent, root):
+    from . import engine
+    st = dict(ent["scalars"])
+    for k, (o, dt, shape) in ent["arrays"].items():
+        n = int(np.prod(shape)) * np.dtype(dt).itemsize
+        st[k] = root[o: o + n].view(np.dtype(dt)).reshape(shape)
+    if "plans" in st:
+        st["plans"] = st["plans"].tobytes()
+    o, n, es = ent["out"]
+    host = root[o: o + 8 * es * n].view(np.complex128 if es == 2 else np.float64)
+    return engine.ShardTables.from_state(st, host)
+
+
+# ---------------------------------------------------------------------------------------------
 # public multi-GPU entry point
 # ---------------------------------------------------------------------------------------------
 def _t(buf):
@@ -202,13 +545,16 @@ def _t(buf):
 
 
 def C_to_MPS(C, trunc_par, *, ortho_center=None, spinful=None, unit_cell_width=None, dst=0, backend=None,
-             n_threads=0):
+             n_threads=0, host_exchange=True):
     """``slater.C_to_MPS`` over all GPUs of the process group (reference slater.py:1216-1353, one process per
     GPU, ``torch.distributed`` initialised by the caller).  Every rank calls it; ``C`` is read on rank ``dst``
     only (the others may pass ``None``).  The correlation matrix is broadcast, every rank converts a contiguous,
-    cost-balanced range of sites (no data-path exchange: a bond is a function of C alone), the block-sparse
-    tensors are gathered on ``dst`` over NCCL / NVLink and the Schmidt tables with them.  Returns the complete
-    ``BlockMPS`` on ``dst`` and ``None`` elsewhere.
+    cost-balanced range of sites (no data-path exchange: a bond is a function of C alone).  The result is wanted in
+    the *host* memory of ``dst``: by default every GPU copies its shard (tensors and Schmidt tables) into a shared
+    pinned host segment over its own PCIe link and ``dst`` wraps the segments in place (:class:`HostExchange`; all
+    ranks on one node); ``host_exchange=False`` gathers the tensors in ``dst``'s HBM over NCCL / NVLink first.
+    (Callers that want the tensors in ``dst``'s HBM use ``engine.run_chain(..., out_provider=FusedGather(...))``.)
+    Returns the complete ``BlockMPS`` on ``dst`` and ``None`` elsewhere.
 
     Sketch-width / fallback decisions (``engine.run_chain``) are taken for all ranks together, so that the
     boundary bond two ranks share comes out of identical kernels on both."""
@@ -236,7 +582,7 @@ def C_to_MPS(C, trunc_par, *, ortho_center=None, spinful=None, unit_cell_width=N
         slater._check_projector(Cp, be=be, Cd=C_dev)
     lo, hi = partition(L, world, tp.chi_max, ortho_center)[rank]
     opts = dict(r_sketch=48, snap=False, nested=None, device_plan=None)
-    codes = {"sketch": 1, "singular": 2, "nested": 3}
+    codes = {"sketch": 1, "singular": 2, "nested": 3, "peer": 0}
     dev = _t(C_dev).device
     while True:
         res, code, err = None, 0, None
@@ -263,40 +609,64 @@ def C_to_MPS(C, trunc_par, *, ortho_center=None, spinful=None, unit_cell_width=N
             raise err or ValueError("site stage failed on another rank")
         else:
             opts["nested"] = False
-    # ---- tensors -> dst (device, NVLink), Schmidt / plan tables with them ---------------------------
-    parts = [(_t(b), n) for b, n in res.out_buffers()]
-    full, offs = gather_tensors(parts, dst=dst)
-    states = [ShardState(engine.ShardTables(c, None, want_sites=True).state(), c.out_elems, c.site_lo, c.site_hi,
-                         (c.nblocks, c.max_chi, c.njobs)) for c in res.chains]
-    gathered = [None] * world if rank == dst else None
-    dist.gather_object(states, gathered, dst=dst)
-    res.close()
-    if rank != dst:
-        return None
-    if hasattr(be, "to_host_async") and full.is_cuda:
-        pinned = be.to_host_async(full)
-        be.sync()
-        host = pinned.numpy()
-    else:
-        pinned, host = None, full.numpy()
+    # ---- results -> dst ------------------------------------------------------------------------------------
     out = engine.ChainResult(L=L, ortho_center=ortho_center or L // 2, site_lo=0, site_hi=L)
-    out._pinned = pinned
-    o = 0
-    nblocks = max_chi = njobs = 0
-    for r in range(world):
-        assert o == int(offs[r])
-        for st in gathered[r]:
-            tab = engine.ShardTables.from_state(st.state, host[o: o + st.out_elems])
-            tab.normalized()
-            o += st.out_elems
-            out.tables.append(tab)
-            out.bonds.add([x for x in range(tab.first_bond, tab.first_bond + tab.n_bonds)
-                           if st.site_lo <= x <= st.site_hi or x == out.ortho_center], tab.bond)
-            out.sites.add(range(st.site_lo, st.site_hi), tab.site)
-            nblocks += st.stats[0]; max_chi = max(max_chi, st.stats[1]); njobs += st.stats[2]
-    out.stats = dict(out_elems=o, nblocks=nblocks, max_chi=max_chi, njobs=njobs, n_ranks=world)
-    out.options = dict(opts)
+    nblocks = max_chi = njobs = o = 0
+
+    def add(tab, site_lo, site_hi, stats):
+        nonlocal nblocks, max_chi, njobs
+        tab.normalized()
+        out.tables.append(tab)
+        out.bonds.add([x for x in range(tab.first_bond, tab.first_bond + tab.n_bonds)
+                       if site_lo <= x <= site_hi or x == out.ortho_center], tab.bond)
+        out.sites.add(range(site_lo, site_hi), tab.site)
+        nblocks += stats[0]; max_chi = max(max_chi, stats[1]); njobs += stats[2]
+
+    if host_exchange:
+        # every GPU copies its shard into a shared pinned host segment over its own PCIe link; dst maps the segments
+        # and wraps tensors and tables in place
+        key = (id(be), dst)
+        ex = _exchanges.get(key)
+        if ex is None:
+            ex = _exchanges[key] = HostExchange(be, dst)
+        got = ex.send(res)
+        res.close()
+        if rank != dst:
+            return None
+        for d, root in got:
+            for ent in d["chunks"]:
+                add(_tables_from_segment(ent, root), ent["site_lo"], ent["site_hi"], ent["stats"])
+                o += ent["out"][1]
+    else:
+        # tensors -> dst's HBM over NCCL / NVLink, pinned device -> host copy there; tables pickled alongside
+        parts = [(_t(b), n) for b, n in res.out_buffers()]
+        full, offs = gather_tensors(parts, dst=dst)
+        states = [ShardState(engine.ShardTables(c, None, want_sites=True).state(), c.out_elems, c.site_lo, c.site_hi,
+                             (c.nblocks, c.max_chi, c.njobs)) for c in res.chains]
+        gathered = [None] * world if rank == dst else None
+        dist.gather_object(states, gathered, dst=dst)
+        res.close()
+        if rank != dst:
+            return None
+        if hasattr(be, "to_host_async") and full.is_cuda:
+            pinned = be.to_host_async(full)
+            be.sync()
+            host = pinned.numpy()
+        else:
+            pinned, host = None, full.numpy()
+        out._pinned = pinned
+        for r in range(world):
+            assert o == int(offs[r])
+            for st in gathered[r]:
+                add(engine.ShardTables.from_state(st.state, host[o: o + st.out_elems]), st.site_lo, st.site_hi, st.stats)
+                o += st.out_elems
+    out.stats = dict(out_elems=o, nblocks=nblocks, max_chi=max_chi, njobs=njobs, n_ranks=world,
+                     transport="host segments" if host_exchange else "nccl gather")
+    out.options = engine._public_opts(opts)
     return slater._chain_to_mps(out, unit_cell_width)
+
+
+_exchanges = {}
 
 
 class ShardState:

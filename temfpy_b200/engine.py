@@ -504,6 +504,12 @@ class SlaterChain:
         check(lib, lib.tmf_chain_enumerate_dev(self.handle, be.ptr(work), nbytes, be.stream))
 
     # -- stage B: tensors -----------------------------------------------------------------------
+    def tensor_doubles(self) -> int:
+        """Doubles of the shard's site tensors (known once the bonds are enumerated)."""
+        q = (C.c_int64 * 8)()
+        check(self.lib, self.lib.tmf_chain_tensor_sizes(self.handle, q))
+        return self.es * int(q[5])
+
     def run_tensors(self, C_dev, ldc, out=None):
         be, lib = self.be, self.lib
         q = (C.c_int64 * 8)()
@@ -650,9 +656,10 @@ SKETCH_WIDTHS = (48, 64, 128, 160)
 
 def _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch, n_threads,
                fetch_tensors, lazy=False, gate=None, snap=False, nested=None, device_plan=None, cplx=False,
-               keep_device=False):
+               keep_device=False, out_provider=None):
     import time
     gate = gate or _NoGate()
+    provided = False
     chain = SlaterChain(backend, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch, n_threads, snap=snap,
                         nested=nested, device_plan=device_plan, cplx=cplx)
     chain.keep_device = keep_device
@@ -670,7 +677,13 @@ def _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r
         tt.append(time.perf_counter())
         chain.run_enumerate()
         tt.append(time.perf_counter())
-        chain.run_tensors(C_dev, ldc)
+        out = None
+        if out_provider is not None:      # (multi-GPU: a slice of the destination rank's peer window, dist.py)
+            provided = True
+            out = out_provider(chain)
+            if not hasattr(out, "device") and hasattr(backend, "torch"):     # memory of another GPU
+                check(chain.lib, chain.lib.tmf_chain_set_option(chain.handle, _lib.OPT_PEER_OUT, 1))
+        chain.run_tensors(C_dev, ldc, out=out)
         tt.append(time.perf_counter())
         if lazy:
             backend.sync()
@@ -690,6 +703,8 @@ def _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r
             raise _Retry("singular", err) from None
         raise
     finally:
+        if out_provider is not None and not provided:
+            out_provider.abort()          # the other ranks must not wait for this one's size
         if not (lazy and ok):
             chain.close()
 
@@ -773,7 +788,7 @@ class DeviceChainResult:
 
 def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_lo=0, site_hi=None,
               r_sketch=48, n_threads=0, fetch_tensors=True, n_chunks=None, lazy=False, snap=False, nested=None,
-              device_plan=None, cplx=False, keep_device=False):
+              device_plan=None, cplx=False, keep_device=False, out_provider=None):
     """C (device) -> Schmidt data of every bond and block-sparse tensor of every site.
 
     The site range is cut into cost-balanced chunks that run as a software pipeline: one worker
@@ -792,12 +807,14 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
     degeneracies below ``degeneracy_tol``; where a multiplet that is degenerate in exact arithmetic straddles
     ``chi_max`` the kept part is decided by the rounding noise of the mode eigenvalues, in the reference as here)."""
     opts = dict(r_sketch=r_sketch, snap=snap, nested=nested, device_plan=device_plan, cplx=cplx,
-                keep_device=keep_device)
+                keep_device=keep_device, out_provider=out_provider)
     while True:
         try:
             return _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi,
                                    n_threads, fetch_tensors, n_chunks, lazy, opts)
         except _Retry as rt:
+            if rt.kind == "peer":           # multi-rank callers decide for all ranks together (dist.C_to_MPS)
+                raise
             if rt.kind == "sketch":
                 wider = [r for r in SKETCH_WIDTHS if r > opts["r_sketch"]]
                 if not wider:
@@ -811,12 +828,19 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
                 opts["nested"] = False
 
 
+def _public_opts(opts):
+    return {k: v for k, v in opts.items() if k != "out_provider"}
+
+
 def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi, n_threads,
                     fetch_tensors, n_chunks, lazy, opts):
     from .dist import partition
     r_sketch, snap, nested, device_plan = opts["r_sketch"], opts["snap"], opts["nested"], opts["device_plan"]
     cplx = opts.get("cplx", False)
     keep = opts.get("keep_device", False)
+    provider = opts.get("out_provider")
+    if provider is not None:
+        n_chunks = 1                     # one slice of the peer window per rank
     site_hi = L if site_hi is None else site_hi
     nsites = site_hi - site_lo
     if n_chunks is None:
@@ -827,10 +851,10 @@ def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site
     if n_chunks == 1:
         r = _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi, r_sketch,
                        n_threads, fetch_tensors, lazy, snap=snap, nested=nested, device_plan=device_plan, cplx=cplx,
-                       keep_device=keep)
+                       keep_device=keep, out_provider=provider)
         if lazy:
             r = DeviceChainResult([r])
-        r.options = dict(opts)
+        r.options = _public_opts(opts)
         return r
     import os
     # equal-cost chunks with a short last one: after the last mode stage only its host stage and tensor
@@ -875,7 +899,7 @@ def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site
         parts[order[pos]] = r
     if lazy:
         out = DeviceChainResult(parts)
-        out.options = dict(opts)
+        out.options = _public_opts(opts)
         return out
     res = ChainResult(L=L, ortho_center=parts[0].ortho_center, site_lo=site_lo, site_hi=site_hi)
     for p in parts:
@@ -887,5 +911,5 @@ def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site
                      nblocks=sum(p.stats["nblocks"] for p in parts),
                      max_chi=max(p.stats["max_chi"] for p in parts),
                      njobs=sum(p.stats["njobs"] for p in parts), n_chunks=n_chunks)
-    res.options = dict(opts)
+    res.options = _public_opts(opts)
     return res

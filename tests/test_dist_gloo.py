@@ -83,7 +83,16 @@ def _worker_public(rank, world, port, L, chi, out_path):
         if rank == 0:
             Cm, _ = so.correlation_matrix(helpers.random_hamiltonian(L, 5))
         mps = tdist.C_to_MPS(Cm, {"chi_max": chi}, backend=be)          # public multi-rank entry point
+        mps_nccl = tdist.C_to_MPS(Cm, {"chi_max": chi}, backend=be, host_exchange=False)
+        mps2 = tdist.C_to_MPS(Cm, {"chi_max": chi}, backend=be)         # (second call: segments leased / reused)
         if rank == 0:
+            assert mps.meta["stats"]["transport"] == "host segments"
+            for other in (mps_nccl, mps2):
+                for x in range(L + 1):
+                    assert np.array_equal(mps.lams[x], other.lams[x])
+                for i in range(L):
+                    assert np.array_equal(mps.tensors[i].dense(), other.tensors[i].dense())
+            del mps2, other
             ref = slater.C_to_MPS(Cm, {"chi_max": chi}, as_tenpy=False, _backend=be)
             ok = mps is not None and mps.L == ref.L and mps.form == ref.form
             for x in range(L + 1):
@@ -103,3 +112,54 @@ def test_two_rank_public_C_to_MPS(tmp_path):
     out = str(tmp_path / "ok.npy")
     mp.spawn(_worker_public, args=(2, _free_port(), 26, 16, out), nprocs=2, join=True)
     assert np.load(out)[0] == 1
+
+
+def _worker_fused(rank, world, port, L, chi, out_path):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import slater_oracle as so
+        from temfpy_b200 import dist as tdist, engine
+        from temfpy_b200.schmidt_utils import to_stopping_condition
+        from tests import helpers
+        from tests.hostsim import NumpyBackend
+        be = NumpyBackend()
+        tp = to_stopping_condition({"chi_max": chi})
+        Cm, nf = so.correlation_matrix(helpers.random_hamiltonian(L, 12))     # (same seed on every rank)
+        Ct = np.ascontiguousarray(Cm).ravel()
+        fused = tdist.FusedGather(be)
+        # the board: an all-gather of integers through shared memory
+        got = fused.board.all_gather([10 + rank, rank * rank])
+        assert got[:, 0].tolist() == [10 + r for r in range(world)] and got[:, 1].tolist() == [r * r for r in range(world)]
+        oks = []
+        for it in range(3):                 # the window is reused (and grown once: the first sizes are tiny)
+            Lc = L if it else 8
+            Cc = Ct if it else np.ascontiguousarray(so.correlation_matrix(helpers.random_hamiltonian(8, 3))[0]).ravel()
+            nfc = nf if it else int(round(np.trace(Cc.reshape(8, 8))))
+            lo, hi = tdist.partition(Lc, world, chi)[rank]
+            res = engine.run_chain(be, Cc, Lc, Lc, tp, nfc, site_lo=lo, site_hi=hi, lazy=True, out_provider=fused)
+            full, offs = fused.complete()
+            if rank == 0:
+                ref = engine.run_chain(be, Cc, Lc, Lc, tp, nfc, n_chunks=1, lazy=True)
+                rbuf, relems = ref.out_buffers()[0]
+                oks.append(int(offs[-1]) == relems and np.array_equal(np.asarray(full), rbuf[:relems]))
+                ref.close()
+            res.close()
+        fused.close()
+        if rank == 0:
+            np.save(out_path, np.array([int(all(oks)), len(oks)]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_fused_gather(tmp_path):
+    """FusedGather: both ranks' tensor stages write straight into their slice of a window owned by rank 0 (shared
+    memory here, a CUDA IPC peer window on GPUs); the window then holds the unsharded result bit for bit."""
+    out = str(tmp_path / "ok.npy")
+    mp.spawn(_worker_fused, args=(2, _free_port(), 24, 16, out), nprocs=2, join=True)
+    ok, n = np.load(out)
+    assert ok == 1 and n == 3
