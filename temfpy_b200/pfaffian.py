@@ -29,9 +29,8 @@ when the small Schur complement of ``U^*`` is singular; the absolute parities fo
 blocks at the two chain ends.
 
 Return type: :class:`temfpy_b200.mps.BlockMPS` with ``conserve="parity"`` (``.to_tenpy()`` builds the
-TeNPy object when ``tenpy`` is importable).  Not supported in this release: modes with eigenvalue
-exactly 1/2 (pfaffian.py:802-816, :857-874) and more than 16 entangled modes per bond
-(``4k <= TMF_MAX_MODES``); both raise ``NotImplementedError``.
+TeNPy object when ``tenpy`` is importable).  Not supported in this release: more than 16 entangled modes per
+bond (``4k <= TMF_MAX_MODES``; raises ``NotImplementedError``).
 """
 from __future__ import annotations
 
@@ -346,12 +345,55 @@ class _PfChain:
         self.kh = st[:, 1].astype(np.int64)
         eo = be.to_host(eod, nj * 16).reshape(nj, 16)
         self.e = [eo[j, : self.k[j]].copy() for j in range(nj)]
-        for side in (_lib.SIDE_L, _lib.SIDE_R):
-            j = self.job_of.get((oc, side))
-            if j is not None and self.kh[j] > 0:
-                raise NotImplementedError("Schmidt modes with eigenvalue 1/2 on the *central* bond "
-                                          "(pfaffian.py:857-874) are not supported in this release; "
-                                          "choose another `ortho_center`")
+        jl, jr = self.job_of.get((oc, _lib.SIDE_L)), self.job_of.get((oc, _lib.SIDE_R))
+        if jl is not None and jr is not None and (self.kh[jl] > 0 or self.kh[jr] > 0):
+            assert self.kh[jl] == self.kh[jr], "Unequal number of 1/2 modes"               # pfaffian.py:845
+            self._centre_half_modes(jl, jr, int(self.kh[jl]))
+
+    def _centre_half_modes(self, jl, jr, kh):
+        """Eigenvalue-1/2 modes on the central bond (pfaffian.py:857-865, :878-891).  The kernel left, on either
+        side, an arbitrary real orthonormal basis r_0 .. r_{2kh-1} of the 1/2 eigenspace packed into complex modes
+        w_j = (r_j + i r_{kh+j}) / sqrt(2).  The two bases are paired by the SVD of r_L^T Im(C_LR) r_R (a 2kh x 2kh
+        matrix, host) and repacked with the reference's conventions -- left: (r_j + i r_{kh+j}) / sqrt 2, right
+        (upper / Nambu-partner column): (r_{kh+j} - i r_j) / sqrt 2 -- so that w_L^+ C_LR conj(w_R) is real
+        positive like for the modes paired by ``block_svd``.  (The reference's quasi-random rotation of the
+        paired bases, :867-874, acts on both sides alike and is a gauge choice; it is not applied.)"""
+        be, oc, L = self.be, self.oc, self.L
+        k = int(self.k[jl])
+        assert int(self.k[jr]) == k, "Unequal number of entangled modes"
+        s2 = 2 ** 0.5
+
+        def real_basis(j):
+            rows = int(self.rows[j])
+            o = int(self.v_off[j]) + rows * 4 * (k - kh)
+            cols = np.array(be.to_host(self.Vd[o: o + rows * 4 * kh], rows * 4 * kh)).reshape(4 * kh, rows)
+            u = cols[0::4]                                  # emb(w_j): re / im interleaved
+            return np.concatenate([s2 * u[:, 0::2], s2 * u[:, 1::2]]).T, rows, o      # (2 n_side, 2kh)
+        RL, rows_l, o_l = real_basis(jl)
+        RR, rows_r, o_r = real_basis(jr)
+        A = np.ascontiguousarray(self.CM[: 2 * oc, 2 * oc:].imag)
+        U, _, Vh = np.linalg.svd(RL.T @ A @ RR)                                           # pfaffian.py:862-865
+        RL, RR = RL @ U, RR @ Vh.T
+
+        def pack(re, im, rows):
+            out = np.empty((4 * kh, rows))
+            for j in range(kh):
+                u = np.empty(rows)
+                u[0::2], u[1::2] = re[:, j] / s2, im[:, j] / s2
+                ju = np.empty(rows)
+                ju[0::2], ju[1::2] = -u[1::2], u[0::2]                                    # J emb(w)
+                cu = u.copy()
+                cu[1::2] *= -1                                                            # emb(conj w)
+                jcu = np.empty(rows)
+                jcu[0::2], jcu[1::2] = u[1::2], u[0::2]                                   # J emb(conj w)
+                out[4 * j: 4 * j + 4] = (u, ju, cu, jcu)
+            return out.ravel()
+        new_l = pack(RL[:, :kh], RL[:, kh:], rows_l)        # w_L = (r_j + i r_{kh+j}) / sqrt 2
+        new_r = pack(RR[:, kh:], RR[:, :kh], rows_r)        # conj(w_R) = (r_{kh+j} - i r_j) / sqrt 2
+        for o, new in ((o_l, new_l), (o_r, new_r)):
+            d = be.from_host(new)
+            self.Vd[o: o + new.size] = d[: new.size]
+        be.sync()
 
     def _job(self, x, side):
         """(job index or None for an empty block, k, f)."""
@@ -423,6 +465,8 @@ class _PfChain:
         e = self.bonds[oc].e
         br = np.flatnonzero(np.abs(np.diff(e)) > self.tp.degeneracy_tol) + 1                 # utils.py:71
         for a, b in zip(np.concatenate(([0], br)), np.concatenate((br, [k]))):
+            if e[a] >= 0.5 - self.tp.degeneracy_tol:        # 1/2 modes: paired by _centre_half_modes (pfaffian.py:857-865)
+                continue
             U, _, Vh = np.linalg.svd(Gc[a:b, a:b])
             self.QL[a:b, a:b] = U
             self.QRup[a:b, a:b] = Vh.conj().T

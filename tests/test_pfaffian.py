@@ -177,6 +177,24 @@ def test_sim_chain_vs_oracle(sim_backend, H, tp, basis):
     helpers.compare_pf_mps(ref, helpers.block_mps_to_dense(got), _half_bonds(Cm, tp, basis))
 
 
+def _centre_half_modes(be, L, oc=None):
+    """Eigenvalue-1/2 Schmidt modes on the *central* bond (pfaffian.py:857-865): the symmetric chain cut at an
+    odd bond.  The two real bases of the 1/2 space are paired by an SVD; the result equals the reference's state."""
+    H = po.bdg_chain(L)
+    Cm = po.correlation_matrix(H, "C->C")
+    tp = {"chi_max": 32}
+    x = oc or L // 2
+    assert x in _half_bonds(Cm, tp), "the test case must carry 1/2 modes on its central bond"
+    ref = po.C_to_MPS(Cm, tp, "C", ortho_center=oc)
+    got = pf.C_to_MPS(Cm, tp, basis="C", ortho_center=oc, _backend=be, as_tenpy=False)
+    return helpers.compare_pf_mps(ref, helpers.block_mps_to_dense(got), _half_bonds(Cm, tp))
+
+
+@pytest.mark.parametrize("L,oc", [(10, None), (26, None), (24, 11)])
+def test_sim_centre_half_modes(sim_backend, L, oc):
+    _centre_half_modes(sim_backend, L, oc)
+
+
 def test_sim_ortho_center_and_errors(sim_backend):
     Cm = po.correlation_matrix(po.random_bdg(10, 31), "C->C")
     tp = {"chi_max": 64}
@@ -218,6 +236,12 @@ def test_gpu_chain_vs_oracle(gpu_backend, H, tp):
     ref = po.C_to_MPS(Cm, tp, "C")
     got = pf.H_to_MPS(H, tp, basis="C", _backend=gpu_backend, as_tenpy=False)
     helpers.compare_pf_mps(ref, helpers.block_mps_to_dense(got), _half_bonds(Cm, tp))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,oc", [(26, None), (50, None), (40, 19)])
+def test_gpu_centre_half_modes(gpu_backend, L, oc):
+    _centre_half_modes(gpu_backend, L, oc)
 
 
 @pytest.mark.gpu
