@@ -393,6 +393,25 @@ int64_t tmf_gutz_desc_bytes(const tmf_gutz_job *jobs_host, int njobs);
 int tmf_gutzwiller_project(const tmf_gutz_job *jobs_host, int njobs, int cplx_flag, void *out_dev,
                            int64_t out_bytes, void *desc_dev, void *stream);
 
+/* f3 -- canonical form of a finite charge-conserving MPS on the device.  replaces: TeNPy's
+ * MPS.canonical_form_finite as called at gutzwiller.py:266 / :471 (left-to-right QR sweep, right-to-left SVD sweep,
+ * block-wise in the charge sectors).  Tensors are dense T[vL, p, vR] (row-major doubles), the charges of a bond are
+ * sorted (contiguous sectors), q(vL) + qp[p] = q(vR).  tmf_canon_create plans both sweeps from the sector tables
+ * (dims0[L+1] bond dimensions, charges0 concatenated, qp[2]); tmf_canon_sizes: q[0] workspace bytes, q[1] doubles
+ * of all output tensors, q[2] number of singular values (bonds 0..L-1), q[3] sum of the final bond dimensions;
+ * tmf_canon_dims: final bond dimensions and charges (before the `cutoff` truncation, which the caller applies to
+ * the returned singular values: a discarded direction only multiplies zeros afterwards).  tmf_canon_run enqueues
+ * the whole sweep (three launches per site and sweep, no host synchronisation): T0_dev + t0_off[j] is the tensor of
+ * site j; outputs: right-canonical tensors (site j at sum_{i<j} dims2[i] * 2 * dims2[i+1]), singular values
+ * (bond j at sum_{i<j} dims2[i], decreasing inside a sector, un-normalised) and inv_dev[j] = 1 / their norm. */
+typedef struct tmf_canon tmf_canon;
+tmf_canon *tmf_canon_create(int L, const int *dims0, const int *charges0, const int *qp);
+void tmf_canon_destroy(tmf_canon *c);
+int tmf_canon_sizes(const tmf_canon *c, int64_t *q);
+int tmf_canon_dims(const tmf_canon *c, int *dims2, int *charges2);
+int tmf_canon_run(tmf_canon *c, const double *T0_dev, const int64_t *t0_off, void *work_dev, int64_t work_bytes,
+                  double *T2_dev, double *S_dev, double *inv_dev, void *stream);
+
 /* Multi-GPU plumbing of the sharded conversion (temfpy_b200/dist.py; SURVEY 8(e): "gather of per-site tensors").
  * Peer window: a buffer in the destination rank's HBM, exported with tmf_ipc_export (64-byte CUDA IPC handle +
  * offset of dev_ptr inside its allocation) and mapped by the other ranks of the node with tmf_ipc_open (returns the

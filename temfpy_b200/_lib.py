@@ -167,6 +167,12 @@ SIGNATURES = {
     "tmf_gutz_desc_bytes": (C.c_int64, [C.POINTER(GutzJob), C.c_int]),
     "tmf_gutzwiller_project": (C.c_int, [C.POINTER(GutzJob), C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
                                          C.c_void_p]),
+    "tmf_canon_create": (C.c_void_p, [C.c_int, c_int_p, c_int_p, c_int_p]),
+    "tmf_canon_destroy": (None, [C.c_void_p]),
+    "tmf_canon_sizes": (C.c_int, [C.c_void_p, c_i64_p]),
+    "tmf_canon_dims": (C.c_int, [C.c_void_p, c_int_p, c_int_p]),
+    "tmf_canon_run": (C.c_int, [C.c_void_p, C.c_void_p, c_i64_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p]),
     "tmf_ipc_export": (C.c_int, [C.c_void_p, C.c_char_p, c_i64_p]),
     "tmf_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "tmf_ipc_close": (C.c_int, [C.c_void_p]),

@@ -248,7 +248,7 @@ def _project(mps: BlockMPS, keep, spin_rules, be, mod=0):
         tensors.append(outs[offs[j]: offs[j] + nLk * 2 * nRk].reshape(nLk, 2, nRk))
     resident = sum(1 for c in chains for X in (c[2], c[3]) if X.src[0] == "dev")
     return tensors, keepers, dict(chains=len(chains), resident_operands=resident, staged_elems=stage_off,
-                                  device=(outd, offs))
+                                  device=(outd, offs), cplx=cplx)
 
 
 def _svd(M):
@@ -331,12 +331,81 @@ def _canonical_form_finite(tensors, qs, qp, cutoff):
     return T, lams, qs
 
 
-def _finish(mps, tensors, keepers, qvirt, qp, conserve, return_canonical, cutoff, unit_cell_width, info):
+def _canonical_form_device(be, dev, qvirt, qp, cutoff):
+    """``canonical_form_finite`` (gutzwiller.py:266 / :471) on the device: ``tmf_canon_*`` plans the QR and SVD sweeps
+    from the sector tables and enqueues them on the projected tensors where ``tmf_gutzwiller_project`` left them
+    (three launches per site and sweep, no host synchronisation); only the final right-canonical tensors and the
+    singular values come back.  Singular values <= cutoff are removed here, at the end (equivalent to the
+    reference's truncation on the fly: a discarded direction only multiplies zeros afterwards).
+    Returns (tensors, lams, charges) or None if a charge block exceeds the kernels' limits."""
+    import ctypes as C
+    lib = be.lib
+    outd, offs = dev
+    L = len(offs)
+    dims0 = np.array([len(q) for q in qvirt], dtype=np.int32)
+    ch0 = np.ascontiguousarray(np.concatenate([np.asarray(q) for q in qvirt]).astype(np.int32))
+    qpi = np.ascontiguousarray(np.asarray(qp, dtype=np.int32))
+    ip = lambda a: a.ctypes.data_as(_lib.c_int_p)
+    h = lib.tmf_canon_create(L, ip(dims0), ip(ch0), ip(qpi))
+    if not h:
+        logger.info("device canonical form not applicable (%s): host sweep", lib.tmf_last_error().decode())
+        return None
+    try:
+        q = (C.c_int64 * 8)()
+        check(lib, lib.tmf_canon_sizes(h, q))
+        wb, nt, ns, nd = int(q[0]), int(q[1]), int(q[2]), int(q[3])
+        dims2 = np.zeros(L + 1, dtype=np.int32)
+        ch2 = np.zeros(max(nd, 1), dtype=np.int32)
+        check(lib, lib.tmf_canon_dims(h, ip(dims2), ip(ch2)))
+        work = be.empty(wb, np.uint8)
+        T2 = be.empty(max(nt, 1), np.float64)
+        S = be.empty(max(ns, 1), np.float64)
+        inv = be.empty(L + 2, np.float64)
+        t0 = (C.c_int64 * L)(*[int(o) for o in offs])
+        check(lib, lib.tmf_canon_run(h, be.ptr(outd), t0, be.ptr(work), wb, be.ptr(T2), be.ptr(S), be.ptr(inv),
+                                     be.stream))
+        be.sync()
+        T2h, Sh = be.to_host(T2, max(nt, 1)), be.to_host(S, max(ns, 1))
+    finally:
+        lib.tmf_canon_destroy(h)
+    boff = np.concatenate(([0], np.cumsum(dims2))).astype(np.int64)
+    keep, lams, charges = [], [], []
+    for j in range(L + 1):
+        d = int(dims2[j])
+        if j < L:
+            s = np.array(Sh[boff[j]: boff[j] + d])
+            k = s > cutoff
+            sk = s[k]
+            lams.append(sk / np.linalg.norm(sk) if sk.size else sk)
+        else:
+            k = np.ones(d, dtype=bool)
+            lams.append(np.ones(d))
+        keep.append(k)
+        charges.append(ch2[boff[j]: boff[j] + d][k].astype(np.int64))
+    tensors, o = [], 0
+    for j in range(L):
+        a, b = int(dims2[j]), int(dims2[j + 1])
+        T = T2h[o: o + a * 2 * b].reshape(a, 2, b)
+        o += a * 2 * b
+        if not keep[j].all():
+            T = T[keep[j]]
+        if not keep[j + 1].all():
+            T = T[:, :, keep[j + 1]]
+        tensors.append(T)
+    return tensors, lams, charges
+
+
+def _finish(mps, tensors, keepers, qvirt, qp, conserve, return_canonical, cutoff, unit_cell_width, info, be=None):
+    import os
     Ls = len(tensors)
     meta = dict(gemm_jobs=info["chains"], kept=[len(k) for k in keepers], resident_operands=info["resident_operands"],
                 staged_elems=info["staged_elems"])
     if return_canonical:
-        T, lams, qs = _canonical_form_finite(tensors, qvirt, qp, cutoff)
+        got = None
+        if be is not None and not info["cplx"] and not os.environ.get("TMF_HOST_CANON"):
+            got = _canonical_form_device(be, info["device"], qvirt, qp, cutoff)
+        meta["canonical_form"] = "device" if got is not None else "host"
+        T, lams, qs = got if got is not None else _canonical_form_finite(tensors, qvirt, qp, cutoff)
         form = ["B"] * Ls
         oc = 0
         logger.info("Transformed MPS to right canonical form")
@@ -379,7 +448,8 @@ def abrikosov(mps: BlockMPS, *, inplace: bool = False, return_canonical: bool = 
     tensors, keepers, info = _project(mps, keep, ((0, 1, 0), (1, 0, 1)), be, mod)
     qvirt = [np.zeros(len(k), dtype=np.int64) for k in keepers]      # all charges dropped (:244)
     logger.info("Completed projection to spin-1/2 space. No conserved charges left.")
-    return _finish(mps, tensors, keepers, qvirt, np.zeros(2, dtype=np.int64), None, return_canonical, cutoff, ucw, info)
+    return _finish(mps, tensors, keepers, qvirt, np.zeros(2, dtype=np.int64), None, return_canonical, cutoff, ucw, info,
+                   be)
 
 
 def abrikosov_ph(mps: BlockMPS, *, inplace: bool = False, return_canonical: bool = True, cutoff: float = 1e-12,
@@ -410,4 +480,4 @@ def abrikosov_ph(mps: BlockMPS, *, inplace: bool = False, return_canonical: bool
         qvirt = [np.zeros(len(k), dtype=np.int64) for k in keepers]
         qp, conserve = np.zeros(2, dtype=np.int64), None
     logger.info("Completed projection to spin-1/2 space. Conserved charge is now %s", conserve)
-    return _finish(mps, tensors, keepers, qvirt, qp, conserve, return_canonical, cutoff, ucw, info)
+    return _finish(mps, tensors, keepers, qvirt, qp, conserve, return_canonical, cutoff, ucw, info, be)

@@ -82,6 +82,7 @@ def _check(be, L, kind, tp, canonical):
     ov = abs(np.vdot(phi, got)) / (np.linalg.norm(phi) * np.linalg.norm(got))
     assert ov > 1 - 1e-10, ov
     if canonical:
+        assert sm.meta["canonical_form"] == "device"
         assert abs(np.linalg.norm(got) - 1) < 1e-12
         for i in range(sm.L):       # right-canonical
             T = sm.get_B_dense(i)
@@ -119,6 +120,34 @@ def test_sim_ortho_center_inside_pair(sim_backend):
         fm = slater.C_to_MPS(C_, tp, spinful="PH", ortho_center=oc, _backend=sim_backend, as_tenpy=False)
         got = spin_state(gw.abrikosov_ph(fm, _backend=sim_backend))
         assert abs(np.vdot(phi, got)) / np.linalg.norm(phi) > 1 - 1e-10
+
+
+def _device_vs_host_canonical(be, L, kind, tp, monkeypatch):
+    """The device sweep (tmf_canon_*) against the host sweep: same Schmidt spectrum on every bond (1e-12), same bond
+    dimensions and charges, same state."""
+    C_, _ = so.correlation_matrix(so.hopping_chain(L))
+    fn = gw.abrikosov if kind == "simple" else gw.abrikosov_ph
+    fm = slater.C_to_MPS(C_, tp, spinful=kind, _backend=be, as_tenpy=False)
+    dev = fn(fm, _backend=be)
+    monkeypatch.setenv("TMF_HOST_CANON", "1")
+    host = fn(fm, _backend=be)
+    monkeypatch.delenv("TMF_HOST_CANON")
+    assert dev.meta["canonical_form"] == "device" and host.meta["canonical_form"] == "host"
+    for x in range(dev.L + 1):
+        a, b = np.sort(dev.lams[x])[::-1], np.sort(host.lams[x])[::-1]
+        assert len(a) == len(b), (x, len(a), len(b))
+        assert np.abs(a - b).max() < 1e-12, (x, np.abs(a - b).max())
+        assert np.array_equal(np.sort(dev.charges[x]), np.sort(host.charges[x]))
+    E = np.ones((1, 1))
+    for i in range(dev.L):
+        E = np.einsum("ab,apc,bpd->cd", E, dev.get_B_dense(i), host.get_B_dense(i), optimize=True)
+    assert abs(abs(E[0, 0]) - 1) < 1e-10, E
+    return dev
+
+
+@pytest.mark.parametrize("L,kind", [(12, "PH"), (12, "simple"), (20, "PH")])
+def test_sim_device_canonical_form(sim_backend, L, kind, monkeypatch):
+    _device_vs_host_canonical(sim_backend, L, kind, {"chi_max": 24}, monkeypatch)
 
 
 def _resident_vs_staged(be, L, kind, tp):
@@ -222,6 +251,12 @@ def test_gpu_cfg3_heisenberg(gpu_backend, L):
     assert abs(abs(E[0, 0]) - 1) < (1e-6 if L <= 64 else 1e-5), E
     assert max(a.chi) <= 256 and max(b.chi) <= 256
     print("cfg3-like chi_proj:", max(a.chi), max(b.chi), "overlap", abs(E[0, 0]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,kind,chi", [(32, "PH", 64), (32, "simple", 64), (96, "PH", 128)])
+def test_gpu_device_canonical_form(gpu_backend, L, kind, chi, monkeypatch):
+    _device_vs_host_canonical(gpu_backend, L, kind, {"chi_max": chi}, monkeypatch)
 
 
 @pytest.mark.gpu

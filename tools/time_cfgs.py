@@ -27,3 +27,9 @@ except Exception as e:
     print("cfg3 failed:", type(e).__name__, str(e)[:200])
 C4, _ = so.correlation_matrix(helpers.cylinder_hamiltonian(64, 6))
 t, m = timed(lambda: slater.C_to_MPS(C4, {"chi_max": 1024}, unit_cell_width=64 if False else None, as_tenpy=False)); print("cfg4 cylinder 6x64 chi=1024: %.1f ms (%.0f sites/s)" % (1e3 * t, 384 / t))
+# cfg3 split: conversion / projection (device) / canonical form (host sweep)
+import warnings
+warnings.simplefilter("ignore")
+t, fm = timed(lambda: slater.C_to_MPS(C3, {"chi_max": 256}, spinful="PH", as_tenpy=False)); print("cfg3 split: conversion %.1f ms" % (1e3 * t))
+t, sm = timed(lambda: gutzwiller.abrikosov_ph(fm, return_canonical=False)); print("cfg3 split: projection (bare tensors to host) %.1f ms, chains %d, resident operands %d" % (1e3 * t, sm.meta["gemm_jobs"], sm.meta["resident_operands"]))
+t, sm = timed(lambda: gutzwiller.abrikosov_ph(fm, return_canonical=True)); print("cfg3 split: projection + canonical form %.1f ms, max chi %d" % (1e3 * t, max(sm.chi)))
