@@ -61,37 +61,34 @@ TMF_DEVICE int cta_gs_qr(double *A, int ra, int ca, int kmax, double *R, double 
   int live = 0;
   for (int c = 0; c < ca; ++c) {
     double *v = A + (int64_t)c * ra;
-    PAR_FOR(lane, 32) {
-      double s = 0.0;
-      for (int r = lane; r < ra; r += 32) s += v[r] * v[r];
-      part[lane] = s;
-    }
-    CTA_SYNC();
     double n0 = 0.0;
-    for (int l = 0; l < 32; ++l) n0 += part[l];
-    CTA_SYNC();
-    for (int pass = 0; pass < 2 && live > 0; ++pass) {
-      PAR_FOR(item, live * 32) {
+    for (int pass = 0; pass < 2; ++pass) {
+      // item `live` is v . v (norm before the pass), items i < live are q_i . v
+      PAR_FOR(item, (live + 1) * 32) {
         const int i = item >> 5, lane = item & 31;
-        const double *q = A + (int64_t)i * ra;
+        const double *q = (i < live) ? A + (int64_t)i * ra : v;
         double s = 0.0;
         for (int r = lane; r < ra; r += 32) s += q[r] * v[r];
         part[i * 33 + lane] = s;
       }
       CTA_SYNC();
-      PAR_FOR(i, live) {
+      PAR_FOR(i, live + 1) {
         double s = 0.0;
         for (int l = 0; l < 32; ++l) s += part[i * 33 + l];
         coef[i] = s;
-        R[i + (int64_t)kmax * c] += s;
+        if (i < live) R[i + (int64_t)kmax * c] += s;
       }
       CTA_SYNC();
-      PAR_FOR(r, ra) {
-        double s = v[r];
-        for (int i = 0; i < live; ++i) s -= A[(int64_t)i * ra + r] * coef[i];
-        v[r] = s;
+      if (pass == 0) n0 = coef[live];
+      if (live > 0) {
+        PAR_FOR(r, ra) {
+          double s = v[r];
+          for (int i = 0; i < live; ++i) s -= A[(int64_t)i * ra + r] * coef[i];
+          v[r] = s;
+        }
       }
       CTA_SYNC();
+      if (live == 0) break;
     }
     PAR_FOR(lane, 32) {
       double s = 0.0;
@@ -101,45 +98,56 @@ TMF_DEVICE int cta_gs_qr(double *A, int ra, int ca, int kmax, double *R, double 
     CTA_SYNC();
     double n1 = 0.0;
     for (int l = 0; l < 32; ++l) n1 += part[l];
+    const bool ok = live < kmax && n1 > 1e-26 * n0 && n1 > 0.0;
+    const double inv = ok ? 1.0 / sqrt(n1) : 0.0;
+    double *q = A + (int64_t)live * ra;
     CTA_SYNC();
-    if (live < kmax && n1 > 1e-26 * n0 && n1 > 0.0) {
-      const double nv = sqrt(n1), inv = 1.0 / nv;
-      double *q = A + (int64_t)live * ra;
-      PAR_FOR(r, ra) q[r] = v[r] * inv;
-      PAR_FOR(one, 1) R[live + (int64_t)kmax * c] = nv;
-      CTA_SYNC();
-      if (live != c) {
-        PAR_FOR(r, ra) v[r] = 0.0;
-        CTA_SYNC();
+    if (ok) {
+      PAR_FOR(r, ra) {
+        const double x = v[r] * inv;
+        if (live != c) v[r] = 0.0;
+        q[r] = x;
       }
+      PAR_FOR(one, 1) R[live + (int64_t)kmax * c] = sqrt(n1);
       ++live;
     } else {
       PAR_FOR(r, ra) v[r] = 0.0;
-      CTA_SYNC();
     }
+    CTA_SYNC();
   }
   return live;
 }
 
-TMF_GLOBAL block_qr_kernel(const BlockQrJob *jobs) {
+// nmax: largest n of the launch (sizes the scratch), mat_doubles: shared memory left for the matrices -- a block whose
+// m x n copy and k x n factor fit works entirely in shared memory (every phase of the Gram-Schmidt loop is a
+// round trip to wherever the matrix lives), larger ones in their global workspace.
+TMF_GLOBAL block_qr_kernel(const BlockQrJob *jobs, int nmax, int mat_doubles) {
   const BlockQrJob jb = jobs[BLOCK_ID];
   const int m0 = jb.m[0], m = jb.m[0] + jb.m[1], n = jb.n, k = jb.k;
   DYN_SMEM(double, sm);
-  double *part = sm;                          // 33 * max(n, 1)
-  double *coef = part + 33 * (n > 0 ? n : 1);  // n + 40
+  double *part = sm;                          // 33 * (nmax + 1)
+  double *coef = part + 33 * (nmax + 1);      // nmax + 40
+  double *mat = coef + nmax + 40;
+  const bool in_smem = (int64_t)m * n + (int64_t)k * n <= mat_doubles;
+  double *W = in_smem ? mat : jb.work;
+  double *Rw = in_smem ? mat + (int64_t)m * n : jb.R;
   const double sc = jb.scale ? *jb.scale : 1.0;
   PAR_FOR(idx, m * n) {
     const int r = idx / n, c = idx - r * n;
     const int t = r >= m0, rr = t ? r - m0 : r;
-    jb.work[(int64_t)c * m + r] = sc * jb.src[t][rr * jb.rs + c];
+    W[(int64_t)c * m + r] = sc * jb.src[t][rr * jb.rs + c];
   }
-  PAR_FOR(idx, k * n) jb.R[idx] = 0.0;
+  PAR_FOR(idx, k * n) Rw[idx] = 0.0;
   CTA_SYNC();
-  cta_gs_qr(jb.work, m, n, k, jb.R, part, coef);
+  cta_gs_qr(W, m, n, k, Rw, part, coef);
   PAR_FOR(idx, m * k) {
     const int r = idx / k, i = idx - r * k;
     const int t = r >= m0, rr = t ? r - m0 : r;
-    jb.dst[t][rr * jb.rd + i] = jb.work[(int64_t)i * m + r];
+    jb.dst[t][rr * jb.rd + i] = W[(int64_t)i * m + r];
+  }
+  if (in_smem) {
+    PAR_FOR(idx, k * n) jb.R[idx] = Rw[idx];
+    CTA_SYNC();
   }
   PAR_FOR(lane, 32) {
     double s = 0.0;
@@ -153,29 +161,33 @@ TMF_GLOBAL block_qr_kernel(const BlockQrJob *jobs) {
     *jb.nrm2 = s;
   }
 }
-inline size_t block_qr_smem(int nmax) { return sizeof(double) * ((size_t)33 * std::max(nmax, 1) + nmax + 48); }
+constexpr int64_t CANON_SMEM_BYTES = 200 * 1024;
+inline size_t block_qr_scratch(int nmax) { return sizeof(double) * ((size_t)33 * (nmax + 1) + nmax + 40); }
 
 inline int64_t svd_work_doubles(int m, int n) {
   const int64_t ra = std::max(m, n), ca = std::min(m, n);
   return ra * ca + 2 * ca * ca + 64;
 }
 
-TMF_GLOBAL block_svd_kernel(const BlockSvdJob *jobs) {
+// camax: largest min(m, n) of the launch (sizes the scratch); mat_doubles: shared memory left for A, R1 and J
+TMF_GLOBAL block_svd_kernel(const BlockSvdJob *jobs, int camax, int mat_doubles) {
   const BlockSvdJob jb = jobs[BLOCK_ID];
   const int m = jb.m, n0 = jb.n[0], n = jb.n[0] + jb.n[1], k = jb.k;
   const bool tall = m >= n;                       // A = M (m x n) or A = M^T (n x m): ra >= ca = k
   const int ra = tall ? m : n, ca = tall ? n : m;
-  double *A = jb.work, *R1 = A + (int64_t)ra * ca, *J = R1 + (int64_t)ca * ca;
   DYN_SMEM(double, sm);
-  const int np = (ca + 1) & ~1;
-  double *rot = sm;                                // np
-  double *part = rot + np + 2;                     // max(33 * ca, (np / 2) * 99)
-  const int npa = 33 * (ca > 0 ? ca : 1), npb = (np / 2) * 99;
+  const int npm = (camax + 1) & ~1;
+  double *rot = sm;                                // npm
+  double *part = rot + npm + 2;                    // max(33 * (camax + 1), (npm / 2) * 99)
+  const int npa = 33 * (camax + 1), npb = (npm / 2) * 99;
   const int npart = (npa > npb ? npa : npb) + 8;
-  double *coef = part + npart;                     // ca + 40
-  double *sig = coef + ca + 40;                    // ca
-  int *iw = reinterpret_cast<int *>(sig + ca + 2);
-  int *flag = iw, *sel = iw + 2, *rank = sel + ca, *cnt = rank + ca;
+  double *coef = part + npart;                     // camax + 40
+  double *sig = coef + camax + 40;                 // camax
+  int *iw = reinterpret_cast<int *>(sig + camax + 2);
+  int *flag = iw, *sel = iw + 2, *rank = sel + camax, *cnt = rank + camax;
+  double *mat = reinterpret_cast<double *>(iw + 2 * camax + 16);
+  const bool in_smem = (int64_t)ra * ca + 2 * (int64_t)ca * ca <= mat_doubles;
+  double *A = in_smem ? mat : jb.work, *R1 = A + (int64_t)ra * ca, *J = R1 + (int64_t)ca * ca;
   const double sc = jb.scale ? *jb.scale : 1.0;
   PAR_FOR(idx, m * n) {
     const int r = idx / n, c = idx - r * n;
@@ -189,7 +201,38 @@ TMF_GLOBAL block_svd_kernel(const BlockSvdJob *jobs) {
   }
   CTA_SYNC();
   cta_gs_qr(A, ra, ca, ca, R1, part, coef);        // A = Q1 (ra x ca), A_in = Q1 R1
-  jacobi_onesided(R1, ca, J, ca, ca, rot, part, flag);   // R1 <- R1 J: orthogonal columns = Un diag(sigma)
+  // The Jacobi routine treats columns with squared norm < 1e-30 as null (rotations with them would never settle);
+  // that test is absolute, so the factor is brought to unit Frobenius norm first.  The blocks of a projected state
+  // routinely carry weights many orders of magnitude apart.
+  PAR_FOR(lane, 32) {
+    double s = 0.0;
+    for (int i = lane; i < ca * ca; i += 32) s += R1[i] * R1[i];
+    part[lane] = s;
+  }
+  CTA_SYNC();
+  double fro = 0.0;
+  for (int l = 0; l < 32; ++l) fro += part[l];
+  fro = sqrt(fro);
+  CTA_SYNC();
+  if (fro > 0.0) {
+    // Jacobi on the *transposed* factor (Drmac / Veselic): the rows of the triangular factor of a graded matrix are
+    // graded themselves, and the one-sided sweeps on L = R1^T settle in a few passes where those on R1 need dozens.
+    const double rf = 1.0 / fro;
+    PAR_FOR(idx, ca * ca) {
+      const int c = idx / ca, r = idx - c * ca;
+      if (r < c) {
+        const double a = R1[(int64_t)c * ca + r] * rf, b = R1[(int64_t)r * ca + c] * rf;
+        R1[(int64_t)c * ca + r] = b;
+        R1[(int64_t)r * ca + c] = a;
+      } else if (r == c) {
+        R1[idx] *= rf;
+      }
+    }
+    CTA_SYNC();
+    jacobi_onesided(R1, ca, J, ca, ca, rot, part, flag);   // G = R1^T:  G J = W diag(sigma)
+    PAR_FOR(idx, ca * ca) R1[idx] *= fro;
+    CTA_SYNC();
+  }
   PAR_FOR(i, ca) {
     double s = 0.0;
     for (int r = 0; r < ca; ++r) s += R1[(int64_t)i * ca + r] * R1[(int64_t)i * ca + r];
@@ -198,32 +241,30 @@ TMF_GLOBAL block_svd_kernel(const BlockSvdJob *jobs) {
   }
   CTA_SYNC();
   rank_desc(sig, sel, ca, rank, cnt);
-  // A_in = (Q1 Un) diag(sigma) J^T.  tall: M = A_in: U = Q1 Un, Vh = J^T;  wide: M = A_in^T: U = J, Vh = (Q1 Un)^T
+  // R1 = J diag(sigma) W^T, so A_in = (Q1 J) diag(sigma) W^T with W diag(sigma) in the R1 buffer.
+  // tall: M = A_in:   U = Q1 J, Vh = W^T;      wide: M = A_in^T:   U = W, Vh = (Q1 J)^T
   if (tall) {
     PAR_FOR(idx, m * k) {
       const int i = idx / m, r = idx - i * m;
       double s = 0.0;
-      for (int t = 0; t < ca; ++t) s += A[(int64_t)t * ra + r] * R1[(int64_t)i * ca + t];
-      jb.US[(int64_t)rank[i] * m + r] = s;
+      for (int t = 0; t < ca; ++t) s += A[(int64_t)t * ra + r] * J[(int64_t)i * ca + t];
+      jb.US[(int64_t)rank[i] * m + r] = s * sig[i];
     }
     PAR_FOR(idx, k * n) {
       const int i = idx / n, c = idx - i * n;
       const int t = c >= n0, cc = t ? c - n0 : c;
-      jb.dst[t][rank[i] * jb.rd + cc] = J[(int64_t)i * ca + c];
+      jb.dst[t][rank[i] * jb.rd + cc] = (sig[i] > 0.0) ? R1[(int64_t)i * ca + c] / sig[i] : 0.0;
     }
   } else {
     PAR_FOR(idx, m * k) {
       const int i = idx / m, r = idx - i * m;
-      jb.US[(int64_t)rank[i] * m + r] = J[(int64_t)i * ca + r] * sig[i];
+      jb.US[(int64_t)rank[i] * m + r] = R1[(int64_t)i * ca + r];
     }
     PAR_FOR(idx, k * n) {
       const int i = idx / n, c = idx - i * n;
       const int t = c >= n0, cc = t ? c - n0 : c;
       double s = 0.0;
-      if (sig[i] > 0.0) {
-        for (int u = 0; u < ca; ++u) s += A[(int64_t)u * ra + c] * R1[(int64_t)i * ca + u];
-        s /= sig[i];
-      }
+      for (int u = 0; u < ca; ++u) s += A[(int64_t)u * ra + c] * J[(int64_t)i * ca + u];
       jb.dst[t][rank[i] * jb.rd + cc] = s;
     }
   }
@@ -234,9 +275,9 @@ TMF_GLOBAL block_svd_kernel(const BlockSvdJob *jobs) {
     *jb.nrm2 = s;
   }
 }
-inline size_t block_svd_smem(int camax) {
+inline size_t block_svd_scratch(int camax) {
   const int np = (camax + 1) & ~1;
-  const size_t npart = std::max(33 * std::max(camax, 1), (np / 2) * 99) + 8;
+  const size_t npart = std::max(33 * (camax + 1), (np / 2) * 99) + 8;
   return sizeof(double) * ((size_t)np + 2 + npart + camax + 40 + camax + 2) + sizeof(int) * ((size_t)2 * camax + 16);
 }
 
@@ -487,6 +528,7 @@ extern "C" int tmf_canon_run(tmf_canon *c, const double *T0_dev, const int64_t *
   std::vector<int64_t> qr_first(L + 1, 0), svd_first(L + 1, 0);
   int64_t ji = 0;
   std::vector<int> qr_nmax(L + 1, 1), svd_camax(L + 1, 1);
+  std::vector<int64_t> qr_need(L + 1, 0), svd_need(L + 1, 0);      // largest matrix footprint of a step (doubles)
   for (int j = 0; j + 1 < L; ++j) {
     qr_first[j] = ji;
     int64_t so = 0;
@@ -512,6 +554,7 @@ extern "C" int tmf_canon_run(tmf_canon *c, const double *T0_dev, const int64_t *
       q.nrm2 = nrm + ji;
       q.scale = (j == 0) ? nullptr : inv1 + j;          // 1 / ||R of bond j||
       qr_nmax[j] = std::max(qr_nmax[j], col.count);
+      qr_need[j] = std::max<int64_t>(qr_need[j], (int64_t)m * col.count + (int64_t)nw.count * col.count);
     }
   }
   for (int j = L - 1; j >= 0; --j) {
@@ -542,6 +585,10 @@ extern "C" int tmf_canon_run(tmf_canon *c, const double *T0_dev, const int64_t *
       q.nrm2 = nrm + ji;
       q.scale = (j == L - 1) ? invx : inv_dev + j + 1;   // 1 / ||last tensor||, 1 / ||S of bond j+1||
       svd_camax[j] = std::max(svd_camax[j], std::min(row.count, n));
+      {
+        const int64_t ra = std::max(row.count, n), ca = std::min(row.count, n);
+        svd_need[j] = std::max<int64_t>(svd_need[j], ra * ca + 2 * ca * ca);
+      }
     }
   }
   rc = copy_h2d(jobs_dev, jh.data(), jh.size(), stream);
@@ -553,8 +600,10 @@ extern "C" int tmf_canon_run(tmf_canon *c, const double *T0_dev, const int64_t *
   for (int j = 0; j + 1 < L; ++j) {
     const int nj = (int)c->s1[j + 1].size();
     if (nj > 0) {
-      rc = launch_t("canon_qr", block_qr_kernel, nj, 256, block_qr_smem(qr_nmax[j]), stream,
-                    reinterpret_cast<const BlockQrJob *>(jobs_dev + 128 * qr_first[j]));
+      const int64_t scr = (int64_t)block_qr_scratch(qr_nmax[j]);
+      const int64_t mat = std::max<int64_t>(0, std::min<int64_t>(qr_need[j], (CANON_SMEM_BYTES - scr) / 8));
+      rc = launch_t("canon_qr", block_qr_kernel, nj, 256, (size_t)(scr + 8 * mat), stream,
+                    reinterpret_cast<const BlockQrJob *>(jobs_dev + 128 * qr_first[j]), qr_nmax[j], (int)mat);
       if (rc) return rc;
     }
     rc = launch_t("canon_norm", inv_norm_kernel, 1, 256, 256 * sizeof(double), stream,
@@ -593,8 +642,10 @@ extern "C" int tmf_canon_run(tmf_canon *c, const double *T0_dev, const int64_t *
   for (int j = L - 1; j >= 0; --j) {
     const int nj = (int)c->s2[j].size();
     if (nj > 0) {
-      rc = launch_t("canon_svd", block_svd_kernel, nj, 256, block_svd_smem(svd_camax[j]), stream,
-                    reinterpret_cast<const BlockSvdJob *>(jobs_dev + 128 * svd_first[j]));
+      const int64_t scr = ((int64_t)block_svd_scratch(svd_camax[j]) + 15) & ~int64_t(15);
+      const int64_t mat = std::max<int64_t>(0, std::min<int64_t>(svd_need[j], (CANON_SMEM_BYTES - scr) / 8));
+      rc = launch_t("canon_svd", block_svd_kernel, nj, 256, (size_t)(scr + 8 * mat), stream,
+                    reinterpret_cast<const BlockSvdJob *>(jobs_dev + 128 * svd_first[j]), svd_camax[j], (int)mat);
       if (rc) return rc;
     }
     rc = launch_t("canon_norm", inv_norm_kernel, 1, 256, 256 * sizeof(double), stream,

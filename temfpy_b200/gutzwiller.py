@@ -18,9 +18,10 @@ Input: the :class:`~temfpy_b200.mps.BlockMPS` returned by ``slater.C_to_MPS(...,
   virtual charge = fermion number - bond index, gutzwiller.py:437-441).
 
 ``return_canonical=True`` brings the result to right-canonical form like ``canonical_form_finite``
-(gutzwiller.py:266 / :471): QR and SVD sweeps over the (small, chi_proj ~ chi/2) projected tensors, done
-block-wise on the host -- SURVEY 8(f) rank 3 lists a device version as follow-up work.
-Infinite MPS input is not supported in this release.
+(gutzwiller.py:266 / :471): QR and SVD sweeps over the (small, chi_proj ~ chi/2) projected tensors, block-wise in
+the charges -- on the host by default, on the device with ``CANONICAL_FORM = "device"`` (``tmf_canon_*``, see there).
+Input may conserve the fermion number (Slater) or the parity (Pfaffian, complex tensors).  Infinite MPS input is
+not supported in this release.
 """
 from __future__ import annotations
 
@@ -35,6 +36,13 @@ from ._lib import check
 from .mps import BlockMPS
 
 logger = logging.getLogger(__name__)
+
+CANONICAL_FORM = "host"
+"""Where ``return_canonical=True`` runs the QR / SVD sweeps of ``canonical_form_finite``: ``"host"`` (block-wise LAPACK,
+the default) or ``"device"`` (``tmf_canon_*``: the sweeps on the projected tensors in HBM, real tensors, charge blocks
+up to 160).  The sweep is sequential in the sites and its blocks are small, so a step is bound by the latency of one
+CTA's dependent Gram-Schmidt / Jacobi phases: measured on a B200 for BASELINE configs[2] (256 spin sites, blocks <= 67)
+the device sweep takes 0.49 s against 0.35 s on the host -- hence the default.  ``TMF_CANONICAL_FORM`` overrides."""
 
 
 def parity_mask(charges, parity: int = 0) -> np.ndarray:
@@ -402,7 +410,8 @@ def _finish(mps, tensors, keepers, qvirt, qp, conserve, return_canonical, cutoff
                 staged_elems=info["staged_elems"])
     if return_canonical:
         got = None
-        if be is not None and not info["cplx"] and not os.environ.get("TMF_HOST_CANON"):
+        mode = os.environ.get("TMF_CANONICAL_FORM", CANONICAL_FORM)
+        if mode == "device" and be is not None and not info["cplx"]:
             got = _canonical_form_device(be, info["device"], qvirt, qp, cutoff)
         meta["canonical_form"] = "device" if got is not None else "host"
         T, lams, qs = got if got is not None else _canonical_form_finite(tensors, qvirt, qp, cutoff)

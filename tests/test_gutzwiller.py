@@ -82,7 +82,6 @@ def _check(be, L, kind, tp, canonical):
     ov = abs(np.vdot(phi, got)) / (np.linalg.norm(phi) * np.linalg.norm(got))
     assert ov > 1 - 1e-10, ov
     if canonical:
-        assert sm.meta["canonical_form"] == "device"
         assert abs(np.linalg.norm(got) - 1) < 1e-12
         for i in range(sm.L):       # right-canonical
             T = sm.get_B_dense(i)
@@ -128,10 +127,14 @@ def _device_vs_host_canonical(be, L, kind, tp, monkeypatch):
     C_, _ = so.correlation_matrix(so.hopping_chain(L))
     fn = gw.abrikosov if kind == "simple" else gw.abrikosov_ph
     fm = slater.C_to_MPS(C_, tp, spinful=kind, _backend=be, as_tenpy=False)
+    monkeypatch.setattr(gw, "CANONICAL_FORM", "device")
     dev = fn(fm, _backend=be)
-    monkeypatch.setenv("TMF_HOST_CANON", "1")
+    if dev.L <= 10:                      # (the device result against the brute-force projection of the dense state)
+        _, psi = fermion_state(so.hopping_chain(L), kind, tp)
+        phi, got = brute_force(psi, kind), spin_state(dev)
+        assert abs(np.vdot(phi, got)) / np.linalg.norm(phi) > 1 - 1e-10
+    monkeypatch.setattr(gw, "CANONICAL_FORM", "host")
     host = fn(fm, _backend=be)
-    monkeypatch.delenv("TMF_HOST_CANON")
     assert dev.meta["canonical_form"] == "device" and host.meta["canonical_form"] == "host"
     for x in range(dev.L + 1):
         a, b = np.sort(dev.lams[x])[::-1], np.sort(host.lams[x])[::-1]
@@ -145,9 +148,10 @@ def _device_vs_host_canonical(be, L, kind, tp, monkeypatch):
     return dev
 
 
-@pytest.mark.parametrize("L,kind", [(12, "PH"), (12, "simple"), (20, "PH")])
-def test_sim_device_canonical_form(sim_backend, L, kind, monkeypatch):
-    _device_vs_host_canonical(sim_backend, L, kind, {"chi_max": 24}, monkeypatch)
+@pytest.mark.parametrize("L,kind,chi", [(8, "PH", 4096), (10, "simple", 4096), (12, "PH", 24), (12, "simple", 24),
+                                        (20, "PH", 24)])
+def test_sim_device_canonical_form(sim_backend, L, kind, chi, monkeypatch):
+    _device_vs_host_canonical(sim_backend, L, kind, {"chi_max": chi, "svd_min": 1e-7}, monkeypatch)
 
 
 def _resident_vs_staged(be, L, kind, tp):

@@ -33,3 +33,13 @@ warnings.simplefilter("ignore")
 t, fm = timed(lambda: slater.C_to_MPS(C3, {"chi_max": 256}, spinful="PH", as_tenpy=False)); print("cfg3 split: conversion %.1f ms" % (1e3 * t))
 t, sm = timed(lambda: gutzwiller.abrikosov_ph(fm, return_canonical=False)); print("cfg3 split: projection (bare tensors to host) %.1f ms, chains %d, resident operands %d" % (1e3 * t, sm.meta["gemm_jobs"], sm.meta["resident_operands"]))
 t, sm = timed(lambda: gutzwiller.abrikosov_ph(fm, return_canonical=True)); print("cfg3 split: projection + canonical form %.1f ms, max chi %d" % (1e3 * t, max(sm.chi)))
+be.lib.tmf_prof_enable(1)
+sm = gutzwiller.abrikosov_ph(fm, return_canonical=True)
+import ctypes as C
+buf = C.create_string_buffer(1 << 22)
+be.lib.tmf_prof_timeline(buf, len(buf))
+be.lib.tmf_prof_enable(0)
+agg = {}
+for ln in buf.value.decode().strip().splitlines():
+    t = ln.split(); a = agg.setdefault(t[0], [0, 0.0]); a[0] += 1; a[1] += float(t[3]) - float(t[2])
+print("cfg3 canonical kernels:", {k: (v[0], round(v[1], 2)) for k, v in agg.items()}, sm.meta.get("canonical_form"))
