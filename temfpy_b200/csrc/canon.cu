@@ -185,15 +185,42 @@ TMF_GLOBAL block_svd_kernel(const BlockSvdJob *jobs, int camax, int mat_doubles)
   double *sig = coef + camax + 40;                 // camax
   int *iw = reinterpret_cast<int *>(sig + camax + 2);
   int *flag = iw, *sel = iw + 2, *rank = sel + camax, *cnt = rank + camax;
-  double *mat = reinterpret_cast<double *>(iw + 2 * camax + 16);
+  double *mat = reinterpret_cast<double *>(iw + ((3 * camax + 34) & ~1));
   const bool in_smem = (int64_t)ra * ca + 2 * (int64_t)ca * ca <= mat_doubles;
   double *A = in_smem ? mat : jb.work, *R1 = A + (int64_t)ra * ca, *J = R1 + (int64_t)ca * ca;
   const double sc = jb.scale ? *jb.scale : 1.0;
+  // columns of A in order of decreasing norm (de Rijk): with the Jacobi sweeps on the transposed triangular factor
+  // below this is what makes a graded block converge in a handful of sweeps
+  int *cperm = cnt + 8;                            // camax
+  PAR_FOR(item, ca * 32) {
+    const int j = item >> 5, lane = item & 31;
+    double s2 = 0.0;
+    if (tall) {
+      const int t = j >= n0, cc = t ? j - n0 : j;
+      for (int r = lane; r < m; r += 32) { const double v = jb.src[t][r * jb.rs + cc]; s2 += v * v; }
+    } else {
+      for (int c = lane; c < n; c += 32) {
+        const int t = c >= n0, cc = t ? c - n0 : c;
+        const double v = jb.src[t][j * jb.rs + cc];
+        s2 += v * v;
+      }
+    }
+    part[j * 33 + lane] = s2;
+  }
+  CTA_SYNC();
+  PAR_FOR(j, ca) {
+    double s2 = 0.0;
+    for (int l = 0; l < 32; ++l) s2 += part[j * 33 + l];
+    sig[j] = s2;
+    sel[j] = 1;
+  }
+  CTA_SYNC();
+  rank_desc(sig, sel, ca, cperm, cnt);
   PAR_FOR(idx, m * n) {
     const int r = idx / n, c = idx - r * n;
     const int t = c >= n0, cc = t ? c - n0 : c;
     const double v = sc * jb.src[t][r * jb.rs + cc];
-    if (tall) A[(int64_t)c * ra + r] = v; else A[(int64_t)r * ra + c] = v;
+    if (tall) A[(int64_t)cperm[c] * ra + r] = v; else A[(int64_t)cperm[r] * ra + c] = v;
   }
   PAR_FOR(idx, ca * ca) {
     R1[idx] = 0.0;
@@ -241,7 +268,7 @@ TMF_GLOBAL block_svd_kernel(const BlockSvdJob *jobs, int camax, int mat_doubles)
   }
   CTA_SYNC();
   rank_desc(sig, sel, ca, rank, cnt);
-  // R1 = J diag(sigma) W^T, so A_in = (Q1 J) diag(sigma) W^T with W diag(sigma) in the R1 buffer.
+  // R1 = J diag(sigma) W^T, so A_in = (Q1 J) diag(sigma) W^T with W diag(sigma) in the R1 buffer (A_in: columns permuted).
   // tall: M = A_in:   U = Q1 J, Vh = W^T;      wide: M = A_in^T:   U = W, Vh = (Q1 J)^T
   if (tall) {
     PAR_FOR(idx, m * k) {
@@ -253,12 +280,12 @@ TMF_GLOBAL block_svd_kernel(const BlockSvdJob *jobs, int camax, int mat_doubles)
     PAR_FOR(idx, k * n) {
       const int i = idx / n, c = idx - i * n;
       const int t = c >= n0, cc = t ? c - n0 : c;
-      jb.dst[t][rank[i] * jb.rd + cc] = (sig[i] > 0.0) ? R1[(int64_t)i * ca + c] / sig[i] : 0.0;
+      jb.dst[t][rank[i] * jb.rd + cc] = (sig[i] > 0.0) ? R1[(int64_t)i * ca + cperm[c]] / sig[i] : 0.0;
     }
   } else {
     PAR_FOR(idx, m * k) {
       const int i = idx / m, r = idx - i * m;
-      jb.US[(int64_t)rank[i] * m + r] = R1[(int64_t)i * ca + r];
+      jb.US[(int64_t)rank[i] * m + r] = R1[(int64_t)i * ca + cperm[r]];
     }
     PAR_FOR(idx, k * n) {
       const int i = idx / n, c = idx - i * n;
@@ -278,7 +305,7 @@ TMF_GLOBAL block_svd_kernel(const BlockSvdJob *jobs, int camax, int mat_doubles)
 inline size_t block_svd_scratch(int camax) {
   const int np = (camax + 1) & ~1;
   const size_t npart = std::max(33 * (camax + 1), (np / 2) * 99) + 8;
-  return sizeof(double) * ((size_t)np + 2 + npart + camax + 40 + camax + 2) + sizeof(int) * ((size_t)2 * camax + 16);
+  return sizeof(double) * ((size_t)np + 2 + npart + camax + 40 + camax + 2) + sizeof(int) * (size_t)((3 * camax + 34) & ~1);
 }
 
 // out[0] = 1 / sqrt(sum) with sum = sum_i vals[i] (squares == 0) or sum_i vals[i]^2 (squares == 1); 1 if the sum is 0

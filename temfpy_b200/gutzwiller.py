@@ -42,7 +42,7 @@ CANONICAL_FORM = "host"
 the default) or ``"device"`` (``tmf_canon_*``: the sweeps on the projected tensors in HBM, real tensors, charge blocks
 up to 160).  The sweep is sequential in the sites and its blocks are small, so a step is bound by the latency of one
 CTA's dependent Gram-Schmidt / Jacobi phases: measured on a B200 for BASELINE configs[2] (256 spin sites, blocks <= 67)
-the device sweep takes 0.49 s against 0.35 s on the host -- hence the default.  ``TMF_CANONICAL_FORM`` overrides."""
+the device sweep takes 0.44 s against 0.34 s on the host -- hence the default.  ``TMF_CANONICAL_FORM`` overrides."""
 
 
 def parity_mask(charges, parity: int = 0) -> np.ndarray:
@@ -129,21 +129,22 @@ def _blocks_of(mps, i, mod):
     t = mps.tensors[i]
     out = {}
     if isinstance(t, SiteTensor):
+        rp, ra = t.row_p, t.row_alpha
+        left = t.mode == "left"
+        cplx = bool(t.blocks) and np.iscomplexobj(t.blocks[0][5])
         for bi, (qk, r0, nr, c0, nc, arr) in enumerate(t.blocks):
-            rp = t.row_p[r0: r0 + nr]
-            for p in (0, 1):
-                sel = np.flatnonzero(rp == p)
-                if sel.size == 0:
+            # the rows of a block are [p = 0 | p = 1] (stable sort by pipe charge), each a contiguous range of alpha
+            n0 = int(np.searchsorted(rp[r0: r0 + nr], 1))
+            for p, s0, n in ((0, 0, n0), (1, n0, nr - n0)):
+                if n == 0:
                     continue
-                s0, n = int(sel[0]), int(sel.size)
-                a0 = int(t.row_alpha[r0 + s0])
-                assert _contiguous(sel) and int(t.row_alpha[r0 + s0 + n - 1]) == a0 + n - 1
+                a0 = int(ra[r0 + s0])
+                assert int(ra[r0 + s0 + n - 1]) == a0 + n - 1
                 src = ("dev", t.dev[0], t.dev[1][bi] + s0 * nc) if t.dev is not None else ("host", arr[s0: s0 + n])
-                if t.mode == "left":
-                    blk = _Blk(qk - p, p, qk, a0, n, c0, nc, src, nc, 1, np.iscomplexobj(arr))
+                if left:
+                    out[(qk - p, p)] = _Blk(qk - p, p, qk, a0, n, c0, nc, src, nc, 1, cplx)
                 else:
-                    blk = _Blk(qk, p, qk + p, c0, nc, a0, n, src, 1, nc, np.iscomplexobj(arr))
-                out[(blk.qL, p)] = blk
+                    out[(qk, p)] = _Blk(qk, p, qk + p, c0, nc, a0, n, src, 1, nc, cplx)
         return out
     T = t.dense()
     cL, cR = np.asarray(mps.charges[i]).ravel(), np.asarray(mps.charges[i + 1]).ravel()
