@@ -573,21 +573,28 @@ def C_to_MPS(C, trunc_par, *, ortho_center=None, spinful=None, unit_cell_width=N
             unit_cell_width = L
         elif L % unit_cell_width != 0:
             raise ValueError(f"{unit_cell_width = } does not divide system size {L}")
-        meta = [(L, int(np.round(np.trace(Cp))), unit_cell_width)]
+        cplx = bool(np.iscomplexobj(Cp))
+        meta = [(L, int(np.round(np.trace(Cp).real)), unit_cell_width, cplx)]
     dist.broadcast_object_list(meta, src=dst)
-    L, n_fermion, unit_cell_width = meta[0]
-    C_dev = be.from_host(Cp.ravel()) if rank == dst else be.empty(L * L, np.float64)
+    L, n_fermion, unit_cell_width, cplx = meta[0]
+    # complex Slater determinants: the kernels work on the 2L x 2L real embedding (cuts at 2x), see slater.C_to_MPS
+    Lc = 2 * L if cplx else L
+    if rank == dst:
+        Ce = slater.embed_complex(Cp) if cplx else Cp
+        C_dev = be.from_host(Ce.ravel())
+    else:
+        C_dev = be.empty(Lc * Lc, np.float64)
     broadcast_C(_t(C_dev), src=dst)
     if rank == dst:
-        slater._check_projector(Cp, be=be, Cd=C_dev)
+        slater._check_projector(Ce, be=be, Cd=C_dev)
     lo, hi = partition(L, world, tp.chi_max, ortho_center)[rank]
-    opts = dict(r_sketch=48, snap=False, nested=None, device_plan=None)
+    opts = dict(r_sketch=96 if cplx else 48, snap=False, nested=None, device_plan=None, cplx=cplx)
     codes = {"sketch": 1, "singular": 2, "nested": 3, "peer": 0}
     dev = _t(C_dev).device
     while True:
         res, code, err = None, 0, None
         try:
-            res = engine._run_chain_once(be, C_dev, L, L, tp, n_fermion, ortho_center, lo, hi, n_threads, True, None,
+            res = engine._run_chain_once(be, C_dev, Lc, L, tp, n_fermion, ortho_center, lo, hi, n_threads, True, None,
                                          True, opts)
         except engine._Retry as rt:
             code, err = codes[rt.kind], rt.err
@@ -605,7 +612,7 @@ def C_to_MPS(C, trunc_par, *, ortho_center=None, spinful=None, unit_cell_width=N
             opts["r_sketch"] = wider[0]
         elif worst == 2 and not opts["snap"]:
             opts["snap"] = True
-        elif opts["nested"] is False:
+        elif opts["nested"] is False or cplx:
             raise err or ValueError("site stage failed on another rank")
         else:
             opts["nested"] = False
@@ -655,10 +662,13 @@ def C_to_MPS(C, trunc_par, *, ortho_center=None, spinful=None, unit_cell_width=N
         else:
             pinned, host = None, full.numpy()
         out._pinned = pinned
+        es = 2 if cplx else 1
         for r in range(world):
-            assert o == int(offs[r])
+            assert es * o == int(offs[r])
             for st in gathered[r]:
-                add(engine.ShardTables.from_state(st.state, host[o: o + st.out_elems]), st.site_lo, st.site_hi, st.stats)
+                blk = host[es * o: es * (o + st.out_elems)]
+                add(engine.ShardTables.from_state(st.state, blk.view(np.complex128) if cplx else blk),
+                    st.site_lo, st.site_hi, st.stats)
                 o += st.out_elems
     out.stats = dict(out_elems=o, nblocks=nblocks, max_chi=max_chi, njobs=njobs, n_ranks=world,
                      transport="host segments" if host_exchange else "nccl gather")

@@ -66,7 +66,7 @@ def test_two_rank_gloo_sharding(tmp_path, L, chi):
     assert ok == 1 and gathered == ref > 0
 
 
-def _worker_public(rank, world, port, L, chi, out_path):
+def _worker_public(rank, world, port, L, chi, out_path, cplx=False):
     for p in (ROOT, os.path.join(ROOT, "oracle")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -81,7 +81,7 @@ def _worker_public(rank, world, port, L, chi, out_path):
         be = NumpyBackend()
         Cm = None
         if rank == 0:
-            Cm, _ = so.correlation_matrix(helpers.random_hamiltonian(L, 5))
+            Cm, _ = so.correlation_matrix(helpers.random_hamiltonian(L, 5, cplx=cplx))
         mps = tdist.C_to_MPS(Cm, {"chi_max": chi}, backend=be)          # public multi-rank entry point
         mps_nccl = tdist.C_to_MPS(Cm, {"chi_max": chi}, backend=be, host_exchange=False)
         mps2 = tdist.C_to_MPS(Cm, {"chi_max": chi}, backend=be)         # (second call: segments leased / reused)
@@ -111,6 +111,14 @@ def test_two_rank_public_C_to_MPS(tmp_path):
     returns the same BlockMPS, bit for bit, as the single-process slater.C_to_MPS."""
     out = str(tmp_path / "ok.npy")
     mp.spawn(_worker_public, args=(2, _free_port(), 26, 16, out), nprocs=2, join=True)
+    assert np.load(out)[0] == 1
+
+
+def test_two_rank_public_C_to_MPS_complex(tmp_path):
+    """the same for a complex Slater determinant (real embedding on every rank, complex tensors through the
+    shared host segments)."""
+    out = str(tmp_path / "ok.npy")
+    mp.spawn(_worker_public, args=(2, _free_port(), 14, 16, out, True), nprocs=2, join=True)
     assert np.load(out)[0] == 1
 
 
