@@ -65,6 +65,12 @@ typedef struct tmf_gemm_job {
 int64_t tmf_gemm_desc_bytes(int njobs);    /* size of desc_dev for the call below */
 int tmf_gemm_grouped(const tmf_gemm_job *jobs_host, int njobs, void *desc_dev, void *stream);
 
+/* Input check of slater.C_to_MPS (the reference's centre-bond assertion eL + eR = 1, slater.py:404, only holds for a
+ * projector): max |(C C - C)[i, j]| over the first `rows` rows of the symmetric C (pitch ldc).  work_dev: rows * L + 1
+ * doubles, the result is work_dev[rows * L]; desc_dev: tmf_gemm_desc_bytes(1). */
+int tmf_projector_defect(const double *C_dev, int L, int ldc, int rows, double *work_dev, void *desc_dev,
+                         void *stream);
+
 /* K3/K4 -- per-bond Schmidt-mode extraction.  replaces: slater.py:324-375 (diag_and_separate:
  * eigh :347, split :350, reorder :353-370) for every (bond, side) job of a chain at once.
  *

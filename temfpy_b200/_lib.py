@@ -93,6 +93,7 @@ SIGNATURES = {
     "tmf_corr_build": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "tmf_gemm_desc_bytes": (C.c_int64, [C.c_int]),
     "tmf_gemm_grouped": (C.c_int, [C.POINTER(GemmJob), C.c_int, C.c_void_p, C.c_void_p]),
+    "tmf_projector_defect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tmf_slater_modes_workspace": (C.c_int64, [C.c_int, C.c_int, c_int_p, c_int_p, C.c_int]),
     "tmf_slater_modes_batched": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p,
                                            C.c_double, C.c_int, c_i64_p, C.c_void_p, C.c_void_p,

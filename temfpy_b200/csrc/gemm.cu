@@ -505,3 +505,47 @@ extern "C" int tmf_corr_build(const double *phi_dev, int L, int N, int ldphi, do
   j.alpha = 1.0; j.beta = 0.0;
   return tmf::gemm_grouped(&j, 1, scratch, stream);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Projector test of the input (slater.C_to_MPS): max |(C C - C)[i, j]| over the first `rows` rows, C symmetric
+// L x L with pitch ldc.  The product runs on the grouped GEMM, the comparison in one CTA; `work_dev` holds
+// rows * L + 1 doubles, the result is the last of them.
+// ---------------------------------------------------------------------------------------------
+namespace tmf {
+TMF_GLOBAL defect_kernel(const double *T, const double *C, int rows, int L, int ldc, double *out) {
+  DYN_SMEM(double, part);
+  PAR_FOR(t, NTHREADS) {
+    double m = 0.0;
+    for (int64_t idx = t; idx < (int64_t)rows * L; idx += NTHREADS) {
+      const int j = (int)(idx / rows), i = (int)(idx - (int64_t)j * rows);
+      const double d = fabs(T[idx] - C[(int64_t)i * ldc + j]);
+      m = (d > m || d != d) ? d : m;          // (a NaN wins)
+    }
+    part[t] = m;
+  }
+  CTA_SYNC();
+  PAR_FOR(one, 1) {
+    double m = 0.0;
+    for (int t = 0; t < NTHREADS; ++t) m = (part[t] > m || part[t] != part[t]) ? part[t] : m;
+    out[0] = m;
+  }
+}
+}  // namespace tmf
+
+extern "C" int tmf_projector_defect(const double *C_dev, int L, int ldc, int rows, double *work_dev, void *desc_dev,
+                                    void *stream) {
+  using namespace tmf;
+  if (rows > L) rows = L;
+  tmf_gemm_job j;
+  std::memset(&j, 0, sizeof(j));
+  // T (rows x L, column-major) = C[:, :rows]^T C = (C C)[:rows, :]
+  j.A = C_dev; j.lda = ldc; j.transA = 1;
+  j.B = C_dev; j.ldb = ldc; j.transB = 0;
+  j.C = work_dev; j.ldc = rows;
+  j.M = rows; j.N = L; j.K = L;
+  j.alpha = 1.0; j.beta = 0.0;
+  int rc = gemm_grouped(&j, 1, desc_dev, stream);
+  if (rc) return rc;
+  return launch_t("defect", defect_kernel, 1, 512, 512 * sizeof(double), stream, (const double *)work_dev, C_dev, rows,
+                  L, ldc, work_dev + (int64_t)rows * L);
+}

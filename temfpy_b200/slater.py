@@ -136,23 +136,16 @@ def _check_projector(C, tol=1e-8, be=None, Cd=None):
     Checked on 64 rows of C^2 with the grouped GEMM on the device copy when one is given (a NumPy
     product here would leave a pool of spinning BLAS threads competing with the pipeline's host stages)."""
     L = len(C)
-    if be is None or Cd is None or not hasattr(be, "torch"):
+    if be is None or Cd is None:
         dev = np.abs(C @ C - C).max() if L <= 256 else np.abs(C[:64] @ C - C[:64]).max()
     else:
-        import ctypes as ct
-        from . import _lib
         r = min(64, L)
-        T = be.empty(r * L, np.float64)
-        g = (_lib.GemmJob * 1)()
+        T = be.empty(r * L + 1, np.float64)
         desc = be.empty(int(be.lib.tmf_gemm_desc_bytes(1)), np.uint8)
-        # T (r x L, column-major) = C[:, :r]^T C = (C C)[:r, :]   (C symmetric)
-        g[0].A, g[0].lda, g[0].transA = be.ptr(Cd), L, 1
-        g[0].B, g[0].ldb, g[0].transB = be.ptr(Cd), L, 0
-        g[0].C, g[0].ldc = be.ptr(T), r
-        g[0].M, g[0].N, g[0].K = r, L, L
-        g[0].alpha, g[0].beta = 1.0, 0.0
-        engine.check(be.lib, be.lib.tmf_gemm_grouped(g, 1, be.ptr(desc), be.stream))
-        dev = float((T[: r * L].view(L, r).t() - Cd[: L * L].view(L, L)[:r]).abs().max().item())
+        engine.check(be.lib, be.lib.tmf_projector_defect(be.ptr(Cd), L, L, r, be.ptr(T), be.ptr(desc), be.stream))
+        dev = float(be.to_host(T[r * L:], 1)[0])
+        if dev != dev:
+            raise ValueError("`C` contains NaN")
     if dev > tol:
         raise ValueError(f"`C` is not the correlation matrix of a Slater determinant (max|C^2 - C| = {dev:.2e})")
 
