@@ -311,6 +311,29 @@ int64_t tmf_pf_desc_bytes(int nblocks);
 int tmf_pfaffians_blocks(const tmf_pf_block *blocks_host, int nblocks, void *desc_dev, void *stream);
 
 
+/* K9p -- per-site finish of the Pfaffian site stage.  replaces: pfaffian.py:1339-1400 (singular values and inverse of
+ * the U* block of V1^+ V2, blocks AA / BA / BB, the antisymmetric contraction matrix N) together with the sign / swap
+ * fixes of :1665, :1708-1719, :915-916 and the centre-bond rotations of :855, applied to the Schur complement S that
+ * tmf_site_overlap_schur_batched (emb = 1) left per site: column-major (sb + sur_b) x (sk + sur_k), surplus rows /
+ * columns last for right tensors (mode 1).  One CTA per job.  out[0] = product, out[1] = smallest of the singular
+ * values of U* (a vanishing one: vacua of opposite parity, :1355-1357); with want_n the m x m complex N (interleaved,
+ * row-major, m = active ket + active bra modes, ket modes first in descending order, :1361-1374, :1400-1408) is
+ * written to N.  idx1_mask / idx2_mask: bit t = bra / ket mode t is occupied in some Schmidt vector.  rot_up / rot_lo:
+ * optional real 2 k2 x 2 k2 matrices (row-major) multiplied from the right onto the upper / lower ket pairs. */
+typedef struct tmf_pf_site_job {
+  const double *S;
+  const double *rot_up, *rot_lo;
+  double *N;
+  double *out;
+  double *work_;             /* unused (the kernel works in shared memory) */
+  uint32_t idx1_mask, idx2_mask;
+  int sb, sk, sur_b, sur_k, mode, k1, k2, fix, want_n, pad0_;
+  double u_p, ket_sign;
+  int pad_[4];
+} tmf_pf_site_job;
+int tmf_pfaffian_site_finish(const tmf_pf_site_job *jobs_host, int njobs, void *desc_dev /* 128 * njobs bytes */,
+                             void *stream);
+
 /* Chain driver -- replaces the per-site loop of slater.C_to_MPS (slater.py:1216-1353) for the
  * sites [site_lo, site_hi) of one chain (one call sequence per GPU; shards need no communication).
  *   create -> modes_sizes -> [caller allocates] -> modes (device + one D2H sync) -> enumerate (host)

@@ -73,6 +73,14 @@ class PfBlock(C.Structure):
                 ("n2", C.c_int), ("pad_", C.c_int)]
 
 
+class PfSiteJob(C.Structure):
+    _fields_ = [("S", C.c_void_p), ("rot_up", C.c_void_p), ("rot_lo", C.c_void_p), ("N", C.c_void_p),
+                ("out", C.c_void_p), ("work_", C.c_void_p), ("idx1_mask", C.c_uint32), ("idx2_mask", C.c_uint32),
+                ("sb", C.c_int), ("sk", C.c_int), ("sur_b", C.c_int), ("sur_k", C.c_int), ("mode", C.c_int),
+                ("k1", C.c_int), ("k2", C.c_int), ("fix", C.c_int), ("want_n", C.c_int), ("pad0_", C.c_int),
+                ("u_p", C.c_double), ("ket_sign", C.c_double), ("pad_", C.c_int * 4)]
+
+
 class GutzJob(C.Structure):
     _fields_ = [("A", C.c_void_p), ("B", C.c_void_p), ("out", C.c_void_p),
                 ("k_scale", C.c_void_p), ("row_scale", C.c_void_p), ("col_scale", C.c_void_p),
@@ -82,7 +90,7 @@ class GutzJob(C.Structure):
 
 assert C.sizeof(GemmJob) == 128 and C.sizeof(SiteJob) == 128 and C.sizeof(MinorBlock) == 64
 assert C.sizeof(PairJob) == 64 and C.sizeof(PfBlock) == 64 and C.sizeof(NestedJob) == 64
-assert C.sizeof(GutzJob) == 128
+assert C.sizeof(GutzJob) == 128 and C.sizeof(PfSiteJob) == 128
 
 # name -> (restype, argtypes); this table is also what tests check against include/temfpy_b200.h
 SIGNATURES = {
@@ -165,6 +173,7 @@ SIGNATURES = {
     "tmf_pfaffian_pair_modes": (C.c_int, [C.POINTER(PairJob), C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "tmf_pf_desc_bytes": (C.c_int64, [C.c_int]),
     "tmf_pfaffians_blocks": (C.c_int, [C.POINTER(PfBlock), C.c_int, C.c_void_p, C.c_void_p]),
+    "tmf_pfaffian_site_finish": (C.c_int, [C.POINTER(PfSiteJob), C.c_int, C.c_void_p, C.c_void_p]),
     "tmf_gutz_desc_bytes": (C.c_int64, [C.POINTER(GutzJob), C.c_int]),
     "tmf_gutzwiller_project": (C.c_int, [C.POINTER(GutzJob), C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
                                          C.c_void_p]),

@@ -532,7 +532,8 @@ class _PfChain:
         desc = be.empty(int(lib.tmf_site_desc_bytes(ns)), np.uint8)
         check(lib, lib.tmf_site_overlap_schur_batched(sj, ns, be.ptr(desc), be.stream))
         be.sync()
-        self.S_host = be.to_host(Sd, s_elems)
+        self.Sd = Sd
+        self.S_host = be.to_host(Sd, s_elems) if __import__('os').environ.get('TMF_PF_HOST_FINISH') else None
         self.det_host = be.to_host(detd, ns)
 
     # -- stage 4: small algebra on the entangled modes (host) --------------------------------------
@@ -617,7 +618,162 @@ class _PfChain:
         s = self.bonds[x].sets
         return s[:, ::-1] if mode == 1 else s
 
+    # -- stage 4: finish on the entangled modes (device: tmf_pfaffian_site_finish) -----------------------------
+    def _centre_rotations(self, s):
+        """Real 2 k2 x 2 k2 matrices that apply the centre-bond rotations of block_svd (pfaffian.py:855) to the upper /
+        lower ket pairs of a site next to the centre bond, in the stored order of the active modes; None elsewhere."""
+        k2 = s["k2"]
+        if s["i"] == self.oc - 1 and s["mode"] == 0 and k2:        # ket = left side of the centre bond
+            rot_lo, rot_up = self.QL, self.QL.conj()
+        elif s["i"] == self.oc and s["mode"] == 1 and k2:          # ket = right side of the centre bond
+            rot_lo, rot_up = self.QRup.conj(), self.QRup
+        else:
+            return None
+        order = np.arange(k2)[::-1] if s["mode"] == 1 else np.arange(k2)
+        inv = np.argsort(order)
+        pairs = lambda idx: np.array([2 * j + t for j in idx for t in (0, 1)])
+        eye = np.eye(2 * k2)
+        return tuple(np.ascontiguousarray(eye[:, pairs(inv)] @ _emb_mat(Q)[:, pairs(order)]) for Q in (rot_up, rot_lo))
+
+    def _finish_jobs(self, want_n, fix, u_p, ket_sign, masks, n_off):
+        be = self.be
+        ns = len(self.sites)
+        jobs = (_lib.PfSiteJob * max(ns, 1))()
+        for u, s in enumerate(self.sites):
+            j = jobs[u]
+            j.S = be.ptr(self.Sd) + 8 * s["s_off"]
+            if s["rot"] is not None:
+                j.rot_up = be.ptr(self.rot_d) + 8 * s["rot"][0]
+                j.rot_lo = be.ptr(self.rot_d) + 8 * s["rot"][1]
+            j.out = be.ptr(self.fin_out) + 16 * u
+            j.sb, j.sk, j.sur_b, j.sur_k, j.mode, j.k1, j.k2 = s["sb"], s["sk"], s["sur_b"], s["sur_k"], s["mode"], \
+                s["k1"], s["k2"]
+            j.want_n, j.fix, j.u_p, j.ket_sign = int(want_n), int(fix[u]), float(u_p[u]), float(ket_sign[u])
+            if want_n:
+                j.idx1_mask, j.idx2_mask = masks[u]
+                j.N = be.ptr(self.Nd) + 8 * n_off[u]
+        desc = be.empty(128 * max(ns, 1), np.uint8)
+        check(self.lib, self.lib.tmf_pfaffian_site_finish(jobs, ns, be.ptr(desc), be.stream))
+        be.sync()
+        return be.to_host(self.fin_out, 2 * ns).reshape(ns, 2).copy()
+
     def tensors(self):
+        import os
+        if os.environ.get("TMF_PF_HOST_FINISH"):
+            return self._tensors_host()
+        be, lib, L, oc = self.be, self.lib, self.L, self.oc
+        ns = len(self.sites)
+        # centre-bond rotations: uploaded once
+        rot_chunks, ro = [], 0
+        for s in self.sites:
+            g = self._centre_rotations(s)
+            s["rot"] = None
+            if g is not None:
+                s["rot"] = (ro, ro + g[0].size)
+                rot_chunks += [g[0].ravel(), g[1].ravel()]
+                ro += g[0].size + g[1].size
+        self.rot_d = be.from_host(np.concatenate(rot_chunks)) if rot_chunks else be.empty(1, np.float64)
+        self.fin_out = be.empty(2 * max(ns, 1), np.float64)
+        ones, zeros = np.ones(ns), np.zeros(ns, dtype=np.int64)
+        # pass 1: singular values of the U* blocks only -- which overlaps vanish decides the vacuum parities
+        out1 = self._finish_jobs(False, zeros, ones, ones, None, None)
+        if np.any(out1[:, 0] < 0):
+            raise AssertionError("inconsistent mode counts")
+        flips = [bool(v < _SINGULAR) for v in out1[:, 1]]
+        # absolute vacuum parities from the empty blocks at the chain ends
+        pL, pR = {0: 0}, {L: 0}
+        for i in range(oc):
+            pL[i + 1] = pL[i] ^ int(flips[i])
+        for i in reversed(range(oc, L)):
+            pR[i] = pR[i + 1] ^ int(flips[i])
+        total = pL[oc] ^ pR[oc]
+        for x in range(oc + 1, L + 1):
+            pL[x] = total ^ pR[x]
+        for x in range(oc):
+            pR[x] = total ^ pL[x]
+        for x, b in self.bonds.items():
+            b.pL, b.pR = pL[x], pR[x]
+        self.total_parity = total
+        # pass 2: the fixes that depend on the parities, N of every site written on the device
+        fix = np.array([int(f) for f in flips])
+        u_p, ket_sign, masks, n_off, per_site = np.ones(ns), np.ones(ns), [], [], []
+        no = 0
+        for u, (s, fl) in enumerate(zip(self.sites, flips)):
+            mode = s["mode"]
+            sets_bra = self._ext_sets(s["xb"], mode).copy()
+            if fl:
+                c = 0 if mode == 1 else -1
+                sets_bra[:, c] = ~sets_bra[:, c]
+            sets_ket = self._ket_sets(s["xk"], mode)
+            if mode == 0 and pL[s["xb"]] == 1:
+                u_p[u] = -1.0                                                                # :1665
+            if mode == 1 and s["i"] == oc and pL[oc] == 1:
+                ket_sign[u] = -1.0                                                           # :915-916
+            idx1 = np.flatnonzero(sets_bra.any(axis=0))                                      # :1361-1374
+            idx2 = np.flatnonzero(sets_ket.any(axis=0))[::-1]
+            masks.append((int(sum(1 << int(t) for t in idx1)), int(sum(1 << int(t) for t in idx2))))
+            m = len(idx1) + len(idx2)
+            n_off.append(no)
+            no += 2 * m * m
+            s1, s2 = sets_bra[:, idx1], sets_ket[:, idx2]
+            n1 = np.concatenate((np.zeros((len(s1), s2.shape[1]), bool), s1), axis=1)
+            n2 = np.concatenate((s2, np.zeros((len(s2), s1.shape[1]), bool)), axis=1)
+            per_site.append((m, n1, n2))
+        self.Nd = be.empty(max(no, 1), np.float64)
+        out2 = self._finish_jobs(True, fix, u_p, ket_sign, masks, n_off)
+        if np.any(out2[:, 1] < _SINGULAR):
+            raise AssertionError("Boguliubov vacua do not overlap (U nearly singular)")      # :1355-1357
+        blocks, site_meta = [], []
+        m_chunks = []
+        m_off = out_off = 0
+        for u, s in enumerate(self.sites):
+            m, n1, n2 = per_site[u]
+            norm = (abs(self.det_host[s["i"]]) * out2[u, 0]) ** 0.25                         # :1352, :1359
+            leg_idx, idx_n_bra, _ = _parity_n_argsort(n1.sum(axis=1))                        # :1732
+            bm, km = _pack(n1[leg_idx]), _pack(n2)
+            m_chunks += [bm, km]
+            bra_m_off, ket_m_off = m_off, m_off + len(bm)
+            m_off += len(bm) + len(km)
+            meta = []
+            for nb_, sb_ in idx_n_bra.items():
+                for nk_, sk_ in self.bonds[s["xk"]].idx_n.items():
+                    if (nb_ + nk_) % 2 == 1:                                                # :1768
+                        continue
+                    nr, nc = sb_.stop - sb_.start, sk_.stop - sk_.start
+                    blocks.append((n_off[u], bra_m_off + sb_.start, ket_m_off + sk_.start, out_off, norm, m, nr, nc,
+                                   int(nb_), int(nk_)))
+                    meta.append((leg_idx[sb_], sk_, out_off, nr, nc))
+                    out_off += 2 * nr * nc
+            site_meta.append((s, norm, meta))
+        Nd = self.Nd
+        Md = be.from_host((np.concatenate(m_chunks).astype(np.uint64) if m_chunks else np.zeros(1, np.uint64)).view(np.int64))
+        outd = be.empty(out_off, np.float64)
+        nbk = len(blocks)
+        pb = (_lib.PfBlock * max(nbk, 1))()
+        for u, (no, bo, ko, oo, norm, m, nr, nc, n1_, n2_) in enumerate(blocks):
+            pb[u].N = be.ptr(Nd) + 8 * no
+            pb[u].bra_masks = be.ptr(Md) + 8 * bo
+            pb[u].ket_masks = be.ptr(Md) + 8 * ko
+            pb[u].out = be.ptr(outd) + 8 * oo
+            pb[u].scale = norm
+            pb[u].m, pb[u].n_bra, pb[u].n_ket, pb[u].n1, pb[u].n2 = m, nr, nc, n1_, n2_
+        desc = be.empty(int(lib.tmf_pf_desc_bytes(nbk)), np.uint8)
+        check(lib, lib.tmf_pfaffians_blocks(pb, nbk, be.ptr(desc), be.stream))
+        be.sync()
+        out = be.to_host(outd, out_off)
+        self.n_pfaffians = out_off // 2
+        self.site_tensors = []
+        for s, norm, meta in site_meta:
+            t = PfSiteTensor(site=s["i"], mode="right" if s["mode"] else "left",
+                             chi_bra=len(self.bonds[s["xb"]].schmidt_values),
+                             chi_ket=len(self.bonds[s["xk"]].schmidt_values), norm=norm)
+            for rows, sk_, oo, nr, nc in meta:
+                blk = out[oo: oo + 2 * nr * nc]
+                t.blocks.append((rows, sk_, (blk[0::2] + 1j * blk[1::2]).reshape(nr, nc)))
+            self.site_tensors.append(t)
+
+    def _tensors_host(self):
+        """The same finish with host NumPy (cross-check of the device kernel; TMF_PF_HOST_FINISH=1)."""
         be, lib, L, oc = self.be, self.lib, self.L, self.oc
         Rs, flips = [], []
         for s in self.sites:

@@ -177,6 +177,25 @@ def test_sim_chain_vs_oracle(sim_backend, H, tp, basis):
     helpers.compare_pf_mps(ref, helpers.block_mps_to_dense(got), _half_bonds(Cm, tp, basis))
 
 
+def _finish_device_vs_host(be, monkeypatch):
+    """tmf_pfaffian_site_finish (one CTA per site: Jacobi SVD of U*, inverse, N) against the same algebra in NumPy:
+    same tensors."""
+    for H, tp, oc in ((po.random_bdg(12, 8), {"chi_max": 40}, None), (po.bdg_chain(24), {"chi_max": 32}, 11)):
+        Cm = po.correlation_matrix(H, "C->C")
+        a = pf.C_to_MPS(Cm, tp, basis="C", ortho_center=oc, _backend=be, as_tenpy=False)
+        monkeypatch.setenv("TMF_PF_HOST_FINISH", "1")
+        b = pf.C_to_MPS(Cm, tp, basis="C", ortho_center=oc, _backend=be, as_tenpy=False)
+        monkeypatch.delenv("TMF_PF_HOST_FINISH")
+        assert a.meta["total_parity"] == b.meta["total_parity"]
+        for i in range(a.L):
+            Ta, Tb = a.get_B_dense(i), b.get_B_dense(i)
+            assert Ta.shape == Tb.shape and np.abs(Ta - Tb).max() <= 1e-11 * max(np.abs(Tb).max(), 1e-300), i
+
+
+def test_sim_site_finish_device_vs_host(sim_backend, monkeypatch):
+    _finish_device_vs_host(sim_backend, monkeypatch)
+
+
 def _centre_half_modes(be, L, oc=None):
     """Eigenvalue-1/2 Schmidt modes on the *central* bond (pfaffian.py:857-865): the symmetric chain cut at an
     odd bond.  The two real bases of the 1/2 space are paired by an SVD; the result equals the reference's state."""
@@ -236,6 +255,11 @@ def test_gpu_chain_vs_oracle(gpu_backend, H, tp):
     ref = po.C_to_MPS(Cm, tp, "C")
     got = pf.H_to_MPS(H, tp, basis="C", _backend=gpu_backend, as_tenpy=False)
     helpers.compare_pf_mps(ref, helpers.block_mps_to_dense(got), _half_bonds(Cm, tp))
+
+
+@pytest.mark.gpu
+def test_gpu_site_finish_device_vs_host(gpu_backend, monkeypatch):
+    _finish_device_vs_host(gpu_backend, monkeypatch)
 
 
 @pytest.mark.gpu
