@@ -18,8 +18,9 @@ symmetric projector of rank ``2L`` -- formally the correlation matrix of a Slate
   plus the blocked LU of ``tmf_site_overlap_schur_batched``: the non-entangled ("always") modes are
   eliminated on the device in whatever real basis the Cholesky produced (a Schur complement does not
   depend on the basis of the eliminated block), leaving a matrix of the size of the entangled modes;
-* the remaining ``O(k^3)`` algebra (finish the inverse on the entangled modes, assemble the
-  antisymmetric contraction matrix ``N``, pfaffian.py:1386-1400) is done on the host with NumPy;
+* the remaining ``O(k^3)`` algebra (singular values and inverse of the small ``U^*`` block, the antisymmetric
+  contraction matrix ``N``, pfaffian.py:1352-1400, with the sign fixes that depend on the vacuum parities) runs
+  in ``tmf_pfaffian_site_finish``, one CTA per site, two launches per chain;
 * all tensor entries ``Pf(N[idx, idx])`` (pfaffian.py:1429-1479, pfapack in the reference) are computed
   by ``tmf_pfaffians_blocks`` (complex128 Parlett-Reid, one warp per entry).
 
