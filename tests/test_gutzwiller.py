@@ -272,3 +272,76 @@ def test_gpu_resident_blocks_and_parity_input(gpu_backend):
             _resident_vs_staged(gpu_backend, 48, kind, {"chi_max": 128})
         _pf_projection(gpu_backend, "PH", True)
         _pf_projection(gpu_backend, "simple", False)
+
+
+def _project_kernel_vs_numpy(be, cplx, seed):
+    """tmf_gutzwiller_project through the C ABI on random jobs: both storage orders of either operand (element
+    strides), the three optional scalings, f64 and c128, output blocks scattered inside a larger tensor -- against
+    NumPy, and the zero fill of everything the jobs do not touch."""
+    import ctypes as C
+    from temfpy_b200 import _lib
+    rng = np.random.default_rng(seed)
+    es = 2 if cplx else 1
+    dt = np.complex128 if cplx else np.float64
+
+    def rnd(*shape):
+        x = rng.normal(size=shape)
+        return x + 1j * rng.normal(size=shape) if cplx else x
+    pool, off, specs = [], 0, []
+    n_out_rows, n_out_cols = 300, 2 * 170            # one "spin tensor": rows vL, columns (s, vR) -> so_i = 2 * 170
+    want = np.zeros((n_out_rows, n_out_cols), dtype=dt)
+    r0 = 0
+    for u, (m, k, n) in enumerate([(1, 1, 1), (7, 3, 5), (64, 16, 64), (65, 17, 66), (130, 40, 3), (20, 70, 90)]):
+        ta, tb = bool(rng.integers(2)), bool(rng.integers(2))
+        A, B = rnd(m, k), rnd(k, n)
+        As, Bs = (A.T.copy() if ta else A.copy()), (B.T.copy() if tb else B.copy())
+        ks = rng.uniform(0.5, 1.5, size=k) if u % 2 == 0 else None
+        rs = rng.uniform(0.5, 1.5, size=m) if u % 3 == 0 else None
+        cs = rng.uniform(0.5, 1.5, size=n) if u % 3 == 1 else None
+        s_idx, c0 = u % 2, int(rng.integers(0, 170 - n + 1))
+        ref = (A * (ks[None, :] if ks is not None else 1.0)) @ B
+        if rs is not None:
+            ref = ref * rs[:, None]
+        if cs is not None:
+            ref = ref * cs[None, :]
+        want[r0: r0 + m, s_idx * 170 + c0: s_idx * 170 + c0 + n] = ref
+        specs.append(dict(m=m, k=k, n=n, ta=ta, tb=tb, a=off, b=off + As.size, ks=ks, rs=rs, cs=cs,
+                          out=r0 * n_out_cols + s_idx * 170 + c0))
+        pool += [As.ravel(), Bs.ravel()]
+        off += As.size + Bs.size
+        r0 += m
+    buf = be.from_host(np.concatenate(pool).astype(dt).view(np.float64))
+    scal = [v for sp in specs for v in (sp["ks"], sp["rs"], sp["cs"]) if v is not None]
+    sc_d = be.from_host(np.concatenate(scal))
+    outd = be.from_host(np.full(es * n_out_rows * n_out_cols, 7.0))          # must be overwritten by the zero fill
+    jobs = (_lib.GutzJob * len(specs))()
+    so_ = 0
+    for g, sp in zip(jobs, specs):
+        g.A, g.B = be.ptr(buf) + 8 * es * sp["a"], be.ptr(buf) + 8 * es * sp["b"]
+        g.sa_i, g.sa_k = (1, sp["m"]) if sp["ta"] else (sp["k"], 1)
+        g.sb_k, g.sb_n = (1, sp["k"]) if sp["tb"] else (sp["n"], 1)
+        g.m, g.k, g.n = sp["m"], sp["k"], sp["n"]
+        g.out, g.so_i = be.ptr(outd) + 8 * es * sp["out"], n_out_cols
+        for name in ("ks", "rs", "cs"):
+            if sp[name] is not None:
+                setattr(g, {"ks": "k_scale", "rs": "row_scale", "cs": "col_scale"}[name], be.ptr(sc_d) + 8 * so_)
+                so_ += len(sp[name])
+    desc = be.empty(int(be.lib.tmf_gutz_desc_bytes(jobs, len(specs))), np.uint8)
+    _lib.check(be.lib, be.lib.tmf_gutzwiller_project(jobs, len(specs), int(cplx), be.ptr(outd),
+                                                     8 * es * n_out_rows * n_out_cols, be.ptr(desc), be.stream))
+    be.sync()
+    got = be.to_host(outd, es * n_out_rows * n_out_cols)
+    got = (got.view(np.complex128) if cplx else got).reshape(n_out_rows, n_out_cols)
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+    assert np.array_equal(got == 0, want == 0)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_sim_project_kernel_vs_numpy(sim_backend, cplx):
+    _project_kernel_vs_numpy(sim_backend, cplx, 5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cplx,seed", [(False, 1), (True, 2), (False, 3)])
+def test_gpu_project_kernel_vs_numpy(gpu_backend, cplx, seed):
+    _project_kernel_vs_numpy(gpu_backend, cplx, seed)
