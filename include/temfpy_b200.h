@@ -441,6 +441,23 @@ int tmf_canon_dims(const tmf_canon *c, int *dims2, int *charges2);
 int tmf_canon_run(tmf_canon *c, const double *T0_dev, const int64_t *t0_off, void *work_dev, int64_t work_bytes,
                   double *T2_dev, double *S_dev, double *inv_dev, void *stream);
 
+/* K15 / f2 -- orthogonal Procrustes of the iMPS gauge fixing on the device.  replaces: the per-sector npc.svd and
+ * U Vh of iMPS.basis_rotation (iMPS.py:150-184) and the two sums behind its error metrics (:139-147, :186-190).
+ * One job per charge sector: C is the overlap block (row-major m x n, row stride ldc, in place in the output of
+ * tmf_minors_blocks), sk the n Schmidt values of the ket sector; R (row-major, row stride ldr) receives U Vh of
+ * C diag(sk^2), metrics[0] = sum |C sk|^2, metrics[1] = sum |(R - C) sk|^2.  Blocks up to min(m, n) = 160. */
+typedef struct tmf_procrustes_job {
+  const double *C;
+  const double *sk;
+  double *R;
+  double *metrics;
+  int64_t ldc, ldr;
+  int m, n, pad_[2];
+} tmf_procrustes_job;
+int64_t tmf_procrustes_workspace(const tmf_procrustes_job *jobs_host, int njobs);
+int tmf_procrustes_blocks(const tmf_procrustes_job *jobs_host, int njobs, void *work_dev, int64_t work_bytes,
+                          void *stream);
+
 /* Multi-GPU plumbing of the sharded conversion (temfpy_b200/dist.py; SURVEY 8(e): "gather of per-site tensors").
  * Peer window: a buffer in the destination rank's HBM, exported with tmf_ipc_export (64-byte CUDA IPC handle +
  * offset of dev_ptr inside its allocation) and mapped by the other ranks of the node with tmf_ipc_open (returns the

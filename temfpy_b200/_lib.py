@@ -81,6 +81,11 @@ class PfSiteJob(C.Structure):
                 ("u_p", C.c_double), ("ket_sign", C.c_double), ("pad_", C.c_int * 4)]
 
 
+class ProcrustesJob(C.Structure):
+    _fields_ = [("C", C.c_void_p), ("sk", C.c_void_p), ("R", C.c_void_p), ("metrics", C.c_void_p),
+                ("ldc", C.c_int64), ("ldr", C.c_int64), ("m", C.c_int), ("n", C.c_int), ("pad_", C.c_int * 2)]
+
+
 class GutzJob(C.Structure):
     _fields_ = [("A", C.c_void_p), ("B", C.c_void_p), ("out", C.c_void_p),
                 ("k_scale", C.c_void_p), ("row_scale", C.c_void_p), ("col_scale", C.c_void_p),
@@ -90,7 +95,7 @@ class GutzJob(C.Structure):
 
 assert C.sizeof(GemmJob) == 128 and C.sizeof(SiteJob) == 128 and C.sizeof(MinorBlock) == 64
 assert C.sizeof(PairJob) == 64 and C.sizeof(PfBlock) == 64 and C.sizeof(NestedJob) == 64
-assert C.sizeof(GutzJob) == 128 and C.sizeof(PfSiteJob) == 128
+assert C.sizeof(GutzJob) == 128 and C.sizeof(PfSiteJob) == 128 and C.sizeof(ProcrustesJob) == 64
 
 # name -> (restype, argtypes); this table is also what tests check against include/temfpy_b200.h
 SIGNATURES = {
@@ -183,6 +188,8 @@ SIGNATURES = {
     "tmf_canon_dims": (C.c_int, [C.c_void_p, c_int_p, c_int_p]),
     "tmf_canon_run": (C.c_int, [C.c_void_p, C.c_void_p, c_i64_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p]),
+    "tmf_procrustes_workspace": (C.c_int64, [C.POINTER(ProcrustesJob), C.c_int]),
+    "tmf_procrustes_blocks": (C.c_int, [C.POINTER(ProcrustesJob), C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "tmf_ipc_export": (C.c_int, [C.c_void_p, C.c_char_p, c_i64_p]),
     "tmf_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "tmf_ipc_close": (C.c_int, [C.c_void_p]),

@@ -49,7 +49,8 @@ struct BlockSvdJob {
   const double *scale;
   int64_t rs, rd;
   int m, n[2], k;
-  int pad_[6];
+  const double *csq;      // optional: column c of the input is multiplied by csq[c]^2 (Procrustes weights)
+  int want_u, pad_[3];    // want_u: the US buffer receives U instead of U diag(S)
 };
 static_assert(sizeof(BlockQrJob) == 128 && sizeof(BlockSvdJob) == 128, "descriptors must be 128 bytes");
 
@@ -197,11 +198,12 @@ TMF_GLOBAL block_svd_kernel(const BlockSvdJob *jobs, int camax, int mat_doubles)
     double s2 = 0.0;
     if (tall) {
       const int t = j >= n0, cc = t ? j - n0 : j;
-      for (int r = lane; r < m; r += 32) { const double v = jb.src[t][r * jb.rs + cc]; s2 += v * v; }
+      const double w = jb.csq ? jb.csq[j] * jb.csq[j] : 1.0;
+      for (int r = lane; r < m; r += 32) { const double v = w * jb.src[t][r * jb.rs + cc]; s2 += v * v; }
     } else {
       for (int c = lane; c < n; c += 32) {
         const int t = c >= n0, cc = t ? c - n0 : c;
-        const double v = jb.src[t][j * jb.rs + cc];
+        const double v = (jb.csq ? jb.csq[c] * jb.csq[c] : 1.0) * jb.src[t][j * jb.rs + cc];
         s2 += v * v;
       }
     }
@@ -219,7 +221,7 @@ TMF_GLOBAL block_svd_kernel(const BlockSvdJob *jobs, int camax, int mat_doubles)
   PAR_FOR(idx, m * n) {
     const int r = idx / n, c = idx - r * n;
     const int t = c >= n0, cc = t ? c - n0 : c;
-    const double v = sc * jb.src[t][r * jb.rs + cc];
+    const double v = sc * (jb.csq ? jb.csq[c] * jb.csq[c] : 1.0) * jb.src[t][r * jb.rs + cc];
     if (tall) A[(int64_t)cperm[c] * ra + r] = v; else A[(int64_t)cperm[r] * ra + c] = v;
   }
   PAR_FOR(idx, ca * ca) {
@@ -275,7 +277,7 @@ TMF_GLOBAL block_svd_kernel(const BlockSvdJob *jobs, int camax, int mat_doubles)
       const int i = idx / m, r = idx - i * m;
       double s = 0.0;
       for (int t = 0; t < ca; ++t) s += A[(int64_t)t * ra + r] * J[(int64_t)i * ca + t];
-      jb.US[(int64_t)rank[i] * m + r] = s * sig[i];
+      jb.US[(int64_t)rank[i] * m + r] = jb.want_u ? s : s * sig[i];
     }
     PAR_FOR(idx, k * n) {
       const int i = idx / n, c = idx - i * n;
@@ -285,7 +287,8 @@ TMF_GLOBAL block_svd_kernel(const BlockSvdJob *jobs, int camax, int mat_doubles)
   } else {
     PAR_FOR(idx, m * k) {
       const int i = idx / m, r = idx - i * m;
-      jb.US[(int64_t)rank[i] * m + r] = R1[(int64_t)i * ca + cperm[r]];
+      const double w = R1[(int64_t)i * ca + cperm[r]];
+      jb.US[(int64_t)rank[i] * m + r] = jb.want_u ? (sig[i] > 0.0 ? w / sig[i] : 0.0) : w;
     }
     PAR_FOR(idx, k * n) {
       const int i = idx / n, c = idx - i * n;
@@ -306,6 +309,42 @@ inline size_t block_svd_scratch(int camax) {
   const int np = (camax + 1) & ~1;
   const size_t npart = std::max(33 * (camax + 1), (np / 2) * 99) + 8;
   return sizeof(double) * ((size_t)np + 2 + npart + camax + 40 + camax + 2) + sizeof(int) * (size_t)((3 * camax + 34) & ~1);
+}
+
+// Orthogonal Procrustes per charge sector (reference iMPS.py:150-184, K15): R = U Vh of M = C diag(sk^2) from the
+// SVD kernel above (want_u), written into the dense rotation matrix, together with the two sums behind the error
+// metrics of iMPS.py:139-147 / :186-190:  metrics[0] = sum |C sk|^2,  metrics[1] = sum |(R - C) sk|^2.
+struct ProcrustesFinish {
+  const double *C, *sk, *U, *Vh, *S;
+  double *R, *metrics;
+  int64_t ldc, ldr;
+  int m, n, k, pad_;
+};
+TMF_GLOBAL procrustes_finish_kernel(const ProcrustesFinish *jobs) {
+  const ProcrustesFinish jb = jobs[BLOCK_ID];
+  DYN_SMEM(double, part);       // 2 * NTHREADS
+  PAR_FOR(t, NTHREADS) {
+    double a = 0.0, b = 0.0;
+    for (int idx = t; idx < jb.m * jb.n; idx += NTHREADS) {
+      const int r = idx / jb.n, c = idx - r * jb.n;
+      double s = 0.0;
+      for (int i = 0; i < jb.k; ++i)
+        if (jb.S[i] > 0.0) s += jb.U[(int64_t)i * jb.m + r] * jb.Vh[(int64_t)i * jb.n + c];
+      jb.R[r * jb.ldr + c] = s;
+      const double cv = jb.C[r * jb.ldc + c], w = jb.sk[c];
+      a += cv * w * cv * w;
+      b += (s - cv) * w * (s - cv) * w;
+    }
+    part[t] = a;
+    part[NTHREADS + t] = b;
+  }
+  CTA_SYNC();
+  PAR_FOR(one, 1) {
+    double a = 0.0, b = 0.0;
+    for (int t = 0; t < NTHREADS; ++t) { a += part[t]; b += part[NTHREADS + t]; }
+    jb.metrics[0] = a;
+    jb.metrics[1] = b;
+  }
 }
 
 // out[0] = 1 / sqrt(sum) with sum = sum_i vals[i] (squares == 0) or sum_i vals[i]^2 (squares == 1); 1 if the sum is 0
@@ -702,4 +741,64 @@ extern "C" int tmf_canon_run(tmf_canon *c, const double *T0_dev, const int64_t *
     }
   }
   return TMF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K15: Procrustes gauge fixing of the iMPS conversion on the device
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int64_t tmf_procrustes_workspace(const tmf_procrustes_job *jobs_host, int njobs) {
+  using namespace tmf;
+  int64_t w = align256(128 * (int64_t)std::max(njobs, 1)) + align256(sizeof(ProcrustesFinish) * (int64_t)std::max(njobs, 1));
+  for (int i = 0; i < njobs; ++i) {
+    const int m = jobs_host[i].m, n = jobs_host[i].n, k = std::min(m, n);
+    w += align256(8 * ((int64_t)k * n)) + align256(8 * ((int64_t)m * k)) + align256(8 * (int64_t)(k + 2)) +
+         align256(8 * svd_work_doubles(m, n));
+  }
+  return w + 4096;
+}
+
+extern "C" int tmf_procrustes_blocks(const tmf_procrustes_job *jobs_host, int njobs, void *work_dev,
+                                     int64_t work_bytes, void *stream) {
+  using namespace tmf;
+  if (njobs <= 0) return TMF_OK;
+  Arena ar(work_dev, work_bytes);
+  unsigned char *sj_dev = ar.take<unsigned char>(128 * (int64_t)njobs);
+  unsigned char *fj_dev = ar.take<unsigned char>((int64_t)sizeof(ProcrustesFinish) * njobs);
+  std::vector<BlockSvdJob> sj(njobs);
+  std::vector<ProcrustesFinish> fj(njobs);
+  int camax = 1;
+  int64_t need = 0;
+  for (int i = 0; i < njobs; ++i) {
+    const tmf_procrustes_job &q = jobs_host[i];
+    const int m = q.m, n = q.n, k = std::min(m, n);
+    if (m <= 0 || n <= 0) { set_error("tmf_procrustes_blocks: empty block"); return TMF_ERR_VALUE; }
+    if (k > CANON_MAX) { set_error("tmf_procrustes_blocks: charge block larger than 160"); return TMF_ERR_VALUE; }
+    BlockSvdJob &s = sj[i];
+    std::memset(&s, 0, sizeof(s));
+    double *Vh = ar.take<double>((int64_t)k * n), *U = ar.take<double>((int64_t)m * k), *S = ar.take<double>(k + 2);
+    s.src[0] = q.C; s.src[1] = q.C; s.rs = q.ldc;
+    s.dst[0] = Vh; s.dst[1] = Vh; s.rd = n;
+    s.US = U; s.S = S; s.nrm2 = S + k;
+    s.work = ar.take<double>(svd_work_doubles(m, n));
+    s.m = m; s.n[0] = n; s.n[1] = 0; s.k = k;
+    s.csq = q.sk; s.want_u = 1;
+    ProcrustesFinish &f = fj[i];
+    f.C = q.C; f.sk = q.sk; f.U = U; f.Vh = Vh; f.S = S; f.R = q.R; f.metrics = q.metrics;
+    f.ldc = q.ldc; f.ldr = q.ldr; f.m = m; f.n = n; f.k = k; f.pad_ = 0;
+    camax = std::max(camax, k);
+    const int64_t ra = std::max(m, n);
+    need = std::max<int64_t>(need, ra * k + 2 * (int64_t)k * k);
+  }
+  if (!ar.ok()) { set_error("tmf_procrustes_blocks: workspace too small"); return TMF_ERR_VALUE; }
+  int rc = copy_h2d(sj_dev, sj.data(), sizeof(BlockSvdJob) * (size_t)njobs, stream);
+  if (rc) return rc;
+  rc = copy_h2d(fj_dev, fj.data(), sizeof(ProcrustesFinish) * (size_t)njobs, stream);
+  if (rc) return rc;
+  const int64_t scr = ((int64_t)block_svd_scratch(camax) + 15) & ~int64_t(15);
+  const int64_t mat = std::max<int64_t>(0, std::min<int64_t>(need, (CANON_SMEM_BYTES - scr) / 8));
+  rc = launch_t("procrustes_svd", block_svd_kernel, njobs, 256, (size_t)(scr + 8 * mat), stream,
+                reinterpret_cast<const BlockSvdJob *>(sj_dev), camax, (int)mat);
+  if (rc) return rc;
+  return launch_t("procrustes", procrustes_finish_kernel, njobs, 256, 2 * 256 * sizeof(double), stream,
+                  reinterpret_cast<const ProcrustesFinish *>(fj_dev));
 }

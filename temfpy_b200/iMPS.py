@@ -106,6 +106,26 @@ def basis_rotation(overlap: np.ndarray, Schmidt_bra, Schmidt_ket, mode: str = "l
     return R, unitary_error, schmidt_error
 
 
+def _procrustes_errors(err2, schmidt_error, mode, numerical_tol, unitary_tol, schmidt_tol):
+    """The bookkeeping of basis_rotation around the two error sums (iMPS.py:139-147, :186-190)."""
+    if err2 < 0:
+        assert_array_less(abs(err2), numerical_tol,
+                          f"{mode.capitalize()} deviation from unitary: the square of the unitary error "
+                          f"{err2} is negative and exceeds the numerical tolerance {numerical_tol:.1e}.")
+        unitary_error = 0.0
+    else:
+        unitary_error = float(np.sqrt(err2))
+    logger.info("%s deviation from unitary: %.4e", mode.capitalize(), unitary_error)
+    if unitary_error > unitary_tol:
+        warnings.warn(f"\n{mode.capitalize()} overlap matrix deviates from unitarity by {unitary_error}.\n"
+                      "Increasing the bond dimension may be useful.")
+    logger.info("%s Schmidt value mixing:   %.4e", mode.capitalize(), schmidt_error)
+    if schmidt_error > schmidt_tol:
+        warnings.warn(f"\nMixing between unequal Schmidt value sectors on the {mode} side is\n"
+                      f"{schmidt_error}. Increasing the number of sites may help.")
+    return unitary_error, float(schmidt_error)
+
+
 def MPS_to_iMPS(*args, **kwargs):
     raise NotImplementedError("MPS_to_iMPS is a generic TeNPy path and out of scope (SURVEY 2.1 #7)")
 
@@ -391,12 +411,42 @@ def slater_C_to_iMPS(C_short, C_long, trunc_par, sites_per_cell, cut, *, diag_to
     blocks, outd, meta = _run_tensors(be, items)
     # ---- gauge fixing: orthogonal Procrustes per charge sector (iMPS.py:65-192) -----------------
     chi_s, chi_l = len(b_short.lam), len(b_long.lam)
-    Cov = np.zeros((chi_s, chi_l))
-    for b, blk in zip(gplan.blocks, blocks[-1]):
-        r0, nr, c0, nc = int(b[0]), int(b[1]), int(b[2]), int(b[3])
-        Cov[gplan.row_alpha[r0: r0 + nr][:, None], np.arange(c0, c0 + nc)[None, :]] = blk
-    R, left_unitary, left_schmidt = basis_rotation(Cov, b_short.lam, b_long.lam, "left", unitary_tol=unitary_tol,
-                                                   schmidt_tol=schmidt_tol, q_bra=b_short.charge, q_ket=b_long.charge)
+    import os
+    gblocks = [(int(b[0]), int(b[1]), int(b[2]), int(b[3])) for b in gplan.blocks]
+    on_device = (not os.environ.get("TMF_HOST_PROCRUSTES") and len(gblocks) > 0
+                 and all(min(nr, nc) <= 160 for (_, nr, _, nc) in gblocks))
+    R, R_d = None, None
+    if on_device:
+        # tmf_procrustes_blocks: SVD of C diag(S_ket^2) per sector, U Vh and the sums behind the two error metrics, on
+        # the overlap blocks where the minors kernel left them; the rotation stays on the device for C . B_0 below
+        R_d = be.from_host(np.zeros(chi_s * chi_l))
+        sk_d = be.from_host(np.ascontiguousarray(b_long.lam, dtype=np.float64))
+        met_d = be.from_host(np.zeros(2 * len(gblocks)))
+        pj = (_lib.ProcrustesJob * len(gblocks))()
+        for u, (r0, nr, c0, nc) in enumerate(gblocks):
+            a0 = int(gplan.row_alpha[r0])
+            assert int(gplan.row_alpha[r0 + nr - 1]) == a0 + nr - 1
+            pj[u].C = be.ptr(outd) + 8 * int(meta[-1]["out"][u])
+            pj[u].sk = be.ptr(sk_d) + 8 * c0
+            pj[u].R = be.ptr(R_d) + 8 * (a0 * chi_l + c0)
+            pj[u].metrics = be.ptr(met_d) + 16 * u
+            pj[u].ldc, pj[u].ldr, pj[u].m, pj[u].n = nc, chi_l, nr, nc
+        wb = int(lib.tmf_procrustes_workspace(pj, len(gblocks)))
+        pwork = be.empty(wb, np.uint8)
+        check(lib, lib.tmf_procrustes_blocks(pj, len(gblocks), be.ptr(pwork), wb, be.stream))
+        be.sync()
+        mt = be.to_host(met_d, 2 * len(gblocks)).reshape(-1, 2)
+        left_unitary, left_schmidt = _procrustes_errors(float(np.sum(np.asarray(b_long.lam) ** 2) - mt[:, 0].sum()),
+                                                        float(np.sqrt(mt[:, 1].sum())), "left", _NUMERICAL_TOL,
+                                                        unitary_tol, schmidt_tol)
+    else:
+        Cov = np.zeros((chi_s, chi_l))
+        for b, blk in zip(gplan.blocks, blocks[-1]):
+            r0, nr, c0, nc = int(b[0]), int(b[1]), int(b[2]), int(b[3])
+            Cov[gplan.row_alpha[r0: r0 + nr][:, None], np.arange(c0, c0 + nc)[None, :]] = blk
+        R, left_unitary, left_schmidt = basis_rotation(Cov, b_short.lam, b_long.lam, "left", unitary_tol=unitary_tol,
+                                                       schmidt_tol=schmidt_tol, q_bra=b_short.charge,
+                                                       q_ket=b_long.charge)
     # ---- assemble; first tensor <- R . B_0 on the device (slater.py:1554) -------------------------
     tensors = []
     for i in range(cell):
@@ -419,20 +469,25 @@ def slater_C_to_iMPS(C_short, C_long, trunc_par, sites_per_cell, cut, *, diag_to
         arows = np.flatnonzero(b_short.charge == q)              # short-chain indices of the same charge
         if arows.size == 0:
             continue
-        Rt = np.ascontiguousarray(R[np.ix_(arows, np.arange(c0, c0 + nc))].T)      # (nc x na) row-major
-        rt_chunks.append(Rt.ravel())
-        gj.append((meta[0]["out"][bi], rt_off, o2_off, nr, nc, arows.size))
+        assert int(arows[-1]) - int(arows[0]) + 1 == arows.size
+        if R_d is None:
+            Rt = np.ascontiguousarray(R[np.ix_(arows, np.arange(c0, c0 + nc))].T)      # (nc x na) row-major
+            rt_chunks.append(Rt.ravel())
+        gj.append((meta[0]["out"][bi], rt_off, o2_off, nr, nc, arows.size, int(arows[0]), c0))
         keep.append((r0, nr, arows))
-        rt_off += Rt.size
+        rt_off += nc * arows.size
         o2_off += nr * arows.size
     if gj:
-        rt_d = be.from_host(np.concatenate(rt_chunks))
+        rt_d = be.from_host(np.concatenate(rt_chunks)) if R_d is None else None
         o2_d = be.empty(o2_off, np.float64)
         jobs = (_lib.GemmJob * len(gj))()
-        for u, (ao, bo, oo, m, k, n) in enumerate(gj):
+        for u, (ao, bo, oo, m, k, n, a0, c0) in enumerate(gj):
             # row-major out (m x n) = B_0 block (m x k: bra rows x long index) . R^T block (k x n: long x short index)
             # == column-major out^T (n x m) = (R^T)^T . (B_0 block)^T
-            jobs[u].A, jobs[u].lda, jobs[u].transA = be.ptr(rt_d) + 8 * bo, n, 0
+            if R_d is None:
+                jobs[u].A, jobs[u].lda, jobs[u].transA = be.ptr(rt_d) + 8 * bo, n, 0
+            else:       # R block in place inside the dense rotation matrix (row-major chi_s x chi_l)
+                jobs[u].A, jobs[u].lda, jobs[u].transA = be.ptr(R_d) + 8 * (a0 * chi_l + c0), chi_l, 1
             jobs[u].B, jobs[u].ldb, jobs[u].transB = be.ptr(outd) + 8 * ao, k, 0
             jobs[u].C, jobs[u].ldc = be.ptr(o2_d) + 8 * oo, n
             jobs[u].M, jobs[u].N, jobs[u].K = n, m, k
@@ -441,7 +496,7 @@ def slater_C_to_iMPS(C_short, C_long, trunc_par, sites_per_cell, cut, *, diag_to
         check(lib, lib.tmf_gemm_grouped(jobs, len(gj), be.ptr(desc), be.stream))
         be.sync()
         o2 = be.to_host(o2_d, o2_off)
-        for (ao, bo, oo, m, k, n), (r0, nr, arows) in zip(gj, keep):
+        for (ao, bo, oo, m, k, n, _a0, _c0), (r0, nr, arows) in zip(gj, keep):
             rows = slice(r0, r0 + nr)
             tensors[0].blocks.append((arows[None, :], plan0.row_p[rows][:, None], plan0.row_alpha[rows][:, None],
                                       o2[oo: oo + m * n].reshape(m, n)))

@@ -118,3 +118,55 @@ def test_gpu_imps_vs_oracle(gpu_backend, Ls, cell, cut, tp):
     # diagnostic reads 3.4e-6 where the reference's own truncation floor is 3.0e-7); the cell itself agrees to 1e-14
     fid = _compare(ref, mps, err, err2_tol=1e-13 if Ls <= 128 else 5e-11)
     print("iMPS cell fidelity", fid, "errors", err)
+
+
+def _procrustes_vs_host(be, seed):
+    """tmf_procrustes_blocks (block SVD kernel + U Vh + metric sums) against iMPS.basis_rotation on the same blocks."""
+    import ctypes as C
+    from temfpy_b200 import _lib
+    rng = np.random.default_rng(seed)
+    sizes = [(1, 1), (5, 5), (17, 17), (40, 40), (12, 9), (9, 12), (64, 64)]
+    q_b = np.concatenate([np.full(m, i) for i, (m, _) in enumerate(sizes)])
+    q_k = np.concatenate([np.full(n, i) for i, (_, n) in enumerate(sizes)])
+    nb, nk = len(q_b), len(q_k)
+    Cov = np.zeros((nb, nk))
+    r0 = c0 = 0
+    for m, n in sizes:        # near-isometric blocks (as in the iMPS conversion) with a little noise
+        Q = np.linalg.qr(rng.normal(size=(max(m, n), max(m, n))))[0][:m, :n]
+        Cov[r0: r0 + m, c0: c0 + n] = Q + 1e-3 * rng.normal(size=(m, n))
+        r0, c0 = r0 + m, c0 + n
+    Sk = np.sort(rng.uniform(0.01, 1.0, size=nk))[::-1]
+    Sb = np.sort(rng.uniform(0.01, 1.0, size=nb))[::-1]
+    R_ref, u_ref, s_ref = iMPS.basis_rotation(Cov, Sb, Sk, "left", unitary_tol=10, schmidt_tol=10, q_bra=q_b, q_ket=q_k)
+    Cd, Skd = be.from_host(Cov.ravel()), be.from_host(Sk)
+    Rd = be.from_host(np.zeros(nb * nk))
+    met = be.from_host(np.zeros(2 * len(sizes)))
+    jobs = (_lib.ProcrustesJob * len(sizes))()
+    r0 = c0 = 0
+    for u, (m, n) in enumerate(sizes):
+        j = jobs[u]
+        j.C = be.ptr(Cd) + 8 * (r0 * nk + c0)
+        j.sk = be.ptr(Skd) + 8 * c0
+        j.R = be.ptr(Rd) + 8 * (r0 * nk + c0)
+        j.metrics = be.ptr(met) + 16 * u
+        j.ldc = j.ldr = nk
+        j.m, j.n = m, n
+        r0, c0 = r0 + m, c0 + n
+    wb = int(be.lib.tmf_procrustes_workspace(jobs, len(sizes)))
+    work = be.empty(wb, np.uint8)
+    _lib.check(be.lib, be.lib.tmf_procrustes_blocks(jobs, len(sizes), be.ptr(work), wb, be.stream))
+    be.sync()
+    R = be.to_host(Rd, nb * nk).reshape(nb, nk)
+    mt = be.to_host(met, 2 * len(sizes)).reshape(-1, 2)
+    assert np.abs(R - R_ref).max() < 1e-11, np.abs(R - R_ref).max()
+    err2 = float(np.sum(Sk ** 2) - mt[:, 0].sum())
+    assert abs(err2 - u_ref ** 2) < 1e-12 and abs(np.sqrt(mt[:, 1].sum()) - s_ref) < 1e-12
+
+
+def test_sim_procrustes_blocks(sim_backend):
+    _procrustes_vs_host(sim_backend, 3)
+
+
+@pytest.mark.gpu
+def test_gpu_procrustes_blocks(gpu_backend):
+    _procrustes_vs_host(gpu_backend, 4)
