@@ -95,8 +95,8 @@ def _validate(mps):
     assert mps.site_type == "FermionSite", f"All sites must be fermionic, found: {mps.site_type}"
     if mps.conserve not in ("N", "parity"):
         raise ValueError(f"FermionSite must conserve either 'N' or 'parity', found {mps.conserve!r}")
-    if mps.bc != "finite":
-        raise NotImplementedError(f"Boundary condition {mps.bc!r} not supported in this release")
+    if mps.bc not in ("finite", "infinite"):
+        raise NotImplementedError(f"Boundary condition {mps.bc!r} not supported")          # gutzwiller.py:207-208
 
 
 @dataclass
@@ -148,7 +148,7 @@ def _blocks_of(mps, i, mod):
         return out
     T = t.dense()
     cL, cR = np.asarray(mps.charges[i]).ravel(), np.asarray(mps.charges[i + 1]).ravel()
-    qt = int(getattr(t, "qtotal", 0) or 0)
+    qt = int(getattr(t, "qtotal", 0) or 0)          # q(vL) + p - q(vR) (unit cells: the last tensor carries the filling)
     for qL in np.unique(cL):
         iL = np.flatnonzero(cL == qL)
         for p in (0, 1):
@@ -404,11 +404,187 @@ def _canonical_form_device(be, dev, qvirt, qp, cutoff):
     return tensors, lams, charges
 
 
+def _infer_qtot(tensors, qs, qp):
+    """q(vL) + qp[s] - q(vR) of every tensor of a unit cell (constant over its non-zero entries)."""
+    out = []
+    L = len(tensors)
+    for j, t in enumerate(tensors):
+        a, p, b = np.nonzero(np.abs(t) > 0)
+        if a.size == 0:
+            out.append(0)
+            continue
+        d = np.unique(np.asarray(qs[j])[a] + np.asarray(qp)[p] - np.asarray(qs[(j + 1) % L])[b])
+        assert d.size == 1, f"spin tensor {j} mixes total charges {d}"
+        out.append(int(d[0]))
+    return out
+
+
+def _sectors(q):
+    q = np.asarray(q)
+    return [(int(v), np.flatnonzero(q == v)) for v in np.unique(q)]
+
+
+def _cell_map_right(T, r):
+    """r (bond 0 of the next cell) -> sum over the cell of T r T^+ (bond 0)."""
+    for t in reversed(T):
+        r = np.einsum("apb,bc,dpc->ad", t, r, t.conj(), optimize=True)
+    return r
+
+
+def _cell_map_left(T, l):
+    for t in T:
+        l = np.einsum("apb,ac,cpd->bd", t.conj(), l, t, optimize=True)
+    return l
+
+
+def _dominant(apply, n, dtype):
+    """Dominant eigenpair of a completely positive map on n x n matrices, started from the identity (so that the
+    iterates keep the block structure of the charge sectors exactly): Arnoldi, power iteration as a fallback."""
+    v0 = np.eye(n, dtype=dtype).ravel()
+    try:
+        from scipy.sparse.linalg import LinearOperator, eigs
+        if n * n <= 4:
+            raise ValueError
+        op = LinearOperator((n * n, n * n), matvec=lambda v: apply(v.reshape(n, n)).ravel(), dtype=np.complex128)
+        w, v = eigs(op, k=1, which="LM", v0=v0.astype(np.complex128), tol=1e-14, maxiter=5000)
+        eta, m = w[0], v[:, 0].reshape(n, n)
+    except Exception:
+        m = v0.reshape(n, n)
+        eta = 1.0
+        for _ in range(20000):
+            m2 = apply(m)
+            eta2 = np.linalg.norm(m2)
+            m2 = m2 / eta2
+            if np.linalg.norm(m2 - m) < 1e-15:
+                m, eta = m2, eta2
+                break
+            m, eta = m2, eta2
+    m = m / (np.trace(m) / abs(np.trace(m)))          # Hermitian positive up to a phase
+    m = (m + m.conj().T) / 2
+    if np.trace(m).real < 0:
+        m = -m
+    return abs(eta), (m if np.iscomplexobj(np.zeros(1, dtype=dtype)) else m.real)
+
+
+def _canonical_form_infinite(tensors, qs, qp, qtot, cutoff=1e-12):
+    """Right-canonical form of an infinite MPS given by the bare tensors ``T_j[vL, p, vR]`` of a unit cell (the job of
+    ``canonical_form_infinite1`` at gutzwiller.py:268 / :473), block-wise in the charges: ``qs[j]`` flat charges of
+    bond j (bond L is bond 0 of the next cell), ``q(vL) + qp[p] - qtot[j] = q(vR)``.
+
+    Dominant left / right eigenvectors l, r of the cell transfer matrix; r = X X^+, l = Y^+ Y per sector, SVD of Y X
+    gives the basis of bond 0 in which r = 1 and l = lambda^2; a right-to-left SVD sweep makes the inner tensors
+    right-canonical, a left-to-right pass of the left environment diagonalises it on the inner bonds.
+    Returns (tensors, lams, charges)."""
+    L = len(tensors)
+    T = [np.asarray(t) for t in tensors]
+    dtype = np.result_type(*[t.dtype for t in T])
+    qs = [np.asarray(q) for q in qs[:L]]
+    qp = np.asarray(qp)
+    n0 = T[0].shape[0]
+    eta, r = _dominant(lambda m: _cell_map_right(T, m), n0, dtype)
+    T = [t / eta ** (0.5 / L) for t in T]
+    _, l = _dominant(lambda m: _cell_map_left(T, m), n0, dtype)
+    # bond 0: per charge sector  r = X X^+,  l = Y^+ Y,  Y X = U lam V^+  ->  G = X V,  G^-1 = V^+ X^-1
+    cols, icols, lam0, q0 = [], [], [], []
+    for q, idx in _sectors(qs[0]):
+        wr, Ur = np.linalg.eigh(r[np.ix_(idx, idx)])
+        wl, Ul = np.linalg.eigh(l[np.ix_(idx, idx)])
+        kr, kl = wr > 1e-14 * max(wr.max(), 1e-300), wl > 1e-14 * max(wl.max(), 1e-300)
+        if not kr.any() or not kl.any():
+            continue
+        X = Ur[:, kr] * np.sqrt(wr[kr])[None, :]
+        Xi = (Ur[:, kr] / np.sqrt(wr[kr])[None, :]).conj().T
+        Y = np.sqrt(wl[kl])[:, None] * Ul[:, kl].conj().T
+        U, sv, Vh = _svd(Y @ X)
+        cols.append((idx, X @ Vh.conj().T))
+        icols.append((idx, Vh @ Xi))
+        lam0.append(sv)
+        q0 += [q] * len(sv)
+    lam0 = np.concatenate(lam0)
+    keep0 = lam0 > cutoff * lam0.max()
+    k0 = int(keep0.sum())
+    G, Gi = np.zeros((n0, len(lam0)), dtype=dtype), np.zeros((len(lam0), n0), dtype=dtype)
+    o = 0
+    for (idx, g), (_, gi) in zip(cols, icols):
+        w = g.shape[1]
+        G[idx, o: o + w] = g
+        Gi[o: o + w, idx] = gi
+        o += w
+    G, Gi, lam0, q0 = G[:, keep0], Gi[keep0], lam0[keep0], np.array(q0, dtype=np.int64)[keep0]
+    lam0 = lam0 / np.linalg.norm(lam0)
+    # right-to-left sweep: B_j = Vh of (T_j G_{j+1}), G_j = U S
+    newq = [None] * (L + 1)
+    newq[0] = newq[L] = q0
+    B = [None] * L
+    Gr = G
+    for j in range(L - 1, 0, -1):
+        A = np.tensordot(T[j], Gr, axes=(2, 0))                       # (a_j, 2, k_{j+1})
+        a, d, b = A.shape
+        colq = (newq[j + 1][None, :] - qp[:, None] + qtot[j]).ravel()
+        M = A.reshape(a, d * b)
+        parts, nq = [], []
+        for q, rows in _sectors(qs[j]):
+            c = np.flatnonzero(colq == q)
+            if c.size == 0:
+                continue
+            U, S, Vh = _svd(M[np.ix_(rows, c)])
+            kp = S > cutoff * max(S.max(), 1e-300)
+            parts.append((rows, c, U[:, kp] * S[kp][None, :], Vh[kp]))
+            nq += [q] * int(kp.sum())
+        k = len(nq)
+        Gn, Bj = np.zeros((a, k), dtype=dtype), np.zeros((k, d * b), dtype=dtype)
+        o = 0
+        for rows, c, us, vh in parts:
+            w = vh.shape[0]
+            Gn[rows, o: o + w] = us
+            Bj[o: o + w, c] = vh
+            o += w
+        B[j] = Bj.reshape(k, d, b)
+        newq[j] = np.array(nq, dtype=np.int64)
+        Gr = Gn
+    B[0] = np.tensordot(Gi, np.tensordot(T[0], Gr, axes=(2, 0)), axes=(1, 0)) if L > 1 else \
+        np.tensordot(Gi, np.tensordot(T[0], G, axes=(2, 0)), axes=(1, 0))
+    # left-to-right: diagonalise the left environment on the inner bonds
+    lams = [None] * (L + 1)
+    lams[0] = lams[L] = lam0
+    lcur = np.diag(lam0 ** 2).astype(dtype)
+    for j in range(L - 1):
+        ln = np.einsum("apb,ac,cpd->bd", B[j].conj(), lcur, B[j], optimize=True)
+        k = ln.shape[0]
+        W, w_all = np.zeros((k, k), dtype=dtype), np.zeros(k)
+        for q, idx in _sectors(newq[j + 1]):
+            w, U = np.linalg.eigh(ln[np.ix_(idx, idx)])
+            W[np.ix_(idx, idx)] = U[:, ::-1]
+            w_all[idx] = w[::-1]
+        w_all = np.clip(w_all, 0.0, None)
+        B[j] = np.tensordot(B[j], W, axes=(2, 0))
+        B[j + 1] = np.tensordot(W.conj().T, B[j + 1], axes=(1, 0))
+        lam = np.sqrt(w_all)
+        lams[j + 1] = lam / np.linalg.norm(lam)
+        lcur = np.diag(w_all / w_all.sum()).astype(dtype)
+    return B, lams, newq
+
+
 def _finish(mps, tensors, keepers, qvirt, qp, conserve, return_canonical, cutoff, unit_cell_width, info, be=None):
     import os
     Ls = len(tensors)
     meta = dict(gemm_jobs=info["chains"], kept=[len(k) for k in keepers], resident_operands=info["resident_operands"],
                 staged_elems=info["staged_elems"])
+    if mps.bc == "infinite":
+        qtot = _infer_qtot(tensors, qvirt, qp)
+        if return_canonical:
+            T, lams, qs = _canonical_form_infinite(tensors, qvirt, qp, qtot, max(cutoff, 1e-14))      # :268 / :473
+            form = ["B"] * Ls
+            meta["canonical_form"] = "host"
+            logger.info("Transformed MPS to right canonical form")
+        else:
+            warn("The MPS is not in canonical form after Gutzwiller projection.\n"
+                 "Consider setting 'return_canonical=True'")
+            T, qs, form = tensors, list(qvirt) + [qvirt[0]], [None] * Ls
+            lams = [np.ones(len(q)) / np.sqrt(max(len(q), 1)) for q in qs]
+        return BlockMPS(L=Ls, tensors=[DenseSite(t, int(qt)) for t, qt in zip(T, qtot)], lams=lams, charges=qs,
+                        form=form, unit_cell_width=unit_cell_width, ortho_center=None, bc="infinite",
+                        site_type="SpinHalfSite", conserve=conserve, meta=meta)
     if return_canonical:
         got = None
         mode = os.environ.get("TMF_CANONICAL_FORM", CANONICAL_FORM)
@@ -440,19 +616,29 @@ def abrikosov(mps: BlockMPS, *, inplace: bool = False, return_canonical: bool = 
     _validate(mps)
     if inplace:
         raise NotImplementedError("`inplace=True` is not supported: BlockMPS results are immutable")
-    total = int(np.asarray(mps.charges[mps.L]).ravel()[0])
     target = mps.L // 2
+    if mps.bc == "finite":
+        total = int(np.asarray(mps.charges[mps.L]).ravel()[0])
+        if q_left not in (None, 0):
+            warn(f"`q_left` must be 0 for finite MPS, got {q_left = }, setting it to 0.")
+        q_left = 0
+    else:                                                                              # gutzwiller.py:197-205
+        total = int(sum(int(getattr(t, "qtotal", 0) or 0) for t in mps.tensors))
+        if q_left is None:
+            raise ValueError("Must specify `q_left` for infinite MPS.")
+        sectors0 = np.unique(np.asarray(mps.charges[0]).ravel())
+        if q_left not in sectors0:
+            raise ValueError(f"`q_left` must be a charge sector of the leftmost virtual leg, got {q_left = }, "
+                             f"valid sectors are {sectors0}")
     err = f"Total charge must match number of spin sites. Got {total}, expected {target}"
     if mps.conserve == "N":
         assert total == target, err                                                    # gutzwiller.py:177-186
         mod = 0
-        keep = lambda j, q: number_mask(q, j)        # exactly one fermion per pair: bond 2j carries charge j (:236-238)
+        keep = lambda j, q: number_mask(q, q_left + j)   # one fermion per pair: bond 2j carries q_left + j (:236-238)
     else:
         assert total % 2 == target % 2, err + " (mod 2)"
         mod = 2
-        keep = lambda j, q: parity_mask(q, j)
-    if q_left not in (None, 0):
-        warn(f"`q_left` must be 0 for finite MPS, got {q_left = }, setting it to 0.")
+        keep = lambda j, q: parity_mask(q, q_left + j)
     ucw = _check_unit_cell_width(mps, unit_cell_width)
     be = _backend or _sl._be()
     tensors, keepers, info = _project(mps, keep, ((0, 1, 0), (1, 0, 1)), be, mod)
@@ -472,19 +658,26 @@ def abrikosov_ph(mps: BlockMPS, *, inplace: bool = False, return_canonical: bool
     _validate(mps)
     if inplace:
         raise NotImplementedError("`inplace=True` is not supported: BlockMPS results are immutable")
-    total = int(np.asarray(mps.charges[mps.L]).ravel()[0])
+    finite = mps.bc == "finite"
+    total = int(np.asarray(mps.charges[mps.L]).ravel()[0]) if finite else \
+        int(sum(int(getattr(t, "qtotal", 0) or 0) for t in mps.tensors))
     assert total % 2 == 0, f"Total fermion parity of MPS must be even, got {total}"
-    if parity != 0:
-        warn(f"Must use even parity sector in finite MPS, ignoring {parity = }")
-    if offset != 0 and mps.conserve == "N":
-        warn(f"Cannot offset charge of finite MPS, ignoring {offset = }")
+    if finite:
+        if parity != 0:
+            warn(f"Must use even parity sector in finite MPS, ignoring {parity = }")
+        if offset != 0 and mps.conserve == "N":
+            warn(f"Cannot offset charge of finite MPS, ignoring {offset = }")
+        offset = parity = 0
     ucw = _check_unit_cell_width(mps, unit_cell_width)
     be = _backend or _sl._be()
-    keep = lambda j, q: parity_mask(q, 0)
+    keep = lambda j, q: parity_mask(q, parity)                                               # :416-417
     # (0,0) -> down (index 0, 2Sz = -1), (1,1) -> up (index 1, 2Sz = +1)
     tensors, keepers, info = _project(mps, keep, ((0, 0, 0), (1, 1, 1)), be, 0 if mps.conserve == "N" else 2)
     if mps.conserve == "N":
-        qvirt = [np.asarray(mps.charges[2 * j])[keepers[j]].astype(np.int64) - j for j in range(len(keepers))]  # :437-441
+        nbond = len(keepers)
+        bond = (lambda j: 2 * j) if finite else (lambda j: (2 * j) % mps.L)
+        qvirt = [np.asarray(mps.charges[bond(j)])[keepers[j]].astype(np.int64) - (offset + j)
+                 for j in range(nbond)]                                                      # :437-441
         qp, conserve = np.array([-1, 1], dtype=np.int64), "Sz"
     else:
         qvirt = [np.zeros(len(k), dtype=np.int64) for k in keepers]

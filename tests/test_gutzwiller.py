@@ -345,3 +345,92 @@ def test_sim_project_kernel_vs_numpy(sim_backend, cplx):
 @pytest.mark.parametrize("cplx,seed", [(False, 1), (True, 2), (False, 3)])
 def test_gpu_project_kernel_vs_numpy(gpu_backend, cplx, seed):
     _project_kernel_vs_numpy(gpu_backend, cplx, seed)
+
+
+# ---------------------------------------------------------------------------------------------
+# infinite MPS input (gutzwiller.py:197-205, :236-244, :268 / :473)
+# ---------------------------------------------------------------------------------------------
+def _heis_two_site(Ba, Bb, lam_left, kind):
+    """<S_i . S_{i+1}> of two neighbouring right-canonical tensors with the Schmidt values on their left bond."""
+    Sz, Sp, Sm = spin_ops(kind)
+    theta = np.einsum("a,apb,bqc->apqc", lam_left, Ba, Bb)
+    val = 0.0
+    for Oa, Ob, w in ((Sz, Sz, 1.0), (Sp, Sm, 0.5), (Sm, Sp, 0.5)):
+        val += w * np.einsum("apqc,rp,sq,arsc->", theta.conj(), Oa, Ob, theta).real
+    return val / np.einsum("apqc,apqc->", theta.conj(), theta).real
+
+
+def _infinite_vs_finite(be, kind, q_left=0):
+    """The Gutzwiller-projected unit cell of slater.C_to_iMPS against the centre of a long finite chain projected the
+    same way (gapped, dimerised chain: finite-size and truncation effects are exponentially small): canonical-form
+    conditions, and the nearest-neighbour <S.S> on the two inequivalent bonds."""
+    from tests.test_imps import dimer_chain
+    fn = gw.abrikosov if kind == "simple" else gw.abrikosov_ph
+    kw = dict(q_left=q_left) if kind == "simple" else {}
+    tp = {"chi_max": 64, "svd_min": 1e-6}
+    Ls, cell, cut = 28, 2, 14
+    Cs, _ = so.correlation_matrix(dimer_chain(Ls, tnn=0.0))
+    Cl, _ = so.correlation_matrix(dimer_chain(Ls + cell, tnn=0.0))
+    im, _err = slater.C_to_iMPS(Cs, Cl, tp, cell, cut, spinful=kind, _backend=be, as_tenpy=False)
+    bare = fn(im, return_canonical=False, _backend=be, **kw)
+    sp = fn(im, return_canonical=True, _backend=be, **kw)
+    assert sp.bc == "infinite" and sp.L == cell and sp.form == ["B"] * cell
+    B = [sp.get_B_dense(i) for i in range(sp.L)]
+    for i in range(sp.L):           # right-canonical, and the left environment lambda^2 is carried to the next bond
+        e = np.einsum("apc,bpc->ab", B[i], B[i].conj())
+        assert np.abs(e - np.eye(len(e))).max() < 1e-9, (i, np.abs(e - np.eye(len(e))).max())
+        le = np.einsum("apb,a,apc->bc", B[i].conj(), sp.lams[i] ** 2, B[i])
+        assert np.abs(le - np.diag(sp.lams[i + 1] ** 2)).max() < 1e-9, i
+        assert abs(np.linalg.norm(sp.lams[i]) - 1) < 1e-12
+    # same state as the bare projected cell: mixed transfer matrix
+    from tests.test_imps import cell_transfer_eig
+    A = [bare.get_B_dense(i) for i in range(bare.L)]
+    fid = abs(cell_transfer_eig(A, B)) ** 2 / abs(cell_transfer_eig(A, A) * cell_transfer_eig(B, B))
+    assert fid > 1 - 1e-9, fid
+    if kind == "PH":                # 2 Sz charges: q(vL) + q_p - qtotal = q(vR), bond L = bond 0
+        qp = np.array([-1, 1])
+        for i in range(sp.L):
+            a, p, b = np.nonzero(np.abs(B[i]) > 1e-13)
+            assert np.all(sp.charges[i][a] + qp[p] - sp.tensors[i].qtotal == sp.charges[i + 1][b])
+        assert np.array_equal(sp.charges[0], sp.charges[sp.L])
+    # against the centre of a finite chain
+    Lf = 40
+    Cf, _ = so.correlation_matrix(dimer_chain(Lf, tnn=0.0))
+    fin = fn(slater.C_to_MPS(Cf, tp, spinful=kind, _backend=be, as_tenpy=False), _backend=be)
+    Bf = [fin.get_B_dense(i) for i in range(fin.L)]
+    j = Lf // 2                     # even site: same position inside the dimer as cell site 0
+    want = [_heis_two_site(Bf[j], Bf[j + 1], fin.lams[j], kind), _heis_two_site(Bf[j + 1], Bf[j + 2], fin.lams[j + 1], kind)]
+    got = [_heis_two_site(B[0], B[1], sp.lams[0], kind), _heis_two_site(B[1], B[0], sp.lams[1], kind)]
+    assert np.abs(np.array(got) - np.array(want)).max() < 1e-4, (got, want)
+    return got, want
+
+
+@pytest.mark.parametrize("kind", ["simple", "PH"])
+def test_sim_infinite_input(sim_backend, kind):
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _infinite_vs_finite(sim_backend, kind)
+
+
+def test_sim_infinite_validation(sim_backend):
+    from tests.test_imps import dimer_chain
+    import warnings
+    Cs, _ = so.correlation_matrix(dimer_chain(20, tnn=0.0))
+    Cl, _ = so.correlation_matrix(dimer_chain(22, tnn=0.0))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        im, _ = slater.C_to_iMPS(Cs, Cl, {"chi_max": 32}, 2, 10, spinful="simple", _backend=sim_backend, as_tenpy=False)
+    with pytest.raises(ValueError):
+        gw.abrikosov(im, _backend=sim_backend)                      # q_left is mandatory (gutzwiller.py:199-200)
+    with pytest.raises(ValueError):
+        gw.abrikosov(im, q_left=99, _backend=sim_backend)           # not a sector of the leftmost leg (:201-205)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["simple", "PH"])
+def test_gpu_infinite_input(gpu_backend, kind):
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        print(_infinite_vs_finite(gpu_backend, kind))
