@@ -20,8 +20,9 @@ Input: the :class:`~temfpy_b200.mps.BlockMPS` returned by ``slater.C_to_MPS(...,
 ``return_canonical=True`` brings the result to right-canonical form like ``canonical_form_finite``
 (gutzwiller.py:266 / :471): QR and SVD sweeps over the (small, chi_proj ~ chi/2) projected tensors, block-wise in
 the charges -- on the host by default, on the device with ``CANONICAL_FORM = "device"`` (``tmf_canon_*``, see there).
-Input may conserve the fermion number (Slater) or the parity (Pfaffian, complex tensors).  Infinite MPS input is
-not supported in this release.
+Input may conserve the fermion number (Slater) or the parity (Pfaffian, complex tensors), and may be finite or the
+unit cell of an infinite MPS (``slater.C_to_iMPS``; ``q_left`` / ``parity`` / ``offset`` as in the reference, canonical
+form by the fixed points of the cell transfer matrix).
 """
 from __future__ import annotations
 
