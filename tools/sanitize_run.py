@@ -20,7 +20,7 @@ for kw in (dict(), dict(nested=False), dict(device_plan=False), dict(snap=True))
 Cc, nc = so.correlation_matrix(so.hopping_chain(48))
 res = helpers.run_native(be, Cc, {"chi_max": 24, "svd_min": 1e-7}, nc, n_chunks=2)
 print("chain 2 chunks", res.stats["max_chi"], flush=True)
-m = pfaffian.H_to_MPS(po.bdg_chain(12, mu=0.0, delta=0.05), {"chi_max": 16}, as_tenpy=False)
+m = pfaffian.H_to_MPS(po.bdg_chain(12, mu=0.0, delta=0.05), {"chi_max": 16}, basis="C", as_tenpy=False)
 print("pfaffian", m.chi, flush=True)
 H1 = np.zeros((24, 24)); H2 = np.zeros((26, 26))
 for H in (H1, H2):
