@@ -289,7 +289,21 @@ def run_native(args):
     # tensor kernels (P2P stores into a peer window on rank 0, dist.FusedGather); TMF_GATHER=nccl selects the
     # NCCL send/recv gather after the conversion (streaming, or TMF_SIMPLE_GATHER for the plain one).
     mode = os.environ.get("TMF_GATHER", "fused") if world > 1 else None
-    fused = tdist.FusedGather(be) if mode == "fused" else None
+    fused = None
+    if mode == "fused":
+        # the peer window needs CUDA IPC between the ranks; if any rank cannot set it up all ranks take the NCCL gather
+        import torch.distributed as dist
+        ok = 1
+        try:
+            fused = tdist.FusedGather(be)
+            fused._ensure(1 << 20)
+        except Exception as exc:      # noqa: BLE001
+            print(f"[bench] rank {rank}: fused gather unavailable ({exc!r}), using the NCCL gather", file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int64, device=be.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            fused, mode = None, "nccl"
     gather = tdist.StreamingGather(be.device) if mode == "nccl" and not os.environ.get("TMF_SIMPLE_GATHER") else None
 
     def step(collect_stats=False, n_chunks=None):

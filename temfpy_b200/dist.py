@@ -271,11 +271,16 @@ class PeerWindow:
         info = [None]
         if self.cuda:
             if self.rank == dst:
-                self.buf = be.empty(self.nbytes, np.uint8)
-                h, off = C.create_string_buffer(64), C.c_int64()
-                check(be.lib, be.lib.tmf_ipc_export(be.ptr(self.buf), h, C.byref(off)))
-                info = [(h.raw, int(off.value))]
+                try:
+                    self.buf = be.empty(self.nbytes, np.uint8)
+                    h, off = C.create_string_buffer(64), C.c_int64()
+                    check(be.lib, be.lib.tmf_ipc_export(be.ptr(self.buf), h, C.byref(off)))
+                    info = [(h.raw, int(off.value))]
+                except Exception as exc:          # the others must not wait for a handle that never comes
+                    info = [("failed", repr(exc))]
             dist.broadcast_object_list(info, src=dst)
+            if info[0][0] == "failed":
+                raise RuntimeError(f"peer window: export failed on rank {dst}: {info[0][1]}")
             if self.rank == dst:
                 self.ptr = be.ptr(self.buf)
             else:
@@ -431,6 +436,14 @@ class HostExchange:
         self.mine = []          # segments this rank fills
         self.peers = {}         # dst: (rank, index) -> _Segment
         atexit.register(self.close)
+        # every rank must be able to create, map and register shared memory; otherwise all ranks use the NCCL gather
+        ok = 1
+        try:
+            probe = _Segment(f"{self.prefix}_probe_r{self.rank}", 1 << 16, be.lib, create=True)
+            probe.close()
+        except Exception:
+            ok = 0
+        self.usable = bool(self.board.all_gather([ok])[:, 0].min())
 
     def _acquire(self, need):
         for i, seg in enumerate(self.mine):
@@ -565,6 +578,11 @@ def C_to_MPS(C, trunc_par, *, ortho_center=None, spinful=None, unit_cell_width=N
     world, rank = dist.get_world_size(), dist.get_rank()
     be = backend or slater._be()
     tp = to_stopping_condition(trunc_par)
+    if host_exchange:           # (shared pinned segments must work on every rank, else the NCCL gather)
+        key = (id(be), dst)
+        if key not in _exchanges:
+            _exchanges[key] = HostExchange(be, dst)
+        host_exchange = _exchanges[key].usable
     meta = [None]
     if rank == dst:
         Cp = slater._prepare_C(np.asarray(C), spinful)
@@ -633,9 +651,7 @@ def C_to_MPS(C, trunc_par, *, ortho_center=None, spinful=None, unit_cell_width=N
         # every GPU copies its shard into a shared pinned host segment over its own PCIe link; dst maps the segments
         # and wraps tensors and tables in place
         key = (id(be), dst)
-        ex = _exchanges.get(key)
-        if ex is None:
-            ex = _exchanges[key] = HostExchange(be, dst)
+        ex = _exchanges[key]
         got = ex.send(res)
         res.close()
         if rank != dst:
