@@ -283,6 +283,18 @@ class _PfChain:
     def modes(self):
         be, lib, L, oc = self.be, self.lib, self.L, self.oc
         self.Pd = be.from_host(_embed(self.CM).ravel())
+        # the kernels use P'^2 = P' (a Bogoliubov vacuum); anything else is not an input the reference converts either
+        # (its Nambu / spectrum assertions, pfaffian.py:795-800)
+        n4 = 4 * L
+        r = min(64, n4)
+        T = be.empty(r * n4 + 1, np.float64)
+        desc = be.empty(int(lib.tmf_gemm_desc_bytes(1)), np.uint8)
+        check(lib, lib.tmf_projector_defect(be.ptr(self.Pd), n4, n4, r, be.ptr(T), be.ptr(desc), be.stream))
+        be.sync()
+        defect = float(be.to_host(T[r * n4:], 1)[0])
+        if not defect <= 1e-8:
+            raise ValueError("`C` is not the correlation matrix of a Bogoliubov vacuum "
+                             f"(max|C^2 - C| = {defect:.2e} in the Majorana basis)")
         jobs = [(x, _lib.SIDE_L) for x in range(1, oc + 1)] + [(x, _lib.SIDE_R) for x in range(oc, L)]
         self.jobs = jobs
         self.job_of = {j: i for i, j in enumerate(jobs)}

@@ -223,6 +223,8 @@ def test_sim_ortho_center_and_errors(sim_backend):
         pf.C_to_MPS(Cm, tp, basis="X", _backend=sim_backend)
     with pytest.raises(ValueError):
         pf.C_to_MPS(Cm, tp, basis="C", unit_cell_width=3, _backend=sim_backend)
+    with pytest.raises(ValueError, match="Bogoliubov vacuum"):          # a mixed state: C^2 != C
+        pf.C_to_MPS(0.9 * Cm + 0.05 * np.eye(len(Cm)), tp, basis="C", _backend=sim_backend)
 
 
 # ---------------------------------------------------------------------------------------------
