@@ -288,22 +288,34 @@ def run_native(args):
     # N > 1: the tensors of all ranks end up in one buffer in rank 0's HBM.  Default: the gather is fused into the
     # tensor kernels (P2P stores into a peer window on rank 0, dist.FusedGather); TMF_GATHER=nccl selects the
     # NCCL send/recv gather after the conversion (streaming, or TMF_SIMPLE_GATHER for the plain one).
-    mode = os.environ.get("TMF_GATHER", "fused") if world > 1 else None
-    fused = None
-    if mode == "fused":
-        # the peer window needs CUDA IPC between the ranks; if any rank cannot set it up all ranks take the NCCL gather
+    mode = os.environ.get("TMF_GATHER", "slotted") if world > 1 else None
+    fused, slotted = None, False
+    if mode in ("fused", "slotted", "exchange"):
+        # the peer window needs CUDA IPC between the ranks; if any rank cannot set it up all ranks take the NCCL gather.
+        # "slotted" (default): slots sized by an upper bound, several pipeline chunks per rank, no exchange before the
+        # completion point; "exchange": exact slices, one chunk per rank, sizes exchanged after the enumeration
         import torch.distributed as dist
         ok = 1
         try:
-            fused = tdist.FusedGather(be)
-            fused._ensure(1 << 20)
+            if mode != "exchange":
+                try:
+                    fused = tdist.SlottedGather(be, L, args.chi)
+                    slotted = True
+                except ValueError:
+                    fused = None
+            if fused is None:
+                fused = tdist.FusedGather(be)
+                fused._ensure(1 << 20)
         except Exception as exc:      # noqa: BLE001
             print(f"[bench] rank {rank}: fused gather unavailable ({exc!r}), using the NCCL gather", file=sys.stderr)
             ok = 0
-        flag = torch.tensor([ok], dtype=torch.int64, device=be.device)
+        flag = torch.tensor([ok, int(slotted)], dtype=torch.int64, device=be.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
+        if int(flag[0].item()) == 0:
             fused, mode = None, "nccl"
+        elif slotted and int(flag[1].item()) == 0:          # (not every rank got the slotted window)
+            fused.close()
+            fused, slotted = tdist.FusedGather(be), False
     gather = tdist.StreamingGather(be.device) if mode == "nccl" and not os.environ.get("TMF_SIMPLE_GATHER") else None
 
     def step(collect_stats=False, n_chunks=None):
@@ -317,7 +329,10 @@ def run_native(args):
         if fused is not None:
             be.sync()
             full, offs = fused.complete()       # every rank's kernels are done: the window on rank 0 is complete
-            state["gathered"] = None if full is None else int(offs[-1])
+            if full is None:
+                state["gathered"] = None
+            else:
+                state["gathered"] = int(sum(n for _, n in offs)) if slotted else int(offs[-1])
         elif world > 1:
             if gather is not None:
                 got = gather.finish(res.out_buffers())
@@ -544,7 +559,9 @@ def run_native(args):
                        "l2": f"working set {(8 * state['out_elems'] + 6e8) / 1e9:.1f} GB per step >> 126 MB L2",
                        "parallelism": (f"sites sharded over {world} GPU(s), broadcast(C) over NCCL, gather(tensors) "
                                        + ("fused into the tensor kernels (P2P stores into a peer window on rank 0 "
-                                          "over NVLink)" if fused is not None else "over NCCL send/recv")
+                                          "over NVLink; " + ("bound-sized slots per pipeline chunk" if slotted else
+                                                             "exact slices, sizes exchanged through shared memory")
+                                          + ")" if fused is not None else "over NCCL send/recv")
                                        if world > 1 else "1 GPU") + f"; {args.chunks or 'auto (3 at >= 384 sites per GPU, 2 at >= 192, else 1)'} pipeline chunks per GPU"},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roof,
             "whole_step": whole, "parity": parity, "cpu_baseline": cpu}

@@ -206,7 +206,7 @@ class HostBoard:
     row (sequence number + two payload banks), publishes its values and spins until all rows carry the sequence
     number.  A few microseconds, no GPU work, no NCCL launch -- used where the ranks must agree on sizes in the
     middle of a conversion (offsets inside the peer window) and as the completion point of a fused gather."""
-    WIDTH = 6
+    WIDTH = 12
 
     def __init__(self, dst=0, timeout=120.0):
         import os
@@ -215,10 +215,10 @@ class HostBoard:
         name = [None]
         if self.rank == dst:
             name = [os.path.join(_shm_dir(), f"tmfpy_board_{os.getpid()}_{id(self):x}")]
-            np.zeros((self.world, 16), dtype=np.int64).tofile(name[0])
+            np.zeros((self.world, 32), dtype=np.int64).tofile(name[0])
         dist.broadcast_object_list(name, src=dst)
         self.path, self.owner = name[0], self.rank == dst
-        self.arr = np.memmap(self.path, dtype=np.int64, mode="r+", shape=(self.world, 16))
+        self.arr = np.memmap(self.path, dtype=np.int64, mode="r+", shape=(self.world, 32))
         self.seq = 0
         dist.barrier()                      # everybody has mapped the file: the name can go
         if self.owner:
@@ -229,7 +229,7 @@ class HostBoard:
         vals = [int(v) for v in vals]
         assert len(vals) <= self.WIDTH
         self.seq += 1
-        bank = 2 + 7 * (self.seq & 1)
+        bank = 2 + 14 * (self.seq & 1)
         row = self.arr[self.rank]
         row[bank: bank + len(vals)] = vals
         row[0] = self.seq                   # published after the payload (x86 keeps the store order)
@@ -365,6 +365,66 @@ class FusedGather:
             return None, None
         offs = np.concatenate(([0], np.cumsum(self.sizes))).astype(np.int64)
         return self.win.slice(0, 8 * int(offs[-1])), offs
+
+    def close(self):
+        if self.win is not None:
+            self.win.close()
+            self.win = None
+
+
+class SlottedGather:
+    """:class:`FusedGather` without the exchange in the middle of the conversion: the window on ``dst`` is laid out by
+    an upper bound of every site's tensor (2 chi_L chi_R elements with chi <= min(chi_max, 2^x, 2^(L-x))), so the
+    slot of a pipeline chunk follows from its site range alone.  Every chunk of every rank writes at its fixed
+    offset as soon as its own tensor stage starts -- several pipeline chunks per rank keep ``dst``'s NVLink port busy
+    while later chunks are still in their mode stage -- and the actual sizes are published once, at the completion
+    point.  ``dst`` ends up with all tensors in its HBM plus the table of (offset, size) per chunk in site order.
+    The bound costs address space, not traffic (17 GB for L = chi_max = 1024); conversions without ``chi_max`` or
+    beyond ``max_bytes`` use :class:`FusedGather`."""
+    multi_chunk = True
+
+    def __init__(self, be, L, chi_max, es=1, dst=0, max_bytes=48 << 30):
+        import torch.distributed as dist
+        if chi_max is None:
+            raise ValueError("SlottedGather needs chi_max")
+        self.be, self.dst, self.es = be, dst, int(es)
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        dmax = [min(int(chi_max), 2 ** min(x, L - x, 40)) for x in range(L + 1)]
+        per_site = np.array([2 * dmax[i] * dmax[i + 1] for i in range(L)], dtype=np.int64) * self.es
+        self.off = np.concatenate(([0], np.cumsum(per_site))).astype(np.int64)      # doubles
+        cap = 8 * int(self.off[-1])
+        if cap > max_bytes:
+            raise ValueError(f"SlottedGather: window of {cap >> 30} GiB exceeds the limit")
+        self.board = HostBoard(dst)
+        self.win = PeerWindow(be, (cap + 255) & ~255, dst)
+        self.chunks = []
+
+    def __call__(self, chain):
+        n = int(chain.tensor_doubles())
+        lo, hi = int(chain.site_lo), int(chain.site_hi)
+        if n > int(self.off[hi] - self.off[lo]):
+            raise RuntimeError("SlottedGather: a chunk exceeds its bound")
+        self.chunks.append((lo, n))
+        return self.win.slice(8 * int(self.off[lo]), 8 * n)
+
+    def abort(self):
+        pass                                    # nobody waits for this rank before the completion point
+
+    def complete(self):
+        """After the local streams are synchronised: (window, [(offset, doubles), ...] in site order) on ``dst`` once
+        every rank's kernels have finished, (None, None) elsewhere."""
+        mine, self.chunks = sorted(self.chunks), []
+        if len(mine) > HostBoard.WIDTH // 2:
+            raise ValueError("too many pipeline chunks for one gather")
+        payload = [-1] * HostBoard.WIDTH
+        for i, (lo, n) in enumerate(mine):
+            payload[2 * i], payload[2 * i + 1] = lo, n
+        got = self.board.all_gather(payload)
+        if self.rank != self.dst:
+            return None, None
+        table = sorted((int(got[r, 2 * i]), int(got[r, 2 * i + 1])) for r in range(self.world)
+                       for i in range(HostBoard.WIDTH // 2) if got[r, 2 * i] >= 0)
+        return self.win.slice(0, self.win.nbytes), [(int(self.off[lo]), n) for lo, n in table]
 
     def close(self):
         if self.win is not None:

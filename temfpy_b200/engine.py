@@ -839,7 +839,7 @@ def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site
     cplx = opts.get("cplx", False)
     keep = opts.get("keep_device", False)
     provider = opts.get("out_provider")
-    if provider is not None:
+    if provider is not None and not getattr(provider, "multi_chunk", False):
         n_chunks = 1                     # one slice of the peer window per rank
     site_hi = L if site_hi is None else site_hi
     nsites = site_hi - site_lo
@@ -880,7 +880,8 @@ def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site
             try:
                 return _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, lo, hi, r_sketch,
                                   n_threads, fetch_tensors, lazy, gate=stages.gate(pos) if stages else None,
-                                  snap=snap, nested=nested, device_plan=device_plan, cplx=cplx, keep_device=keep)
+                                  snap=snap, nested=nested, device_plan=device_plan, cplx=cplx, keep_device=keep,
+                                  out_provider=provider)
             except _Retry as rt:        # the other chunks finish; the driver then starts over
                 return rt
 

@@ -52,3 +52,11 @@ class NumpyBackend:
 
     def sync(self):
         pass
+
+    # pipeline chunks (engine.run_chain with n_chunks > 1): the simulator has no streams
+    def side_stream(self, i):
+        return None
+
+    def stream_context(self, stream):
+        import contextlib
+        return contextlib.nullcontext()

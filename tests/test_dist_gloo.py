@@ -171,3 +171,52 @@ def test_two_rank_fused_gather(tmp_path):
     mp.spawn(_worker_fused, args=(2, _free_port(), 24, 16, out), nprocs=2, join=True)
     ok, n = np.load(out)
     assert ok == 1 and n == 3
+
+
+def _worker_slotted(rank, world, port, L, chi, out_path):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import slater_oracle as so
+        from temfpy_b200 import dist as tdist, engine
+        from temfpy_b200.schmidt_utils import to_stopping_condition
+        from tests import helpers
+        from tests.hostsim import NumpyBackend
+        be = NumpyBackend()
+        tp = to_stopping_condition({"chi_max": chi})
+        Cm, nf = so.correlation_matrix(helpers.random_hamiltonian(L, 12))
+        Ct = np.ascontiguousarray(Cm).ravel()
+        os.environ["TMF_NO_STAGE_GATE"] = "1"             # (the stage gate orders CUDA streams; none in the simulator)
+        slots = tdist.SlottedGather(be, L, chi)
+        lo, hi = tdist.partition(L, world, chi)[rank]
+        oks = []
+        for it in range(2):
+            res = engine.run_chain(be, Ct, L, L, tp, nf, site_lo=lo, site_hi=hi, lazy=True, n_chunks=2,
+                                   out_provider=slots)
+            assert len(res.chains) == 2                    # two pipeline chunks per rank, each with its own slot
+            win, table = slots.complete()
+            if rank == 0:
+                ref = engine.run_chain(be, Ct, L, L, tp, nf, n_chunks=1, lazy=True)
+                rbuf, relems = ref.out_buffers()[0]
+                got = np.concatenate([np.asarray(win)[o: o + n] for o, n in table])
+                oks.append(len(table) == 2 * world and got.size == relems and np.array_equal(got, rbuf[:relems]))
+                ref.close()
+            res.close()
+        slots.close()
+        if rank == 0:
+            np.save(out_path, np.array([int(all(oks)), len(oks)]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_slotted_gather(tmp_path):
+    """SlottedGather: every pipeline chunk of every rank writes into its bound-sized slot of rank 0's window without
+    any exchange before the completion point; the slots, in site order, hold the unsharded result bit for bit."""
+    out = str(tmp_path / "ok.npy")
+    mp.spawn(_worker_slotted, args=(2, _free_port(), 24, 16, out), nprocs=2, join=True)
+    ok, n = np.load(out)
+    assert ok == 1 and n == 2
