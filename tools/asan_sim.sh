@@ -8,7 +8,7 @@ B=/tmp/simasan
 mkdir -p $B
 cd $ROOT/temfpy_b200/csrc
 FLAGS="-O1 -g -std=c++17 -fPIC -ffp-contract=off -pthread -fsanitize=address,undefined -fno-omit-frame-pointer -DTMF_HOSTSIM"
-for f in gemm modes siteprep minors chain misc gutzwiller pfaffian enumerate plan; do g++ $FLAGS -x c++ -c $f.cu -o $B/$f.o 2>/dev/null & done
+for f in gemm modes canon pfsite siteprep siteprep_c pair_c minors minors_c chain misc gutzwiller pfaffian enumerate plan; do g++ $FLAGS -x c++ -c $f.cu -o $B/$f.o 2>/dev/null & done
 g++ $FLAGS -c hostlogic.cpp -o $B/hostlogic.o
 wait
 g++ -shared -pthread -fsanitize=address,undefined -o $B/libtemfpy_b200_hostsim.so $B/*.o
