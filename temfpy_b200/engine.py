@@ -846,7 +846,7 @@ def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site
     if n_chunks is None:
         # (measured on B200 at L = 1024: 3 chunks 14.8 ms, 6 chunks 15.6 ms, 1 chunk 18 ms per conversion -- the host
         #  stages are short since the site planning moved to the device, more chunks only add contention)
-        n_chunks = (3 if nsites >= 384 else 2 if nsites >= 192 else 1) if hasattr(backend, "side_stream") else 1
+        n_chunks = (3 if nsites >= 384 else 2 if nsites >= 192 else 1) if hasattr(backend, "torch") else 1
     n_chunks = max(1, min(n_chunks, nsites))
     if n_chunks == 1:
         r = _run_range(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi, r_sketch,
@@ -865,7 +865,8 @@ def _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site
     cuts = partition(L, n_chunks, trunc.chi_max, ortho_center, lo=site_lo, hi=site_hi, weights=weights)
     backend.sync()                       # C_dev must be complete before the side streams read it
 
-    stages = _StageGate(backend, n_chunks) if not os.environ.get("TMF_NO_STAGE_GATE") else None
+    stages = _StageGate(backend, n_chunks) if hasattr(backend, "torch") and not os.environ.get("TMF_NO_STAGE_GATE") \
+        else None
 
     # pipeline order: natural (left to right) unless TMF_CHUNK_ORDER=ends asks for "chain ends first, centre
     # last"; measured within noise of each other on B200, the natural order brings the tensors to the host sooner

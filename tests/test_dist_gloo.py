@@ -190,7 +190,6 @@ def _worker_slotted(rank, world, port, L, chi, out_path):
         tp = to_stopping_condition({"chi_max": chi})
         Cm, nf = so.correlation_matrix(helpers.random_hamiltonian(L, 12))
         Ct = np.ascontiguousarray(Cm).ravel()
-        os.environ["TMF_NO_STAGE_GATE"] = "1"             # (the stage gate orders CUDA streams; none in the simulator)
         slots = tdist.SlottedGather(be, L, chi)
         lo, hi = tdist.partition(L, world, chi)[rank]
         oks = []
