@@ -24,7 +24,14 @@ def load_sim():
     global _sim
     if _sim is None:
         if not os.environ.get("TMF_SIM_PATH"):
-            subprocess.run(["make", "-s", "-C", CSRC, "hostsim"], check=True, capture_output=True)
+            import fcntl
+            # several test processes (the two-rank gloo tests) may get here at once: one make at a time
+            with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+                fcntl.flock(lock, fcntl.LOCK_EX)
+                try:
+                    subprocess.run(["make", "-s", "-C", CSRC, "hostsim"], check=True, capture_output=True)
+                finally:
+                    fcntl.flock(lock, fcntl.LOCK_UN)
         _sim = _lib.bind(SIM_PATH)
         assert _sim.tmf_is_cuda() == 0
     return _sim
