@@ -327,7 +327,7 @@ typedef struct tmf_pf_site_job {
   double *out;
   double *work_;             /* unused (the kernel works in shared memory) */
   uint32_t idx1_mask, idx2_mask;
-  int sb, sk, sur_b, sur_k, mode, k1, k2, fix, want_n, pad0_;
+  int sb, sk, sur_b, sur_k, mode, k1, k2, fix, want_n, no_phys;  /* no_phys: no physical mode among the bra modes */
   double u_p, ket_sign;
   int pad_[4];
 } tmf_pf_site_job;

@@ -562,3 +562,50 @@ def state_correlators(psi):
             G[i, j] = np.vdot(psi, apply(1, i, apply(0, j, psi)))
             F[i, j] = np.vdot(psi, apply(0, i, apply(0, j, psi)))
     return G, F
+
+
+# --------------------------------------------------------------------------------------------
+# iMPS driver (pfaffian.py:1924-2091)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class PfDenseIMPS:
+    tensors: list          # T[vL, p, vR], right-canonical ("B" form)
+    lams: list             # cell + 1 normalised Schmidt vectors
+    charges: list          # cell + 1 parity arrays (parity left of the bond)
+    errors: tuple          # (left_unitary, left_schmidt, 0.0, 0.0)
+    qtotal: list
+
+
+def C_to_iMPS(C_short, C_long, trunc, sites_per_cell, cut, basis) -> PfDenseIMPS:
+    """pfaffian.py:1924-2091 with dense tensors: Schmidt vectors of both chains at ``cut`` (:1998-2005), right
+    tensors of the additional unit cell of the long chain with the short chain's right environment closing the cell
+    (:2009-2048), gauge fixing of the first tensor by the overlap of the two left Schmidt bases (:2051-2063)."""
+    from slater_oracle import basis_rotation
+    trunc = Trunc.make(trunc)
+    assert len(C_short) // 2 + sites_per_cell == len(C_long) // 2
+
+    def unit(v):
+        return v / np.linalg.norm(v)
+
+    short = bond_vectors_from_C(C_short, cut, trunc, basis)
+    long_ = bond_vectors_from_C(C_long, cut, trunc, basis)
+    lams, tensors, qtot = [unit(short.lam)], [], []
+    charges = [long_.charges(long_.modes.pL)]
+    prev = long_
+    for i in range(sites_per_cell):
+        if i == sites_per_cell - 1:
+            new = short
+            lams.append(lams[0])
+        else:
+            new = bond_vectors_from_C(C_long, cut + i + 1, trunc, basis, "R", long_.modes.parity())
+            lams.append(unit(new.lam))
+        td = tensor_data(new, prev, "right")
+        tensors.append(np.transpose(dense_tensor(td), (2, 0, 1)))
+        charges.append(td.q_bra)
+        qtot.append(td.qtotal)
+        prev = new
+    td = tensor_data(short, long_, "left")                                        # no physical leg
+    R, uerr, serr = basis_rotation(dense_tensor(td), td.q_bra, td.q_ket, short.lam, long_.lam)
+    tensors[0] = np.tensordot(R, tensors[0], axes=(1, 0))
+    charges[0] = td.q_bra
+    return PfDenseIMPS(tensors=tensors, lams=lams, charges=charges, errors=(uerr, serr, 0.0, 0.0), qtotal=qtot)

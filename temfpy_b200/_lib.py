@@ -77,7 +77,7 @@ class PfSiteJob(C.Structure):
     _fields_ = [("S", C.c_void_p), ("rot_up", C.c_void_p), ("rot_lo", C.c_void_p), ("N", C.c_void_p),
                 ("out", C.c_void_p), ("work_", C.c_void_p), ("idx1_mask", C.c_uint32), ("idx2_mask", C.c_uint32),
                 ("sb", C.c_int), ("sk", C.c_int), ("sur_b", C.c_int), ("sur_k", C.c_int), ("mode", C.c_int),
-                ("k1", C.c_int), ("k2", C.c_int), ("fix", C.c_int), ("want_n", C.c_int), ("pad0_", C.c_int),
+                ("k1", C.c_int), ("k2", C.c_int), ("fix", C.c_int), ("want_n", C.c_int), ("no_phys", C.c_int),
                 ("u_p", C.c_double), ("ket_sign", C.c_double), ("pad_", C.c_int * 4)]
 
 

@@ -22,7 +22,7 @@ constexpr int PFS_NX = 44;      // largest dimension of X (2 (k + 1) + surplus)
 TMF_GLOBAL pf_site_kernel(const tmf_pf_site_job *jobs) {
   const tmf_pf_site_job jb = jobs[BLOCK_ID];
   const int sb = jb.sb, sk = jb.sk, sur_b = jb.sur_b, sur_k = jb.sur_k, mode = jb.mode;
-  const int a1 = jb.k1 + 1, a2 = jb.k2;
+  const int a1 = jb.k1 + (jb.no_phys ? 0 : 1), a2 = jb.k2;   // bra modes incl. the physical one (absent: iMPS gauge overlap)
   const int nr = sb + sur_b, nc = sk + sur_k;
   const int nx = sur_b + 2 * a1;                       // X is nx x nx (== sur_k + 2 a2)
   DYN_SMEM(double, sm);
@@ -70,7 +70,7 @@ TMF_GLOBAL pf_site_kernel(const tmf_pf_site_job *jobs) {
     }
   }
   // ---- signs and the physical-mode swap ---------------------------------------------------------------------------
-  const int phys = (mode == 1) ? 0 : jb.k1;
+  const int phys = (mode == 1) ? 0 : a1 - 1;     // the physical mode, or the most entangled bra mode (pfaffian.py:1709-1719)
   const int up0 = sur_b, lo0 = sur_b + 2 * a1;
   const int p0 = up0 + 2 * phys, p1 = lo0 + 2 * phys;   // first rows of the upper / lower pair of the physical mode
   PAR_FOR(idx, nr * nc) {

@@ -362,6 +362,57 @@ class _PfChain:
         if jl is not None and jr is not None and (self.kh[jl] > 0 or self.kh[jr] > 0):
             assert self.kh[jl] == self.kh[jr], "Unequal number of 1/2 modes"               # pfaffian.py:845
             self._centre_half_modes(jl, jr, int(self.kh[jl]))
+        self._align_filled()
+
+    def _align_filled(self):
+        """Makes the basis of the non-entangled ("filled") space of every job orthogonal to its *final* entangled
+        columns.  The mode extraction built that basis as the complement of its raw eigenvectors; ``pair_modes_kernel``
+        then replaced the raw columns of eigenvalue 1 - e by the Nambu partners of the columns of eigenvalue e.  For a
+        mode whose e is close to the cutoff the two differ by the rounding-level mixing angle theta ~ eps / e of an
+        eigenvector with its nearly degenerate neighbours, the filled basis overlaps the partner column by theta and
+        the vacuum-overlap norms come out wrong by theta^2 (5e-8 at e = 3e-12).  F <- F - E (E^T F) restores the exact
+        complement (the basis of an eliminated block does not matter, its span does); the volume the basis loses,
+        sqrt(det(1 - G G^T)) with G = E^T F, is divided out of the per-site determinants (``self.vol``)."""
+        be, lib = self.be, self.lib
+        nj = len(self.jobs)
+        self.vol = np.ones(nj)
+        todo = [j for j in range(nj) if self.k[j] > 0 and self.f[j] > 0]
+        if not todo:
+            return
+        g_off = np.concatenate(([0], np.cumsum([4 * int(self.k[j]) * int(self.f[j]) for j in todo])))
+        m_off = np.concatenate(([0], np.cumsum([(4 * int(self.k[j])) ** 2 for j in todo])))
+        Gd = be.empty(int(g_off[-1]), np.float64)
+        Md = be.empty(int(m_off[-1]), np.float64)
+        desc = be.empty(int(lib.tmf_gemm_desc_bytes(len(todo))), np.uint8)
+        for stage in range(3):
+            g = (_lib.GemmJob * len(todo))()
+            for u, j in enumerate(todo):
+                rows, k4, f = int(self.rows[j]), 4 * int(self.k[j]), int(self.f[j])
+                E = be.ptr(self.Vd) + 8 * int(self.v_off[j])
+                F = E + 8 * rows * k4
+                G = be.ptr(Gd) + 8 * int(g_off[u])
+                q = g[u]
+                q.alpha, q.beta = 1.0, 0.0
+                if stage == 0:      # G (k4 x f) = E^T F
+                    q.A, q.lda, q.transA = E, rows, 1
+                    q.B, q.ldb, q.transB = F, rows, 0
+                    q.C, q.ldc, q.M, q.N, q.K = G, k4, k4, f, rows
+                elif stage == 1:    # F -= E G
+                    q.A, q.lda, q.transA = E, rows, 0
+                    q.B, q.ldb, q.transB = G, k4, 0
+                    q.C, q.ldc, q.M, q.N, q.K = F, rows, rows, f, k4
+                    q.alpha, q.beta = -1.0, 1.0
+                else:               # M (k4 x k4) = G G^T
+                    q.A, q.lda, q.transA = G, k4, 0
+                    q.B, q.ldb, q.transB = G, k4, 1
+                    q.C, q.ldc, q.M, q.N, q.K = be.ptr(Md) + 8 * int(m_off[u]), k4, k4, k4, f
+            check(lib, lib.tmf_gemm_grouped(g, len(todo), be.ptr(desc), be.stream))
+        be.sync()
+        Mh = be.to_host(Md, int(m_off[-1]))
+        for u, j in enumerate(todo):
+            k4 = 4 * int(self.k[j])
+            M = Mh[m_off[u]: m_off[u + 1]].reshape(k4, k4)
+            self.vol[j] = float(np.sqrt(max(np.linalg.det(np.eye(k4) - M), 0.0)))
 
     def _centre_half_modes(self, jl, jr, kh):
         """Eigenvalue-1/2 modes on the central bond (pfaffian.py:857-865, :878-891).  The kernel left, on either
@@ -741,7 +792,8 @@ class _PfChain:
         m_off = out_off = 0
         for u, s in enumerate(self.sites):
             m, n1, n2 = per_site[u]
-            norm = (abs(self.det_host[s["i"]]) * out2[u, 0]) ** 0.25                         # :1352, :1359
+            vol = (self.vol[s["jb"]] if s["jb"] is not None else 1.0) * (self.vol[s["jk"]] if s["jk"] is not None else 1.0)
+            norm = (abs(self.det_host[s["i"]]) / vol * out2[u, 0]) ** 0.25                   # :1352, :1359
             leg_idx, idx_n_bra, _ = _parity_n_argsort(n1.sum(axis=1))                        # :1732
             bm, km = _pack(n1[leg_idx]), _pack(n2)
             m_chunks += [bm, km]
@@ -825,7 +877,8 @@ class _PfChain:
             if res is None:
                 raise AssertionError("Boguliubov vacua do not overlap (U nearly singular)")  # :1355-1357
             svprod, N, n1, n2 = res
-            norm = (abs(self.det_host[s["i"]]) * svprod) ** 0.25                             # :1352, :1359
+            vol = (self.vol[s["jb"]] if s["jb"] is not None else 1.0) * (self.vol[s["jk"]] if s["jk"] is not None else 1.0)
+            norm = (abs(self.det_host[s["i"]]) / vol * svprod) ** 0.25                       # :1352, :1359
             leg_idx, idx_n_bra, _ = _parity_n_argsort(n1.sum(axis=1))                        # :1732
             bm, km = _pack(n1[leg_idx]), _pack(n2)
             m = N.shape[0]
@@ -931,12 +984,256 @@ def H_to_MPS(H: np.ndarray, trunc_par: dict | StoppingCondition, *, basis: str, 
                     unit_cell_width=unit_cell_width, as_tenpy=as_tenpy, _backend=_backend)
 
 
-def C_to_iMPS(C_short, C_long, trunc_par, sites_per_cell, cut, *, basis, **kwargs):
-    r"""iMPS representation of a Pfaffian state (pfaffian.py:1924-2091)."""
-    raise NotImplementedError("pfaffian.C_to_iMPS: the unit-cell conversion of Pfaffian states is not part of "
-                              "this release (SURVEY 8a row a19, iMPS half)")
+#### iMPS (pfaffian.py:1924-2242) ####
+@dataclass
+class PfCellTensor:
+    """Dense site tensor ``T[vL, p, vR]`` of the unit cell (the gauge-rotated first tensor)."""
+    T: np.ndarray
+    qtotal: int = 0
+
+    def dense(self):
+        return self.T
 
 
-def H_to_iMPS(H_short, H_long, trunc_par, sites_per_cell, cut, *, basis, **kwargs):
-    r"""iMPS representation from BdG Hamiltonians (pfaffian.py:2151-2242)."""
-    raise NotImplementedError("pfaffian.H_to_iMPS: see C_to_iMPS")
+def _rotated_slot(chain, job, Q, sign):
+    """Copy of the V slot of ``job`` whose k entangled complex modes are replaced by ``sign * sum_b w_b Q[b, a]``
+    (the centre-bond rotation of block_svd, pfaffian.py:855, and the sign of :915-916 baked into the modes; the chain
+    driver applies both lazily, to ket columns of the site matrices)."""
+    be = chain.be
+    rows, k = int(chain.rows[job]), int(chain.k[job])
+    o = int(chain.v_off[job])
+    slot = chain.Vd[o: o + rows * rows]
+    slot = slot.clone() if hasattr(slot, "clone") else slot.copy()
+    if k == 0:
+        return slot
+    cols = np.array(be.to_host(chain.Vd[o: o + rows * 4 * k], rows * 4 * k)).reshape(4 * k, rows)
+    W = (cols[0::4, 0::2] + 1j * cols[0::4, 1::2]).T                # (2 n_side, k) complex modes, e ascending
+    W = sign * (W @ Q)
+    out = np.empty((4 * k, rows))
+    for a in range(k):
+        u = np.empty(rows)
+        u[0::2], u[1::2] = W[:, a].real, W[:, a].imag
+        ju = np.empty(rows)
+        ju[0::2], ju[1::2] = -u[1::2], u[0::2]
+        cu = u.copy()
+        cu[1::2] *= -1
+        jcu = np.empty(rows)
+        jcu[0::2], jcu[1::2] = u[1::2], u[0::2]
+        out[4 * a: 4 * a + 4] = (u, ju, cu, jcu)
+    d = be.from_host(out.ravel())
+    slot[: out.size] = d[: out.size]
+    return slot
+
+
+def _cross_tensor(be, bra, ket, mode, physical, trunc):
+    """One tensor between Schmidt vectors of two different chains (pfaffian.py:1578-1748 as called at :2027 and
+    :2051): ``bra`` / ``ket`` = (chain, bond, job, V slot, nb sites on that side).  Same device stages as a chain site --
+    overlap + elimination of the non-entangled modes, site finish, Pfaffian blocks -- with the parity fix decided by
+    the known vacuum parities of the two chains.  Returns (PfSiteTensor, qtotal)."""
+    lib = be.lib
+    (cb, xb, jb, Vb, nb), (ck, xk, jk, Vk, nk) = bra, ket
+    side = _lib.SIDE_R if mode else _lib.SIDE_L
+    k1, f1 = int(cb.k[jb]), int(cb.f[jb])
+    k2, f2 = int(ck.k[jk]), int(ck.f[jk])
+    assert nk == nb + (1 if physical else 0), "bra and ket sizes do not match"
+    act_b = list(range(k1 - 1, -1, -1)) if mode else list(range(k1))
+    act_k = list(range(k2 - 1, -1, -1)) if mode else list(range(k2))
+    ent_up = [4 * a + t for a in act_b for t in (2, 3)]
+    ent_lo = [4 * a + t for a in act_b for t in (0, 1)]
+    if not physical:
+        bra_some = ent_up + ent_lo
+    elif mode:
+        bra_some = [-3, -4] + ent_up + [-1, -2] + ent_lo
+    else:
+        bra_some = ent_up + [-3, -4] + ent_lo + [-1, -2]
+    bra_cols = [4 * k1 + c for c in range(f1)] + bra_some
+    ket_cols = [4 * k2 + c for c in range(f2)] + [4 * a + t for a in act_k for t in (2, 3)] + \
+               [4 * a + t for a in act_k for t in (0, 1)]
+    sb, sk = 4 * (k1 + (1 if physical else 0)), 4 * k2
+    sur_b, sur_k = max(f1 - f2, 0), max(f2 - f1, 0)
+    cols_d = be.from_host(np.array(bra_cols + ket_cols, dtype=np.int32))
+    ones_d = be.from_host(np.ones(max(f1 + sb, f2 + sk, 1), dtype=np.float64))
+    Od = be.empty(max((f1 + sb) * (f2 + sk), 1), np.float64)
+    Sd = be.empty(max((sb + sur_b) * (sk + sur_k), 1), np.float64)
+    detd = be.empty(1, np.float64)
+    sj = (_lib.SiteJob * 1)()
+    j = sj[0]
+    j.Vb, j.Vk = be.ptr(Vb), be.ptr(Vk)
+    j.bra_cols, j.ket_cols = be.ptr(cols_d), be.ptr(cols_d) + 4 * len(bra_cols)
+    j.bra_sign = j.ket_sign = be.ptr(ones_d)
+    j.O, j.S, j.det = be.ptr(Od), be.ptr(Sd), be.ptr(detd)
+    j.ldb, j.ldk = max(4 * nb, 1), 4 * nk
+    j.n_bra, j.n_ket = nb, nk
+    j.mode, j.physical = mode, int(physical)
+    j.ka_bra, j.ka_ket = f1, f2
+    j.sb, j.sk = sb, sk
+    j.emb = 1
+    desc = be.empty(int(lib.tmf_site_desc_bytes(1)), np.uint8)
+    check(lib, lib.tmf_site_overlap_schur_batched(sj, 1, be.ptr(desc), be.stream))
+    be.sync()
+    det = float(be.to_host(detd, 1)[0])
+    # parities (pfaffian.py:1631-1646, :1708-1719)
+    Bb, Bk = cb.bonds[xb], ck.bonds[xk]
+    par_b, par_k = (Bb.pR, Bk.pR) if mode else (Bb.pL, Bk.pL)
+    fix = (par_b % 2) != (par_k % 2)
+    # (the same fact read off the matrix itself, as the chain driver does: vacua of opposite parity do not overlap)
+    pj0 = (_lib.PfSiteJob * 1)()
+    outd0 = be.empty(2, np.float64)
+    q0 = pj0[0]
+    q0.S, q0.out = be.ptr(Sd), be.ptr(outd0)
+    q0.sb, q0.sk, q0.sur_b, q0.sur_k, q0.mode, q0.k1, q0.k2 = sb, sk, sur_b, sur_k, mode, k1, k2
+    q0.fix, q0.want_n, q0.no_phys, q0.u_p, q0.ket_sign = 0, 0, int(not physical), 1.0, 1.0
+    d0 = be.empty(128, np.uint8)
+    check(lib, lib.tmf_pfaffian_site_finish(pj0, 1, be.ptr(d0), be.stream))
+    be.sync()
+    singular = bool(be.to_host(outd0, 2)[1] < _SINGULAR)
+    if singular != fix:
+        logger.warning("vacuum parities of the two chains (%d, %d) disagree with the overlap of their vacua; "
+                       "following the overlap", par_b, par_k)
+        fix = singular
+    qtotal = ((Bb.pL + Bb.pR) + (Bk.pL + Bk.pR)) % 2 if mode else 0
+    sets_b = Bb.sets[:, ::-1] if mode else Bb.sets
+    sets_k = Bk.sets[:, ::-1] if mode else Bk.sets
+    if physical:
+        off, on = np.zeros((len(sets_b), 1), bool), np.ones((len(sets_b), 1), bool)
+        sets_bra = np.block([[off, sets_b], [on, sets_b]]) if mode else np.block([[sets_b, off], [sets_b, on]])
+    else:
+        sets_bra = sets_b.copy()
+    if fix:
+        c = 0 if mode == 1 else -1
+        sets_bra[:, c] = ~sets_bra[:, c]
+    u_p = -1.0 if (physical and mode == 0 and Bb.pL == 1) else 1.0
+    idx1 = np.flatnonzero(sets_bra.any(axis=0))
+    idx2 = np.flatnonzero(sets_k.any(axis=0))[::-1]
+    m = len(idx1) + len(idx2)
+    Nd = be.empty(max(2 * m * m, 1), np.float64)
+    outd = be.empty(2, np.float64)
+    pj = (_lib.PfSiteJob * 1)()
+    q = pj[0]
+    q.S, q.N, q.out = be.ptr(Sd), be.ptr(Nd), be.ptr(outd)
+    q.idx1_mask, q.idx2_mask = int(sum(1 << int(t) for t in idx1)), int(sum(1 << int(t) for t in idx2))
+    q.sb, q.sk, q.sur_b, q.sur_k, q.mode, q.k1, q.k2 = sb, sk, sur_b, sur_k, mode, k1, k2
+    q.fix, q.want_n, q.no_phys, q.u_p, q.ket_sign = int(fix), 1, int(not physical), u_p, 1.0
+    d2 = be.empty(128, np.uint8)
+    check(lib, lib.tmf_pfaffian_site_finish(pj, 1, be.ptr(d2), be.stream))
+    be.sync()
+    fin = be.to_host(outd, 2)
+    if fin[0] < 0:
+        raise AssertionError("inconsistent mode counts")
+    if fin[1] < _SINGULAR:
+        raise AssertionError("Boguliubov vacua do not overlap (U nearly singular)")
+    norm = (abs(det) / (cb.vol[jb] * ck.vol[jk]) * float(fin[0])) ** 0.25
+    s1, s2 = sets_bra[:, idx1], sets_k[:, idx2]
+    n1 = np.concatenate((np.zeros((len(s1), s2.shape[1]), bool), s1), axis=1)
+    n2 = np.concatenate((s2, np.zeros((len(s2), s1.shape[1]), bool)), axis=1)
+    leg_idx, idx_n_bra, _ = _parity_n_argsort(n1.sum(axis=1))
+    bm, km = _pack(n1[leg_idx]), _pack(n2)
+    Md = be.from_host(np.concatenate([bm, km]).astype(np.uint64).view(np.int64))
+    blocks, out_off = [], 0
+    for nb_, sb_ in idx_n_bra.items():
+        for nk_, sk_ in Bk.idx_n.items():
+            if (nb_ + nk_) % 2 == 1:
+                continue
+            nr, nc = sb_.stop - sb_.start, sk_.stop - sk_.start
+            blocks.append((sb_, sk_, out_off, nr, nc, int(nb_), int(nk_)))
+            out_off += 2 * nr * nc
+    outb = be.empty(max(out_off, 1), np.float64)
+    pb = (_lib.PfBlock * max(len(blocks), 1))()
+    for u, (sb_, sk_, oo, nr, nc, n1_, n2_) in enumerate(blocks):
+        pb[u].N = be.ptr(Nd)
+        pb[u].bra_masks = be.ptr(Md) + 8 * sb_.start
+        pb[u].ket_masks = be.ptr(Md) + 8 * (len(bm) + sk_.start)
+        pb[u].out = be.ptr(outb) + 8 * oo
+        pb[u].scale = norm
+        pb[u].m, pb[u].n_bra, pb[u].n_ket, pb[u].n1, pb[u].n2 = m, nr, nc, n1_, n2_
+    d3 = be.empty(int(lib.tmf_pf_desc_bytes(len(blocks))), np.uint8)
+    check(lib, lib.tmf_pfaffians_blocks(pb, len(blocks), be.ptr(d3), be.stream))
+    be.sync()
+    out = be.to_host(outb, max(out_off, 1))
+    chi_b, chi_k = len(Bb.schmidt_values), len(Bk.schmidt_values)
+    t = PfSiteTensor(site=-1, mode="right" if mode else "left", chi_bra=chi_b, chi_ket=chi_k, norm=norm,
+                     qtotal=int(qtotal))
+    for (sb_, sk_, oo, nr, nc, _a, _b) in blocks:
+        blk = out[oo: oo + 2 * nr * nc]
+        t.blocks.append((leg_idx[sb_], sk_, (blk[0::2] + 1j * blk[1::2]).reshape(nr, nc)))
+    return t
+
+
+def C_to_iMPS(C_short, C_long, trunc_par, sites_per_cell, cut, *, basis, diag_tol: float = _DIAG_TOL,
+              unitary_tol: float = _iMPS._UNITARY_TOL, schmidt_tol: float = _iMPS._SCHMIDT_TOL,
+              unit_cell_width: int | None = None, as_tenpy: bool | None = None, _backend=None):
+    r"""iMPS representation of a Nambu mean-field state from the correlation matrices of two chains that differ by
+    one unit cell (pfaffian.py:1924-2091; same parameters).  Returns ``(BlockMPS(bc="infinite"), iMPSError)``.
+
+    The right-canonical tensors of the additional unit cell are site tensors of the long chain converted with its
+    orthogonality centre at ``cut``; the tensor that closes the cell (right environment of the *short* chain,
+    :2018-2027) and the gauge overlap of the two left Schmidt bases (:2051) join Schmidt vectors of different chains
+    and run through the same device stages one at a time; the gauge fixing is ``iMPS.basis_rotation`` (:2053-2061).
+    Both chains are converted completely (the vacuum parities of this implementation come from the chain ends,
+    see the module docstring)."""
+    trunc_par = to_stopping_condition(trunc_par)
+    C_short, C_long = np.asarray(C_short), np.asarray(C_long)
+    L_short, L_long = len(C_short) // 2, len(C_long) // 2
+    assert C_short.shape == (2 * L_short, 2 * L_short), f"Got correlation matrix of invalid shape {C_short.shape}."
+    assert C_long.shape == (2 * L_long, 2 * L_long), f"Got correlation matrix of invalid shape {C_long.shape}."
+    assert L_short + sites_per_cell == L_long, ("The given two MPS must differ by one unit cell, got "
+                                                f"{L_long} - {L_short} != {sites_per_cell}")
+    if unit_cell_width is None:
+        unit_cell_width = sites_per_cell
+    elif sites_per_cell % unit_cell_width != 0:
+        raise ValueError(f"{unit_cell_width = } does not divide {sites_per_cell = }")
+    assert 0 < cut < L_short, "`cut` must lie inside the short chain"
+    be = _backend or _be()
+    cutoff = trunc_par.svd_min ** 2
+    cell = sites_per_cell
+    long_ = _PfChain(be, _prepare_CM(C_long, basis, cutoff), trunc_par, cut).run()
+    short = _PfChain(be, _prepare_CM(C_short, basis, cutoff), trunc_par, cut).run()
+    L_, R_ = _lib.SIDE_L, _lib.SIDE_R
+    js_l, js_r = short.job_of[(cut, L_)], short.job_of[(cut, R_)]
+    jl_l = long_.job_of[(cut, L_)]
+    sgn_s = -1.0 if short.bonds[cut].pL == 1 else 1.0                                     # pfaffian.py:915-916
+    Vs_r = _rotated_slot(short, js_r, short.QRup.conj(), sgn_s)
+    Vs_l = _rotated_slot(short, js_l, short.QL, 1.0)
+    Vl_l = _rotated_slot(long_, jl_l, long_.QL, 1.0)
+    # cell tensors: sites cut .. cut + cell - 2 of the long chain, then the closing tensor
+    tensors = [long_.site_tensors[cut + i] for i in range(cell - 1)]
+    xk = cut + cell - 1
+    if cell == 1:      # ket = centre bond of the long chain: its right modes carry the centre rotation too
+        jk = long_.job_of[(cut, R_)]
+        sgn_l = -1.0 if long_.bonds[cut].pL == 1 else 1.0
+        Vk = _rotated_slot(long_, jk, long_.QRup.conj(), sgn_l)
+    else:
+        jk = long_.job_of[(xk, R_)]
+        o = int(long_.v_off[jk])
+        Vk = long_.Vd[o: o + int(long_.rows[jk]) ** 2]
+    nb = L_short - cut
+    tensors.append(_cross_tensor(be, (short, cut, js_r, Vs_r, nb), (long_, xk, jk, Vk, nb + 1), 1, True, trunc_par))
+    gauge = _cross_tensor(be, (short, cut, js_l, Vs_l, cut), (long_, cut, jl_l, Vl_l, cut), 0, False, trunc_par)
+    b_short, b_long = short.bonds[cut], long_.bonds[cut]
+    Cov = np.zeros((gauge.chi_bra, gauge.chi_ket), dtype=complex)
+    for rows, sk_, blk in gauge.blocks:
+        Cov[rows, sk_] = blk
+    R, left_unitary, left_schmidt = _iMPS.basis_rotation(Cov, b_short.schmidt_values, b_long.schmidt_values, "left",
+                                                         unitary_tol=unitary_tol, schmidt_tol=schmidt_tol,
+                                                         q_bra=b_short.charge, q_ket=b_long.charge)
+    first = np.tensordot(R, tensors[0].dense(), axes=(1, 0))                             # pfaffian.py:2063
+    tensors[0] = PfCellTensor(first, int(getattr(tensors[0], "qtotal", 0)))
+    lam0 = normalize_SV(b_short.schmidt_values, logger)
+    lams = [lam0] + [normalize_SV(long_.bonds[cut + i + 1].schmidt_values, logger) for i in range(cell - 1)] + [lam0]
+    charges = [b_short.charge] + [long_.bonds[cut + i + 1].charge for i in range(cell - 1)] + [b_short.charge]
+    mps = BlockMPS(L=cell, tensors=tensors, lams=lams, charges=charges, form=["B"] * cell,
+                   unit_cell_width=unit_cell_width, ortho_center=None, bc="infinite", conserve="parity",
+                   meta=dict(qtotal=[int(getattr(t, "qtotal", 0)) for t in tensors]))
+    err = _iMPS.iMPSError(left_unitary, left_schmidt, 0.0, 0.0)
+    return (mps.to_tenpy() if _want_tenpy(as_tenpy) else mps), err
+
+
+def H_to_iMPS(H_short, H_long, trunc_par, sites_per_cell, cut, *, basis, diag_tol: float = _DIAG_TOL,
+              unitary_tol: float = _iMPS._UNITARY_TOL, schmidt_tol: float = _iMPS._SCHMIDT_TOL,
+              unit_cell_width: int | None = None, as_tenpy: bool | None = None, _backend=None):
+    r"""iMPS representation from BdG Hamiltonians (pfaffian.py:2094-2242)."""
+    C_short = correlation_matrix(H_short, basis=f"{basis}->{basis}", _backend=_backend)
+    C_long = correlation_matrix(H_long, basis=f"{basis}->{basis}", _backend=_backend)
+    return C_to_iMPS(C_short, C_long, trunc_par, sites_per_cell, cut, basis=basis, diag_tol=diag_tol,
+                     unitary_tol=unitary_tol, schmidt_tol=schmidt_tol, unit_cell_width=unit_cell_width,
+                     as_tenpy=as_tenpy, _backend=_backend)

@@ -196,6 +196,28 @@ def test_sim_site_finish_device_vs_host(sim_backend, monkeypatch):
     _finish_device_vs_host(sim_backend, monkeypatch)
 
 
+def _site_norms_vs_oracle(be):
+    """Onishi norms of the site tensors (pfaffian.py:1352-1359) against the oracle for a chain whose weakest
+    entangled mode sits just above the cutoff (e = 3e-12): the non-entangled basis must be the exact complement of the
+    *final* entangled columns (_PfChain._align_filled), otherwise the norms are off by theta^2 ~ 5e-8."""
+    from temfpy_b200.schmidt_utils import to_stopping_condition
+    L, cut, tp = 22, 10, {"chi_max": 32}
+    Cl = po.correlation_matrix(po.bdg_chain(L, mu=0.3, delta=0.4), "C->C")
+    trunc, t = po.Trunc.make(tp), to_stopping_condition(tp)
+    chain = pf._PfChain(be, pf._prepare_CM(Cl, "C", t.svd_min ** 2), t, cut).run()
+    centre = po.bond_vectors_from_C(Cl, cut, trunc, "C")
+    assert centre.modes.e.min() < 1e-11
+    par, prev = centre.modes.parity(), centre
+    for i in range(cut, L):
+        new = po.bond_vectors_from_C(Cl, i + 1, trunc, "C", "R", par)
+        assert abs(po.tensor_data(new, prev, "right").norm - chain.site_tensors[i].norm) < 1e-12, i
+        prev = new
+
+
+def test_sim_site_norms_vs_oracle(sim_backend):
+    _site_norms_vs_oracle(sim_backend)
+
+
 def _centre_half_modes(be, L, oc=None):
     """Eigenvalue-1/2 Schmidt modes on the *central* bond (pfaffian.py:857-865): the symmetric chain cut at an
     odd bond.  The two real bases of the 1/2 space are paired by an SVD; the result equals the reference's state."""
@@ -262,6 +284,7 @@ def test_gpu_chain_vs_oracle(gpu_backend, H, tp):
 @pytest.mark.gpu
 def test_gpu_site_finish_device_vs_host(gpu_backend, monkeypatch):
     _finish_device_vs_host(gpu_backend, monkeypatch)
+    _site_norms_vs_oracle(gpu_backend)
 
 
 @pytest.mark.gpu
@@ -281,3 +304,47 @@ def test_gpu_cfg2_kitaev_chain_L128(gpu_backend):
     rep = helpers.compare_pf_mps(ref, helpers.block_mps_to_dense(got), _half_bonds(Cm, tp))
     assert max(len(l) for l in got.lams) == 128
     print("cfg2 parity:", rep)
+
+
+# ---------------------------------------------------------------------------------------------
+# iMPS (pfaffian.py:1924-2242)
+# ---------------------------------------------------------------------------------------------
+def _imps_vs_oracle(be, Ls, cell, cut, tp, mu=0.3, delta=0.4):
+    """pfaffian.C_to_iMPS against the oracle restatement: bond dimensions, Schmidt values, parity charges, the two
+    error metrics and the unit cell itself (dominant eigenvalue of the mixed transfer matrix)."""
+    from tests.test_imps import cell_transfer_eig
+    import warnings
+    Cs = po.correlation_matrix(po.bdg_chain(Ls, mu=mu, delta=delta), "C->C")
+    Cl = po.correlation_matrix(po.bdg_chain(Ls + cell, mu=mu, delta=delta), "C->C")
+    ref = po.C_to_iMPS(Cs, Cl, tp, cell, cut, "C")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mps, err = pf.C_to_iMPS(Cs, Cl, tp, cell, cut, basis="C", _backend=be, as_tenpy=False)
+    assert mps.bc == "infinite" and mps.L == cell and mps.conserve == "parity"
+    assert [len(l) for l in mps.lams] == [len(l) for l in ref.lams]
+    for a, b in zip(ref.lams, mps.lams):
+        assert np.all(np.abs(a - b) <= 1e-12 * a + np.minimum(1e-13 / (2 * a), 1e-8)), np.abs(a - b).max()
+    for a, b in zip(ref.charges, mps.charges):
+        assert np.array_equal(np.sort(a), np.sort(b))
+    got = [mps.get_B_dense(i) for i in range(mps.L)]
+    for i, T in enumerate(got):         # parity rule of every tensor: q(vL) + p - qtotal = q(vR) (mod 2)
+        a, p, b = np.nonzero(np.abs(T) > 1e-12)
+        d = np.unique((np.asarray(mps.charges[i])[a] + p - np.asarray(mps.charges[i + 1])[b]) % 2)
+        assert d.size == 1, (i, d)
+    assert abs(err.left_unitary ** 2 - ref.errors[0] ** 2) < 1e-12 and abs(err.left_schmidt - ref.errors[1]) < 1e-9
+    e_mix = cell_transfer_eig(ref.tensors, got)
+    fid = abs(e_mix) ** 2 / abs(cell_transfer_eig(ref.tensors, ref.tensors) * cell_transfer_eig(got, got))
+    assert fid >= 1 - 1e-9, fid
+    return fid, err
+
+
+@pytest.mark.parametrize("Ls,cell,cut,tp", [(20, 2, 10, {"chi_max": 32}), (18, 1, 9, {"chi_max": 24}),
+                                            (24, 4, 12, {"chi_max": 40})])
+def test_sim_imps_vs_oracle(sim_backend, Ls, cell, cut, tp):
+    _imps_vs_oracle(sim_backend, Ls, cell, cut, tp)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Ls,cell,cut,tp", [(32, 2, 16, {"chi_max": 64}), (64, 2, 32, {"chi_max": 96})])
+def test_gpu_imps_vs_oracle(gpu_backend, Ls, cell, cut, tp):
+    print(_imps_vs_oracle(gpu_backend, Ls, cell, cut, tp))
