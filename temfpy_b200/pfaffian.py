@@ -30,7 +30,8 @@ when the small Schur complement of ``U^*`` is singular; the absolute parities fo
 blocks at the two chain ends.
 
 Return type: :class:`temfpy_b200.mps.BlockMPS` with ``conserve="parity"`` (``.to_tenpy()`` builds the
-TeNPy object when ``tenpy`` is importable).  Not supported in this release: more than 16 entangled modes per
+TeNPy object when ``tenpy`` is importable); ``C_to_iMPS`` / ``H_to_iMPS`` return the unit cell as a
+``BlockMPS(bc="infinite")`` plus the ``iMPSError``.  Not supported in this release: more than 16 entangled modes per
 bond (``4k <= TMF_MAX_MODES``; raises ``NotImplementedError``).
 """
 from __future__ import annotations
