@@ -434,3 +434,25 @@ def test_gpu_infinite_input(gpu_backend, kind):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         print(_infinite_vs_finite(gpu_backend, kind))
+
+
+def test_sim_infinite_parity_input(sim_backend):
+    """Unit cell of pfaffian.C_to_iMPS (parity-conserving, complex): the projected cell tensor equals the dense
+    contraction of the two fermion tensors under the three masks (gutzwiller.py:236-244 with parity masks)."""
+    import warnings
+    import pfaffian_oracle as po
+    from temfpy_b200 import pfaffian as pf
+    Ls, cell, cut = 20, 2, 10
+    Cs = po.correlation_matrix(po.bdg_chain(Ls, mu=0.3, delta=0.4), "C->C")
+    Cl = po.correlation_matrix(po.bdg_chain(Ls + cell, mu=0.3, delta=0.4), "C->C")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        im, _ = pf.C_to_iMPS(Cs, Cl, {"chi_max": 32}, cell, cut, basis="C", _backend=sim_backend, as_tenpy=False)
+        th = np.einsum("apb,bqc->apqc", im.get_B_dense(0), im.get_B_dense(1))
+        cL, cR = np.asarray(im.charges[0]), np.asarray(im.charges[2])
+        for q_left in (0, 1):
+            sp = gw.abrikosov(im, q_left=q_left, return_canonical=False, _backend=sim_backend)
+            ref = np.stack([th[:, 1, 0, :], th[:, 0, 1, :]], axis=1)[cL % 2 == q_left][:, :, cR % 2 == q_left]
+            assert sp.bc == "infinite" and sp.L == 1 and np.array_equal(sp.get_B_dense(0), ref)
+        with pytest.raises(AssertionError):
+            gw.abrikosov_ph(im, _backend=sim_backend)          # odd parity per cell (gutzwiller.py:370-372)
