@@ -345,6 +345,9 @@ def test_sim_imps_vs_oracle(sim_backend, Ls, cell, cut, tp):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("Ls,cell,cut,tp", [(32, 2, 16, {"chi_max": 64}), (64, 2, 32, {"chi_max": 96})])
-def test_gpu_imps_vs_oracle(gpu_backend, Ls, cell, cut, tp):
-    print(_imps_vs_oracle(gpu_backend, Ls, cell, cut, tp))
+@pytest.mark.parametrize("Ls,cell,cut,tp,mu", [(32, 2, 16, {"chi_max": 64}, 0.3), (64, 2, 32, {"chi_max": 96}, 2.5),
+                                               (96, 3, 45, {"chi_max": 64}, -2.3)])
+def test_gpu_imps_vs_oracle(gpu_backend, Ls, cell, cut, tp, mu):
+    # (|mu| > 2 t: the trivial phase -- the topological one has Majorana zero modes, split by ~exp(-L), which
+    #  correlation_matrix refuses at these lengths like the reference, pfaffian.py:377-380)
+    print(_imps_vs_oracle(gpu_backend, Ls, cell, cut, tp, mu=mu))
