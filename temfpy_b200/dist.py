@@ -666,7 +666,8 @@ def C_to_MPS(C, trunc_par, *, ortho_center=None, spinful=None, unit_cell_width=N
     if rank == dst:
         slater._check_projector(Ce, be=be, Cd=C_dev)
     lo, hi = partition(L, world, tp.chi_max, ortho_center)[rank]
-    opts = dict(r_sketch=96 if cplx else 48, snap=False, nested=None, device_plan=None, cplx=cplx)
+    opts = dict(r_sketch=96 if cplx else 48, snap=False, nested=engine.default_nested(None, tp, cplx), device_plan=None,
+                cplx=cplx)
     codes = {"sketch": 1, "singular": 2, "nested": 3, "peer": 0}
     dev = _t(C_dev).device
     while True:

@@ -806,8 +806,8 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
     ``snap=False`` (default) is the reference's literal truncation (schmidt_utils.py:140-185 only sees
     degeneracies below ``degeneracy_tol``; where a multiplet that is degenerate in exact arithmetic straddles
     ``chi_max`` the kept part is decided by the rounding noise of the mode eigenvalues, in the reference as here)."""
-    opts = dict(r_sketch=r_sketch, snap=snap, nested=nested, device_plan=device_plan, cplx=cplx,
-                keep_device=keep_device, out_provider=out_provider)
+    opts = dict(r_sketch=r_sketch, snap=snap, nested=default_nested(nested, trunc, cplx), device_plan=device_plan,
+                cplx=cplx, keep_device=keep_device, out_provider=out_provider)
     while True:
         try:
             return _run_chain_once(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center, site_lo, site_hi,
@@ -826,6 +826,20 @@ def run_chain(backend, C_dev, ldc, L, trunc, n_fermion, ortho_center=None, site_
                 raise rt.err
             else:
                 opts["nested"] = False
+
+
+NESTED_MAX_SVD_MIN = 3e-5
+
+
+def default_nested(nested, trunc, cplx=False):
+    """The nested-projector site stage is exact up to O(cutoff), cutoff = svd_min^2: modes below the cutoff count as
+    exactly filled / empty when the filled spaces of neighbouring bonds are related.  At the default svd_min = 1e-6
+    that is 1e-12; for coarse truncations (svd_min = 1e-3: overlap with the reference 1 - 4e-9, found by
+    tools/campaign_sim.py) the explicit filled bases are used instead (exact; the coarse conversions are cheap).
+    Complex determinants have the nested form only."""
+    if nested is None and not cplx and trunc.svd_min > NESTED_MAX_SVD_MIN:
+        return False
+    return nested
 
 
 def _public_opts(opts):

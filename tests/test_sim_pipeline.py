@@ -231,3 +231,24 @@ def test_complex_public_api_vs_oracle(sim_backend):
         assert rep["overlap"] >= 1 - 1e-10
     finally:
         testing.TEST_ACTION = old
+
+
+def test_coarse_truncation_uses_exact_site_stage(sim_backend):
+    """svd_min = 1e-3 (cutoff 1e-6): the nested-projector site stage would be off by O(cutoff) (overlap with the
+    reference 1 - 3e-11 here, 1 - 4e-9 in the worst case tools/campaign_sim.py found); run_chain switches to the
+    explicit filled bases and agrees to rounding."""
+    from temfpy_b200 import engine
+    from temfpy_b200.schmidt_utils import to_stopping_condition
+    rng = np.random.default_rng(2)
+    L = 100
+    H = np.zeros((L, L))
+    i = np.arange(L - 1)
+    H[i, i + 1] = H[i + 1, i] = -1.0
+    H += np.diag(2.0 * rng.standard_normal(L))
+    tp = {"chi_max": 16, "svd_min": 1e-3}
+    Cm, n = so.correlation_matrix(H)
+    ref = so.C_to_MPS(Cm, tp)
+    res = engine.run_chain(sim_backend, np.ascontiguousarray(Cm).ravel(), L, L, to_stopping_condition(tp), n)
+    assert res.options["nested"] is False
+    rep = helpers.compare_mps(ref, helpers.chain_to_dense(res), tp)
+    assert abs(1 - rep["overlap"]) < 1e-13, rep

@@ -41,5 +41,6 @@ while time.time() < t_end:
         n_ok += 1
     except Exception as e:
         n_bad += 1
+        np.savez(f"/tmp/campaign_fail_{n_bad}.npz", H=H, chi_max=tp["chi_max"], svd_min=tp.get("svd_min", -1.0), oc=-1 if oc is None else oc)
         print("FAIL", kind, "L", L, tp, "oc", oc, type(e).__name__, str(e)[:200], flush=True)
 print("ok", n_ok, "bad", n_bad)
