@@ -456,3 +456,55 @@ def test_sim_infinite_parity_input(sim_backend):
             assert sp.bc == "infinite" and sp.L == 1 and np.array_equal(sp.get_B_dense(0), ref)
         with pytest.raises(AssertionError):
             gw.abrikosov_ph(im, _backend=sim_backend)          # odd parity per cell (gutzwiller.py:370-372)
+
+
+def _canon_abi_vs_host(be, seed):
+    """tmf_canon_* through the C ABI on a random charge-conserving MPS with rank-deficient, tall and wide blocks
+    (bond dimensions that grow and shrink, a dead sector): same Schmidt spectra as the host sweep, right-canonical
+    tensors, same state."""
+    import ctypes as C
+    from temfpy_b200 import _lib
+    rng = np.random.default_rng(seed)
+    qp = np.array([-1, 1])
+    dims = [{0: 1}, {-1: 1, 1: 1}, {-2: 3, 0: 5, 2: 2}, {-3: 2, -1: 7, 1: 9, 3: 1}, {-2: 12, 0: 4, 2: 6},
+            {-1: 3, 1: 3}, {0: 2}, {-1: 1, 1: 1}, {0: 1}]
+    qs = [np.concatenate([np.full(n, q) for q, n in sorted(d.items())]).astype(np.int64) for d in dims]
+    L = len(dims) - 1
+    T = []
+    for j in range(L):
+        a, b = len(qs[j]), len(qs[j + 1])
+        t = np.zeros((a, 2, b))
+        for s in range(2):
+            mask = (qs[j][:, None] + qp[s]) == qs[j + 1][None, :]
+            t[:, s, :] = rng.normal(size=(a, b)) * mask
+        if j == 3:                       # a rank-deficient block: two equal columns inside one sector
+            t[:, :, 1] = t[:, :, 0]
+        T.append(t)
+    ref_T, ref_l, ref_q = gw._canonical_form_finite(T, qs, qp, 1e-12)
+    flat = np.concatenate([t.ravel() for t in T])
+    offs = np.concatenate(([0], np.cumsum([t.size for t in T])))[:-1]
+    got = gw._canonical_form_device(be, (be.from_host(flat), [int(o) for o in offs]), qs, qp, 1e-12)
+    assert got is not None
+    dT, dl, dq = got
+    for x in range(L + 1):
+        a, b = np.sort(dl[x])[::-1], np.sort(ref_l[x])[::-1]
+        assert len(a) == len(b) and np.abs(a - b).max() < 1e-12, (x, a, b)
+        assert np.array_equal(np.sort(dq[x]), np.sort(ref_q[x]))
+    for t in dT:
+        e = np.einsum("apc,bpc->ab", t, t)
+        assert np.abs(e - np.eye(len(e))).max() < 1e-12
+    E = np.ones((1, 1))
+    for a, b in zip(dT, ref_T):
+        E = np.einsum("ab,apc,bpd->cd", E, a, b, optimize=True)
+    assert abs(abs(E[0, 0]) - 1) < 1e-12
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_sim_canon_abi_vs_host(sim_backend, seed):
+    _canon_abi_vs_host(sim_backend, seed)
+
+
+@pytest.mark.gpu
+def test_gpu_canon_abi_vs_host(gpu_backend):
+    for seed in (3, 4):
+        _canon_abi_vs_host(gpu_backend, seed)
