@@ -352,3 +352,20 @@ def test_gpu_imps_vs_oracle(gpu_backend, Ls, cell, cut, tp, mu):
     # (|mu| > 2 t: the trivial phase -- the topological one has Majorana zero modes, split by ~exp(-L), which
     #  correlation_matrix refuses at these lengths like the reference, pfaffian.py:377-380)
     print(_imps_vs_oracle(gpu_backend, Ls, cell, cut, tp, mu=mu))
+
+
+def test_oracle_imps_known_answers():
+    """The oracle restatement of pfaffian.C_to_iMPS (pfaffian.py:1924-2091; the reference driver itself needs TeNPy):
+    the unit cell reproduces the bulk density of the long chain, is unitarily gauged and has a normalised transfer
+    matrix."""
+    import slater_oracle as so
+    from tests.test_imps import cell_transfer_eig
+    L, cell, cut = 24, 2, 12
+    Cs = po.correlation_matrix(po.bdg_chain(L, mu=2.5, delta=0.4), "C->C")
+    Cl = po.correlation_matrix(po.bdg_chain(L + cell, mu=2.5, delta=0.4), "C->C")
+    im = po.C_to_iMPS(Cs, Cl, {"chi_max": 64}, cell, cut, "C")
+    assert im.errors[0] < 1e-6 and im.errors[1] < 1e-9
+    n, I = np.diag([0, 1.0]), np.eye(2)
+    assert abs(so.imps_expectation(im, [n, I]).real - Cl[2 * cut, 2 * cut].real) < 1e-6
+    assert abs(so.imps_expectation(im, [I, n]).real - Cl[2 * cut + 2, 2 * cut + 2].real) < 1e-6
+    assert abs(abs(cell_transfer_eig(im.tensors, im.tensors)) - 1) < 1e-6
