@@ -607,16 +607,27 @@ def _finish(mps, tensors, keepers, qvirt, qp, conserve, return_canonical, cutoff
                     conserve=conserve, meta=meta)
 
 
+def _deliver(given, inner, out, inplace):
+    """``inplace=True`` (gutzwiller.py:210 / :280): the projected state replaces the contents of the given
+    :class:`BlockMPS` and nothing is returned, like the reference does with the TeNPy object.  A TeNPy MPS made by
+    ``to_tenpy()`` cannot be rewritten from here (its tensors are TeNPy's): ask for the result instead."""
+    if not inplace:
+        return out
+    if given is not inner:
+        raise NotImplementedError("`inplace=True` needs the BlockMPS itself (a TeNPy MPS is not rewritten in place)")
+    inner.__dict__.update(out.__dict__)
+    return None
+
+
 def abrikosov(mps: BlockMPS, *, inplace: bool = False, return_canonical: bool = True, cutoff: float = 1e-12,
               q_left: None | int = None, unit_cell_width: int | None = None, _backend=None):
     r"""Projection from Abrikosov fermions to a spin-1/2 Hilbert space (gutzwiller.py:95-281):
     single occupation of :math:`f_{i\uparrow}` -> up, of :math:`f_{i\downarrow}` -> down.  The input may conserve
     the fermion number (``slater.C_to_MPS``) or only the parity (``pfaffian.C_to_MPS``)."""
     from . import slater as _sl
+    given = mps
     mps = _unwrap(mps)
     _validate(mps)
-    if inplace:
-        raise NotImplementedError("`inplace=True` is not supported: BlockMPS results are immutable")
     target = mps.L // 2
     if mps.bc == "finite":
         total = int(np.asarray(mps.charges[mps.L]).ravel()[0])
@@ -645,8 +656,8 @@ def abrikosov(mps: BlockMPS, *, inplace: bool = False, return_canonical: bool = 
     tensors, keepers, info = _project(mps, keep, ((0, 1, 0), (1, 0, 1)), be, mod)
     qvirt = [np.zeros(len(k), dtype=np.int64) for k in keepers]      # all charges dropped (:244)
     logger.info("Completed projection to spin-1/2 space. No conserved charges left.")
-    return _finish(mps, tensors, keepers, qvirt, np.zeros(2, dtype=np.int64), None, return_canonical, cutoff, ucw, info,
-                   be)
+    return _deliver(given, mps, _finish(mps, tensors, keepers, qvirt, np.zeros(2, dtype=np.int64), None,
+                                        return_canonical, cutoff, ucw, info, be), inplace)
 
 
 def abrikosov_ph(mps: BlockMPS, *, inplace: bool = False, return_canonical: bool = True, cutoff: float = 1e-12,
@@ -655,10 +666,9 @@ def abrikosov_ph(mps: BlockMPS, *, inplace: bool = False, return_canonical: bool
     zero occupation -> down, double occupation -> up.  For number-conserving input :math:`2S^z` = number - bond
     index is conserved; parity-conserving input (``pfaffian.C_to_MPS``) leaves no charge (:364-367, :444)."""
     from . import slater as _sl
+    given = mps
     mps = _unwrap(mps)
     _validate(mps)
-    if inplace:
-        raise NotImplementedError("`inplace=True` is not supported: BlockMPS results are immutable")
     finite = mps.bc == "finite"
     total = int(np.asarray(mps.charges[mps.L]).ravel()[0]) if finite else \
         int(sum(int(getattr(t, "qtotal", 0) or 0) for t in mps.tensors))
@@ -684,4 +694,5 @@ def abrikosov_ph(mps: BlockMPS, *, inplace: bool = False, return_canonical: bool
         qvirt = [np.zeros(len(k), dtype=np.int64) for k in keepers]
         qp, conserve = np.zeros(2, dtype=np.int64), None
     logger.info("Completed projection to spin-1/2 space. Conserved charge is now %s", conserve)
-    return _finish(mps, tensors, keepers, qvirt, qp, conserve, return_canonical, cutoff, ucw, info, be)
+    return _deliver(given, mps, _finish(mps, tensors, keepers, qvirt, qp, conserve, return_canonical, cutoff, ucw, info,
+                                        be), inplace)

@@ -225,8 +225,13 @@ def test_sim_validation(sim_backend):
     fm = slater.C_to_MPS(C_, {"chi_max": 64}, _backend=sim_backend, as_tenpy=False)
     with pytest.raises(AssertionError):
         gw.abrikosov(fm, _backend=sim_backend)            # 2 fermions on 3 spin sites
-    with pytest.raises(NotImplementedError):
-        gw.abrikosov_ph(fm, inplace=True, _backend=sim_backend)
+    # inplace=True rewrites the given BlockMPS and returns nothing (gutzwiller.py:210 / :280)
+    C_, _ = so.correlation_matrix(so.hopping_chain(6))
+    fm = slater.C_to_MPS(C_, {"chi_max": 64}, spinful="PH", _backend=sim_backend, as_tenpy=False)
+    want = gw.abrikosov_ph(fm, _backend=sim_backend)
+    assert gw.abrikosov_ph(fm, inplace=True, _backend=sim_backend) is None
+    assert fm.site_type == "SpinHalfSite" and fm.L == want.L and fm.conserve == "Sz"
+    assert all(np.array_equal(fm.get_B_dense(i), want.get_B_dense(i)) for i in range(fm.L))
 
 
 @pytest.mark.gpu
