@@ -4,7 +4,14 @@ The path shards without any data-path exchange between the compute stages: every
 data is a function of C alone and every site tensor needs its two adjacent bonds (reference
 slater.py:1303-1309, 1328-1334), so rank r converts a contiguous, cost-balanced range of sites and
 recomputes the one shared boundary bond with the same deterministic kernels (bit-identical results,
-see tests).  Collectives: one broadcast of C in, one gather of the block-sparse tensors out.
+see tests).  Collectives: one broadcast of C in; the block-sparse tensors go out either
+
+* into the HBM of the destination rank with the gather fused into the minors kernel -- the kernel's output pointer is
+  a slice of a CUDA-IPC peer window on the destination GPU (:class:`SlottedGather`: slots sized by an upper bound, no
+  exchange before the completion point; :class:`FusedGather`: exact slices, sizes exchanged through shared memory
+  after the enumeration stage), or by NCCL send / recv (:class:`StreamingGather`, :func:`gather_tensors`), or
+* into the host memory of the destination *process* over every GPU's own PCIe link (:class:`HostExchange`: shared
+  pinned segments, tables included, zero copy on the destination) -- what :func:`C_to_MPS` uses.
 """
 from __future__ import annotations
 
