@@ -219,3 +219,26 @@ def test_two_rank_slotted_gather(tmp_path):
     mp.spawn(_worker_slotted, args=(2, _free_port(), 24, 16, out), nprocs=2, join=True)
     ok, n = np.load(out)
     assert ok == 1 and n == 2
+
+
+def test_slotted_bound_covers_every_site():
+    """The slot of a site range is at least the size of its tensors: 2 chi_L chi_R elements per site with
+    chi <= min(chi_max, 2^x, 2^(L - x)) -- checked against actual conversions on the simulator."""
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import slater_oracle as so
+    from temfpy_b200 import engine
+    from temfpy_b200.schmidt_utils import to_stopping_condition
+    from tests import helpers
+    from tests.hostsim import NumpyBackend
+    be = NumpyBackend()
+    for L, chi, seed in ((20, 8, 1), (30, 64, 2), (16, 1000, 3)):
+        Cm, nf = so.correlation_matrix(helpers.random_hamiltonian(L, seed))
+        dmax = [min(chi, 2 ** min(x, L - x, 40)) for x in range(L + 1)]
+        off = np.concatenate(([0], np.cumsum([2 * dmax[i] * dmax[i + 1] for i in range(L)])))
+        for lo, hi in ((0, L), (3, 11), (L // 2, L)):
+            res = engine.run_chain(be, np.ascontiguousarray(Cm).ravel(), L, L, to_stopping_condition({"chi_max": chi}), nf,
+                                   site_lo=lo, site_hi=hi, n_chunks=1, lazy=True)
+            assert res.out_elems <= off[hi] - off[lo], (L, chi, lo, hi)
+            res.close()
